@@ -1,0 +1,196 @@
+"""ctypes binding of oracle/libldcore.so (the CPU restatement in ldcore.c) and
+helpers to run the compiled reference binaries under oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; never by tomahawk_b200/.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+
+from . import twk_format as tf
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+REF_CALC = os.path.join(REF_DIR, "tomahawk_calc")
+REF_VIEW = os.path.join(REF_DIR, "tomahawk_view")
+REF_FISHER = os.path.join(REF_DIR, "libref_fisher.so")
+
+VARIANT_DTYPE = np.dtype(
+    [("rid", "<u4"), ("pos", "<u4"), ("ac", "<u4"), ("an", "<u4"), ("hwe", "<f8"), ("gt_missing", "u1"), ("gt_phase", "u1"), ("pad", "u1", (6,))]
+)
+assert VARIANT_DTYPE.itemsize == 32
+
+
+class Params(ctypes.Structure):
+    """ld_params of ldcore.c: the twk_ld_settings fields calc reads
+    (include/core.h:909-924; defaults lib/core.cpp:297-306)."""
+
+    _fields_ = [
+        ("minP", ctypes.c_double),
+        ("minR2", ctypes.c_double),
+        ("maxR2", ctypes.c_double),
+        ("minDprime", ctypes.c_double),
+        ("maxDprime", ctypes.c_double),
+        ("force_phased", ctypes.c_int32),
+        ("forced_unphased", ctypes.c_int32),
+        ("window", ctypes.c_int32),
+        ("l_window", ctypes.c_int32),
+        ("emulate_quirks", ctypes.c_int32),
+        ("block_size", ctypes.c_int32),
+    ]
+
+
+def default_params(**kw) -> Params:
+    p = Params(1.0, 0.1, 100.0, 0.0, 100.0, 0, 0, 0, 1000000, 1, 500)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE, "libldcore.so"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "libldcore.so")
+        if not os.path.exists(path):
+            build()
+        L = ctypes.CDLL(path)
+        L.ldcore_fisher.restype = ctypes.c_double
+        L.ldcore_fisher.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p]
+        L.ldcore_calc.restype = ctypes.c_int64
+        L.ldcore_calc.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32,
+            ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64),
+        ]
+        L.ldcore_phased_stats.restype = ctypes.c_int
+        L.ldcore_phased_stats.argtypes = [ctypes.c_uint64] * 4 + [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.ldcore_unphased_stats.restype = ctypes.c_int
+        L.ldcore_unphased_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+STATS_DTYPE = np.dtype(
+    [("flags", "<u2"), ("pad", "u1", (6,)), ("cnt", "<f8", (4,)), ("D", "<f8"), ("Dprime", "<f8"), ("R", "<f8"), ("R2", "<f8"), ("P", "<f8"), ("chi_fisher", "<f8"), ("chi_model", "<f8")]
+)
+assert STATS_DTYPE.itemsize == 96
+
+
+def fisher(n11, n12, n21, n22) -> float:
+    return lib().ldcore_fisher(int(n11), int(n12), int(n21), int(n22), None, None)
+
+
+def phased_stats(c0, c1, c4, c5, params=None, a=None, b=None):
+    """counts in the reference's slot order (REFREF, slot1, slot4, ALTALT)."""
+    params = params or default_params()
+    va = np.zeros(1, VARIANT_DTYPE) if a is None else a
+    vb = np.zeros(1, VARIANT_DTYPE) if b is None else b
+    if a is None:
+        va["hwe"] = 1.0
+        va["ac"] = c1 + c5
+    if b is None:
+        vb["hwe"] = 1.0
+        vb["ac"] = c4 + c5
+    s = np.zeros(1, STATS_DTYPE)
+    ok = lib().ldcore_phased_stats(int(c0), int(c1), int(c4), int(c5), ctypes.byref(params), va.ctypes.data, vb.ctypes.data, s.ctypes.data)
+    return bool(ok), s[0]
+
+
+def unphased_stats(table, params=None):
+    params = params or default_params()
+    t = np.ascontiguousarray(np.asarray(table, dtype=np.uint64).reshape(3, 3))
+    va = np.zeros(1, VARIANT_DTYPE)
+    vb = np.zeros(1, VARIANT_DTYPE)
+    va["hwe"] = vb["hwe"] = 1.0
+    va["ac"] = vb["ac"] = 100
+    s = np.zeros(1, STATS_DTYPE)
+    ok = lib().ldcore_unphased_stats(t.ctypes.data, ctypes.byref(params), va.ctypes.data, vb.ctypes.data, s.ctypes.data)
+    return bool(ok), s[0]
+
+
+def variant_meta(s: tf.Synth) -> np.ndarray:
+    m = np.zeros(s.n_variants, VARIANT_DTYPE)
+    m["rid"] = s.rid
+    m["pos"] = s.pos
+    m["ac"] = s.ac
+    m["an"] = s.an
+    m["hwe"] = 1.0
+    m["gt_missing"] = s.an != 0
+    m["gt_phase"] = 1 if s.phased else 0
+    return m
+
+
+def calc(s: tf.Synth, params: Params, cap: int | None = None):
+    """Run the CPU restatement over all pairs -> (records[TWO_DTYPE], pairs_visited)."""
+    data, mask = tf.pack_bits(s)
+    meta = variant_meta(s)
+    M = s.n_variants
+    if cap is None:
+        cap = M * (M - 1) // 2 + 1
+    out = np.zeros(cap, tf.TWO_DTYPE)
+    visited = ctypes.c_uint64(0)
+    n = lib().ldcore_calc(
+        data.ctypes.data, mask.ctypes.data if mask is not None else None, data.shape[1], s.n_samples, M,
+        meta.ctypes.data, ctypes.byref(params), out.ctypes.data, cap, ctypes.byref(visited),
+    )
+    if n < 0:
+        raise RuntimeError("ldcore_calc: output capacity too small")
+    return out[:n].copy(), int(visited.value)
+
+
+# ---------------------------------------------------------- compiled reference
+def have_reference() -> bool:
+    return os.path.exists(REF_CALC) and os.access(REF_CALC, os.X_OK)
+
+
+_PROGRESS_RE = re.compile(r"\[PROGRESS\]\s+([\d,]+) variants/s and ([\d,]+) genotypes/s")
+_FINISHED_RE = re.compile(r"Finished in (\S+)\. Variants: ([\d,]+), genotypes: ([\d,]+), output: ([\d,]+)")
+
+
+def run_reference_calc(twk_path: str, out_prefix: str, args: list[str], threads: int | None = None, timeout=None):
+    """`tomahawk calc` of the reference itself. Returns dict(records, pairs, pairs_per_s, stderr)."""
+    threads = threads or os.cpu_count() or 1
+    cmd = [REF_CALC, "calc", "-i", twk_path, "-o", out_prefix, "-t", str(threads)] + list(args)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference calc failed ({r.returncode}): {r.stderr[-2000:]}")
+    info = {"stderr": r.stderr, "cmd": cmd}
+    m = _PROGRESS_RE.search(r.stderr)
+    if m:
+        info["pairs_per_s"] = int(m.group(1).replace(",", ""))
+        info["genotypes_per_s"] = int(m.group(2).replace(",", ""))
+    m = _FINISHED_RE.search(r.stderr)
+    if m:
+        info["pairs"] = int(m.group(2).replace(",", ""))
+        info["n_out"] = int(m.group(4).replace(",", ""))
+        info["elapsed_str"] = m.group(1)
+    return info
+
+
+_ref_fisher = None
+
+
+def reference_fisher(n11, n12, n21, n22) -> float:
+    """The reference's own kt_fisher_exact (lib/fisher_math.cpp:231) via oracle/_ref/libref_fisher.so."""
+    global _ref_fisher
+    if _ref_fisher is None:
+        L = ctypes.CDLL(REF_FISHER)
+        f = getattr(L, "_Z15kt_fisher_exactiiiiPdS_S_")
+        f.restype = ctypes.c_double
+        f.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_double)] * 3
+        _ref_fisher = f
+    l, r, t = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    _ref_fisher(int(n11), int(n12), int(n21), int(n22), ctypes.byref(l), ctypes.byref(r), ctypes.byref(t))
+    return t.value

@@ -1,0 +1,389 @@
+"""Test-side tooling for the Tomahawk on-disk formats and synthetic inputs.
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs. The product (tomahawk_b200/)
+never imports this module.
+
+What is here, and the reference layout each piece follows (paths relative to the
+reference tree):
+
+* ``synth_genotypes``    seeded synthetic diploid genotypes with a skewed
+                         allele-frequency spectrum and LD blocks.
+* ``pack_bits``          genotype codes -> the 1-bit/haplotype bitvector + missing
+                         mask of ``twk_igt_vec::Build`` (lib/core.cpp:349-383):
+                         haplotype p is bit p%64 of word p/64, sample s owns bits
+                         2s, 2s+1; both mask bits are set if either allele is
+                         missing.
+* ``write_twk``          a valid ``.twk`` file (magic, zstd(VcfHeader), blocks of
+                         <=500 ``twk1_t`` with run-length genotypes, zstd(Index)
+                         footer, offset, 32-char EOF): lib/importer.cpp:82-326,
+                         lib/core.cpp:59-73,245-251, include/core.h:195-205,
+                         lib/index.cpp:8-18,90-99,158-166, lib/header.cpp:330-345,
+                         include/header.h:115-128.
+* ``read_two``           ``.two`` -> numpy structured array of the 106-byte records
+                         (lib/core.cpp:470-490,626-631; include/writer.h:70-87).
+"""
+from __future__ import annotations
+
+import ctypes
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+
+# --------------------------------------------------------------------------- zstd
+_zstd = None
+
+
+def _libzstd():
+    global _zstd
+    if _zstd is None:
+        lib = ctypes.CDLL("libzstd.so.1")
+        lib.ZSTD_compressBound.restype = ctypes.c_size_t
+        lib.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+        lib.ZSTD_compress.restype = ctypes.c_size_t
+        lib.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        lib.ZSTD_decompress.restype = ctypes.c_size_t
+        lib.ZSTD_decompress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        lib.ZSTD_isError.restype = ctypes.c_uint
+        lib.ZSTD_isError.argtypes = [ctypes.c_size_t]
+        _zstd = lib
+    return _zstd
+
+
+def zstd_compress(data: bytes, level: int = 1) -> bytes:
+    lib = _libzstd()
+    cap = lib.ZSTD_compressBound(len(data))
+    dst = ctypes.create_string_buffer(cap)
+    n = lib.ZSTD_compress(dst, cap, data, len(data), level)
+    if lib.ZSTD_isError(n):
+        raise RuntimeError("ZSTD_compress failed")
+    return dst.raw[:n]
+
+
+def zstd_decompress(data: bytes, n_unc: int) -> bytes:
+    lib = _libzstd()
+    dst = ctypes.create_string_buffer(max(n_unc, 1))
+    n = lib.ZSTD_decompress(dst, n_unc, data, len(data))
+    if lib.ZSTD_isError(n) or n != n_unc:
+        raise RuntimeError("ZSTD_decompress failed")
+    return dst.raw[:n]
+
+
+# ---------------------------------------------------------------- synthetic data
+@dataclass
+class Synth:
+    """Genotypes as allele codes (0 ref, 1 alt, 2 missing; genotype_encoder.h:11-17)."""
+
+    alleles: np.ndarray  # uint8 [n_variants, 2*n_samples]
+    pos: np.ndarray  # uint32 [n_variants], 0-based, strictly increasing
+    rid: np.ndarray  # uint32 [n_variants]
+    n_samples: int
+    phased: bool = True
+
+    @property
+    def n_variants(self) -> int:
+        return int(self.alleles.shape[0])
+
+    @property
+    def ac(self) -> np.ndarray:
+        return (self.alleles == 1).sum(axis=1).astype(np.uint32)
+
+    @property
+    def an(self) -> np.ndarray:
+        """Number of missing alleles (what the reference stores in twk1_t::an)."""
+        return (self.alleles == 2).sum(axis=1).astype(np.uint32)
+
+
+def synth_genotypes(
+    n_samples: int,
+    n_variants: int,
+    seed: int = 1,
+    missing_rate: float = 0.0,
+    rare_fraction: float = 0.0,
+    pos_step: int = 100,
+    p_copy: float = 0.7,
+    redraw: float = 0.05,
+    chunk: int = 2048,
+) -> Synth:
+    """LD-block generator.
+
+    Variants come in blocks: a founder is drawn fresh with alt-allele frequency
+    0.5*U^3 (floored at 1/2N); each following variant continues the block with
+    probability ``p_copy`` and copies the founder's haplotypes with an
+    independent per-haplotype re-draw probability 1-(1-redraw)^depth.
+    ``rare_fraction`` of the founders are forced to MAF < 1 % (config 5).
+    Every variant is resampled until 1 <= ac <= 2N-1 (the reference asserts on
+    monomorphic sites, include/core.h:536-548). Missing genotypes knock out both
+    alleles of a sample i.i.d. with ``missing_rate``.
+    """
+    rng = np.random.default_rng(seed)
+    H = 2 * n_samples
+    out = np.zeros((n_variants, H), dtype=np.uint8)
+    # block structure
+    new_block = rng.random(n_variants) >= p_copy
+    new_block[0] = True
+    founder = np.maximum.accumulate(np.where(new_block, np.arange(n_variants), 0))
+    depth = np.arange(n_variants) - founder
+    af = 0.5 * rng.random(n_variants) ** 3
+    if rare_fraction > 0:
+        rare = rng.random(n_variants) < rare_fraction
+        af = np.where(rare, 0.01 * rng.random(n_variants), af)
+    af = np.maximum(af, 1.0 / H)
+    af = af[founder]
+    founders_idx = np.flatnonzero(new_block)
+    # founders first (fresh draws), in chunks
+    for s in range(0, len(founders_idx), chunk):
+        idx = founders_idx[s : s + chunk]
+        u = rng.random((len(idx), H), dtype=np.float32)
+        out[idx] = u < af[idx, None].astype(np.float32)
+    # members: copy founder with per-haplotype redraw
+    members_idx = np.flatnonzero(~new_block)
+    for s in range(0, len(members_idx), chunk):
+        idx = members_idx[s : s + chunk]
+        pr = 1.0 - (1.0 - redraw) ** depth[idx]
+        u = rng.random((len(idx), H), dtype=np.float32)
+        fresh = rng.random((len(idx), H), dtype=np.float32) < af[idx, None].astype(np.float32)
+        out[idx] = np.where(u < pr[:, None].astype(np.float32), fresh, out[founder[idx]])
+    # guarantee 1 <= ac <= H-1
+    ac = out.sum(axis=1)
+    for v in np.flatnonzero(ac == 0):
+        out[v, rng.integers(0, H)] = 1
+    for v in np.flatnonzero(ac == H):
+        out[v, rng.integers(0, H)] = 0
+    if missing_rate > 0:
+        for s in range(0, n_variants, chunk):
+            m = rng.random((min(chunk, n_variants - s), n_samples), dtype=np.float32) < missing_rate
+            m2 = np.repeat(m, 2, axis=1)
+            blk = out[s : s + chunk]
+            blk[m2] = 2
+        # keep at least one alt allele (ac >= 1) after knocking genotypes out
+        ac = (out == 1).sum(axis=1)
+        for v in np.flatnonzero(ac == 0):
+            out[v, 0] = 1
+            out[v, 1] = 0 if out[v, 1] == 2 else out[v, 1]
+    pos = (np.arange(n_variants, dtype=np.uint64) * pos_step).astype(np.uint32)
+    rid = np.zeros(n_variants, dtype=np.uint32)
+    return Synth(alleles=out, pos=pos, rid=rid, n_samples=n_samples)
+
+
+def words_per_variant(n_samples: int) -> int:
+    """Row stride (u64 words) of the packed matrix: ceil(2N/64) rounded up to a
+    multiple of 2 so every row is 128-bit aligned (the reference aligns rows to
+    SIMD_ALIGNMENT, include/core.h:52-60,126-136)."""
+    w = (2 * n_samples + 63) // 64
+    return (w + 1) // 2 * 2
+
+
+def pack_bits(s: Synth):
+    """-> (data[u64 M x W], mask[u64 M x W] or None). lib/core.cpp:365-383."""
+    M, H = s.alleles.shape
+    W = words_per_variant(s.n_samples)
+    pad = W * 64 - H
+    a = s.alleles
+    data_bits = (a == 1).astype(np.uint8)
+    miss = a == 2
+    has_missing = bool(miss.any())
+
+    def _pack(bits):
+        bits = np.pad(bits, ((0, 0), (0, pad)))
+        by = np.packbits(bits, axis=1, bitorder="little")
+        return np.ascontiguousarray(by).view("<u8").reshape(M, W)
+
+    data = _pack(data_bits)
+    mask = None
+    if has_missing:
+        ms = miss.reshape(M, s.n_samples, 2).any(axis=2)
+        mask = _pack(np.repeat(ms, 2, axis=1).astype(np.uint8))
+    return data, mask
+
+
+# ------------------------------------------------------------------- .twk writer
+def _wstr(b: bytearray, s: str | bytes):
+    if isinstance(s, str):
+        s = s.encode()
+    b += struct.pack("<I", len(s)) + s
+
+
+def _header_bytes(n_samples: int, contigs, literals: str) -> bytes:
+    b = bytearray()
+    _wstr(b, "##fileformat=VCFv4.2")
+    _wstr(b, literals)
+    b += struct.pack("<I", n_samples)
+    for i in range(n_samples):
+        _wstr(b, f"S{i}")
+    b += struct.pack("<I", len(contigs))
+    for idx, (name, n_bases) in enumerate(contigs):
+        b += struct.pack("<I", idx)
+        _wstr(b, name)
+        _wstr(b, "")
+        b += struct.pack("<q", n_bases)
+        b += struct.pack("<I", 0)
+    return bytes(b)
+
+
+def _rle_variant(al: np.ndarray, has_missing: bool):
+    """Run-length encode one variant's 2N allele codes -> (ptype, runs ndarray).
+
+    Run word = len << (2+2*miss) | refA << (1+miss) | refB (include/core.h:195-198).
+    """
+    n = al.shape[0] // 2
+    a = al[0::2].astype(np.uint32)
+    b = al[1::2].astype(np.uint32)
+    shift = 2 if has_missing else 1
+    code = (a << shift) | b
+    brk = np.flatnonzero(np.diff(code)) + 1
+    starts = np.concatenate(([0], brk))
+    lens = np.diff(np.concatenate((starts, [n])))
+    codes = code[starts]
+    lbits = 2 + 2 * int(has_missing)
+    for ptype, dt in ((1, np.uint8), (2, np.uint16), (4, np.uint32)):
+        maxlen = (1 << (8 * ptype - lbits)) - 1
+        # split long runs into pieces of <= maxlen
+        pieces = (lens + maxlen - 1) // maxlen
+        total = int(pieces.sum())
+        if ptype < 4 and total > 2 * len(lens) + 8:
+            continue  # too much splitting; use a wider primitive
+        rl = np.repeat(lens, pieces)
+        rc = np.repeat(codes, pieces)
+        # every piece but the last of each run is maxlen long
+        last = np.cumsum(pieces) - 1
+        full = np.full(total, maxlen, dtype=np.int64)
+        full[last] = lens - (pieces - 1) * maxlen
+        del rl
+        runs = ((full.astype(np.uint64) << lbits) | rc.astype(np.uint64)).astype(dt)
+        return ptype, runs
+    raise AssertionError
+
+
+def write_twk(path: str, s: Synth, block_size: int = 500, c_level: int = 1, contigs=None):
+    """Write ``s`` as a .twk file the reference's twk_reader::Open accepts."""
+    if contigs is None:
+        contigs = [("1", int(s.pos.max()) + 1000)]
+    M = s.n_variants
+    ac = s.ac
+    an = s.an
+    out = bytearray()
+    out += b"TOMAHAWK\x01"
+    hdr = _header_bytes(s.n_samples, contigs, "##fileformat=VCFv4.2\n##source=tomahawk_b200-synth\n")
+    hc = zstd_compress(hdr, c_level)
+    out += struct.pack("<QQ", len(hdr), len(hc)) + hc
+    index_entries = []
+    # blocks: <= block_size variants, one contig per block
+    start = 0
+    while start < M:
+        end = min(start + block_size, M)
+        same = np.flatnonzero(s.rid[start:end] != s.rid[start])
+        if len(same):
+            end = start + int(same[0])
+        n = end - start
+        blk = bytearray()
+        blk += struct.pack("<III", n, max(n, 500), int(s.rid[start]))
+        for v in range(start, end):
+            al = s.alleles[v]
+            miss = bool(an[v] != 0)
+            ptype, runs = _rle_variant(al, miss)
+            g = al.reshape(-1, 2)
+            n_het = int(((g[:, 0] != g[:, 1]) & (g[:, 0] != 2) & (g[:, 1] != 2)).sum())
+            n_hom = int(((g[:, 0] == 1) & (g[:, 1] == 1)).sum())
+            pack = (ptype << 3) | (0 << 2) | (int(s.phased) << 1) | int(miss)
+            blk += struct.pack("<BB", pack, (0 << 4) | 1)
+            blk += struct.pack("<IIIIII", int(s.pos[v]), int(ac[v]), int(an[v]), int(s.rid[v]), n_het, n_hom)
+            blk += struct.pack("<d", 1.0)
+            blk += struct.pack("<I", (len(runs) << 1) | int(miss))
+            blk += runs.astype(runs.dtype.newbyteorder("<")).tobytes()
+        bc = zstd_compress(bytes(blk), c_level)
+        foff = len(out)
+        out += struct.pack("<BII", 1, len(blk), len(bc)) + bc
+        fend = len(out)
+        index_entries.append(
+            (int(s.rid[start]), n, int(s.pos[start]) + 1, int(s.pos[end - 1]) + 1, len(blk), len(bc), foff, fend)
+        )
+        start = end
+    # footer
+    idx = bytearray()
+    n_ent = len(index_entries)
+    idx += struct.pack("<QQQQ", 1954702206512158641, n_ent, max(n_ent, 1), len(contigs))
+    for e in index_entries:
+        idx += struct.pack("<iIIIIIQQ", *e)
+    for c in range(len(contigs)):
+        ents = [e for e in index_entries if e[0] == c]
+        if ents:
+            idx += struct.pack(
+                "<iIIIQQQ", c, sum(e[1] for e in ents), ents[0][2], ents[-1][3], ents[0][6], ents[-1][7], len(ents)
+            )
+        else:
+            idx += struct.pack("<iIIIQQQ", 0, 0, 0, 0, 0, 0, 0)
+    ic = zstd_compress(bytes(idx), c_level)
+    off = len(out)
+    out += struct.pack("<BQQ", 0, len(idx), len(ic)) + ic
+    out += struct.pack("<Q", off)
+    out += b"a4f54f39f5e251a6993796f48164ccf554f1b680c2ebbb13be301f3ff76f82cf"[:32]
+    with open(path, "wb") as f:
+        f.write(out)
+    return n_ent
+
+
+# ------------------------------------------------------------------ .two reader
+TWO_DTYPE = np.dtype(
+    [
+        ("controller", "<u2"),
+        ("ridA", "<u4"),
+        ("ridB", "<u4"),
+        ("packA", "<u4"),
+        ("packB", "<u4"),
+        ("cnt", "<f8", (4,)),
+        ("D", "<f8"),
+        ("Dprime", "<f8"),
+        ("R", "<f8"),
+        ("R2", "<f8"),
+        ("P", "<f8"),
+        ("ChiSqFisher", "<f8"),
+        ("ChiSqModel", "<f8"),
+    ]
+)
+assert TWO_DTYPE.itemsize == 106
+
+
+def read_two(path: str) -> np.ndarray:
+    """All records of a .two file (both orientations, file order)."""
+    with open(path, "rb") as f:
+        buf = f.read()
+    assert buf[:4] == b"TWO\x01", "bad .two magic"
+    p = 4
+    unc, cmp_ = struct.unpack_from("<QQ", buf, p)
+    p += 16 + cmp_
+    chunks = []
+    while True:
+        marker = buf[p]
+        p += 1
+        if marker == 0:
+            break
+        assert marker == 1
+        unc, cmp_ = struct.unpack_from("<II", buf, p)
+        p += 8
+        raw = zstd_decompress(buf[p : p + cmp_], unc)
+        p += cmp_
+        n, m = struct.unpack_from("<II", raw, 0)
+        assert unc == 8 + 106 * n
+        chunks.append(np.frombuffer(raw, dtype=TWO_DTYPE, count=n, offset=8))
+    if not chunks:
+        return np.zeros(0, dtype=TWO_DTYPE)
+    return np.concatenate(chunks)
+
+
+def records_from_bytes(raw: bytes | np.ndarray) -> np.ndarray:
+    return np.frombuffer(bytes(raw), dtype=TWO_DTYPE)
+
+
+def canonical(recs: np.ndarray, forward_only: bool = True) -> np.ndarray:
+    """Sort records by (ridA,posA,ridB,posB); optionally keep only the forward
+    orientation (posA < posB on one contig) -- the reference emits each passing
+    pair twice (lib/ld/ld_engine.cpp:1290-1298)."""
+    posA = recs["packA"] >> 2
+    posB = recs["packB"] >> 2
+    if forward_only:
+        keep = (recs["ridA"] < recs["ridB"]) | ((recs["ridA"] == recs["ridB"]) & (posA < posB))
+        recs, posA, posB = recs[keep], posA[keep], posB[keep]
+    order = np.lexsort((posB, recs["ridB"], posA, recs["ridA"]))
+    return recs[order]
