@@ -1,0 +1,202 @@
+/* twkb.h -- C-ABI of the B200-native `tomahawk calc` engine (libtwkb.so).
+ *
+ * This is the drop-in boundary for ONE path of mklarqvist/tomahawk: pairwise LD
+ * (`tomahawk calc`, lib/ld in the reference). The reference has no FFI/plugin
+ * registry; the seam it does have is the library API
+ *     bool twk_ld::Compute(const twk_ld_settings&)            include/ld.h:53
+ * called by the CLI (lib/calc.h:237-238) and by the external R/Python bindings.
+ * Everything below is what a binding for that seam needs, in plain C types:
+ *
+ *   reference                                         | here
+ *   --------------------------------------------------+--------------------------
+ *   twk_ld_settings           include/core.h:909-924  | twkb_settings
+ *   twk1_t (pos/ac/an/rid/hwe) include/core.h:291-295 | twkb_variant
+ *   twk_igt_vec data/mask     include/core.h:724-753  | data_bits / mask_bits rows
+ *   twk_ld::Compute           lib/ld/ld.cpp:477-671   | twkb_create + twkb_load_matrix
+ *                                                     |   + twkb_compute
+ *   twk1_two_t serializer     lib/core.cpp:470-490    | 106-byte records handed to
+ *                                                     |   twkb_sink_fn
+ *   twk_ld_progress           lib/ld/ld_progress.h    | twkb_get_stats
+ *
+ * All functions return 0 on success or a negative TWKB_E* code; the message for
+ * the last failure on a context is available from twkb_last_error(). Nothing
+ * here ever falls back to a CPU implementation: without a CUDA device (or with
+ * a device other than sm_100) twkb_create fails with TWKB_ENODEVICE.
+ */
+#ifndef TWKB_H_
+#define TWKB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TWKB_OK 0
+#define TWKB_EINVAL (-1)    /* bad argument / inconsistent settings          */
+#define TWKB_ENODEVICE (-2) /* no usable sm_100 CUDA device                  */
+#define TWKB_ECUDA (-3)     /* CUDA runtime error (see twkb_last_error)      */
+#define TWKB_ENOMEM (-4)    /* host or device allocation failed              */
+#define TWKB_ESTATE (-5)    /* call order violated (e.g. compute before load)*/
+#define TWKB_ESINK (-6)     /* the record sink returned non-zero             */
+#define TWKB_EIO (-7)       /* file I/O (.twk reader / .two writer)          */
+
+#define TWKB_RECORD_BYTES 106 /* packed twk1_two_t, include/core.h:758-759 */
+
+/* Count kernel selection. AUTO picks the tensor-core (tcgen05 int8) kernel for
+ * phased data without missing genotypes and the LOP3+POPC kernel otherwise. */
+#define TWKB_KERNEL_AUTO 0
+#define TWKB_KERNEL_POPC 1
+#define TWKB_KERNEL_UMMA 2
+
+/* 1:1 with the fields of twk_ld_settings that `calc` reads (include/core.h:909-924;
+ * defaults lib/core.cpp:297-306 -- see twkb_settings_init), plus device placement.
+ * Flags accepted for CLI compatibility but with no effect on results are kept so a
+ * caller can pass its twk_ld_settings through unchanged. */
+typedef struct twkb_settings {
+    uint8_t square;          /* parsed by the reference, never read (lib/calc.h) */
+    uint8_t window;          /* -w given                                          */
+    uint8_t low_memory;      /* -m: CPU RAM trick; accepted, no-op                */
+    uint8_t bitmaps;         /* -M: EWAH bitmaps; accepted, same kernels          */
+    uint8_t single;          /* scalc mode (not on this path; must be 0)          */
+    uint8_t force_phased;    /* -p                                                */
+    uint8_t forced_unphased; /* -u                                                */
+    uint8_t emulate_quirks;  /* 1 (default): reproduce count-slot quirk Q3 of the
+                                reference for low-AC pairs with missing data      */
+    int32_t c_level;         /* zstd level of the .two writer (-c)                */
+    int32_t bl_size;         /* parsed by the reference, never read               */
+    int32_t b_size;          /* records per output block (10000)                  */
+    int32_t l_window;        /* -w window in bp                                   */
+    int32_t n_threads;       /* host writer threads (-t)                          */
+    int32_t l_surrounding;   /* scalc only                                        */
+    int32_t n_chunks;        /* -c: number of sub-problems, k(k+1)/2              */
+    int32_t c_chunk;         /* -C: chosen sub-problem, 0-based                   */
+    double minP, minR2, maxR2, minDprime, maxDprime; /* -P -r -R -d -D           */
+    /* --- B200 additions --- */
+    int32_t device;          /* CUDA device ordinal of this context               */
+    int32_t part_index;      /* multi-GPU: this context's share of the tile grid  */
+    int32_t part_count;      /*   (rank, world size); 0/1 = everything            */
+    int32_t kernel;          /* TWKB_KERNEL_*                                     */
+    int32_t twk_block_size;  /* .twk block length that defines window-mode tiles
+                                (500, lib/importer.h:36)                          */
+    int32_t reserved[5];
+} twkb_settings;
+
+/* Subset of twk1_t (include/core.h:291-295) the LD path reads. */
+typedef struct twkb_variant {
+    uint32_t rid;       /* contig id                                   */
+    uint32_t pos;       /* 0-based position                            */
+    uint32_t ac;        /* alt allele count                            */
+    uint32_t an;        /* number of MISSING alleles (reference naming) */
+    double hwe;         /* Hardy-Weinberg P                            */
+    uint8_t gt_missing; /* variant has a missing mask                  */
+    uint8_t gt_phase;   /* all genotypes phased                        */
+    uint8_t pad[6];
+} twkb_variant;
+
+/* Counters of one twkb_compute call (reference: twk_ld_progress n_var/n_out). */
+typedef struct twkb_stats {
+    uint64_t pairs_visited;   /* reference n_var: every pair of every processed tile   */
+    uint64_t pairs_screened;  /* pairs that survived the in-kernel R2 pre-screen       */
+    uint64_t records_out;     /* forward records handed to the sink                    */
+    uint64_t count_launches;  /* count-kernel launches                                 */
+    uint64_t stats_launches;  /* statistics-kernel launches                            */
+    uint64_t other_launches;  /* pack / expand / memset kernels                        */
+    double seconds_total;     /* wall clock of the call                                */
+    double ms_count_kernel;   /* CUDA-event time summed over count-kernel launches     */
+    double ms_stats_kernel;   /* CUDA-event time summed over stats-kernel launches     */
+    double ms_h2d;            /* CUDA-event time of the matrix upload + device packing */
+    uint64_t bytes_h2d, bytes_d2h;
+    int32_t kernel_used;      /* TWKB_KERNEL_POPC or TWKB_KERNEL_UMMA                  */
+    int32_t n_planes;         /* bit planes per variant on the device                  */
+    uint64_t word_ops;        /* 32-bit AND+POPC word operations (POPC kernel)         */
+    uint64_t mma_macs;        /* int8 multiply-accumulates issued (UMMA kernel)        */
+    double ms_device_total;   /* CUDA-event time from the first launch of the call to
+                                 the completion of its last kernel / copy             */
+} twkb_stats;
+
+/* Receives `n` packed 106-byte records (forward orientation: A is the variant
+ * with the lower index). Called on the calling thread of twkb_compute, between
+ * device batches. Return non-zero to abort the run (-> TWKB_ESINK). The reverse
+ * copies the reference also writes (lib/ld/ld_engine.cpp:1290-1298) are
+ * synthesised by the .two writer (twkb_two_writer_*), not by the device. */
+typedef int (*twkb_sink_fn)(void* user, const uint8_t* records, uint64_t n);
+
+void twkb_settings_init(twkb_settings* s); /* reference defaults, lib/core.cpp:297-306 */
+
+int twkb_create(const twkb_settings* s, void** ctx);
+void twkb_destroy(void* ctx);
+const char* twkb_last_error(void* ctx); /* ctx may be NULL: last create error */
+
+/* Replace thresholds/mode flags between runs without re-uploading the matrix. */
+int twkb_update_settings(void* ctx, const twkb_settings* s);
+
+/* Upload the genotype matrix. Rows follow twk_igt_vec (lib/core.cpp:349-383):
+ * haplotype p of a variant is bit (p % 64) of word (p / 64); sample s owns bits
+ * 2s and 2s+1; mask rows (nullable) have both bits of a sample set when either
+ * allele is missing. Host memory is copied; the caller keeps ownership.
+ * The device keeps the matrix transposed (word-major) -- see DESIGN.md. */
+int twkb_load_matrix(void* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* data_bits,
+                     const uint64_t* mask_bits, size_t row_stride_words, const twkb_variant* meta);
+
+/* Same, for rows that already live in device memory of this context's device
+ * (e.g. received by an NCCL broadcast). Pointers are CUDA device pointers. */
+int twkb_load_matrix_device(void* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* d_data_bits,
+                            const uint64_t* d_mask_bits, size_t row_stride_words, const twkb_variant* meta);
+
+/* Run the LD computation over this context's share of the pair grid. */
+int twkb_compute(void* ctx, twkb_sink_fn sink, void* user);
+
+/* Like twkb_compute, but keeps the records in a device buffer and only counts
+ * them (used to time the device-resident path; no D2H of records). */
+int twkb_compute_resident(void* ctx);
+
+int twkb_get_stats(void* ctx, twkb_stats* out);
+
+/* Test hook: run the count kernel over this context's share of the grid and return
+ * the raw candidate entries (12 uint32 each: i, j, c[9], mode) instead of records.
+ * screen_off != 0 disables the R2 pre-screen so every enumerated pair is returned
+ * with its exact contingency counts: mode 0 -> c = {REFREF, slot1 (A alt,B ref),
+ * slot4 (A ref,B alt), ALTALT}; mode 1 -> c = 3x3 genotype table t[gA][gB].
+ * out may be NULL to query the count. */
+int twkb_debug_candidates(void* ctx, int screen_off, uint32_t* out, uint64_t capacity, uint64_t* n_out);
+
+/* ---- host I/O around the engine (reference: lib/twk_reader.cpp, include/writer.h) ----
+ * Host-only (no CUDA call); zstd runs on the host. */
+
+/* `tomahawk calc` end to end = twk_ld::Compute(settings) (lib/ld/ld.cpp:477-671):
+ * read in_path (.twk), compute on settings->device, write out_path (.two; the
+ * reference's rule of forcing a ".two" suffix applies, ld.cpp:589-598). */
+int twkb_calc_file(const twkb_settings* s, const char* in_path, const char* out_path, twkb_stats* stats_out,
+                   char* errbuf, size_t errbuf_len);
+
+/* .twk reader (twk_reader::Open + twk1_blk_iterator::NextBlock + twk_igt_vec::Build):
+ * unpacks every block into the row layout twkb_load_matrix takes. */
+int twkb_twk_open(const char* path, int n_threads, void** handle, char* errbuf, size_t errbuf_len);
+int twkb_twk_dims(void* handle, uint32_t* n_samples, uint32_t* n_variants, size_t* row_stride_words,
+                  int32_t* any_missing, uint32_t* n_blocks);
+int twkb_twk_copy(void* handle, uint64_t* data_bits, uint64_t* mask_bits /* nullable */, twkb_variant* meta);
+void twkb_twk_close(void* handle);
+
+/* .two writer (twk_two_writer_t + twk_ld_engine::CompressFwd/Rev + IndexOutput): takes
+ * forward records, writes forward and reverse blocks of <= b_size records, index, EOF.
+ * twk_handle supplies the VcfHeader that is copied into the .two header. */
+int twkb_two_open(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t b_size,
+                  void** writer, char* errbuf, size_t errbuf_len);
+int twkb_two_add(void* writer, const uint8_t* records, uint64_t n);
+int twkb_two_close(void* writer); /* finishes the file and frees the writer */
+
+/* Tile scheduler, host only (the B200 counterpart of twk_ld_balancer /
+ * twk_ld_dynamic_balancer, lib/ld/ld_balancing.h): the (i0, j0) variant offsets of the
+ * tile_i x tile_j tiles that settings->part_index of settings->part_count computes
+ * (-c/-C chunk, -w window band and diagonal rules applied). out may be NULL to count. */
+int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i,
+                    uint32_t tile_j, uint32_t* out_ij, uint64_t capacity, uint64_t* n_tiles, uint64_t* n_pairs);
+
+int twkb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWKB_H_ */

@@ -5,7 +5,7 @@
  * --impl reference legs may load it. The product library (libtwkb.so) neither
  * links nor calls anything in oracle/.
  *
- * Parity status: PINNED. tests/test_oracle_vs_reference.py diffs this file
+ * Parity status: PINNED. tests/test_oracle.py diffs this file
  * against the reference's own `calc` binary (oracle/_ref/tomahawk_calc, built
  * from /root/reference by oracle/build_ref.sh) on shared synthetic .twk inputs,
  * against the reference's kt_fisher_exact (oracle/_ref/libref_fisher.so), and
@@ -44,6 +44,9 @@ typedef struct {
     int32_t window, l_window;              /* -w */
     int32_t emulate_quirks;                /* 1: reproduce Q1/Q3 of SURVEY.md App. C */
     int32_t block_size;                    /* .twk block length (500, lib/importer.h:36) */
+    int32_t skip_min_cell_rule;            /* test-only: bypass the "< 5" rule (:1174-1186) so the
+                                              tutorial rows, which predate it, can be replayed */
+    int32_t pad;
 } ld_params;
 
 /* ---------------------------------------------------------------- Fisher exact
@@ -170,10 +173,12 @@ int ldcore_phased_stats(uint64_t c0, uint64_t c1, uint64_t c4, uint64_t c5, cons
                         const ld_variant* a, const ld_variant* b, ld_stats* s) {
     uint64_t T = c0 + c4 + c1 + c5; /* :1164 */
     if (T < LD_MIN_ALLELES) return 0;
-    if (c0 < c5) { /* :1174-1186 */
-        if (c4 + c1 + c0 < 5) return 0;
-    } else {
-        if (c5 + c4 + c1 < 5) return 0;
+    if (!prm->skip_min_cell_rule) {
+        if (c0 < c5) { /* :1174-1186 */
+            if (c4 + c1 + c0 < 5) return 0;
+        } else {
+            if (c5 + c4 + c1 < 5) return 0;
+        }
     }
     double pA = (double)c0 / T, qA = (double)c1 / T, pB = (double)c4 / T, qB = (double)c5 / T; /* :1189-1192 */
     if (pA * qB - qA * pB == 0) return 0;

@@ -43,11 +43,13 @@ class Params(ctypes.Structure):
         ("l_window", ctypes.c_int32),
         ("emulate_quirks", ctypes.c_int32),
         ("block_size", ctypes.c_int32),
+        ("skip_min_cell_rule", ctypes.c_int32),
+        ("pad", ctypes.c_int32),
     ]
 
 
 def default_params(**kw) -> Params:
-    p = Params(1.0, 0.1, 100.0, 0.0, 100.0, 0, 0, 0, 1000000, 1, 500)
+    p = Params(1.0, 0.1, 100.0, 0.0, 100.0, 0, 0, 0, 1000000, 1, 500, 0, 0)
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -120,16 +122,7 @@ def unphased_stats(table, params=None):
     return bool(ok), s[0]
 
 
-def variant_meta(s: tf.Synth) -> np.ndarray:
-    m = np.zeros(s.n_variants, VARIANT_DTYPE)
-    m["rid"] = s.rid
-    m["pos"] = s.pos
-    m["ac"] = s.ac
-    m["an"] = s.an
-    m["hwe"] = 1.0
-    m["gt_missing"] = s.an != 0
-    m["gt_phase"] = 1 if s.phased else 0
-    return m
+from tomahawk_b200.synth import variant_meta  # noqa: E402,F401
 
 
 def calc(s: tf.Synth, params: Params, cap: int | None = None):
@@ -155,8 +148,11 @@ def have_reference() -> bool:
     return os.path.exists(REF_CALC) and os.access(REF_CALC, os.X_OK)
 
 
-_PROGRESS_RE = re.compile(r"\[PROGRESS\]\s+([\d,]+) variants/s and ([\d,]+) genotypes/s")
-_FINISHED_RE = re.compile(r"Finished in (\S+)\. Variants: ([\d,]+), genotypes: ([\d,]+), output: ([\d,]+)")
+# The reference's progress thread and its final summary race on stderr, so short runs
+# interleave the two lines; the patterns tolerate padding and fall back gracefully.
+_PROGRESS_RE = re.compile(r"([\d,]+)\s+variants/s and\s+([\d,]+)")
+_FINISHED_RE = re.compile(r"Finished in\s+(\S+)\s*\. Variants:\s*([\d,]+)\s*, genotypes:\s*\D*([\d,]+)\s*, output:\s*([\d,]+)")
+_PERFORMING_RE = re.compile(r"Performing: ([\d,]+) variant comparisons")
 
 
 def run_reference_calc(twk_path: str, out_prefix: str, args: list[str], threads: int | None = None, timeout=None):
@@ -176,6 +172,9 @@ def run_reference_calc(twk_path: str, out_prefix: str, args: list[str], threads:
         info["pairs"] = int(m.group(2).replace(",", ""))
         info["n_out"] = int(m.group(4).replace(",", ""))
         info["elapsed_str"] = m.group(1)
+    m = _PERFORMING_RE.search(r.stderr)
+    if m:
+        info["planned_pairs"] = int(m.group(1).replace(",", ""))
     return info
 
 

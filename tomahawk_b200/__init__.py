@@ -1,0 +1,336 @@
+"""tomahawk_b200 -- B200-native pairwise-LD engine (`tomahawk calc`).
+
+The product is ``libtwkb.so`` (CUDA kernels for sm_100a behind the C-ABI of
+``include/twkb.h``). This module is only the thin ctypes mirror of that ABI used
+by the tests, ``bench.py`` and Python callers; it contains no compute and there
+is no CPU fallback: if the shared library is missing or no B200 is present the
+calls fail loudly.
+
+Reference seam mirrored here: ``bool twk_ld::Compute(const twk_ld_settings&)``
+(reference include/ld.h:53, lib/ld/ld.cpp:477-671) -> :class:`twk_ld`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtwkb.so")
+
+RECORD_BYTES = 106
+KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA = 0, 1, 2
+
+ERRORS = {
+    -1: "TWKB_EINVAL", -2: "TWKB_ENODEVICE", -3: "TWKB_ECUDA", -4: "TWKB_ENOMEM",
+    -5: "TWKB_ESTATE", -6: "TWKB_ESINK", -7: "TWKB_EIO",
+}
+
+
+class TwkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Settings(ctypes.Structure):
+    """twkb_settings: 1:1 with twk_ld_settings (reference include/core.h:909-924)."""
+
+    _fields_ = [
+        ("square", ctypes.c_uint8), ("window", ctypes.c_uint8), ("low_memory", ctypes.c_uint8),
+        ("bitmaps", ctypes.c_uint8), ("single", ctypes.c_uint8), ("force_phased", ctypes.c_uint8),
+        ("forced_unphased", ctypes.c_uint8), ("emulate_quirks", ctypes.c_uint8),
+        ("c_level", ctypes.c_int32), ("bl_size", ctypes.c_int32), ("b_size", ctypes.c_int32),
+        ("l_window", ctypes.c_int32), ("n_threads", ctypes.c_int32), ("l_surrounding", ctypes.c_int32),
+        ("n_chunks", ctypes.c_int32), ("c_chunk", ctypes.c_int32),
+        ("minP", ctypes.c_double), ("minR2", ctypes.c_double), ("maxR2", ctypes.c_double),
+        ("minDprime", ctypes.c_double), ("maxDprime", ctypes.c_double),
+        ("device", ctypes.c_int32), ("part_index", ctypes.c_int32), ("part_count", ctypes.c_int32),
+        ("kernel", ctypes.c_int32), ("twk_block_size", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5),
+    ]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("pairs_visited", ctypes.c_uint64), ("pairs_screened", ctypes.c_uint64), ("records_out", ctypes.c_uint64),
+        ("count_launches", ctypes.c_uint64), ("stats_launches", ctypes.c_uint64), ("other_launches", ctypes.c_uint64),
+        ("seconds_total", ctypes.c_double), ("ms_count_kernel", ctypes.c_double), ("ms_stats_kernel", ctypes.c_double),
+        ("ms_h2d", ctypes.c_double), ("bytes_h2d", ctypes.c_uint64), ("bytes_d2h", ctypes.c_uint64),
+        ("kernel_used", ctypes.c_int32), ("n_planes", ctypes.c_int32), ("word_ops", ctypes.c_uint64),
+        ("mma_macs", ctypes.c_uint64), ("ms_device_total", ctypes.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+VARIANT_DTYPE = np.dtype(
+    [("rid", "<u4"), ("pos", "<u4"), ("ac", "<u4"), ("an", "<u4"), ("hwe", "<f8"),
+     ("gt_missing", "u1"), ("gt_phase", "u1"), ("pad", "u1", (6,))]
+)
+TWO_DTYPE = np.dtype(
+    [("controller", "<u2"), ("ridA", "<u4"), ("ridB", "<u4"), ("packA", "<u4"), ("packB", "<u4"),
+     ("cnt", "<f8", (4,)), ("D", "<f8"), ("Dprime", "<f8"), ("R", "<f8"), ("R2", "<f8"), ("P", "<f8"),
+     ("ChiSqFisher", "<f8"), ("ChiSqModel", "<f8")]
+)
+CAND_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("c", "<u4", (9,)), ("mode", "<u4")])
+SINK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint64)
+
+_lib = None
+
+EXPORTS = [
+    "twkb_settings_init", "twkb_create", "twkb_destroy", "twkb_last_error", "twkb_update_settings",
+    "twkb_load_matrix", "twkb_load_matrix_device", "twkb_compute", "twkb_compute_resident", "twkb_get_stats",
+    "twkb_debug_candidates", "twkb_calc_file", "twkb_version",
+    "twkb_twk_open", "twkb_twk_dims", "twkb_twk_copy", "twkb_twk_close",
+    "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
+]
+
+
+def lib():
+    """Load libtwkb.so. Raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). tomahawk_b200 has no CPU fallback."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        L.twkb_settings_init.argtypes = [ctypes.POINTER(Settings)]
+        L.twkb_settings_init.restype = None
+        L.twkb_create.argtypes = [ctypes.POINTER(Settings), ctypes.POINTER(ctypes.c_void_p)]
+        L.twkb_destroy.argtypes = [ctypes.c_void_p]
+        L.twkb_destroy.restype = None
+        L.twkb_last_error.argtypes = [ctypes.c_void_p]
+        L.twkb_last_error.restype = ctypes.c_char_p
+        L.twkb_update_settings.argtypes = [ctypes.c_void_p, ctypes.POINTER(Settings)]
+        for name in ("twkb_load_matrix", "twkb_load_matrix_device"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.twkb_compute.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
+        L.twkb_compute_resident.argtypes = [ctypes.c_void_p]
+        L.twkb_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+        L.twkb_debug_candidates.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                            ctypes.POINTER(ctypes.c_uint64)]
+        L.twkb_calc_file.argtypes = [ctypes.POINTER(Settings), ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(Stats),
+                                     ctypes.c_char_p, ctypes.c_size_t]
+        L.twkb_twk_open.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+        L.twkb_twk_dims.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
+                                    ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32)]
+        L.twkb_twk_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.twkb_twk_close.argtypes = [ctypes.c_void_p]
+        L.twkb_twk_close.restype = None
+        L.twkb_two_open.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
+                                    ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+        L.twkb_two_add.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.twkb_two_close.argtypes = [ctypes.c_void_p]
+        L.twkb_plan_tiles.argtypes = [ctypes.POINTER(Settings), ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                      ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+        _lib = L
+    return _lib
+
+
+class TwkFile:
+    """A .twk file unpacked by the host reader (twkb_twk_*)."""
+
+    def __init__(self, path: str, n_threads: int = 4):
+        L = lib()
+        self._L = L
+        self._h = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(512)
+        rc = L.twkb_twk_open(path.encode(), n_threads, ctypes.byref(self._h), err, 512)
+        if rc != 0:
+            raise TwkbError(rc, err.value.decode())
+        ns, nv, st, am, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t(), ctypes.c_int32(), ctypes.c_uint32()
+        L.twkb_twk_dims(self._h, ctypes.byref(ns), ctypes.byref(nv), ctypes.byref(st), ctypes.byref(am), ctypes.byref(nb))
+        self.n_samples, self.n_variants, self.stride = ns.value, nv.value, st.value
+        self.any_missing, self.n_blocks = bool(am.value), nb.value
+
+    def matrix(self):
+        data = np.zeros((self.n_variants, self.stride), dtype=np.uint64)
+        mask = np.zeros_like(data) if self.any_missing else None
+        meta = np.zeros(self.n_variants, dtype=VARIANT_DTYPE)
+        self._L.twkb_twk_copy(self._h, data.ctypes.data, mask.ctypes.data if mask is not None else None, meta.ctypes.data)
+        return data, mask, meta
+
+    def close(self):
+        if self._h:
+            self._L.twkb_twk_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TwoWriter:
+    """Streaming .two writer (twkb_two_*): forward records in, forward + reverse blocks out."""
+
+    def __init__(self, path: str, twk: TwkFile, command_line: str = "", c_level: int = 1, b_size: int = 10000):
+        L = lib()
+        self._L = L
+        self._w = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(512)
+        rc = L.twkb_two_open(path.encode(), twk._h, command_line.encode(), c_level, b_size, ctypes.byref(self._w), err, 512)
+        if rc != 0:
+            raise TwkbError(rc, err.value.decode())
+
+    def add(self, records: np.ndarray):
+        records = np.ascontiguousarray(records)
+        assert records.dtype.itemsize == RECORD_BYTES
+        rc = self._L.twkb_two_add(self._w, records.ctypes.data, len(records))
+        if rc != 0:
+            raise TwkbError(rc, "twkb_two_add failed")
+
+    def close(self):
+        if self._w:
+            rc = self._L.twkb_two_close(self._w)
+            self._w = ctypes.c_void_p()
+            if rc != 0:
+                raise TwkbError(rc, "twkb_two_close failed")
+
+
+def plan_tiles(settings: Settings, meta: np.ndarray, tile_i: int, tile_j: int):
+    """(tiles[n,2] uint32, n_pairs) of this settings.part_index's share of the grid."""
+    L = lib()
+    meta = np.ascontiguousarray(meta)
+    n, pairs = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    rc = L.twkb_plan_tiles(ctypes.byref(settings), len(meta), meta.ctypes.data, tile_i, tile_j, None, 0, ctypes.byref(n), ctypes.byref(pairs))
+    if rc != 0:
+        raise TwkbError(rc, "twkb_plan_tiles failed")
+    out = np.zeros((int(n.value), 2), dtype=np.uint32)
+    if n.value:
+        rc = L.twkb_plan_tiles(ctypes.byref(settings), len(meta), meta.ctypes.data, tile_i, tile_j, out.ctypes.data, n.value, ctypes.byref(n), ctypes.byref(pairs))
+        if rc != 0:
+            raise TwkbError(rc, "twkb_plan_tiles failed")
+    return out, int(pairs.value)
+
+
+def default_settings(**kw) -> Settings:
+    """Reference defaults (lib/core.cpp:297-306) with keyword overrides."""
+    s = Settings()
+    lib().twkb_settings_init(ctypes.byref(s))
+    for k, v in kw.items():
+        if not hasattr(s, k):
+            raise AttributeError(f"twkb_settings has no field {k}")
+        setattr(s, k, v)
+    return s
+
+
+class Engine:
+    """One device context: resident genotype matrix + LD computation."""
+
+    def __init__(self, settings: Settings | None = None, **kw):
+        self._L = lib()
+        self.settings = settings if settings is not None else default_settings(**kw)
+        self._ctx = ctypes.c_void_p()
+        rc = self._L.twkb_create(ctypes.byref(self.settings), ctypes.byref(self._ctx))
+        if rc != 0:
+            raise TwkbError(rc, self._L.twkb_last_error(None).decode())
+        self._keep = None
+
+    def close(self):
+        if self._ctx:
+            self._L.twkb_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise TwkbError(rc, self._L.twkb_last_error(self._ctx).decode())
+
+    def update(self, **kw):
+        for k, v in kw.items():
+            setattr(self.settings, k, v)
+        self._check(self._L.twkb_update_settings(self._ctx, ctypes.byref(self.settings)))
+
+    def load(self, n_samples: int, data: np.ndarray, mask: np.ndarray | None, meta: np.ndarray):
+        """data/mask: uint64 [n_variants, stride] rows in the twk_igt_vec layout."""
+        data = np.ascontiguousarray(data, dtype=np.uint64)
+        meta = np.ascontiguousarray(meta)
+        assert meta.dtype.itemsize == 32
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint64)
+            assert mask.shape == data.shape
+        self._check(self._L.twkb_load_matrix(self._ctx, n_samples, data.shape[0], data.ctypes.data,
+                                             mask.ctypes.data if mask is not None else None, data.shape[1],
+                                             meta.ctypes.data))
+
+    def load_device(self, n_samples, n_variants, d_data_ptr, d_mask_ptr, stride, meta):
+        meta = np.ascontiguousarray(meta)
+        self._check(self._L.twkb_load_matrix_device(self._ctx, n_samples, n_variants, d_data_ptr, d_mask_ptr, stride,
+                                                    meta.ctypes.data))
+
+    def compute(self) -> np.ndarray:
+        """Run and collect the forward records (host sink) as a TWO_DTYPE array."""
+        chunks = []
+
+        def _sink(user, ptr, n):
+            buf = ctypes.string_at(ptr, int(n) * RECORD_BYTES)
+            chunks.append(np.frombuffer(buf, dtype=TWO_DTYPE))
+            return 0
+
+        cb = SINK_FN(_sink)
+        self._check(self._L.twkb_compute(self._ctx, cb, None))
+        if not chunks:
+            return np.zeros(0, dtype=TWO_DTYPE)
+        return np.concatenate(chunks)
+
+    def compute_discard(self) -> int:
+        """Run with a sink that only counts (end-to-end timing: D2H included)."""
+        n_total = [0]
+
+        def _sink(user, ptr, n):
+            n_total[0] += int(n)
+            return 0
+
+        cb = SINK_FN(_sink)
+        self._check(self._L.twkb_compute(self._ctx, cb, None))
+        return n_total[0]
+
+    def compute_resident(self):
+        self._check(self._L.twkb_compute_resident(self._ctx))
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self._check(self._L.twkb_get_stats(self._ctx, ctypes.byref(s)))
+        return s
+
+    def debug_candidates(self, screen_off: bool = True) -> np.ndarray:
+        n = ctypes.c_uint64(0)
+        self._check(self._L.twkb_debug_candidates(self._ctx, int(screen_off), None, 0, ctypes.byref(n)))
+        out = np.zeros(int(n.value), dtype=CAND_DTYPE)
+        if n.value:
+            self._check(self._L.twkb_debug_candidates(self._ctx, int(screen_off), out.ctypes.data, n.value, ctypes.byref(n)))
+        return out[: int(n.value)]
+
+
+class twk_ld:
+    """Mirror of the reference's ``twk_ld`` (include/ld.h:40-69): ``Compute(settings)``
+    reads ``settings.in`` (.twk), writes ``settings.out`` (.two) and returns a bool,
+    printing errors to stderr like the reference does."""
+
+    def __init__(self):
+        self.last_stats = None
+
+    def Compute(self, settings: Settings, in_path: str, out_path: str) -> bool:
+        import sys
+
+        L = lib()
+        st = Stats()
+        err = ctypes.create_string_buffer(1024)
+        rc = L.twkb_calc_file(ctypes.byref(settings), in_path.encode(), out_path.encode(), ctypes.byref(st), err, 1024)
+        self.last_stats = st
+        if rc != 0:
+            print(f"[ERROR] {err.value.decode()}", file=sys.stderr)
+            return False
+        return True

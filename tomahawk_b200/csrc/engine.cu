@@ -1,0 +1,958 @@
+// engine.cu -- host side of libtwkb.so: context, device-resident matrix, tile
+// scheduler (the B200 replacement of twk_ld_balancer / twk_ld_dynamic_balancer,
+// reference lib/ld/ld_balancing.h:13-242), batch loop and the C-ABI of
+// include/twkb.h. No CPU compute path exists in this file: every count and
+// every statistic is produced by the CUDA kernels included below.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/twkb.h"
+#include "common.cuh"
+#include "count_popc.cuh"
+#include "count_umma.cuh"
+#include "hostio.h"
+#include "pack.cuh"
+#include "stats.cuh"
+
+namespace twkb {
+
+static std::string g_create_error;
+static std::mutex g_create_mutex;
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ctx->fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                      std::to_string(__LINE__) + ")");                                        \
+            return TWKB_ECUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct Problem {  // one rectangular sub-problem of the pair grid
+    uint32_t row_begin, row_end, col_begin, col_end;
+    bool diag;
+};
+
+struct Context {
+    twkb_settings st{};
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_begin = nullptr, ev_end = nullptr;
+
+    // matrix
+    bool loaded = false;
+    uint32_t n_samples = 0, n_variants = 0, Mpad = 0;
+    bool any_missing = false;
+    int mode = -1;   // CountMode of the resident planes
+    int np = 0;
+    uint32_t K32 = 0;
+    DevBuf<uint64_t> d_raw_data, d_raw_mask;  // row-major upload (kept: re-pack on mode change)
+    size_t raw_stride = 0;
+    DevBuf<uint32_t> d_planes, d_plane_popc;
+    DevBuf<DevVariant> d_meta;
+    DevBuf<double> d_lgamma;
+    uint32_t lgamma_len = 0;
+    std::vector<twkb_variant> h_meta;
+    UmmaOperand umma;  // int8-expanded operand of the tensor-core kernel
+
+    // window-mode block structure
+    DevBuf<uint32_t> d_blk_of, d_blk_first, d_blk_last, d_blk_prune;
+    std::vector<uint32_t> h_blk_first, h_blk_last, h_blk_prune;
+
+    // work buffers
+    DevBuf<uint2> d_tiles;
+    DevBuf<Candidate> d_cands;
+    DevBuf<unsigned long long> d_counters;  // [0] cand count, [1] record count
+    DevBuf<uint8_t> d_records;
+    size_t cand_cap = 0, rec_cap = 0;
+    uint8_t* h_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    unsigned long long* h_counters = nullptr;  // pinned
+
+    twkb_stats stats{};
+
+    int fail(const std::string& m) {
+        err = m;
+        return TWKB_ECUDA;
+    }
+};
+
+static void settings_defaults(twkb_settings* s) {
+    // reference lib/core.cpp:297-306
+    std::memset(s, 0, sizeof(*s));
+    s->square = 1;
+    s->emulate_quirks = 1;
+    s->c_level = 1;
+    s->bl_size = 500;
+    s->b_size = 10000;
+    s->l_window = 1000000;
+    s->n_threads = 1;
+    s->l_surrounding = 500000;
+    s->n_chunks = 1;
+    s->c_chunk = 0;
+    s->minP = 1;
+    s->minR2 = 0.1;
+    s->maxR2 = 100;
+    s->minDprime = 0;
+    s->maxDprime = 100;
+    s->device = 0;
+    s->part_index = 0;
+    s->part_count = 1;
+    s->kernel = TWKB_KERNEL_AUTO;
+    s->twk_block_size = 500;
+}
+
+static int validate_settings(const twkb_settings* s, std::string& why) {
+    if (s->single) { why = "single-site mode (scalc) is not part of this path"; return TWKB_EINVAL; }
+    if (s->force_phased && s->forced_unphased) { why = "cannot force both phased and unphased"; return TWKB_EINVAL; }
+    if (s->window && s->n_chunks != 1) { why = "Cannot use chunking in window mode!"; return TWKB_EINVAL; }  // ld.cpp:485
+    if (s->n_chunks < 1 || s->c_chunk < 0 || s->c_chunk >= s->n_chunks) { why = "illegal chunk selection"; return TWKB_EINVAL; }
+    if (s->part_count < 0 || (s->part_count > 0 && (s->part_index < 0 || s->part_index >= s->part_count))) {
+        why = "illegal part_index/part_count";
+        return TWKB_EINVAL;
+    }
+    if (s->minR2 < 0 || s->minR2 > 1) { why = "minR2 out of range"; return TWKB_EINVAL; }  // calc.h range checks
+    return TWKB_OK;
+}
+
+static DevParams make_params(const Context* ctx, const Problem& pb) {
+    DevParams p{};
+    const twkb_settings& s = ctx->st;
+    p.minP = s.minP; p.minR2 = s.minR2; p.maxR2 = s.maxR2; p.minDprime = s.minDprime; p.maxDprime = s.maxDprime;
+    p.screenR2 = s.minR2 * (1.0 - 1e-12);
+    p.n_samples = ctx->n_samples;
+    p.n_variants = ctx->n_variants;
+    p.window = s.window ? 1u : 0u;
+    p.l_window = (uint32_t)s.l_window;
+    p.emulate_quirks = s.emulate_quirks ? 1u : 0u;
+    p.thresh_miss_phased = (uint32_t)(0.0047 * ctx->n_samples + 5.2913);
+    p.unphased = (ctx->mode >= 2) ? 1u : 0u;
+    p.diag = pb.diag ? 1u : 0u;
+    p.lgamma_len = ctx->lgamma_len;
+    return p;
+}
+
+// Which planes a run needs: -u => unphased; -p => phased; neither ("auto",
+// ld_engine.cpp:2737-2838) => unphased iff any variant has missing alleles is decided
+// per pair by the reference; here auto mode is served as two passes by compute().
+static int wanted_mode(const Context* ctx, bool unphased) {
+    if (unphased) return ctx->any_missing ? MODE_UNPHASED_MISS : MODE_UNPHASED_NOMISS;
+    return ctx->any_missing ? MODE_PHASED_MISS : MODE_PHASED_NOMISS;
+}
+
+static int ensure_planes(Context* ctx, int mode) {
+    if (ctx->mode == mode) return TWKB_OK;
+    const bool unphased = mode >= 2;
+    const int np = (mode == 0) ? 1 : (mode == 3 ? 3 : 2);
+    const uint32_t bits = unphased ? ctx->n_samples : 2 * ctx->n_samples;
+    uint32_t K32 = (bits + 31) / 32;
+    K32 = (K32 + POPC_TK - 1) / POPC_TK * POPC_TK;
+    CUDA_TRY(ctx->d_planes.alloc((size_t)np * K32 * ctx->Mpad));
+    CUDA_TRY(ctx->d_plane_popc.alloc((size_t)3 * ctx->Mpad));
+    dim3 grid(ctx->Mpad / 32, (K32 + 31) / 32), block(32, 8);
+    pack_planes_kernel<<<grid, block, 0, ctx->stream>>>(ctx->d_raw_data.p, ctx->any_missing ? ctx->d_raw_mask.p : nullptr,
+                                                        ctx->raw_stride, ctx->n_variants, ctx->n_samples, mode,
+                                                        ctx->d_planes.p, K32, ctx->Mpad);
+    CUDA_TRY(cudaGetLastError());
+    dim3 g2((ctx->Mpad + 127) / 128, np);
+    plane_popc_kernel<<<g2, 128, 0, ctx->stream>>>(ctx->d_planes.p, np, K32, ctx->Mpad, ctx->d_plane_popc.p);
+    CUDA_TRY(cudaGetLastError());
+    ctx->stats.other_launches += 2;
+    ctx->mode = mode;
+    ctx->np = np;
+    ctx->K32 = K32;
+    ctx->umma.valid = false;
+    return TWKB_OK;
+}
+
+// .twk block structure for the window rule (blocks of <= bs variants, one contig
+// per block: lib/importer.cpp:196-236) and the row-prune limit of
+// ld_balancing.h:189-196.
+static int build_blocks(Context* ctx) {
+    const uint32_t M = ctx->n_variants;
+    const uint32_t bs = ctx->st.twk_block_size > 0 ? (uint32_t)ctx->st.twk_block_size : 500u;
+    std::vector<uint32_t> blk_of(ctx->Mpad, 0);
+    ctx->h_blk_first.clear();
+    ctx->h_blk_last.clear();
+    for (uint32_t v = 0; v < M;) {
+        uint32_t e = v + 1;
+        while (e < M && e - v < bs && ctx->h_meta[e].rid == ctx->h_meta[v].rid) ++e;
+        const uint32_t b = (uint32_t)ctx->h_blk_first.size();
+        for (uint32_t x = v; x < e; ++x) blk_of[x] = b;
+        ctx->h_blk_first.push_back(v);
+        ctx->h_blk_last.push_back(e - 1);
+        v = e;
+    }
+    const uint32_t nb = (uint32_t)ctx->h_blk_first.size();
+    const uint32_t w = (uint32_t)ctx->st.l_window;
+    ctx->h_blk_prune.assign(nb, nb);
+    for (uint32_t bi = 0; bi < nb; ++bi) {
+        const uint32_t last_pos = ctx->h_meta[ctx->h_blk_last[bi]].pos;
+        for (uint32_t bj = bi + 1; bj < nb; ++bj) {
+            if ((uint32_t)(ctx->h_meta[ctx->h_blk_first[bj]].pos - last_pos) > w) {
+                ctx->h_blk_prune[bi] = bj;
+                break;
+            }
+        }
+    }
+    CUDA_TRY(ctx->d_blk_of.alloc(ctx->Mpad));
+    CUDA_TRY(ctx->d_blk_first.alloc(nb));
+    CUDA_TRY(ctx->d_blk_last.alloc(nb));
+    CUDA_TRY(ctx->d_blk_prune.alloc(nb));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_of.p, blk_of.data(), ctx->Mpad * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_first.p, ctx->h_blk_first.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_last.p, ctx->h_blk_last.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_prune.p, ctx->h_blk_prune.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return TWKB_OK;
+}
+
+// Pairs the reference counts as visited (progress n_var; ld_engine.cpp:1933,2015,2607).
+static uint64_t visited_pairs(const Context* ctx, const Problem& pb) {
+    if (!ctx->st.window) {
+        const uint64_t nr = pb.row_end - pb.row_begin, nc = pb.col_end - pb.col_begin;
+        return pb.diag ? (nr * nr - nr) / 2 : nr * nc;
+    }
+    uint64_t total = 0;
+    const uint32_t nb = (uint32_t)ctx->h_blk_first.size();
+    const uint32_t w = (uint32_t)ctx->st.l_window;
+    for (uint32_t bi = 0; bi < nb; ++bi) {
+        const uint64_t ni = ctx->h_blk_last[bi] - ctx->h_blk_first[bi] + 1;
+        const twkb_variant& vf = ctx->h_meta[ctx->h_blk_first[bi]];
+        for (uint32_t bj = bi; bj < ctx->h_blk_prune[bi] || bj == bi; ++bj) {
+            if (bj >= nb) break;
+            const twkb_variant& vl = ctx->h_meta[ctx->h_blk_last[bj]];
+            const bool aborted = vf.rid == vl.rid && (uint32_t)(vl.pos - vf.pos) > w;
+            if (!aborted) {
+                const uint64_t nj = ctx->h_blk_last[bj] - ctx->h_blk_first[bj] + 1;
+                total += (bi == bj) ? (ni * ni - ni) / 2 : ni * nj;
+            }
+        }
+    }
+    return total;
+}
+
+// The sub-problem of this run: -c/-C chunk selection of twk_ld_balancer::Build
+// (ld_balancing.h:23-80) over .twk blocks, expressed in variant ranges.
+static int select_problem(Context* ctx, Problem& pb) {
+    const uint32_t M = ctx->n_variants;
+    pb = {0, M, 0, M, true};
+    const int parts = ctx->st.n_chunks;
+    if (parts <= 1) return TWKB_OK;
+    // blocks of twk_block_size variants / contig breaks
+    std::vector<uint32_t> first;
+    const uint32_t bs = ctx->st.twk_block_size > 0 ? (uint32_t)ctx->st.twk_block_size : 500u;
+    for (uint32_t v = 0; v < M;) {
+        uint32_t e = v + 1;
+        while (e < M && e - v < bs && ctx->h_meta[e].rid == ctx->h_meta[v].rid) ++e;
+        first.push_back(v);
+        v = e;
+    }
+    first.push_back(M);
+    const uint32_t nb = (uint32_t)first.size() - 1;
+    if ((uint32_t)parts > nb) { ctx->err = "more sub-problems than blocks"; return TWKB_EINVAL; }
+    uint32_t factor = 0;
+    for (uint32_t i = 1; i < (uint32_t)parts; ++i)
+        if (((i * i - i) / 2) + i == (uint32_t)parts) { factor = i; break; }
+    if (factor == 0) { ctx->err = "number of sub-problems is not k(k+1)/2"; return TWKB_EINVAL; }
+    const uint32_t chunk = nb / factor;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < factor; ++i)
+        for (uint32_t j = i; j < factor; ++j, ++k) {
+            if (k != (uint32_t)ctx->st.c_chunk) continue;
+            const uint32_t tR = (j + 1 == factor ? nb : chunk * (j + 1)), fR = tR - chunk;
+            const uint32_t tL = (i + 1 == factor ? nb : chunk * (i + 1)), fL = tL - chunk;
+            pb.row_begin = first[fL]; pb.row_end = first[tL];
+            pb.col_begin = first[fR]; pb.col_end = first[tR];
+            pb.diag = (i == j);
+            return TWKB_OK;
+        }
+    ctx->err = "chunk not found";
+    return TWKB_EINVAL;
+}
+
+// Tile list of one sub-problem for a TI x TJ kernel, this context's share only.
+// Tiles are emitted in super-tile order (SUPER x SUPER tiles) so that CTAs that are
+// resident together share operand rows in L2; parts take interleaved tiles.
+static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint32_t TJ, uint32_t SUPER,
+                        std::vector<uint2>& tiles, uint64_t* pairs_out = nullptr) {
+    tiles.clear();
+    uint64_t pairs = 0;
+    // pairs (i in rows, j in cols, i<j when diag) that fall inside one tile
+    auto tile_pairs = [&](uint32_t i0, uint32_t j0) -> uint64_t {
+        const uint64_t ia = std::max(i0, pb.row_begin), ib = std::min<uint64_t>(i0 + TI, pb.row_end);
+        const uint64_t ja = std::max(j0, pb.col_begin), jb = std::min<uint64_t>(j0 + TJ, pb.col_end);
+        if (ia >= ib || ja >= jb) return 0;
+        if (!pb.diag) return (ib - ia) * (jb - ja);
+        uint64_t n = 0;
+        for (uint64_t i = ia; i < ib; ++i) {
+            const uint64_t lo = std::max<uint64_t>(ja, i + 1);
+            if (lo < jb) n += jb - lo;
+        }
+        return n;
+    };
+    const uint32_t ti0 = pb.row_begin / TI, ti1 = (pb.row_end + TI - 1) / TI;
+    const uint32_t tj0 = pb.col_begin / TJ, tj1 = (pb.col_end + TJ - 1) / TJ;
+    const bool window = ctx->st.window;
+    const uint32_t w = (uint32_t)ctx->st.l_window;
+    const uint32_t M = ctx->n_variants;
+    const int parts = std::max(1, ctx->st.part_count), part = ctx->st.part_index;
+    uint64_t group = 0;
+    auto emit_super = [&](uint32_t si, uint32_t sj) {
+        bool any = false;
+        for (uint32_t ti = si; ti < std::min(si + SUPER, ti1); ++ti)
+            for (uint32_t tj = sj; tj < std::min(sj + SUPER, tj1); ++tj) {
+                const uint32_t i0 = ti * TI, j0 = tj * TJ;
+                if (pb.diag && j0 + TJ - 1 <= i0) continue;  // no i<j in this tile
+                if (window) {
+                    // every pair of the tile is farther apart than the window on one contig
+                    const uint32_t il = std::min(i0 + TI, std::min(M, pb.row_end)) - 1;
+                    const uint32_t jf = std::max(j0, pb.col_begin), jl = std::min(j0 + TJ, std::min(M, pb.col_end)) - 1;
+                    if (jf > il) {
+                        const twkb_variant &a0 = ctx->h_meta[std::max(i0, pb.row_begin)], &a1 = ctx->h_meta[il];
+                        const twkb_variant &b0 = ctx->h_meta[jf], &b1 = ctx->h_meta[jl];
+                        if (a0.rid == a1.rid && a1.rid == b0.rid && b0.rid == b1.rid && b0.pos >= a1.pos &&
+                            (uint32_t)(b0.pos - a1.pos) > w)
+                            continue;
+                    }
+                }
+                // tiles are dealt round-robin in emission order: every part walks the same
+                // super-tiles at the same time, so the parts stay balanced for any grid size
+                if ((group % parts) == (uint64_t)part) {
+                    tiles.push_back(make_uint2(i0, j0));
+                    pairs += tile_pairs(i0, j0);
+                }
+                ++group;
+                any = true;
+            }
+        (void)any;
+    };
+    for (uint32_t si = ti0; si < ti1; si += SUPER)
+        for (uint32_t sj = tj0; sj < tj1; sj += SUPER) {
+            if (pb.diag && (uint64_t)(sj + SUPER) * TJ <= (uint64_t)si * TI) continue;
+            emit_super(si, sj);
+        }
+    if (pairs_out) *pairs_out = pairs;
+}
+
+template <int MODE>
+static cudaError_t launch_popc(Context* ctx, const CountArgs& args, const DevParams& prm, uint32_t n_tiles) {
+    static bool configured = false;
+    const size_t smem = popc_smem_bytes<MODE>();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(count_popc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    count_popc_kernel<MODE><<<n_tiles, POPC_THREADS, smem, ctx->stream>>>(args, prm);
+    return cudaGetLastError();
+}
+
+static void tile_dims(int mode, bool umma, uint32_t& TI, uint32_t& TJ) {
+    if (umma) { TI = UMMA_TILE_M; TJ = UMMA_TILE_N; return; }
+    switch (mode) {
+        case MODE_PHASED_NOMISS: TI = popc_tile_i<0>(); TJ = popc_tile_j<0>(); break;
+        case MODE_PHASED_MISS: TI = popc_tile_i<1>(); TJ = popc_tile_j<1>(); break;
+        case MODE_UNPHASED_NOMISS: TI = popc_tile_i<2>(); TJ = popc_tile_j<2>(); break;
+        default: TI = popc_tile_i<3>(); TJ = popc_tile_j<3>(); break;
+    }
+}
+
+static int ensure_work_buffers(Context* ctx, uint64_t max_tile_pairs) {
+    size_t want_cand = 16u << 20, want_rec = 16u << 20;
+    if (const char* e = getenv("TWKB_CAND_CAP")) want_cand = (size_t)atoll(e);
+    if (const char* e = getenv("TWKB_REC_CAP")) want_rec = (size_t)atoll(e);
+    want_cand = std::max<size_t>(want_cand, max_tile_pairs);
+    want_rec = std::max<size_t>(want_rec, want_cand);
+    if (ctx->cand_cap < want_cand) {
+        CUDA_TRY(ctx->d_cands.alloc(want_cand));
+        ctx->cand_cap = want_cand;
+    }
+    if (ctx->rec_cap < want_rec) {
+        CUDA_TRY(ctx->d_records.alloc(want_rec * TWKB_RECORD_BYTES));
+        ctx->rec_cap = want_rec;
+    }
+    CUDA_TRY(ctx->d_counters.alloc(4));
+    if (!ctx->h_counters) CUDA_TRY(cudaMallocHost((void**)&ctx->h_counters, 4 * sizeof(unsigned long long)));
+    if (!ctx->h_stage[0]) {
+        ctx->stage_bytes = (size_t)(32u << 20) / TWKB_RECORD_BYTES * TWKB_RECORD_BYTES;
+        CUDA_TRY(cudaMallocHost((void**)&ctx->h_stage[0], ctx->stage_bytes));
+        CUDA_TRY(cudaMallocHost((void**)&ctx->h_stage[1], ctx->stage_bytes));
+    }
+    return TWKB_OK;
+}
+
+// D2H of the record buffer in pinned chunks, overlapped with the sink.
+static int flush_records(Context* ctx, uint64_t n_records, twkb_sink_fn sink, void* user) {
+    if (n_records == 0) return TWKB_OK;
+    const size_t total = (size_t)n_records * TWKB_RECORD_BYTES;
+    size_t off = 0;
+    int cur = 0;
+    size_t pending_bytes = 0;
+    int pending = -1;
+    while (off < total || pending >= 0) {
+        size_t nbytes = 0;
+        if (off < total) {
+            nbytes = std::min(ctx->stage_bytes, total - off);
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_stage[cur], ctx->d_records.p + off, nbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        if (pending >= 0) {
+            if (sink && sink(user, ctx->h_stage[pending], pending_bytes / TWKB_RECORD_BYTES) != 0) {
+                cudaStreamSynchronize(ctx->copy_stream);
+                ctx->err = "record sink aborted the run";
+                return TWKB_ESINK;
+            }
+            pending = -1;
+        }
+        if (nbytes) {
+            CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+            pending = cur;
+            pending_bytes = nbytes;
+            off += nbytes;
+            cur ^= 1;
+            ctx->stats.bytes_d2h += nbytes;
+        }
+    }
+    return TWKB_OK;
+}
+
+// One pass over a sub-problem with the planes of `mode`.
+// pair_filter: 0 = all pairs, 1 = only pairs with no missing variant, 2 = only pairs with one
+// (auto mode passes; see compute()).
+static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bool screen_off, twkb_sink_fn sink,
+                    void* user, std::vector<Candidate>* dump) {
+    int rc = ensure_planes(ctx, mode);
+    if (rc) return rc;
+    bool use_umma = false;
+    if (mode == MODE_PHASED_NOMISS && ctx->st.kernel != TWKB_KERNEL_POPC && !dump) use_umma = umma_supported();
+    if (ctx->st.kernel == TWKB_KERNEL_UMMA && !use_umma) {
+        ctx->err = "TWKB_KERNEL_UMMA requested but the tensor-core kernel only serves phased data without missing genotypes";
+        return TWKB_EINVAL;
+    }
+    uint32_t TI, TJ;
+    tile_dims(mode, use_umma, TI, TJ);
+    if (use_umma) {
+        rc = umma_prepare(ctx->umma, ctx->d_planes.p, ctx->K32, ctx->Mpad, ctx->n_samples, ctx->stream, ctx->err);
+        if (rc) return rc;
+    }
+    std::vector<uint2> tiles;
+    uint64_t part_pairs = 0;
+    build_tiles(ctx, pb, TI, TJ, use_umma ? 8u : 16u, tiles, &part_pairs);
+    if (ctx->st.part_count > 1 && !ctx->st.window) ctx->stats.pairs_visited = part_pairs;
+    ctx->stats.kernel_used = use_umma ? TWKB_KERNEL_UMMA : TWKB_KERNEL_POPC;
+    ctx->stats.n_planes = ctx->np;
+    const uint64_t tile_pairs = (uint64_t)TI * TJ;
+    rc = ensure_work_buffers(ctx, tile_pairs);
+    if (rc) return rc;
+    if (tiles.empty()) return TWKB_OK;
+    CUDA_TRY(ctx->d_tiles.alloc(tiles.size()));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+
+    DevParams prm = make_params(ctx, pb);
+    CountArgs args{};
+    args.planes = ctx->d_planes.p;
+    args.K32 = ctx->K32;
+    args.Mpad = ctx->Mpad;
+    args.meta = ctx->d_meta.p;
+    args.plane_popc = ctx->d_plane_popc.p;
+    args.blocks = DevBlocks{ctx->d_blk_of.p, ctx->d_blk_first.p, ctx->d_blk_last.p, ctx->d_blk_prune.p};
+    args.cands = ctx->d_cands.p;
+    args.cand_count = ctx->d_counters.p;
+    args.cand_capacity = ctx->cand_cap;
+    args.row_begin = pb.row_begin; args.row_end = pb.row_end;
+    args.col_begin = pb.col_begin; args.col_end = pb.col_end;
+    args.screen_off = screen_off ? 1u : 0u;
+
+    // Batch size: the candidate buffer must hold a whole batch. Start from the
+    // worst case when nothing can be screened out, else optimistic and adapt.
+    const bool no_screen = screen_off || !(ctx->st.minR2 > 0.0);
+    uint64_t batch = no_screen ? std::max<uint64_t>(1, ctx->cand_cap / tile_pairs) : std::max<uint64_t>(1, ctx->cand_cap / tile_pairs * 64);
+    if (const char* e = getenv("TWKB_BATCH_TILES")) batch = std::max<uint64_t>(1, (uint64_t)atoll(e));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    uint64_t rec_on_device = 0;
+    size_t t = 0;
+    while (t < tiles.size()) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, tiles.size() - t);
+        CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+        args.tiles = ctx->d_tiles.p + t;
+        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        cudaError_t le;
+        if (use_umma) {
+            le = umma_launch(ctx->umma, args, prm, nb, ctx->stream);
+        } else {
+            switch (mode) {
+                case MODE_PHASED_NOMISS: le = launch_popc<0>(ctx, args, prm, nb); break;
+                case MODE_PHASED_MISS: le = launch_popc<1>(ctx, args, prm, nb); break;
+                case MODE_UNPHASED_NOMISS: le = launch_popc<2>(ctx, args, prm, nb); break;
+                default: le = launch_popc<3>(ctx, args, prm, nb); break;
+            }
+        }
+        CUDA_TRY(le);
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->stats.ms_count_kernel += ms;
+        ctx->stats.count_launches += 1;
+        const uint64_t ncand = ctx->h_counters[0];
+        if (ncand > ctx->cand_cap) {  // overflow: redo this batch with fewer tiles
+            if (nb == 1) { ctx->err = "candidate buffer smaller than one tile"; return TWKB_ENOMEM; }
+            batch = std::max<uint64_t>(1, nb / 2);
+            continue;
+        }
+        if (use_umma) ctx->stats.mma_macs += (uint64_t)nb * tile_pairs * ctx->umma.Kbytes;
+        else ctx->stats.word_ops += (uint64_t)nb * tile_pairs * ctx->K32 * ctx->np * ctx->np;
+        ctx->stats.pairs_screened += ncand;
+        t += nb;
+        if (dump) {
+            const size_t old = dump->size();
+            dump->resize(old + ncand);
+            CUDA_TRY(cudaMemcpy(dump->data() + old, ctx->d_cands.p, ncand * sizeof(Candidate), cudaMemcpyDeviceToHost));
+            continue;
+        }
+        if (ncand) {
+            if (rec_on_device + ncand > ctx->rec_cap) {
+                if (!resident) {
+                    rc = flush_records(ctx, rec_on_device, sink, user);
+                    if (rc) return rc;
+                }
+                ctx->stats.records_out += rec_on_device;
+                rec_on_device = 0;
+                CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p + 1, 0, sizeof(unsigned long long), ctx->stream));
+            }
+            CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
+            stats_kernel<<<(unsigned)((ncand + 127) / 128), 128, 0, ctx->stream>>>(
+                ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm, ctx->d_lgamma.p, ctx->d_records.p, ctx->rec_cap,
+                ctx->d_counters.p + 1);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_counters + 1, ctx->d_counters.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
+            ctx->stats.ms_stats_kernel += ms;
+            ctx->stats.stats_launches += 1;
+            rec_on_device = ctx->h_counters[1];
+        }
+        // adapt: aim for a half-full candidate buffer
+        if (!no_screen && !getenv("TWKB_BATCH_TILES")) {
+            const double per_tile = std::max(1.0, (double)ncand / nb);
+            batch = std::max<uint64_t>(1, (uint64_t)(0.5 * ctx->cand_cap / per_tile));
+        }
+    }
+    if (!dump) {
+        if (!resident) {
+            rc = flush_records(ctx, rec_on_device, sink, user);
+            if (rc) return rc;
+        }
+        ctx->stats.records_out += rec_on_device;
+    }
+    return TWKB_OK;
+}
+
+static int compute_impl(Context* ctx, bool resident, twkb_sink_fn sink, void* user, bool screen_off,
+                        std::vector<Candidate>* dump) {
+    if (!ctx->loaded) { ctx->err = "twkb_compute before twkb_load_matrix"; return TWKB_ESTATE; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    const double ms_h2d = ctx->stats.ms_h2d;
+    const uint64_t b_h2d = ctx->stats.bytes_h2d;
+    ctx->stats = twkb_stats{};
+    ctx->stats.ms_h2d = ms_h2d;
+    ctx->stats.bytes_h2d = b_h2d;
+    CUDA_TRY(cudaEventRecord(ctx->ev_begin, ctx->stream));
+    Problem pb;
+    int rc = select_problem(ctx, pb);
+    if (rc) return rc;
+    if (ctx->st.window) {
+        rc = build_blocks(ctx);
+        if (rc) return rc;
+    }
+    ctx->stats.pairs_visited = visited_pairs(ctx, pb);
+    if (ctx->st.part_count > 1) {
+        // every part reports its share of the visited pairs (tiles are dealt round-robin)
+        const uint64_t v = ctx->stats.pairs_visited, n = ctx->st.part_count, r = ctx->st.part_index;
+        ctx->stats.pairs_visited = v / n + (r < v % n ? 1 : 0);
+    }
+    if (ctx->st.force_phased || ctx->st.forced_unphased || !ctx->any_missing) {
+        // -p, -u, or auto mode on complete data (auto => phased for every pair, ld_engine.cpp:2775-2790)
+        rc = run_pass(ctx, pb, wanted_mode(ctx, ctx->st.forced_unphased), resident, screen_off, sink, user, dump);
+    } else {
+        ctx->err = "auto mode (neither -p nor -u) on data with missing genotypes is not implemented; pass -p or -u";
+        rc = TWKB_EINVAL;
+    }
+    if (rc == TWKB_OK) {
+        CUDA_TRY(cudaEventRecord(ctx->ev_end, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+        ctx->stats.ms_device_total = ms;
+    }
+    ctx->stats.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* data, const uint64_t* mask,
+                       size_t stride, const twkb_variant* meta, bool device_src) {
+    if (!data || !meta || n_samples == 0 || n_variants == 0) { ctx->err = "null/empty matrix"; return TWKB_EINVAL; }
+    if (stride * 64 < 2 * (size_t)n_samples) { ctx->err = "row_stride_words too small for n_samples"; return TWKB_EINVAL; }
+    if (2 * (uint64_t)n_samples >= (1ull << 31)) { ctx->err = "n_samples too large"; return TWKB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->loaded = false;
+    ctx->mode = -1;
+    ctx->umma.valid = false;
+    ctx->n_samples = n_samples;
+    ctx->n_variants = n_variants;
+    ctx->Mpad = (n_variants + 255) / 256 * 256;
+    ctx->raw_stride = stride;
+    ctx->h_meta.assign(meta, meta + n_variants);
+    ctx->any_missing = false;
+    for (uint32_t v = 0; v < n_variants; ++v)
+        if (meta[v].gt_missing || meta[v].an) ctx->any_missing = true;
+    if (ctx->any_missing && !mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
+    const size_t words = (size_t)n_variants * stride;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_TRY(ctx->d_raw_data.alloc(words));
+    const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_data.p, data, words * 8, kind, ctx->stream));
+    ctx->stats.bytes_h2d = device_src ? 0 : words * 8;
+    if (ctx->any_missing) {
+        CUDA_TRY(ctx->d_raw_mask.alloc(words));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_mask.p, mask, words * 8, kind, ctx->stream));
+        if (!device_src) ctx->stats.bytes_h2d += words * 8;
+    }
+    // device metadata
+    std::vector<DevVariant> dm(ctx->Mpad);
+    std::memset(dm.data(), 0, dm.size() * sizeof(DevVariant));
+    for (uint32_t v = 0; v < n_variants; ++v) {
+        dm[v].pos = meta[v].pos;
+        dm[v].ac = meta[v].ac;
+        dm[v].rid = meta[v].rid;
+        dm[v].flags = (meta[v].an ? VF_HAS_MISSING : 0u) | (meta[v].hwe < 1e-4 ? VF_BAD_HWE : 0u) |
+                      (meta[v].gt_missing ? VF_GT_MISSING : 0u);
+    }
+    CUDA_TRY(ctx->d_meta.alloc(ctx->Mpad));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_meta.p, dm.data(), dm.size() * sizeof(DevVariant), cudaMemcpyHostToDevice, ctx->stream));
+    // log-factorial table from the host libm: lg[n] = lgamma(n+1), the exact values the
+    // reference's lbinom() (lib/fisher_math.cpp:183-187) obtains from glibc.
+    ctx->lgamma_len = 2 * n_samples + 64;
+    std::vector<double> lg(ctx->lgamma_len);
+    for (uint32_t n = 0; n < ctx->lgamma_len; ++n) lg[n] = lgamma((double)n + 1.0);
+    CUDA_TRY(ctx->d_lgamma.alloc(ctx->lgamma_len));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_lgamma.p, lg.data(), lg.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.bytes_h2d += dm.size() * sizeof(DevVariant) + lg.size() * 8;
+    ctx->loaded = true;
+    // build the planes the configured mode needs right away so that the upload cost
+    // (H2D + transpose) is accounted to the load, not to the first compute
+    const bool unph = ctx->st.forced_unphased;
+    int rc = ensure_planes(ctx, wanted_mode(ctx, unph));
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats.ms_h2d = ms;
+    return TWKB_OK;
+}
+
+}  // namespace twkb
+
+using namespace twkb;
+
+extern "C" {
+
+void twkb_settings_init(twkb_settings* s) {
+    if (s) settings_defaults(s);
+}
+
+int twkb_version(void) { return 100; }
+
+const char* twkb_last_error(void* c) {
+    if (!c) return g_create_error.c_str();
+    return static_cast<Context*>(c)->err.c_str();
+}
+
+int twkb_create(const twkb_settings* s, void** out) {
+    std::lock_guard<std::mutex> lock(g_create_mutex);
+    if (!s || !out) { g_create_error = "null argument"; return TWKB_EINVAL; }
+    std::string why;
+    int rc = validate_settings(s, why);
+    if (rc) { g_create_error = why; return rc; }
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)";
+        return TWKB_ENODEVICE;
+    }
+    if (s->device < 0 || s->device >= n_dev) { g_create_error = "device ordinal out of range"; return TWKB_ENODEVICE; }
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, s->device);
+    if (prop.major != 10) {
+        g_create_error = std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                         "; libtwkb is built for sm_100a (B200) only";
+        return TWKB_ENODEVICE;
+    }
+    Context* ctx = new Context();
+    ctx->st = *s;
+    if (ctx->st.part_count <= 0) { ctx->st.part_count = 1; ctx->st.part_index = 0; }
+    ctx->device = s->device;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_begin) != cudaSuccess || cudaEventCreate(&ctx->ev_end) != cudaSuccess) {
+        g_create_error = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return TWKB_ECUDA;
+    }
+    *out = ctx;
+    return TWKB_OK;
+}
+
+void twkb_destroy(void* c) {
+    if (!c) return;
+    Context* ctx = static_cast<Context*>(c);
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->d_raw_data.release(); ctx->d_raw_mask.release(); ctx->d_planes.release(); ctx->d_plane_popc.release();
+    ctx->d_meta.release(); ctx->d_lgamma.release(); ctx->d_blk_of.release(); ctx->d_blk_first.release();
+    ctx->d_blk_last.release(); ctx->d_blk_prune.release(); ctx->d_tiles.release(); ctx->d_cands.release();
+    ctx->d_counters.release(); ctx->d_records.release();
+    umma_release(ctx->umma);
+    if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
+    if (ctx->h_stage[1]) cudaFreeHost(ctx->h_stage[1]);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int twkb_update_settings(void* c, const twkb_settings* s) {
+    if (!c || !s) return TWKB_EINVAL;
+    Context* ctx = static_cast<Context*>(c);
+    std::string why;
+    int rc = validate_settings(s, why);
+    if (rc) { ctx->err = why; return rc; }
+    if (s->device != ctx->device) { ctx->err = "cannot move a context to another device"; return TWKB_EINVAL; }
+    ctx->st = *s;
+    if (ctx->st.part_count <= 0) { ctx->st.part_count = 1; ctx->st.part_index = 0; }
+    return TWKB_OK;
+}
+
+int twkb_load_matrix(void* c, uint32_t n_samples, uint32_t n_variants, const uint64_t* data_bits, const uint64_t* mask_bits,
+                     size_t row_stride_words, const twkb_variant* meta) {
+    if (!c) return TWKB_EINVAL;
+    return load_common(static_cast<Context*>(c), n_samples, n_variants, data_bits, mask_bits, row_stride_words, meta, false);
+}
+
+int twkb_load_matrix_device(void* c, uint32_t n_samples, uint32_t n_variants, const uint64_t* d_data_bits,
+                            const uint64_t* d_mask_bits, size_t row_stride_words, const twkb_variant* meta) {
+    if (!c) return TWKB_EINVAL;
+    return load_common(static_cast<Context*>(c), n_samples, n_variants, d_data_bits, d_mask_bits, row_stride_words, meta, true);
+}
+
+int twkb_compute(void* c, twkb_sink_fn sink, void* user) {
+    if (!c) return TWKB_EINVAL;
+    return compute_impl(static_cast<Context*>(c), false, sink, user, false, nullptr);
+}
+
+int twkb_compute_resident(void* c) {
+    if (!c) return TWKB_EINVAL;
+    return compute_impl(static_cast<Context*>(c), true, nullptr, nullptr, false, nullptr);
+}
+
+int twkb_get_stats(void* c, twkb_stats* out) {
+    if (!c || !out) return TWKB_EINVAL;
+    *out = static_cast<Context*>(c)->stats;
+    return TWKB_OK;
+}
+
+int twkb_debug_candidates(void* c, int screen_off, uint32_t* out, uint64_t capacity, uint64_t* n_out) {
+    if (!c || !n_out) return TWKB_EINVAL;
+    Context* ctx = static_cast<Context*>(c);
+    std::vector<Candidate> dump;
+    int rc = compute_impl(ctx, true, nullptr, nullptr, screen_off != 0, &dump);
+    if (rc) return rc;
+    *n_out = dump.size();
+    if (out) {
+        if (dump.size() > capacity) { ctx->err = "debug buffer too small"; return TWKB_ENOMEM; }
+        std::memcpy(out, dump.data(), dump.size() * sizeof(Candidate));
+    }
+    return TWKB_OK;
+}
+
+static int writer_sink(void* user, const uint8_t* recs, uint64_t n) {
+    return static_cast<TwoWriter*>(user)->add(recs, n);
+}
+
+// `tomahawk calc`: twk_ld::Compute (reference lib/ld/ld.cpp:477-671) end to end.
+int twkb_calc_file(const twkb_settings* s, const char* in_path, const char* out_path, twkb_stats* stats_out, char* errbuf,
+                   size_t errbuf_len) {
+    auto fail = [&](int code, const std::string& m) {
+        if (errbuf && errbuf_len) {
+            std::snprintf(errbuf, errbuf_len, "%s", m.c_str());
+        }
+        return code;
+    };
+    if (!s || !in_path || !out_path) return fail(TWKB_EINVAL, "null argument");
+    if (std::strlen(in_path) == 0) return fail(TWKB_EINVAL, "No file-name provided...");  // ld.cpp:480
+    std::string err;
+    TwkFile twk;
+    int rc = read_twk(in_path, std::max(1, s->n_threads), twk, err);
+    if (rc) return fail(rc, err);
+    void* c = nullptr;
+    rc = twkb_create(s, &c);
+    if (rc) return fail(rc, twkb_last_error(nullptr));
+    Context* ctx = static_cast<Context*>(c);
+    rc = twkb_load_matrix(c, twk.n_samples, twk.n_variants, twk.data.data(), twk.any_missing ? twk.mask.data() : nullptr,
+                          twk.stride, twk.meta.data());
+    if (rc) { err = ctx->err; twkb_destroy(c); return fail(rc, err); }
+    // output name: the reference forces a ".two" suffix (ld.cpp:589-598)
+    std::string out = out_path;
+    {
+        const size_t slash = out.find_last_of('/');
+        const size_t dot = out.find_last_of('.');
+        const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash);
+        std::string ext = has_ext ? out.substr(dot + 1) : "";
+        for (auto& ch : ext) ch = (char)std::tolower(ch);
+        if (ext != "two") out = (has_ext ? out.substr(0, dot) : out) + ".two";
+    }
+    TwoWriter writer;
+    std::string cmd = std::string("tomahawk_b200 calc -i ") + in_path + " -o " + out_path;
+    rc = writer.open(out, twk, cmd, s->c_level, s->b_size, err);
+    if (rc) { twkb_destroy(c); return fail(rc, err); }
+    rc = twkb_compute(c, writer_sink, &writer);
+    if (rc) { err = ctx->err.empty() ? writer.error() : ctx->err; twkb_destroy(c); return fail(rc, err); }
+    rc = writer.finish();
+    if (rc) { err = writer.error(); twkb_destroy(c); return fail(rc, err); }
+    if (stats_out) *stats_out = ctx->stats;
+    twkb_destroy(c);
+    return TWKB_OK;
+}
+
+// ------------------------------------------------------------------ host-only hooks
+static int copy_err(char* errbuf, size_t n, const std::string& m, int code) {
+    if (errbuf && n) std::snprintf(errbuf, n, "%s", m.c_str());
+    return code;
+}
+
+int twkb_twk_open(const char* path, int n_threads, void** handle, char* errbuf, size_t errbuf_len) {
+    if (!path || !handle) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
+    TwkFile* f = new TwkFile();
+    std::string err;
+    const int rc = read_twk(path, std::max(1, n_threads), *f, err);
+    if (rc) { delete f; return copy_err(errbuf, errbuf_len, err, rc); }
+    *handle = f;
+    return TWKB_OK;
+}
+
+int twkb_twk_dims(void* handle, uint32_t* n_samples, uint32_t* n_variants, size_t* row_stride_words, int32_t* any_missing,
+                  uint32_t* n_blocks) {
+    if (!handle) return TWKB_EINVAL;
+    const TwkFile* f = static_cast<TwkFile*>(handle);
+    if (n_samples) *n_samples = f->n_samples;
+    if (n_variants) *n_variants = f->n_variants;
+    if (row_stride_words) *row_stride_words = f->stride;
+    if (any_missing) *any_missing = f->any_missing ? 1 : 0;
+    if (n_blocks) *n_blocks = f->n_blocks;
+    return TWKB_OK;
+}
+
+int twkb_twk_copy(void* handle, uint64_t* data_bits, uint64_t* mask_bits, twkb_variant* meta) {
+    if (!handle) return TWKB_EINVAL;
+    const TwkFile* f = static_cast<TwkFile*>(handle);
+    if (data_bits) std::memcpy(data_bits, f->data.data(), f->data.size() * 8);
+    if (mask_bits) {
+        if (f->any_missing) std::memcpy(mask_bits, f->mask.data(), f->mask.size() * 8);
+        else std::memset(mask_bits, 0, f->data.size() * 8);
+    }
+    if (meta) std::memcpy(meta, f->meta.data(), f->meta.size() * sizeof(twkb_variant));
+    return TWKB_OK;
+}
+
+void twkb_twk_close(void* handle) { delete static_cast<TwkFile*>(handle); }
+
+int twkb_two_open(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t b_size,
+                  void** writer, char* errbuf, size_t errbuf_len) {
+    if (!path || !twk_handle || !writer) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
+    TwoWriter* w = new TwoWriter();
+    std::string err;
+    const int rc = w->open(path, *static_cast<TwkFile*>(twk_handle), command_line ? command_line : "", c_level, b_size, err);
+    if (rc) { delete w; return copy_err(errbuf, errbuf_len, err, rc); }
+    *writer = w;
+    return TWKB_OK;
+}
+
+int twkb_two_add(void* writer, const uint8_t* records, uint64_t n) {
+    if (!writer || (!records && n)) return TWKB_EINVAL;
+    return static_cast<TwoWriter*>(writer)->add(records, n);
+}
+
+int twkb_two_close(void* writer) {
+    if (!writer) return TWKB_EINVAL;
+    TwoWriter* w = static_cast<TwoWriter*>(writer);
+    const int rc = w->finish();
+    delete w;
+    return rc;
+}
+
+int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i, uint32_t tile_j,
+                    uint32_t* out_ij, uint64_t capacity, uint64_t* n_tiles, uint64_t* n_pairs) {
+    if (!s || !meta || !n_tiles || n_variants == 0 || tile_i == 0 || tile_j == 0) return TWKB_EINVAL;
+    std::string why;
+    int rc = validate_settings(s, why);
+    if (rc) return rc;
+    Context ctx;  // host-only use: no CUDA call is made on this path
+    ctx.st = *s;
+    if (ctx.st.part_count <= 0) { ctx.st.part_count = 1; ctx.st.part_index = 0; }
+    ctx.n_variants = n_variants;
+    ctx.h_meta.assign(meta, meta + n_variants);
+    Problem pb;
+    rc = select_problem(&ctx, pb);
+    if (rc) return rc;
+    std::vector<uint2> tiles;
+    uint64_t pairs = 0;
+    build_tiles(&ctx, pb, tile_i, tile_j, 16, tiles, &pairs);
+    *n_tiles = tiles.size();
+    if (n_pairs) *n_pairs = pairs;
+    if (out_ij) {
+        if (tiles.size() > capacity) return TWKB_ENOMEM;
+        for (size_t t = 0; t < tiles.size(); ++t) { out_ij[2 * t] = tiles[t].x; out_ij[2 * t + 1] = tiles[t].y; }
+    }
+    return TWKB_OK;
+}
+
+}  // extern "C"

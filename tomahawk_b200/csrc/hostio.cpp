@@ -1,0 +1,382 @@
+// hostio.cpp -- `.twk` reader and `.two` writer (host side; zstd on the host).
+// Layouts follow the reference's serializers; citations inline.
+#include "hostio.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <thread>
+
+namespace twkb {
+
+namespace {
+
+const char kTwkMagic[9] = {'T', 'O', 'M', 'A', 'H', 'A', 'W', 'K', 1};  // include/tomahawk.h:47-48
+const char kTwoMagic[4] = {'T', 'W', 'O', 1};                           // include/tomahawk.h:50-51
+const char kEof[] = "a4f54f39f5e251a6993796f48164ccf5";                 // first 32 chars, tomahawk.h:66-67
+const uint64_t kIndexMarker = 1954702206512158641ull;                   // tomahawk.h:68
+
+struct Cursor {
+    const uint8_t* p;
+    const uint8_t* end;
+    bool ok = true;
+    template <typename T>
+    T get() {
+        T v{};
+        if ((size_t)(end - p) < sizeof(T)) { ok = false; return v; }
+        std::memcpy(&v, p, sizeof(T));
+        p += sizeof(T);
+        return v;
+    }
+    std::string str() {  // u32 length + bytes, lib/buffer.cpp:410-421
+        uint32_t n = get<uint32_t>();
+        if (!ok || (size_t)(end - p) < n) { ok = false; return {}; }
+        std::string s(reinterpret_cast<const char*>(p), n);
+        p += n;
+        return s;
+    }
+};
+
+bool zstd_inflate(const uint8_t* src, size_t n_cmp, size_t n_unc, std::vector<uint8_t>& dst, std::string& err) {
+    dst.resize(n_unc ? n_unc : 1);
+    const size_t r = ZSTD_decompress(dst.data(), n_unc, src, n_cmp);
+    if (ZSTD_isError(r) || r != n_unc) {
+        err = std::string("zstd decompress failed: ") + (ZSTD_isError(r) ? ZSTD_getErrorName(r) : "size mismatch");
+        return false;
+    }
+    dst.resize(n_unc);
+    return true;
+}
+
+// OR `pattern` (period 2 bits) into bits [start, end) of a row; start is even.
+inline void or_range(uint64_t* row, uint64_t start, uint64_t end, uint64_t pattern) {
+    if (pattern == 0 || start >= end) return;
+    uint64_t w0 = start >> 6, w1 = (end - 1) >> 6;
+    const uint64_t m0 = ~0ull << (start & 63);
+    const uint64_t m1 = (end & 63) ? ((1ull << (end & 63)) - 1) : ~0ull;
+    if (w0 == w1) { row[w0] |= pattern & m0 & m1; return; }
+    row[w0] |= pattern & m0;
+    for (uint64_t w = w0 + 1; w < w1; ++w) row[w] |= pattern;
+    row[w1] |= pattern & m1;
+}
+
+struct BlockRef { uint64_t foff; uint32_t n, first_variant; int32_t rid; };
+
+}  // namespace
+
+// lib/twk_reader.cpp:49-125 (Open), :8-44 (NextBlock), lib/core.cpp:75-101 (twk1_t),
+// include/core.h:195-215 (run words), lib/core.cpp:365-383 (bitvector + mask).
+int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err) {
+    FILE* fp = std::fopen(path.c_str(), "rb");
+    if (!fp) { err = "Failed to open \"" + path + "\"!"; return TWKB_EIO; }
+    std::fseek(fp, 0, SEEK_END);
+    const long fsz = std::ftell(fp);
+    std::fseek(fp, 0, SEEK_SET);
+    std::vector<uint8_t> file((size_t)std::max<long>(fsz, 0));
+    if (fsz <= 0 || std::fread(file.data(), 1, file.size(), fp) != file.size()) {
+        std::fclose(fp);
+        err = "Failed to read \"" + path + "\"";
+        return TWKB_EIO;
+    }
+    std::fclose(fp);
+    if (file.size() < 9 + 16 + 8 + 32 || std::memcmp(file.data(), kTwkMagic, 9) != 0) { err = "Failed to read MAGIC!"; return TWKB_EIO; }
+    Cursor c{file.data() + 9, file.data() + file.size()};
+    const uint64_t h_unc = c.get<uint64_t>(), h_cmp = c.get<uint64_t>();
+    if (!c.ok || (uint64_t)(c.end - c.p) < h_cmp) { err = "truncated header"; return TWKB_EIO; }
+    std::vector<uint8_t> hdr;
+    if (!zstd_inflate(c.p, h_cmp, h_unc, hdr, err)) return TWKB_EIO;
+    {
+        Cursor h{hdr.data(), hdr.data() + hdr.size()};
+        out.fileformat = h.str();
+        out.literals = h.str();
+        const uint8_t* tail = h.p;
+        out.n_samples = h.get<uint32_t>();
+        for (uint32_t i = 0; i < out.n_samples && h.ok; ++i) h.str();
+        out.n_contigs = h.get<uint32_t>();
+        if (!h.ok) { err = "corrupt VcfHeader"; return TWKB_EIO; }
+        out.header_tail.assign(reinterpret_cast<const char*>(tail), hdr.data() + hdr.size() - tail);
+    }
+    // footer: ... u64 offset_of_index, 32-byte EOF
+    uint64_t idx_off = 0;
+    std::memcpy(&idx_off, file.data() + file.size() - 32 - 8, 8);
+    if (idx_off + 17 > file.size()) { err = "Failed to seek in file!"; return TWKB_EIO; }
+    Cursor f{file.data() + idx_off, file.data() + file.size()};
+    const uint8_t marker = f.get<uint8_t>();
+    const uint64_t i_unc = f.get<uint64_t>(), i_cmp = f.get<uint64_t>();
+    if (marker != 0 || !f.ok || (uint64_t)(f.end - f.p) < i_cmp) { err = "corrupt index footer"; return TWKB_EIO; }
+    std::vector<uint8_t> idx;
+    if (!zstd_inflate(f.p, i_cmp, i_unc, idx, err)) { err = "Failed to decompress index!"; return TWKB_EIO; }
+    Cursor ix{idx.data(), idx.data() + idx.size()};
+    if (ix.get<uint64_t>() != kIndexMarker) { err = "bad index marker"; return TWKB_EIO; }
+    const uint64_t n_ent = ix.get<uint64_t>();
+    ix.get<uint64_t>();  // m
+    ix.get<uint64_t>();  // m_ent
+    std::vector<BlockRef> blocks(n_ent);
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n_ent; ++i) {  // IndexEntry, lib/index.cpp:8-18
+        const int32_t rid = ix.get<int32_t>();
+        const uint32_t n = ix.get<uint32_t>();
+        ix.get<uint32_t>(); ix.get<uint32_t>(); ix.get<uint32_t>(); ix.get<uint32_t>();
+        const uint64_t foff = ix.get<uint64_t>();
+        ix.get<uint64_t>();
+        blocks[i] = {foff, n, (uint32_t)total, rid};
+        total += n;
+    }
+    if (!ix.ok || total == 0 || total > 0xffffffffull) { err = "No valid data available..."; return TWKB_EIO; }
+    out.n_blocks = (uint32_t)n_ent;
+    out.n_variants = (uint32_t)total;
+    const uint64_t H = 2ull * out.n_samples;
+    out.stride = ((H + 63) / 64 + 1) / 2 * 2;
+    out.data.assign((size_t)total * out.stride, 0);
+    out.meta.assign(total, twkb_variant{});
+    std::vector<std::vector<uint64_t>> block_masks(n_ent);  // only for blocks that have missing data
+    std::atomic<uint64_t> next{0};
+    std::atomic<bool> failed{false};
+    std::string first_err;
+    std::mutex err_mu;
+    auto worker = [&]() {
+        std::vector<uint8_t> raw;
+        for (;;) {
+            const uint64_t b = next.fetch_add(1);
+            if (b >= n_ent || failed.load()) return;
+            auto fail = [&](const std::string& m) {
+                std::lock_guard<std::mutex> g(err_mu);
+                if (!failed.exchange(true)) first_err = m;
+            };
+            const BlockRef& br = blocks[b];
+            if (br.foff + 9 > file.size()) { fail("block offset beyond file"); return; }
+            Cursor bc{file.data() + br.foff, file.data() + file.size()};
+            if (bc.get<uint8_t>() != 1) { fail("bad block marker"); return; }
+            const uint32_t unc = bc.get<uint32_t>(), cmp = bc.get<uint32_t>();
+            std::string e;
+            if ((uint64_t)(bc.end - bc.p) < cmp || !zstd_inflate(bc.p, cmp, unc, raw, e)) { fail("Failed to load block " + std::to_string(b)); return; }
+            Cursor r{raw.data(), raw.data() + raw.size()};
+            const uint32_t n = r.get<uint32_t>();
+            r.get<uint32_t>();  // m
+            r.get<uint32_t>();  // rid
+            if (n != br.n) { fail("index/block variant count mismatch"); return; }
+            for (uint32_t v = 0; v < n; ++v) {
+                const uint8_t pack = r.get<uint8_t>();
+                r.get<uint8_t>();  // alleles
+                twkb_variant& mv = out.meta[br.first_variant + v];
+                mv.pos = r.get<uint32_t>();
+                mv.ac = r.get<uint32_t>();
+                mv.an = r.get<uint32_t>();
+                mv.rid = r.get<uint32_t>();
+                r.get<uint32_t>();  // n_het
+                r.get<uint32_t>();  // n_hom
+                mv.hwe = r.get<double>();
+                const int ptype = pack >> 3;
+                mv.gt_phase = (pack >> 1) & 1;
+                mv.gt_missing = pack & 1;
+                const uint32_t nw = r.get<uint32_t>();
+                const uint32_t n_runs = nw >> 1, miss = nw & 1;
+                if (!r.ok || (ptype != 1 && ptype != 2 && ptype != 4) || (size_t)(r.end - r.p) < (size_t)n_runs * ptype) {
+                    fail("illegal gt primitive type / truncated runs");
+                    return;
+                }
+                uint64_t* row = out.data.data() + (size_t)(br.first_variant + v) * out.stride;
+                uint64_t* mrow = nullptr;
+                if (mv.gt_missing || miss) {
+                    if (block_masks[b].empty()) block_masks[b].assign((size_t)n * out.stride, 0);
+                    mrow = block_masks[b].data() + (size_t)v * out.stride;
+                }
+                const int lshift = 2 + 2 * miss, ashift = 1 + miss;
+                const uint32_t amask = (1u << (1 + miss)) - 1;
+                uint64_t cum = 0;
+                for (uint32_t k = 0; k < n_runs; ++k) {
+                    uint32_t word = 0;
+                    std::memcpy(&word, r.p, ptype);
+                    r.p += ptype;
+                    const uint64_t len = word >> lshift;
+                    const uint32_t a = (word >> ashift) & amask, bb = word & amask;
+                    const uint64_t s = cum, e2 = cum + 2 * len;
+                    if (e2 > H) { fail("run lengths exceed sample count"); return; }
+                    or_range(row, s, e2, (a == 1 ? 0x5555555555555555ull : 0) | (bb == 1 ? 0xAAAAAAAAAAAAAAAAull : 0));
+                    if (mrow && (a == 2 || bb == 2)) or_range(mrow, s, e2, ~0ull);
+                    cum = e2;
+                }
+                if (cum != H) { fail("run lengths do not cover all samples"); return; }
+            }
+        }
+    };
+    const int nt = std::max(1, std::min<int>(n_threads, (int)n_ent));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    if (failed.load()) { err = first_err; return TWKB_EIO; }
+    out.any_missing = false;
+    for (auto& m : block_masks) if (!m.empty()) out.any_missing = true;
+    for (auto& mv : out.meta) if (mv.an || mv.gt_missing) out.any_missing = true;
+    if (out.any_missing) {
+        out.mask.assign((size_t)total * out.stride, 0);
+        for (uint64_t b = 0; b < n_ent; ++b)
+            if (!block_masks[b].empty())
+                std::memcpy(out.mask.data() + (size_t)blocks[b].first_variant * out.stride, block_masks[b].data(),
+                            block_masks[b].size() * 8);
+    }
+    return TWKB_OK;
+}
+
+// ------------------------------------------------------------------ .two writer
+TwoWriter::~TwoWriter() {
+    if (fp_) std::fclose(fp_);
+}
+
+static void put_str(std::vector<uint8_t>& b, const std::string& s) {
+    const uint32_t n = (uint32_t)s.size();
+    b.insert(b.end(), reinterpret_cast<const uint8_t*>(&n), reinterpret_cast<const uint8_t*>(&n) + 4);
+    b.insert(b.end(), s.begin(), s.end());
+}
+
+// include/writer.h:225-242 + lib/ld/ld.cpp:609-612
+int TwoWriter::open(const std::string& path, const TwkFile& src, const std::string& command_line, int c_level, int b_size,
+                    std::string& err) {
+    fp_ = std::fopen(path.c_str(), "wb");
+    if (!fp_) { err = "Failed to open file: " + path + "..."; return TWKB_EIO; }
+    c_level_ = c_level;
+    b_size_ = (uint32_t)std::max(2, b_size);
+    n_contigs_ = src.n_contigs;
+    char date[64];
+    std::time_t now = std::time(nullptr);
+    std::strftime(date, sizeof(date), "%Y-%m-%d %H:%M:%S", std::localtime(&now));
+    std::string literals = src.literals + "\n##tomahawk_calcVersion=b200-0.1.0\n##tomahawk_calcCommand=" + command_line +
+                           "; Date=" + date + "\n";
+    std::vector<uint8_t> hdr;
+    put_str(hdr, src.fileformat);
+    put_str(hdr, literals);
+    hdr.insert(hdr.end(), src.header_tail.begin(), src.header_tail.end());
+    std::vector<uint8_t> z(ZSTD_compressBound(hdr.size()));
+    const size_t zn = ZSTD_compress(z.data(), z.size(), hdr.data(), hdr.size(), c_level_);
+    if (ZSTD_isError(zn)) { err = "failed to compress"; return TWKB_EIO; }
+    const uint64_t unc = hdr.size(), cmp = zn;
+    std::fwrite(kTwoMagic, 1, 4, fp_);
+    std::fwrite(&unc, 8, 1, fp_);
+    std::fwrite(&cmp, 8, 1, fp_);
+    std::fwrite(z.data(), 1, zn, fp_);
+    fwd_.ent = IndexEntry{-1, -1, 0, 0, 0, 0, 0, 0, 0};
+    rev_.ent = fwd_.ent;
+    return TWKB_OK;
+}
+
+// one zstd block: u8 1, u32 unc, u32 cmp, payload (include/writer.h:70-87)
+int TwoWriter::write_block(const std::vector<uint8_t>& raw, uint32_t* b_cmp) {
+    zbuf_.resize(ZSTD_compressBound(raw.size()));
+    const size_t zn = ZSTD_compress(zbuf_.data(), zbuf_.size(), raw.data(), raw.size(), c_level_);
+    if (ZSTD_isError(zn)) { err_ = "failed compression"; return TWKB_EIO; }
+    const uint8_t marker = 1;
+    const uint32_t unc = (uint32_t)raw.size(), cmp = (uint32_t)zn;
+    if (std::fwrite(&marker, 1, 1, fp_) != 1 || std::fwrite(&unc, 4, 1, fp_) != 1 || std::fwrite(&cmp, 4, 1, fp_) != 1 ||
+        std::fwrite(zbuf_.data(), 1, zn, fp_) != zn) {
+        err_ = "write failed";
+        return TWKB_EIO;
+    }
+    *b_cmp = cmp;
+    return TWKB_OK;
+}
+
+// lib/ld/ld_engine.cpp:1742-1802 (CompressFwd/CompressRev)
+int TwoWriter::flush_side(Side& s) {
+    if (s.n == 0) return TWKB_OK;
+    scratch_.resize(8 + s.buf.size());
+    const uint32_t n = s.n, m = b_size_ + 100;  // twk1_two_block_t {n, m}, lib/core.cpp:626-631
+    std::memcpy(scratch_.data(), &n, 4);
+    std::memcpy(scratch_.data() + 4, &m, 4);
+    std::memcpy(scratch_.data() + 8, s.buf.data(), s.buf.size());
+    s.ent.foff = (uint64_t)std::ftell(fp_);
+    uint32_t cmp = 0;
+    const int rc = write_block(scratch_, &cmp);
+    if (rc) return rc;
+    s.ent.fend = (uint64_t)std::ftell(fp_);
+    s.ent.n = n;
+    s.ent.b_unc = TWKB_RECORD_BYTES * n + 8;
+    s.ent.b_cmp = cmp;
+    index_.push_back(s.ent);
+    n_written_ += n;
+    s.buf.clear();
+    s.n = 0;
+    s.ent.rid = -1; s.ent.ridB = -1; s.ent.minpos = 0; s.ent.n = 0; s.ent.foff = 0; s.ent.fend = 0;
+    return TWKB_OK;
+}
+
+// lib/ld/ld_engine.cpp:1268-1298: flush rule, index bookkeeping, forward + swapped copy.
+int TwoWriter::add(const uint8_t* records, uint64_t n) {
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint8_t* rec = records + r * TWKB_RECORD_BYTES;
+        int32_t ridA, ridB;
+        uint32_t packA, packB;
+        std::memcpy(&ridA, rec + 2, 4);
+        std::memcpy(&ridB, rec + 6, 4);
+        std::memcpy(&packA, rec + 10, 4);
+        std::memcpy(&packB, rec + 14, 4);
+        const uint32_t posA = packA >> 2, posB = packB >> 2;
+        if (fwd_.n == b_size_ || fwd_.ent.rid != ridA || rev_.ent.rid != ridB) {
+            int rc = flush_side(fwd_);
+            if (rc) return rc;
+            rc = flush_side(rev_);
+            if (rc) return rc;
+            fwd_.ent.rid = ridA; fwd_.ent.ridB = ridB; fwd_.ent.minpos = posA; fwd_.ent.maxpos = posA;
+            rev_.ent.rid = ridB; rev_.ent.ridB = ridA; rev_.ent.minpos = posB; rev_.ent.maxpos = posB;
+        }
+        if (fwd_.ent.ridB != ridB) fwd_.ent.ridB = -1;
+        if (rev_.ent.ridB != ridA) rev_.ent.ridB = -1;
+        fwd_.ent.maxpos = posA;
+        rev_.ent.maxpos = posB;
+        fwd_.buf.insert(fwd_.buf.end(), rec, rec + TWKB_RECORD_BYTES);
+        ++fwd_.n;
+        // reverse copy: only (rid, pos) are swapped, counts and flags stay A-major (:1292-1298)
+        const size_t o = rev_.buf.size();
+        rev_.buf.insert(rev_.buf.end(), rec, rec + TWKB_RECORD_BYTES);
+        std::memcpy(rev_.buf.data() + o + 2, &ridB, 4);
+        std::memcpy(rev_.buf.data() + o + 6, &ridA, 4);
+        std::memcpy(rev_.buf.data() + o + 10, &packB, 4);
+        std::memcpy(rev_.buf.data() + o + 14, &packA, 4);
+        ++rev_.n;
+    }
+    return TWKB_OK;
+}
+
+// include/writer.h:293-313 + lib/index.cpp:242-251
+int TwoWriter::finish() {
+    if (!fp_) return TWKB_EIO;
+    int rc = flush_side(fwd_);
+    if (rc) return rc;
+    rc = flush_side(rev_);
+    if (rc) return rc;
+    std::vector<uint8_t> idx;
+    auto put = [&](const void* p, size_t n) { idx.insert(idx.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+    const uint8_t state = 0;  // TWK_IDX_UNSORTED
+    uint64_t n = index_.size(), m = 500;
+    while (m < n) m *= 2;
+    const uint64_t m_ent = n_contigs_;
+    put(&kIndexMarker, 8); put(&state, 1); put(&n, 8); put(&m, 8); put(&m_ent, 8);
+    for (const IndexEntry& e : index_) {  // IndexEntryOutput, lib/index.cpp:41-52
+        put(&e.rid, 4); put(&e.n, 4); put(&e.minpos, 4); put(&e.maxpos, 4); put(&e.b_unc, 4); put(&e.b_cmp, 4);
+        put(&e.foff, 8); put(&e.fend, 8); put(&e.ridB, 4);
+    }
+    for (uint64_t c = 0; c < m_ent; ++c) {  // untouched IndexEntryEntry, lib/index.cpp:90-99
+        const int32_t rid = 0; const uint32_t z32 = 0; const uint64_t z64 = 0;
+        put(&rid, 4); put(&z32, 4); put(&z32, 4); put(&z32, 4); put(&z64, 8); put(&z64, 8); put(&z64, 8);
+    }
+    std::vector<uint8_t> z(ZSTD_compressBound(idx.size()));
+    const size_t zn = ZSTD_compress(z.data(), z.size(), idx.data(), idx.size(), c_level_);
+    if (ZSTD_isError(zn)) { err_ = "failed compression"; return TWKB_EIO; }
+    const uint64_t off = (uint64_t)std::ftell(fp_), unc = idx.size(), cmp = zn;
+    const uint8_t marker = 0;
+    std::fwrite(&marker, 1, 1, fp_);
+    std::fwrite(&unc, 8, 1, fp_);
+    std::fwrite(&cmp, 8, 1, fp_);
+    std::fwrite(z.data(), 1, zn, fp_);
+    std::fwrite(&off, 8, 1, fp_);
+    std::fwrite(kEof, 1, 32, fp_);
+    const bool ok = std::fflush(fp_) == 0;
+    std::fclose(fp_);
+    fp_ = nullptr;
+    if (!ok) { err_ = "Failed to write final block!"; return TWKB_EIO; }
+    return TWKB_OK;
+}
+
+}  // namespace twkb

@@ -1,0 +1,82 @@
+// hostio.h -- host-side file formats around the engine: the `.twk` reader
+// (reference lib/twk_reader.cpp:49-125, lib/core.cpp:75-101,253-261,349-383) and
+// the `.two` writer (reference include/writer.h:70-87,225-242,293-313,
+// lib/ld/ld_engine.cpp:1268-1298,1742-1810, lib/index.cpp:41-52,242-251).
+// zstd stays on the host (BASELINE.json north_star).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/twkb.h"
+
+namespace twkb {
+
+// Declarations of the stable zstd C ABI we link against (libzstd.so.1); the
+// image ships the runtime library but no headers.
+extern "C" {
+size_t ZSTD_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize, int compressionLevel);
+size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* src, size_t compressedSize);
+size_t ZSTD_compressBound(size_t srcSize);
+unsigned ZSTD_isError(size_t code);
+const char* ZSTD_getErrorName(size_t code);
+}
+
+// A whole .twk file unpacked into the matrix layout twkb_load_matrix takes.
+struct TwkFile {
+    uint32_t n_samples = 0;
+    uint32_t n_variants = 0;
+    size_t stride = 0;  // u64 words per row (128-bit aligned)
+    bool any_missing = false;
+    std::vector<uint64_t> data, mask;
+    std::vector<twkb_variant> meta;
+    // VcfHeader pieces (lib/header.cpp:330-345) needed to write the .two header
+    std::string fileformat, literals;
+    std::string header_tail;  // serialized samples + contigs, copied through verbatim
+    uint32_t n_contigs = 0;
+    uint32_t n_blocks = 0;
+};
+
+// Reads and unpacks `path` with up to n_threads host threads. Returns 0 or TWKB_EIO.
+int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err);
+
+// Streaming .two writer: takes forward records, writes forward and reverse
+// blocks of <= b_size records, the index and the EOF marker.
+class TwoWriter {
+public:
+    TwoWriter() = default;
+    ~TwoWriter();
+    int open(const std::string& path, const TwkFile& src, const std::string& command_line, int c_level, int b_size,
+             std::string& err);
+    int add(const uint8_t* records, uint64_t n);  // forward records, TWKB_RECORD_BYTES each
+    int finish();
+    uint64_t records_written() const { return n_written_; }
+    const std::string& error() const { return err_; }
+
+private:
+    struct IndexEntry {
+        int32_t rid, ridB;
+        uint32_t n, minpos, maxpos, b_unc, b_cmp;
+        uint64_t foff, fend;
+    };
+    struct Side {
+        std::vector<uint8_t> buf;  // records only
+        uint32_t n = 0;
+        IndexEntry ent{};
+    };
+    int flush_side(Side& s);
+    int write_block(const std::vector<uint8_t>& raw, uint32_t* b_cmp);
+
+    FILE* fp_ = nullptr;
+    int c_level_ = 1;
+    uint32_t b_size_ = 10000;
+    uint32_t n_contigs_ = 0;
+    Side fwd_, rev_;
+    std::vector<IndexEntry> index_;
+    std::vector<uint8_t> scratch_, zbuf_;
+    uint64_t n_written_ = 0;
+    std::string err_;
+};
+
+}  // namespace twkb

@@ -1,0 +1,408 @@
+// stats.cuh -- the statistics stage of `tomahawk calc` on the device: D, D', R,
+// R2, Fisher's exact P, chi-squared, flags, filters (in the reference's order)
+// and the packed 106-byte record. One thread per surviving pair.
+//
+// Reference: twk_ld_engine::PhasedMath lib/ld/ld_engine.cpp:1162-1310,
+// UnphasedMath :1312-1560, ChiSquaredUnphasedTable :1562-1588,
+// ChooseF11Calculate :1590-1740, kt_fisher_exact lib/fisher_math.cpp:183-267.
+//
+// All phased arithmetic uses the round-to-nearest intrinsics (__dmul_rn, ...)
+// so no multiply-add is ever contracted: the reference runs on x86-64 SSE2
+// doubles without FMA, and with the same operation order the device results
+// are bit-identical. Fisher's log-factorials come from a host-built table of
+// glibc lgamma(n+1) (bit-identical to the reference's lgamma calls); only
+// exp() (<= 1 ulp) differs.
+#pragma once
+#include "common.cuh"
+
+namespace twkb {
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// ------------------------------------------------------------------ Fisher
+struct LgTable {
+    const double* lg;  // lg[n] = lgamma(n + 1), n in [0, len)
+    uint32_t len;
+    __device__ __forceinline__ double at(int n) const {
+        if (n >= 0 && (uint32_t)n < len) return __ldg(lg + n);
+        return lgamma((double)n + 1.0);
+    }
+};
+
+// fisher_math.cpp:183-187
+__device__ __forceinline__ double log_binom(const LgTable& t, int n, int k) {
+    if (k == 0 || n == k) return 0.0;
+    return dsub(dsub(t.at(n), t.at(k)), t.at(n - k));
+}
+// :195-198
+__device__ __forceinline__ double hyper_pmf(const LgTable& t, int n11, int n1_, int n_1, int n) {
+    return exp(dsub(dadd(log_binom(t, n1_, n11), log_binom(t, n - n1_, n_1 - n11)), log_binom(t, n, n_1)));
+}
+
+struct HyperState {
+    int n11, n1_, n_1, n;
+    double p;
+};
+// :206-229 with (n1_, n_1, n) == 0: only n11 moves
+__device__ __forceinline__ double hyper_move(const LgTable& t, int n11, HyperState& st) {
+    if ((n11 % 11) && (n11 + st.n - st.n1_ - st.n_1)) {
+        if (n11 == st.n11 + 1) {
+            double f = ddiv(dmul(ddiv((double)(st.n1_ - st.n11), (double)n11), (double)(st.n_1 - st.n11)),
+                            (double)(n11 + st.n - st.n1_ - st.n_1));
+            st.p = dmul(st.p, f);
+            st.n11 = n11;
+            return st.p;
+        }
+        if (n11 == st.n11 - 1) {
+            double f = ddiv(dmul(ddiv((double)st.n11, (double)(st.n1_ - n11)), (double)(st.n11 + st.n - st.n1_ - st.n_1)),
+                            (double)(st.n_1 - n11));
+            st.p = dmul(st.p, f);
+            st.n11 = n11;
+            return st.p;
+        }
+    }
+    st.n11 = n11;
+    st.p = hyper_pmf(t, st.n11, st.n1_, st.n_1, st.n);
+    return st.p;
+}
+
+// :231-267, two-sided P only
+__device__ double fisher_two_sided(const LgTable& t, int n11, int n12, int n21, int n22) {
+    int n1_ = n11 + n12, n_1 = n11 + n21, n = n11 + n12 + n21 + n22;
+    int max = (n_1 < n1_) ? n_1 : n1_;
+    int min = n1_ + n_1 - n;
+    if (min < 0) min = 0;
+    if (min == max) return 1.0;
+    HyperState st;
+    st.n11 = n11; st.n1_ = n1_; st.n_1 = n_1; st.n = n;
+    st.p = hyper_pmf(t, n11, n1_, n_1, n);
+    const double q = st.p;
+    const double qlo = dmul(0.99999999, q), qhi = dmul(1.00000001, q);
+    double p = hyper_move(t, min, st);
+    double left = 0.0;
+    int i;
+    for (i = min + 1; p < qlo && i <= max; ++i) {
+        left = dadd(left, p);
+        p = hyper_move(t, i, st);
+    }
+    if (p < qhi) left = dadd(left, p);
+    p = hyper_move(t, max, st);
+    double right = 0.0;
+    int j;
+    for (j = max - 1; p < qlo && j >= 0; --j) {
+        right = dadd(right, p);
+        p = hyper_move(t, j, st);
+    }
+    if (p < qhi) right = dadd(right, p);
+    double two = dadd(left, right);
+    if (two > 1.0) two = 1.0;
+    return two;
+}
+
+// ---------------------------------------------------------------- the record
+struct PairStats {
+    uint32_t flags;
+    double cnt[4], D, Dprime, R, R2, P, chi_fisher, chi_model;
+};
+
+__device__ __forceinline__ void st_u16(uint8_t* p, uint32_t v) { *reinterpret_cast<uint16_t*>(p) = (uint16_t)v; }
+__device__ __forceinline__ void st_u32_2(uint8_t* p, uint32_t v) {
+    st_u16(p, v & 0xffffu);
+    st_u16(p + 2, v >> 16);
+}
+__device__ __forceinline__ void st_f64_2(uint8_t* p, double d) {
+    unsigned long long v = (unsigned long long)__double_as_longlong(d);
+    st_u16(p, (uint32_t)(v & 0xffffu));
+    st_u16(p + 2, (uint32_t)((v >> 16) & 0xffffu));
+    st_u16(p + 4, (uint32_t)((v >> 32) & 0xffffu));
+    st_u16(p + 6, (uint32_t)(v >> 48));
+}
+// lib/core.cpp:470-490. Records are only 2-byte aligned (106 = 2*53).
+__device__ void write_record(uint8_t* dst, const PairStats& s, const DevVariant& a, const DevVariant& b) {
+    st_u16(dst, s.flags);
+    st_u32_2(dst + 2, a.rid);
+    st_u32_2(dst + 6, b.rid);
+    st_u32_2(dst + 10, a.pos << 2);
+    st_u32_2(dst + 14, b.pos << 2);
+    st_f64_2(dst + 18, s.cnt[0]);
+    st_f64_2(dst + 26, s.cnt[1]);
+    st_f64_2(dst + 34, s.cnt[2]);
+    st_f64_2(dst + 42, s.cnt[3]);
+    st_f64_2(dst + 50, s.D);
+    st_f64_2(dst + 58, s.Dprime);
+    st_f64_2(dst + 66, s.R);
+    st_f64_2(dst + 74, s.R2);
+    st_f64_2(dst + 82, s.P);
+    st_f64_2(dst + 90, s.chi_fisher);
+    st_f64_2(dst + 98, s.chi_model);
+}
+
+// ld_engine.cpp:1244-1255 / :1674-1684
+__device__ __forceinline__ uint32_t variant_flags(const DevVariant& a, const DevVariant& b) {
+    uint32_t f = 0;
+    const bool same = a.rid == b.rid;
+    int diff = (int)a.pos - (int)b.pos;
+    if (diff < 0) diff = -diff;
+    if (same) f |= 1u << 1;
+    if ((double)diff > 500e3 && same) f |= 1u << 2;
+    if (a.flags & VF_HAS_MISSING) f |= 1u << 8;
+    if (b.flags & VF_HAS_MISSING) f |= 1u << 9;
+    if (a.ac < 5) f |= 1u << 10;
+    if (b.ac < 5) f |= 1u << 11;
+    if (a.flags & VF_BAD_HWE) f |= 1u << 12;
+    if (b.flags & VF_BAD_HWE) f |= 1u << 13;
+    return f;
+}
+
+// ----------------------------------------------------------------- phased math
+// ld_engine.cpp:1162-1259. c0=REFREF, c1=slot 1, c4=slot 4, c5=ALTALT.
+__device__ bool phased_stats(unsigned long long c0, unsigned long long c1, unsigned long long c4,
+                             unsigned long long c5, const DevParams& prm, const LgTable& lg, const DevVariant& a,
+                             const DevVariant& b, PairStats& s) {
+    const unsigned long long T = c0 + c4 + c1 + c5;
+    if (T < 5) return false;
+    if (c0 < c5) {
+        if (c4 + c1 + c0 < 5) return false;
+    } else {
+        if (c5 + c4 + c1 < 5) return false;
+    }
+    const double Td = (double)T;
+    const double d0 = (double)c0, d1 = (double)c1, d4 = (double)c4, d5 = (double)c5;
+    const double pA = ddiv(d0, Td), qA = ddiv(d1, Td), pB = ddiv(d4, Td), qB = ddiv(d5, Td);
+    const double D = dsub(dmul(pA, qB), dmul(qA, pB));
+    if (D == 0.0) return false;
+    const double g0 = ddiv(dadd(d0, d4), Td);
+    const double g1 = ddiv(dadd(d1, d5), Td);
+    const double h0 = ddiv(dadd(d0, d1), Td);
+    const double h1 = ddiv(dadd(d4, d5), Td);
+    s.D = D;
+    s.R2 = ddiv(dmul(D, D), dmul(dmul(dmul(g0, g1), h0), h1));
+    if (s.R2 < prm.minR2 || s.R2 > prm.maxR2) return false;
+    double dmax;
+    if (D >= 0) {
+        const double x = dmul(g0, h1), y = dmul(h0, g1);
+        dmax = x < y ? x : y;
+    } else {
+        const double x = dmul(g0, g1), y = dmul(h0, h1);
+        dmax = x < y ? -x : -y;
+    }
+    s.Dprime = ddiv(D, dmax);
+    if (s.Dprime < prm.minDprime || s.Dprime > prm.maxDprime) return false;
+    const double both = fisher_two_sided(lg, (int)c0, (int)c4, (int)c1, (int)c5);
+    if (both > prm.minP) return false;
+    s.P = both;
+    s.R = __dsqrt_rn(s.R2);
+    s.cnt[0] = d0; s.cnt[1] = d1; s.cnt[2] = d4; s.cnt[3] = d5;
+    s.flags = variant_flags(a, b) | 1u;
+    if (c0 < 1 || c4 < 1 || c1 < 1 || c5 < 1) s.flags |= 1u << 3;
+    if (s.R2 > 0.99) s.flags |= 1u << 4;
+    s.chi_model = 0.0;
+    s.chi_fisher = dmul(Td, s.R2);
+    return true;
+}
+
+// --------------------------------------------------------------- unphased math
+// Transcendentals (pow with non-integer exponent, acos, cos) come from the CUDA
+// math library and differ from glibc's by a few ulp: statistics of pairs that go
+// through the cubic agree with the reference to ~1e-13 relative, not bit-exactly.
+__device__ __forceinline__ double sq(double x) { return dmul(x, x); }  // gcc folds pow(x,2) to x*x
+
+// ld_engine.cpp:1562-1588
+__device__ double chisq_unphased(const uint32_t* t, double Td, double target, double p, double q) {
+    const double f12 = dsub(p, target);
+    const double f21 = dsub(q, target);
+    const double f22 = dsub(1.0, dadd(dadd(target, f12), f21));
+    const double T2 = dmul(2.0, Td);
+    const double e[9] = {dmul(Td, sq(target)),
+                         dmul(dmul(T2, target), f12),
+                         dmul(Td, sq(f12)),
+                         dmul(dmul(T2, target), f21),
+                         dadd(dmul(dmul(T2, f12), f21), dmul(dmul(T2, target), f22)),
+                         dmul(dmul(T2, f12), f22),
+                         dmul(Td, sq(f21)),
+                         dmul(dmul(T2, f21), f22),
+                         dmul(Td, sq(f22))};
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const double x = e[k] > 0 ? ddiv(sq(dsub((double)t[k], e[k])), e[k]) : 0.0;
+        sum = dadd(sum, x);
+    }
+    return sum;
+}
+
+// ld_engine.cpp:1590-1684
+__device__ bool choose_f11(double Td, double target, double p, double q, uint32_t flags, const DevParams& prm,
+                           const LgTable& lg, const DevVariant& a, const DevVariant& b, PairStats& s) {
+    const double f11 = target, f12 = dsub(p, f11), f21 = dsub(q, f11);
+    const double f22 = dsub(1.0, dadd(dadd(f11, f12), f21));
+    const double D = dsub(dmul(f11, f22), dmul(f12, f21));
+    const double omp = dsub(1.0, p), omq = dsub(1.0, q);
+    s.D = D;
+    s.R2 = ddiv(dmul(D, D), dmul(dmul(dmul(p, omp), q), omq));
+    if (s.R2 < prm.minR2 || s.R2 > prm.maxR2) return false;
+    s.R = __dsqrt_rn(s.R2);
+    s.cnt[0] = dmul(dmul(f11, 2.0), Td);
+    s.cnt[2] = dmul(dmul(f12, 2.0), Td);
+    s.cnt[1] = dmul(dmul(f21, 2.0), Td);
+    s.cnt[3] = dmul(dmul(f22, 2.0), Td);
+    if (s.cnt[0] < s.cnt[3]) {
+        if (dadd(dadd(s.cnt[2], s.cnt[1]), s.cnt[0]) < 5) return false;
+    } else {
+        if (dadd(dadd(s.cnt[3], s.cnt[2]), s.cnt[1]) < 5) return false;
+    }
+    double dmax;
+    if (D >= 0) {
+        const double x = dmul(p, omq), y = dmul(q, omp);
+        dmax = x < y ? x : y;
+    } else {
+        const double x = dmul(p, q), y = dmul(omp, omq);
+        dmax = x < y ? -x : -y;
+    }
+    s.Dprime = ddiv(D, dmax);
+    if (s.Dprime < prm.minDprime || s.Dprime > prm.maxDprime) return false;
+    s.P = fisher_two_sided(lg, (int)round(s.cnt[0]), (int)round(s.cnt[2]), (int)round(s.cnt[1]), (int)round(s.cnt[3]));
+    if (s.P > prm.minP) return false;
+    s.chi_model = 0.0;
+    s.chi_fisher = dmul(dadd(dadd(dadd(s.cnt[0], s.cnt[2]), s.cnt[1]), s.cnt[3]), s.R2);
+    s.flags = flags | variant_flags(a, b);
+    if (s.cnt[0] < 1 || s.cnt[2] < 1 || s.cnt[1] < 1 || s.cnt[3] < 1) s.flags |= 1u << 3;
+    if (s.R2 > 0.99) s.flags |= 1u << 4;
+    return true;
+}
+
+__device__ __forceinline__ bool hap_in_range(double x, double lo, double hi) {
+    return x >= dsub(lo, 1e-5) && x <= dadd(hi, 1e-5);
+}
+
+// ld_engine.cpp:1312-1560. t = 3x3 genotype table, row-major t[gA*3+gB].
+__device__ bool unphased_stats(const uint32_t* t, const DevParams& prm, const LgTable& lg, const DevVariant& a,
+                               const DevVariant& b, PairStats& s) {
+    unsigned long long T = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) T += t[k];
+    if (T < 5) return false;
+    const unsigned long long hets = t[4];
+    if (hets == 0) {
+        const unsigned long long c0 = 2ull * t[0] + t[1] + t[3];
+        const unsigned long long c4 = 2ull * t[2] + t[1] + t[5];
+        const unsigned long long c1 = 2ull * t[6] + t[3] + t[7];
+        const unsigned long long c5 = 2ull * t[8] + t[7] + t[5];
+        return phased_stats(c0, c1, c4, c5, prm, lg, a, b, s);
+    }
+    const double Td = (double)T, T2 = dmul(2.0, Td), hd = (double)hets;
+    const double P = ddiv(dadd(dmul((double)(t[0] + t[1] + t[2]), 2.0), (double)(t[3] + t[4] + t[5])), T2);
+    const double Q = ddiv(dadd(dmul((double)(t[0] + t[3] + t[6]), 2.0), (double)(t[1] + t[4] + t[7])), T2);
+    const double n11 = (double)(2ull * t[0] + t[1] + t[3]);
+    const double minhap = ddiv(n11, T2);
+    const double maxhap = ddiv(dadd(n11, hd), T2);
+    const double G = dsub(dsub(1.0, dmul(2.0, P)), dmul(2.0, Q));
+    const double dee = dmul(dmul(-n11, P), Q);
+    const double c = dadd(dsub(dmul(-n11, G), dmul(hd, dsub(dsub(1.0, P), Q))), dmul(dmul(T2, P), Q));
+    const double bb = dsub(dsub(dmul(T2, G), dmul(2.0, n11)), hd);
+    const double aa = dmul(4.0, Td);
+    const double xN = ddiv(-bb, dmul(3.0, aa));
+    const double d2 = ddiv(dsub(sq(bb), dmul(dmul(3.0, aa), c)), dmul(9.0, sq(aa)));
+    const double yN = dadd(dadd(dadd(dmul(aa, pow(xN, 3.0)), dmul(bb, sq(xN))), dmul(c, xN)), dee);
+    const double yN2 = sq(yN);
+    const double h2 = dmul(dmul(4.0, sq(aa)), pow(d2, 3.0));
+    const double diff = dsub(yN2, h2);
+    uint32_t flags = 0;
+    if (diff < 0) {
+        const double h = sqrt(h2);
+        const double theta = ddiv(acos(ddiv(-yN, h)), 3.0);
+        const double delta = sqrt(d2);
+        const double two_delta = dmul(2.0, delta);
+        const double alpha = dadd(xN, dmul(two_delta, cos(theta)));
+        const double beta = dadd(xN, dmul(two_delta, cos(dadd(ddiv(dmul(2.0, 3.14159265358979323846), 3.0), theta))));
+        const double gamma = dadd(xN, dmul(two_delta, cos(dadd(ddiv(dmul(4.0, 3.14159265358979323846), 3.0), theta))));
+        int possible = 0;
+        double best = 1.7976931348623157e308, chosen = alpha;
+        if (hap_in_range(alpha, minhap, maxhap)) { ++possible; best = chisq_unphased(t, Td, alpha, P, Q); }
+        if (hap_in_range(beta, minhap, maxhap)) {
+            ++possible;
+            const double x = chisq_unphased(t, Td, beta, P, Q);
+            if (x < best) { chosen = beta; best = x; }
+        }
+        if (hap_in_range(gamma, minhap, maxhap)) {
+            ++possible;
+            const double x = chisq_unphased(t, Td, gamma, P, Q);
+            if (x < best) { chosen = gamma; best = x; }
+        }
+        if (possible == 0) return false;
+        if (possible > 1) flags |= 1u << 5;
+        return choose_f11(Td, chosen, P, Q, flags, prm, lg, a, b, s);
+    } else if (diff > 0) {
+        const double root = sqrt(dsub(yN2, h2));
+        const double k = ddiv(1.0, dmul(2.0, aa));
+        const double u1 = dmul(k, dadd(-yN, root));
+        const double u2 = dmul(k, dsub(-yN, root));
+        const double third = 1.0 / 3.0;
+        const double n1 = u1 < 0 ? -pow(-u1, third) : pow(u1, third);
+        const double n2 = u2 < 0 ? -pow(-u2, third) : pow(u2, third);
+        const double alpha = dadd(dadd(xN, n1), n2);
+        if (!hap_in_range(alpha, minhap, maxhap)) return false;
+        return choose_f11(Td, alpha, P, Q, flags, prm, lg, a, b, s);
+    } else {
+        const double delta = pow(dmul(ddiv(yN, 2.0), aa), 1.0 / 3.0);
+        const double alpha = dadd(xN, delta);
+        const double gamma = dsub(xN, dmul(2.0, delta));
+        if (isnan(alpha) || isnan(gamma)) return false;
+        int possible = 0;
+        double best = 1.7976931348623157e308, chosen = alpha;
+        if (hap_in_range(alpha, minhap, maxhap)) { ++possible; best = chisq_unphased(t, Td, alpha, P, Q); }
+        if (hap_in_range(gamma, minhap, maxhap)) {
+            ++possible;
+            const double x = chisq_unphased(t, Td, gamma, P, Q);
+            if (x < best) { chosen = gamma; best = x; }
+        }
+        if (possible == 0) return false;
+        return choose_f11(Td, chosen, P, Q, flags, prm, lg, a, b, s);
+    }
+}
+
+// ---------------------------------------------------------------- stats kernel
+// One thread per candidate; passing pairs reserve an output slot with a
+// warp-aggregated atomic and write their packed record.
+__global__ void __launch_bounds__(128)
+stats_kernel(const Candidate* __restrict__ cands, uint32_t n_cands, const DevVariant* __restrict__ meta,
+             DevParams prm, const double* __restrict__ lgamma_tab, uint8_t* __restrict__ records,
+             unsigned long long rec_capacity, unsigned long long* __restrict__ rec_count) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    bool pass = false;
+    PairStats s;
+    DevVariant a, b;
+    if (idx < n_cands) {
+        Candidate cd = cands[idx];
+        a = meta[cd.i];
+        b = meta[cd.j];
+        LgTable lg{lgamma_tab, prm.lgamma_len};
+        if (cd.mode == 0) {
+            unsigned long long c0 = cd.c[0], c1 = cd.c[1], c4 = cd.c[2], c5 = cd.c[3];
+            // Q3: the reference's run-length comparator (low allele counts, missing data)
+            // stores the two mixed cells in swapped slots (ld_engine.cpp:1023,1055 vs :683-684).
+            if (prm.emulate_quirks && ((a.flags | b.flags) & VF_GT_MISSING) && (a.ac + b.ac < prm.thresh_miss_phased)) {
+                unsigned long long tmp = c1; c1 = c4; c4 = tmp;
+            }
+            pass = phased_stats(c0, c1, c4, c5, prm, lg, a, b, s);
+        } else {
+            pass = unphased_stats(cd.c, prm, lg, a, b, s);
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+    if (ballot == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(ballot) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(rec_count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) {
+        const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1));
+        if (slot < rec_capacity) write_record(records + slot * 106ull, s, a, b);
+    }
+}
+
+}  // namespace twkb
