@@ -35,7 +35,11 @@ def assert_records_bitexact(got, ref, p_rtol=0.0):
     assert len(got) == len(ref), f"record count {len(got)} != {len(ref)}: only_ref={sorted(keyset(ref) - keyset(got))[:5]} only_got={sorted(keyset(got) - keyset(ref))[:5]}"
     for f in tf.TWO_DTYPE.names:
         if f == "P" and p_rtol > 0:
-            np.testing.assert_allclose(got[f], ref[f], rtol=p_rtol, atol=0, err_msg=f)
+            # P sums pmf terms that underflow; below ~1e-290 (denormal territory) a last-ulp
+            # difference in exp() is an O(1) relative change, so only require "both tiny" there
+            big = ref[f] > 1e-290
+            np.testing.assert_allclose(got[f][big], ref[f][big], rtol=p_rtol, atol=0, err_msg=f)
+            assert np.all(got[f][~big] <= 1e-289), "P underflow region"
         else:
             assert np.array_equal(got[f], ref[f]), f"field {f} differs"
 

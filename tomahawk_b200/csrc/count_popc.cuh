@@ -113,10 +113,10 @@ template <int NP> struct PairAcc { uint32_t v[NP][NP]; };
 // Called convergently by all 32 lanes of a warp.
 template <int MODE>
 __device__ __noinline__ void emit_pair(const CountArgs& args, const DevParams& prm, uint32_t i, uint32_t j,
-                                       DevVariant vi, PairAcc<PopcCfg<MODE>::NP> pa, int lane) {
+                                       DevVariant vi, PairAcc<PopcCfg<MODE>::NP> pa, int lane, bool pre_ok = true) {
     constexpr int NP = PopcCfg<MODE>::NP;
     const uint32_t M = prm.n_variants;
-    bool ok = i >= args.row_begin && i < args.row_end && j >= args.col_begin && j < args.col_end && i < M && j < M;
+    bool ok = pre_ok && i >= args.row_begin && i < args.row_end && j >= args.col_begin && j < args.col_end && i < M && j < M;
     if (prm.diag) ok = ok && (i < j);
     uint32_t c[9];
 #pragma unroll

@@ -1,7 +1,33 @@
-// count_umma.cuh -- tensor-core (tcgen05 / TMEM) variant of the count kernel.
-// Placeholder interface: filled in once the LOP3+POPC path is parity-green.
+// count_umma.cuh -- tensor-core variant of the phased (no missing data) count
+// kernel: the all-pairs haplotype co-occurrence n11[i][j] = sum_h a[i][h]*a[j][h]
+// is a dense 0/1 contraction, computed as an int8 x int8 -> int32 GEMM on the
+// 5th-generation tensor cores (tcgen05.mma kind::i8, accumulator in TMEM).
+//
+// Replaces (with bit-identical counts) the same reference comparators as
+// count_popc.cuh: PhasedListVector / PhasedVectorizedNoMissing,
+// lib/ld/ld_engine.cpp:185-267, 636-707; the three other cells follow from the
+// allele counts exactly as :244-246.
+//
+// Operand: the haplotype matrix expanded to one byte per haplotype (0/1),
+// row-major [Mpad][Kbytes], Kbytes = 2N rounded up to 128. int8 products
+// accumulate exactly in int32 for any N < 2^31.
+//
+// CTA = one 128 x 128 tile of variant pairs, 256 threads, 2 CTAs per SM:
+//   warp 0   TMA producer: per 128-byte K block two 2-D tensor-map loads
+//            (A rows i0.., B rows j0.., 128B swizzle) into a 3-stage ring,
+//   warp 1   MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 32) per
+//            K block and commits to the stage's "empty" mbarrier,
+//   warp 2   TMEM allocator (128 columns),
+//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time, fp32 conservative R2
+//            screen inline, exact fp64 screen + warp-aggregated compaction for
+//            the survivors (same candidate format as the POPC kernel).
+// While one CTA of an SM drains its accumulator the other one keeps the tensor
+// pipe busy.
 #pragma once
+#include <cuda.h>
+
 #include <string>
+
 #include "common.cuh"
 #include "count_popc.cuh"
 
@@ -9,15 +35,313 @@ namespace twkb {
 
 constexpr uint32_t UMMA_TILE_M = 128;
 constexpr uint32_t UMMA_TILE_N = 128;
+constexpr uint32_t UMMA_BLOCK_K = 128;  // bytes of K per pipeline stage (one 128B swizzle atom)
+constexpr uint32_t UMMA_K = 32;         // K of one kind::i8 instruction
+constexpr int UMMA_STAGES = 3;
+constexpr int UMMA_THREADS = 256;
+constexpr uint32_t UMMA_TMEM_COLS = 128;
+constexpr uint32_t UMMA_STAGE_BYTES = (UMMA_TILE_M + UMMA_TILE_N) * UMMA_BLOCK_K;
+constexpr size_t UMMA_SMEM_BYTES = 1024 /*align*/ + (size_t)UMMA_STAGES * UMMA_STAGE_BYTES + 128 * sizeof(DevVariant) + 256;
 
 struct UmmaOperand {
     bool valid = false;
+    uint8_t* d_bytes = nullptr;  // [Mpad][Kbytes]
+    size_t capacity = 0;
     uint32_t Kbytes = 0;
+    uint32_t Mpad = 0;
+    CUtensorMap tmap;
 };
 
-inline bool umma_supported() { return false; }
-inline int umma_prepare(UmmaOperand&, const uint32_t*, uint32_t, uint32_t, uint32_t, cudaStream_t, std::string&) { return 0; }
-inline cudaError_t umma_launch(UmmaOperand&, const CountArgs&, const DevParams&, uint32_t, cudaStream_t) { return cudaErrorNotSupported; }
-inline void umma_release(UmmaOperand&) {}
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 inputs, int32 accumulate, issued by one thread.
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128B swizzle (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) =
+// 1024 B between 8-row groups | version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 @ bit 4), A/B unsigned
+// 8-bit (0 @ bits 7, 10), both K-major, N>>3 @ bit 17, M>>4 @ bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_i8(uint32_t M, uint32_t N) { return (2u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+
+// One byte per haplotype from the reference-layout rows (row-major u64 words).
+__global__ void expand_bits_to_bytes_kernel(const uint64_t* __restrict__ rows, size_t stride64, uint32_t n_variants,
+                                            uint32_t n_bits, uint8_t* __restrict__ out, uint32_t Kbytes, uint32_t Mpad) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;  // 64-haplotype group
+    const uint32_t v = blockIdx.y;
+    if (w * 64 >= Kbytes || v >= Mpad) return;
+    uint64_t x = 0;
+    if (v < n_variants && (size_t)w < stride64 && (uint64_t)w * 64 < n_bits) {
+        x = rows[(size_t)v * stride64 + w];
+        if ((uint64_t)w * 64 + 64 > n_bits) x &= (1ull << (n_bits - w * 64)) - 1ull;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)v * Kbytes + (size_t)w * 64);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t nib = (uint32_t)(x >> (16 * q + 4 * r)) & 0xFu;
+            b[r] = (nib * 0x00204081u) & 0x01010101u;  // bit t of the nibble -> byte t
+        }
+        dst[q] = make_uint4(b[0], b[1], b[2], b[3]);
+    }
+}
+
+__global__ void __launch_bounds__(UMMA_THREADS, 2)
+count_umma_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, DevParams prm, uint32_t num_kblocks) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled operand tiles need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    DevVariant* s_meta = reinterpret_cast<DevVariant*>(smem + (size_t)UMMA_STAGES * UMMA_STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_meta + 128);
+    uint64_t* empty_bar = full_bar + UMMA_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + UMMA_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint2 tile = args.tiles[blockIdx.x];
+    const uint32_t i0 = tile.x, j0 = tile.y;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < UMMA_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, UMMA_TMEM_COLS);
+    if (warp >= 4) s_meta[threadIdx.x - 128] = args.meta[j0 + (threadIdx.x - 128)];
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================ TMA producer ============================
+        if (lane == 0) {
+            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
+                const int s = kb % UMMA_STAGES;
+                if (kb >= UMMA_STAGES) mbar_wait(&empty_bar[s], ((kb / UMMA_STAGES) - 1) & 1);
+                uint8_t* sA = stage_base + (size_t)s * UMMA_STAGE_BYTES;
+                uint8_t* sB = sA + UMMA_TILE_M * UMMA_BLOCK_K;
+                mbar_arrive_expect_tx(&full_bar[s], UMMA_STAGE_BYTES);
+                tma_load_2d(sA, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)i0);
+                tma_load_2d(sB, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)j0);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================= MMA issuer =============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(UMMA_TILE_M, UMMA_TILE_N);
+            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
+                const int s = kb % UMMA_STAGES;
+                mbar_wait(&full_bar[s], (kb / UMMA_STAGES) & 1);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(stage_base + (size_t)s * UMMA_STAGE_BYTES);
+                const uint32_t b_addr = a_addr + UMMA_TILE_M * UMMA_BLOCK_K;
+                const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(b_addr);
+#pragma unroll
+                for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k) {
+                    // advance the start address by 32 bytes inside the 128-byte swizzled row
+                    umma_i8(tmem_base, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else if (warp >= 4) {
+        // ============================== epilogue ==============================
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const uint32_t i = i0 + 32 * q + lane;
+        const DevVariant vi = args.meta[i];
+        const uint32_t M = prm.n_variants;
+        const bool i_ok = i >= args.row_begin && i < args.row_end && i < M;
+        const float Tf = (float)(2u * prm.n_samples);
+        const float acA = (float)vi.ac;
+        const float dA = acA * (Tf - acA);
+        const float thr = (float)prm.screenR2 * (1.0f - 1.0e-5f);
+        const bool no_screen = args.screen_off || !(prm.minR2 > 0.0);
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int chunk = 0; chunk < (int)(UMMA_TILE_N / 32); ++chunk) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(chunk * 32), r);
+            // pass bits of this thread's 32 pairs: pure arithmetic, fully unrolled (ILP)
+            uint32_t passmask = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int jl = chunk * 32 + c;
+                const uint32_t j = j0 + jl;
+                const DevVariant vj = s_meta[jl];
+                bool pass = i_ok && j >= args.col_begin && j < args.col_end && j < M && (!prm.diag || i < j) && (vi.ac + vj.ac > 2);
+                if (!no_screen) {
+                    // fp32 conservative form of R2 >= minR2: x = n11*T - acA*acB (error bounded by
+                    // `slack`), den = acA(T-acA) acB(T-acB); the exact decision is the fp64 screen
+                    // in emit_pair.
+                    const float n11 = (float)r[c];
+                    const float acB = (float)vj.ac;
+                    const float pab = acA * acB;
+                    const float x = fabsf(fmaf(n11, Tf, -pab));
+                    const float slack = 4.0f + 4.0e-7f * fmaxf(n11 * Tf, pab);
+                    const float lhs = (x + slack) * (x + slack);
+                    const float rhs = thr * (dA * (acB * (Tf - acB)));
+                    pass = pass && (lhs >= rhs);
+                }
+                passmask |= (pass ? 1u : 0u) << c;
+            }
+            // columns in which any lane of the warp has a survivor (warp-uniform)
+            const uint32_t colmask = __reduce_or_sync(0xffffffffu, passmask);
+            if (colmask) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if ((colmask >> c) & 1u) {
+                        PairAcc<1> pa;
+                        pa.v[0][0] = r[c];
+                        emit_pair<MODE_PHASED_NOMISS>(args, prm, i, j0 + chunk * 32 + c, vi, pa, lane, (passmask >> c) & 1u);
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, UMMA_TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled get_tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+inline bool umma_supported() {
+    if (const char* e = getenv("TWKB_DISABLE_UMMA")) {
+        if (e[0] == '1') return false;
+    }
+    return get_tmap_encoder() != nullptr;
+}
+
+// Builds (once per matrix) the byte-expanded operand and its tensor map.
+inline int umma_prepare(UmmaOperand& op, const uint64_t* d_rows, size_t stride64, uint32_t n_variants, uint32_t Mpad,
+                        uint32_t n_samples, cudaStream_t stream, std::string& err, uint64_t* launches) {
+    if (op.valid) return 0;
+    const uint32_t n_bits = 2 * n_samples;
+    const uint32_t Kbytes = (n_bits + UMMA_BLOCK_K - 1) / UMMA_BLOCK_K * UMMA_BLOCK_K;
+    const size_t need = (size_t)Mpad * Kbytes;
+    if (op.capacity < need) {
+        if (op.d_bytes) cudaFree(op.d_bytes);
+        op.d_bytes = nullptr;
+        op.capacity = 0;
+        cudaError_t e = cudaMalloc((void**)&op.d_bytes, need);
+        if (e != cudaSuccess) { err = std::string("cudaMalloc(int8 operand): ") + cudaGetErrorString(e); return -3; }
+        op.capacity = need;
+    }
+    op.Kbytes = Kbytes;
+    op.Mpad = Mpad;
+    dim3 grid((Kbytes / 64 + 127) / 128, Mpad), block(128);
+    expand_bits_to_bytes_kernel<<<grid, block, 0, stream>>>(d_rows, stride64, n_variants, n_bits, op.d_bytes, Kbytes, Mpad);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("expand kernel: ") + cudaGetErrorString(e); return -3; }
+    if (launches) *launches += 1;
+    PFN_tmapEncodeTiled enc = get_tmap_encoder();
+    if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return -3; }
+    cuuint64_t gdim[2] = {Kbytes, Mpad};
+    cuuint64_t gstride[1] = {Kbytes};
+    cuuint32_t box[2] = {UMMA_BLOCK_K, UMMA_TILE_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&op.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, op.d_bytes, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return -3; }
+    op.valid = true;
+    return 0;
+}
+
+inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(count_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    count_umma_kernel<<<n_tiles, UMMA_THREADS, UMMA_SMEM_BYTES, stream>>>(op.tmap, args, prm, op.Kbytes / UMMA_BLOCK_K);
+    return cudaGetLastError();
+}
+
+inline void umma_release(UmmaOperand& op) {
+    if (op.d_bytes) cudaFree(op.d_bytes);
+    op.d_bytes = nullptr;
+    op.capacity = 0;
+    op.valid = false;
+}
 
 }  // namespace twkb

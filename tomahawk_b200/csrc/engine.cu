@@ -452,14 +452,15 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
     if (rc) return rc;
     bool use_umma = false;
     if (mode == MODE_PHASED_NOMISS && ctx->st.kernel != TWKB_KERNEL_POPC && !dump) use_umma = umma_supported();
-    if (ctx->st.kernel == TWKB_KERNEL_UMMA && !use_umma) {
+    if (ctx->st.kernel == TWKB_KERNEL_UMMA && !use_umma && !dump) {
         ctx->err = "TWKB_KERNEL_UMMA requested but the tensor-core kernel only serves phased data without missing genotypes";
         return TWKB_EINVAL;
     }
     uint32_t TI, TJ;
     tile_dims(mode, use_umma, TI, TJ);
     if (use_umma) {
-        rc = umma_prepare(ctx->umma, ctx->d_planes.p, ctx->K32, ctx->Mpad, ctx->n_samples, ctx->stream, ctx->err);
+        rc = umma_prepare(ctx->umma, ctx->d_raw_data.p, ctx->raw_stride, ctx->n_variants, ctx->Mpad, ctx->n_samples, ctx->stream,
+                          ctx->err, &ctx->stats.other_launches);
         if (rc) return rc;
     }
     std::vector<uint2> tiles;
