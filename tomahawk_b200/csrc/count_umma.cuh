@@ -117,8 +117,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(uint32_t M, uint32_t N) { r
 // One byte per haplotype from the reference-layout rows (row-major u64 words).
 __global__ void expand_bits_to_bytes_kernel(const uint64_t* __restrict__ rows, size_t stride64, uint32_t n_variants,
                                             uint32_t n_bits, uint8_t* __restrict__ out, uint32_t Kbytes, uint32_t Mpad) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;  // 64-haplotype group
-    const uint32_t v = blockIdx.y;
+    const uint32_t w = blockIdx.y * blockDim.x + threadIdx.x;  // 64-haplotype group
+    const uint32_t v = blockIdx.x;
     if (w * 64 >= Kbytes || v >= Mpad) return;
     uint64_t x = 0;
     if (v < n_variants && (size_t)w < stride64 && (uint64_t)w * 64 < n_bits) {
@@ -267,6 +267,194 @@ count_umma_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, DevP
     }
 }
 
+// =====================================================================================
+// 2-CTA variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a
+// 256 x 256 tile. Each CTA stages only ITS 128 rows of A and ITS 128 rows of B per K
+// block (32 KB instead of 64 KB for the same 256x256x128 MACs), the leader CTA issues
+// M=256 x N=256 MMAs that read both CTAs' shared memory, and each CTA's TMEM receives
+// its 128 accumulator rows x 256 columns. This halves the L2->SM operand traffic per
+// MAC, which is what bounds the 1-CTA kernel (ncu: xbar2l1tex at 45 % with the tensor
+// pipe at 43 %; profiles/round1_umma_1cta.md).
+constexpr uint32_t UMMA2_TILE = 256;
+constexpr int UMMA2_STAGES = 3;
+constexpr uint32_t UMMA2_TMEM_COLS = 256;
+constexpr uint32_t UMMA2_STAGE_BYTES = 2 * 128 * UMMA_BLOCK_K;  // per CTA: 128 A rows + 128 B rows
+constexpr size_t UMMA2_SMEM_BYTES = 1024 + (size_t)UMMA2_STAGES * UMMA2_STAGE_BYTES + 256 * sizeof(DevVariant) + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load executed by both CTAs of the pair; the transaction bytes are credited to the
+// LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+    const uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the same-offset mbarrier of both CTAs once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA_THREADS, 2)
+count_umma2_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, DevParams prm, uint32_t num_kblocks) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    DevVariant* s_meta = reinterpret_cast<DevVariant*>(smem + (size_t)UMMA2_STAGES * UMMA2_STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_meta + UMMA2_TILE);
+    uint64_t* empty_bar = full_bar + UMMA2_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + UMMA2_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint2 tile = args.tiles[blockIdx.x >> 1];
+    const uint32_t i0 = tile.x, j0 = tile.y;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < UMMA2_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc_2sm(tmem_slot, UMMA2_TMEM_COLS);
+    if (warp >= 4) {
+        const int t = threadIdx.x - 128;
+        s_meta[t] = args.meta[j0 + t];
+        s_meta[t + 128] = args.meta[j0 + t + 128];
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();  // barriers of both CTAs initialised before any remote complete_tx / commit
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs, own halves of A and B) =================
+        if (lane == 0) {
+            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
+                const int s = kb % UMMA2_STAGES;
+                if (kb >= (uint32_t)UMMA2_STAGES) mbar_wait(&empty_bar[s], ((kb / UMMA2_STAGES) - 1) & 1);
+                uint8_t* sA = stage_base + (size_t)s * UMMA2_STAGE_BYTES;
+                uint8_t* sB = sA + 128 * UMMA_BLOCK_K;
+                if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * UMMA2_STAGE_BYTES);  // both CTAs' bytes
+                tma_load_2d_2sm(sA, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(i0 + 128 * rank));
+                tma_load_2d_2sm(sB, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(j0 + 128 * rank));
+            }
+        }
+    } else if (warp == 1) {
+        // ========================= MMA issuer (leader CTA only) =========================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(256, 256);
+            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
+                const int s = kb % UMMA2_STAGES;
+                mbar_wait(&full_bar[s], (kb / UMMA2_STAGES) & 1);
+                tcgen05_fence_after();
+                const uint32_t a_addr = smem_u32(stage_base + (size_t)s * UMMA2_STAGE_BYTES);
+                const uint32_t b_addr = a_addr + 128 * UMMA_BLOCK_K;
+                const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(b_addr);
+#pragma unroll
+                for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k)
+                    umma_i8_2sm(tmem_base, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
+                                (kb | k) != 0 ? 1u : 0u);
+                umma_commit_2sm(&empty_bar[s]);
+            }
+            umma_commit_2sm(tmem_full_bar);
+        }
+    } else if (warp >= 4) {
+        // ============== epilogue (both CTAs, own 128 accumulator rows x 256 columns) ==============
+        const int q = warp & 3;
+        const uint32_t i = i0 + 128 * rank + 32 * q + lane;
+        const DevVariant vi = args.meta[i];
+        const uint32_t M = prm.n_variants;
+        const bool i_ok = i >= args.row_begin && i < args.row_end && i < M;
+        const float Tf = (float)(2u * prm.n_samples);
+        const float acA = (float)vi.ac;
+        const float dA = acA * (Tf - acA);
+        const float thr = (float)prm.screenR2 * (1.0f - 1.0e-5f);
+        const bool no_screen = args.screen_off || !(prm.minR2 > 0.0);
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        // whole-warp shortcut: on diagonal tiles the rows of this warp may lie entirely at or
+        // below every column of a chunk (no i<j pair); the per-pair test covers it as well.
+#pragma unroll 1
+        for (int chunk = 0; chunk < (int)(UMMA2_TILE / 32); ++chunk) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(chunk * 32), r);
+            uint32_t passmask = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int jl = chunk * 32 + c;
+                const uint32_t j = j0 + jl;
+                const DevVariant vj = s_meta[jl];
+                bool pass = i_ok && j >= args.col_begin && j < args.col_end && j < M && (!prm.diag || i < j) && (vi.ac + vj.ac > 2);
+                if (!no_screen) {
+                    const float n11 = (float)r[c];
+                    const float acB = (float)vj.ac;
+                    const float pab = acA * acB;
+                    const float x = fabsf(fmaf(n11, Tf, -pab));
+                    const float slack = 4.0f + 4.0e-7f * fmaxf(n11 * Tf, pab);
+                    const float lhs = (x + slack) * (x + slack);
+                    const float rhs = thr * (dA * (acB * (Tf - acB)));
+                    pass = pass && (lhs >= rhs);
+                }
+                passmask |= (pass ? 1u : 0u) << c;
+            }
+            const uint32_t colmask = __reduce_or_sync(0xffffffffu, passmask);
+            if (colmask) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    if ((colmask >> c) & 1u) {
+                        PairAcc<1> pa;
+                        pa.v[0][0] = r[c];
+                        emit_pair<MODE_PHASED_NOMISS>(args, prm, i, j0 + chunk * 32 + c, vi, pa, lane, (passmask >> c) & 1u);
+                    }
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();  // the peer may still be reading this CTA's smem / TMEM pair allocation
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm(tmem_base, UMMA2_TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -308,7 +496,7 @@ inline int umma_prepare(UmmaOperand& op, const uint64_t* d_rows, size_t stride64
     }
     op.Kbytes = Kbytes;
     op.Mpad = Mpad;
-    dim3 grid((Kbytes / 64 + 127) / 128, Mpad), block(128);
+    dim3 grid(Mpad, (Kbytes / 64 + 127) / 128), block(128);
     expand_bits_to_bytes_kernel<<<grid, block, 0, stream>>>(d_rows, stride64, n_variants, n_bits, op.d_bytes, Kbytes, Mpad);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("expand kernel: ") + cudaGetErrorString(e); return -3; }
@@ -326,7 +514,24 @@ inline int umma_prepare(UmmaOperand& op, const uint64_t* d_rows, size_t stride64
     return 0;
 }
 
+// 2 = CTA-pair kernel (256x256 tiles), 1 = single-CTA kernel (128x128 tiles)
+inline int umma_cta_group() {
+    if (const char* e = getenv("TWKB_UMMA_CTAS")) return e[0] == '1' ? 1 : 2;
+    return 2;
+}
+inline uint32_t umma_tile() { return umma_cta_group() == 2 ? UMMA2_TILE : UMMA_TILE_M; }
+
 inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
+    if (umma_cta_group() == 2) {
+        static bool configured2 = false;
+        if (!configured2) {
+            cudaError_t e = cudaFuncSetAttribute(count_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA2_SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            configured2 = true;
+        }
+        count_umma2_kernel<<<2 * n_tiles, UMMA_THREADS, UMMA2_SMEM_BYTES, stream>>>(op.tmap, args, prm, op.Kbytes / UMMA_BLOCK_K);
+        return cudaGetLastError();
+    }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(count_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_BYTES);

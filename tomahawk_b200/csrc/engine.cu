@@ -86,6 +86,12 @@ struct Context {
     DevBuf<uint32_t> d_blk_of, d_blk_first, d_blk_last, d_blk_prune;
     std::vector<uint32_t> h_blk_first, h_blk_last, h_blk_prune;
 
+    // tile plan of the last run, reused while the sub-problem and the partition are unchanged
+    std::vector<uint2> plan_tiles;
+    uint64_t plan_pairs = 0;
+    std::string plan_key;
+    uint64_t matrix_epoch = 0;
+
     // work buffers
     DevBuf<uint2> d_tiles;
     DevBuf<Candidate> d_cands;
@@ -287,8 +293,12 @@ static int select_problem(Context* ctx, Problem& pb) {
     for (uint32_t i = 0; i < factor; ++i)
         for (uint32_t j = i; j < factor; ++j, ++k) {
             if (k != (uint32_t)ctx->st.c_chunk) continue;
-            const uint32_t tR = (j + 1 == factor ? nb : chunk * (j + 1)), fR = tR - chunk;
-            const uint32_t tL = (i + 1 == factor ? nb : chunk * (i + 1)), fL = tL - chunk;
+            // The reference takes from = to - chunk_size (ld_balancing.h:64-67), which silently
+            // drops blocks [chunk*(factor-1), nb - chunk) of the last chunk whenever nb is not a
+            // multiple of factor; here the last chunk starts where the previous one ended, so
+            // the chunks always tile the whole triangle (explained disagreements).
+            const uint32_t tR = (j + 1 == factor ? nb : chunk * (j + 1)), fR = chunk * j;
+            const uint32_t tL = (i + 1 == factor ? nb : chunk * (i + 1)), fL = chunk * i;
             pb.row_begin = first[fL]; pb.row_end = first[tL];
             pb.col_begin = first[fR]; pb.col_end = first[tR];
             pb.diag = (i == j);
@@ -310,7 +320,7 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
         const uint64_t ia = std::max(i0, pb.row_begin), ib = std::min<uint64_t>(i0 + TI, pb.row_end);
         const uint64_t ja = std::max(j0, pb.col_begin), jb = std::min<uint64_t>(j0 + TJ, pb.col_end);
         if (ia >= ib || ja >= jb) return 0;
-        if (!pb.diag) return (ib - ia) * (jb - ja);
+        if (!pb.diag || ib <= ja) return (ib - ia) * (jb - ja);  // every i is below every j
         uint64_t n = 0;
         for (uint64_t i = ia; i < ib; ++i) {
             const uint64_t lo = std::max<uint64_t>(ja, i + 1);
@@ -376,7 +386,7 @@ static cudaError_t launch_popc(Context* ctx, const CountArgs& args, const DevPar
 }
 
 static void tile_dims(int mode, bool umma, uint32_t& TI, uint32_t& TJ) {
-    if (umma) { TI = UMMA_TILE_M; TJ = UMMA_TILE_N; return; }
+    if (umma) { TI = TJ = umma_tile(); return; }
     switch (mode) {
         case MODE_PHASED_NOMISS: TI = popc_tile_i<0>(); TJ = popc_tile_j<0>(); break;
         case MODE_PHASED_MISS: TI = popc_tile_i<1>(); TJ = popc_tile_j<1>(); break;
@@ -463,18 +473,29 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
                           ctx->err, &ctx->stats.other_launches);
         if (rc) return rc;
     }
-    std::vector<uint2> tiles;
-    uint64_t part_pairs = 0;
-    build_tiles(ctx, pb, TI, TJ, use_umma ? 8u : 16u, tiles, &part_pairs);
-    if (ctx->st.part_count > 1 && !ctx->st.window) ctx->stats.pairs_visited = part_pairs;
+    // The tile plan depends only on the sub-problem, the tile shape, the window and the
+    // partition: build it (and upload it) once and reuse it across runs.
+    char keybuf[256];
+    std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u|w%d:%d:%d|p%d/%d", (unsigned long long)ctx->matrix_epoch,
+                  pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, (int)ctx->st.window,
+                  ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
+    if (ctx->plan_key != keybuf) {
+        build_tiles(ctx, pb, TI, TJ, use_umma ? (TI >= 256 ? 4u : 8u) : 16u, ctx->plan_tiles, &ctx->plan_pairs);
+        CUDA_TRY(ctx->d_tiles.alloc(std::max<size_t>(ctx->plan_tiles.size(), 1)));
+        if (!ctx->plan_tiles.empty())
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_tiles.p, ctx->plan_tiles.data(), ctx->plan_tiles.size() * sizeof(uint2),
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->plan_key = keybuf;
+    }
+    const std::vector<uint2>& tiles = ctx->plan_tiles;
+    if (ctx->st.part_count > 1 && !ctx->st.window) ctx->stats.pairs_visited = ctx->plan_pairs;
     ctx->stats.kernel_used = use_umma ? TWKB_KERNEL_UMMA : TWKB_KERNEL_POPC;
     ctx->stats.n_planes = ctx->np;
     const uint64_t tile_pairs = (uint64_t)TI * TJ;
     rc = ensure_work_buffers(ctx, tile_pairs);
     if (rc) return rc;
     if (tiles.empty()) return TWKB_OK;
-    CUDA_TRY(ctx->d_tiles.alloc(tiles.size()));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
 
     DevParams prm = make_params(ctx, pb);
     CountArgs args{};
@@ -629,6 +650,7 @@ static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, co
     ctx->loaded = false;
     ctx->mode = -1;
     ctx->umma.valid = false;
+    ctx->matrix_epoch += 1;
     ctx->n_samples = n_samples;
     ctx->n_variants = n_variants;
     ctx->Mpad = (n_variants + 255) / 256 * 256;
