@@ -26,6 +26,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
 #include <string>
 
 #include "common.cuh"
@@ -455,6 +456,174 @@ count_umma2_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
     }
 }
 
+// =====================================================================================
+// Persistent 2-CTA variant: one CTA pair per TPC loops over 256 x 256 tiles. The operand
+// ring is 6 stages deep (192 KB of the SM's shared memory in flight hides the ~1-2 us
+// L2 latency that starves the 3-stage kernels), TMEM holds two 256-column accumulators,
+// and the epilogue warps drain tile n while the tensor pipe already works on tile n+1.
+constexpr int UMMA3_STAGES = 6;
+constexpr uint32_t UMMA3_TMEM_COLS = 512;
+constexpr size_t UMMA3_SMEM_BYTES = 1024 + (size_t)UMMA3_STAGES * UMMA2_STAGE_BYTES + 2 * 256 * sizeof(DevVariant) + 256;
+
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target_cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(target_cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA_THREADS, 1)
+count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, DevParams prm, uint32_t num_kblocks, uint32_t n_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    DevVariant* s_meta = reinterpret_cast<DevVariant*>(smem + (size_t)UMMA3_STAGES * UMMA2_STAGE_BYTES);  // [2][256]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_meta + 2 * 256);
+    uint64_t* empty_bar = full_bar + UMMA3_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + UMMA3_STAGES;  // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2], the leader's copy is the one used
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < UMMA3_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc_2sm(tmem_slot, UMMA3_TMEM_COLS);
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters) {
+                const uint2 tile = args.tiles[t];
+                for (uint32_t kb = 0; kb < num_kblocks; ++kb, ++it) {
+                    const int s = it % UMMA3_STAGES;
+                    if (it >= (uint32_t)UMMA3_STAGES) mbar_wait(&empty_bar[s], ((it / UMMA3_STAGES) - 1) & 1);
+                    uint8_t* sA = stage_base + (size_t)s * UMMA2_STAGE_BYTES;
+                    uint8_t* sB = sA + 128 * UMMA_BLOCK_K;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * UMMA2_STAGE_BYTES);
+                    tma_load_2d_2sm(sA, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(tile.x + 128 * rank));
+                    tma_load_2d_2sm(sB, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(tile.y + 128 * rank));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ========================= MMA issuer (leader only) =========================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(256, 256);
+            uint32_t it = 0, n = 0;
+            for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters, ++n) {
+                const uint32_t acc = n & 1;
+                if (n >= 2) mbar_wait(&tmem_empty_bar[acc], ((n >> 1) - 1) & 1);  // epilogue drained tile n-2
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (uint32_t kb = 0; kb < num_kblocks; ++kb, ++it) {
+                    const int s = it % UMMA3_STAGES;
+                    mbar_wait(&full_bar[s], (it / UMMA3_STAGES) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_u32(stage_base + (size_t)s * UMMA2_STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + 128 * UMMA_BLOCK_K;
+                    const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(b_addr);
+#pragma unroll
+                    for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k)
+                        umma_i8_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_2sm(&empty_bar[s]);
+                }
+                umma_commit_2sm(&tmem_full_bar[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue ================================
+        const int q = warp & 3;
+        const uint32_t M = prm.n_variants;
+        const float Tf = (float)(2u * prm.n_samples);
+        const float thr = (float)prm.screenR2 * (1.0f - 1.0e-5f);
+        const bool no_screen = args.screen_off || !(prm.minR2 > 0.0);
+        const int te = threadIdx.x - 128;
+        uint32_t n = 0;
+        for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters, ++n) {
+            const uint32_t acc = n & 1;
+            const uint2 tile = args.tiles[t];
+            const uint32_t i0 = tile.x, j0 = tile.y;
+            DevVariant* meta_j = s_meta + acc * 256;
+            meta_j[te] = args.meta[j0 + te];
+            meta_j[te + 128] = args.meta[j0 + te + 128];
+            const uint32_t i = i0 + 128 * rank + 32 * q + lane;
+            const DevVariant vi = args.meta[i];
+            const bool i_ok = i >= args.row_begin && i < args.row_end && i < M;
+            const float acA = (float)vi.ac;
+            const float dA = acA * (Tf - acA);
+            epilogue_bar_sync();  // column metadata of this tile visible to the 4 epilogue warps
+            mbar_wait(&tmem_full_bar[acc], (n >> 1) & 1);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int chunk = 0; chunk < (int)(UMMA2_TILE / 32); ++chunk) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + (uint32_t)(chunk * 32), r);
+                uint32_t passmask = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int jl = chunk * 32 + c;
+                    const uint32_t j = j0 + jl;
+                    const DevVariant vj = meta_j[jl];
+                    bool pass = i_ok && j >= args.col_begin && j < args.col_end && j < M && (!prm.diag || i < j) && (vi.ac + vj.ac > 2);
+                    if (!no_screen) {
+                        const float n11 = (float)r[c];
+                        const float acB = (float)vj.ac;
+                        const float pab = acA * acB;
+                        const float x = fabsf(fmaf(n11, Tf, -pab));
+                        const float slack = 4.0f + 4.0e-7f * fmaxf(n11 * Tf, pab);
+                        const float lhs = (x + slack) * (x + slack);
+                        const float rhs = thr * (dA * (acB * (Tf - acB)));
+                        pass = pass && (lhs >= rhs);
+                    }
+                    passmask |= (pass ? 1u : 0u) << c;
+                }
+                const uint32_t colmask = __reduce_or_sync(0xffffffffu, passmask);
+                if (colmask) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if ((colmask >> c) & 1u) {
+                            PairAcc<1> pa;
+                            pa.v[0][0] = r[c];
+                            emit_pair<MODE_PHASED_NOMISS>(args, prm, i, j0 + chunk * 32 + c, vi, pa, lane, (passmask >> c) & 1u);
+                        }
+                    }
+                }
+            }
+            // this warp has read everything it needs from accumulator `acc`
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+        }
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc_2sm(tmem_base, UMMA3_TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -514,14 +683,33 @@ inline int umma_prepare(UmmaOperand& op, const uint64_t* d_rows, size_t stride64
     return 0;
 }
 
-// 2 = CTA-pair kernel (256x256 tiles), 1 = single-CTA kernel (128x128 tiles)
+// 3 (default) = persistent CTA-pair kernel, 2 = one 256x256 tile per CTA pair,
+// 1 = single-CTA kernel (128x128 tiles). The older variants are kept for A/B profiling.
 inline int umma_cta_group() {
-    if (const char* e = getenv("TWKB_UMMA_CTAS")) return e[0] == '1' ? 1 : 2;
-    return 2;
+    if (const char* e = getenv("TWKB_UMMA_CTAS")) {
+        if (e[0] == '1') return 1;
+        if (e[0] == '2') return 2;
+    }
+    return 3;
 }
-inline uint32_t umma_tile() { return umma_cta_group() == 2 ? UMMA2_TILE : UMMA_TILE_M; }
+inline uint32_t umma_tile() { return umma_cta_group() >= 2 ? UMMA2_TILE : UMMA_TILE_M; }
 
 inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
+    if (umma_cta_group() == 3) {
+        static bool configured3 = false;
+        static int n_sm = 0;
+        if (!configured3) {
+            cudaError_t e = cudaFuncSetAttribute(count_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA3_SMEM_BYTES);
+            if (e != cudaSuccess) return e;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            configured3 = true;
+        }
+        const uint32_t n_clusters = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, n_sm / 2));
+        count_umma3_kernel<<<2 * n_clusters, UMMA_THREADS, UMMA3_SMEM_BYTES, stream>>>(op.tmap, args, prm, op.Kbytes / UMMA_BLOCK_K, n_tiles);
+        return cudaGetLastError();
+    }
     if (umma_cta_group() == 2) {
         static bool configured2 = false;
         if (!configured2) {
