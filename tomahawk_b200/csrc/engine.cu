@@ -91,6 +91,7 @@ struct Context {
     uint64_t plan_pairs = 0;
     std::string plan_key;
     uint64_t matrix_epoch = 0;
+    double est_cand_per_tile = -1.0;  // survivors per tile seen by the previous run (batch sizing)
 
     // work buffers
     DevBuf<uint2> d_tiles;
@@ -480,7 +481,9 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
                   pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, (int)ctx->st.window,
                   ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
     if (ctx->plan_key != keybuf) {
-        build_tiles(ctx, pb, TI, TJ, use_umma ? (TI >= 256 ? 4u : 8u) : 16u, ctx->plan_tiles, &ctx->plan_pairs);
+        uint32_t super = 16u;  // super-tile edge (in tiles) of the L2-friendly order
+        if (const char* e = getenv("TWKB_SUPER")) super = (uint32_t)std::max(1, atoi(e));
+        build_tiles(ctx, pb, TI, TJ, super, ctx->plan_tiles, &ctx->plan_pairs);
         CUDA_TRY(ctx->d_tiles.alloc(std::max<size_t>(ctx->plan_tiles.size(), 1)));
         if (!ctx->plan_tiles.empty())
             CUDA_TRY(cudaMemcpyAsync(ctx->d_tiles.p, ctx->plan_tiles.data(), ctx->plan_tiles.size() * sizeof(uint2),
@@ -516,6 +519,8 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
     // worst case when nothing can be screened out, else optimistic and adapt.
     const bool no_screen = screen_off || !(ctx->st.minR2 > 0.0);
     uint64_t batch = no_screen ? std::max<uint64_t>(1, ctx->cand_cap / tile_pairs) : std::max<uint64_t>(1, ctx->cand_cap / tile_pairs * 64);
+    if (!no_screen && ctx->est_cand_per_tile >= 0.0)  // the previous run over this matrix measured the survivor rate
+        batch = std::max<uint64_t>(batch, (uint64_t)(0.25 * ctx->cand_cap / std::max(1.0, ctx->est_cand_per_tile)));
     if (const char* e = getenv("TWKB_BATCH_TILES")) batch = std::max<uint64_t>(1, (uint64_t)atoll(e));
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     uint64_t rec_on_device = 0;
@@ -587,6 +592,7 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
         if (!no_screen && !getenv("TWKB_BATCH_TILES")) {
             const double per_tile = std::max(1.0, (double)ncand / nb);
             batch = std::max<uint64_t>(1, (uint64_t)(0.5 * ctx->cand_cap / per_tile));
+            ctx->est_cand_per_tile = std::max(ctx->est_cand_per_tile, per_tile);
         }
     }
     if (!dump) {
@@ -651,6 +657,7 @@ static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, co
     ctx->mode = -1;
     ctx->umma.valid = false;
     ctx->matrix_epoch += 1;
+    ctx->est_cand_per_tile = -1.0;
     ctx->n_samples = n_samples;
     ctx->n_variants = n_variants;
     ctx->Mpad = (n_variants + 255) / 256 * 256;
@@ -792,6 +799,7 @@ int twkb_update_settings(void* c, const twkb_settings* s) {
     if (s->device != ctx->device) { ctx->err = "cannot move a context to another device"; return TWKB_EINVAL; }
     ctx->st = *s;
     if (ctx->st.part_count <= 0) { ctx->st.part_count = 1; ctx->st.part_index = 0; }
+    ctx->est_cand_per_tile = -1.0;
     return TWKB_OK;
 }
 
