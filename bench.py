@@ -45,13 +45,13 @@ REF_SAMPLE_VARIANTS = 30_000  # bounded CPU sample of the same workload (first M
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variants", type=int, default=BASE_VARIANTS)
     ap.add_argument("--samples", type=int, default=BASE_SAMPLES)
     ap.add_argument("--min-r2", type=float, default=0.1)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "umma"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "popc", "umma", "i8", "fp4"])
     ap.add_argument("--seed", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-variants", type=int, default=REF_SAMPLE_VARIANTS)
@@ -221,7 +221,8 @@ def main():
         meta = np.zeros(n_variants, dtype=synth.VARIANT_DTYPE)
     t_gen = time.perf_counter() - t_gen0
 
-    kernel = {"auto": tb.KERNEL_AUTO, "popc": tb.KERNEL_POPC, "umma": tb.KERNEL_UMMA}[args.kernel]
+    kernel = {"auto": tb.KERNEL_AUTO, "popc": tb.KERNEL_POPC, "umma": tb.KERNEL_UMMA, "i8": tb.KERNEL_UMMA,
+              "fp4": tb.KERNEL_UMMA_FP4}[args.kernel]
     eng = tb.Engine(force_phased=1, minR2=args.min_r2, kernel=kernel, device=local_rank,
                     part_index=rank, part_count=world)
     # host copy in pinned memory (the e2e leg copies from here every step)
@@ -321,15 +322,22 @@ def main():
     H = 2 * n_samples
     avg_launch_s = (sum(cnt_ms) / max(cnt_launches, 1)) * 1e-3
     pairs_per_launch = pairs_rank * args.steps / max(cnt_launches, 1)
-    if st.kernel_used == tb.KERNEL_UMMA:
-        # GEMM view: 2N bit-MACs per visited pair = 2*2N flop
+    tensor = st.kernel_used in (tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4)
+    fp4 = st.kernel_used == tb.KERNEL_UMMA_FP4
+    if tensor:
+        # GEMM view: 2N bit-MACs per visited pair = 2*2N flop. The tensor peak of the
+        # operand type is the bf16 figure scaled by the nominal dense ratio (bf16 : int8/fp8 : fp4 =
+        # 1 : 2 : 4; B200_PROFILING.md); the step is longer than a burst, so the sustained figure.
         flop_per_pair = 2.0 * H
         achieved = pairs_per_launch * flop_per_pair / avg_launch_s / 1e12
-        peak = 2.0 * peaks["bf16_tflops_sustained"]
+        ratio = 4.0 if fp4 else 2.0
+        peak = ratio * peaks["bf16_tflops_sustained"]
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "count_umma_kernel",
-                    "note": f"int8 tcgen05 peak taken as 2x the {peak_src} sustained bf16 figure; "
-                            f"algorithmic work = pairs x 2 x {H} haplotypes"}
+                    "traffic": None, "kernel": "count_umma3_kernel<%s>" % ("true" if fp4 else "false"),
+                    "frac_of_nominal": achieved / (9000.0 if fp4 else 4500.0),
+                    "note": f"{'e2m1 kind::mxf4' if fp4 else 'int8 kind::i8'} tcgen05 peak taken as {ratio:.0f}x the {peak_src} "
+                            f"sustained bf16 figure ({peaks['bf16_tflops_sustained']:.0f} TFLOP/s); nominal dense "
+                            f"{'9' if fp4 else '4.5'} PFLOP/s; algorithmic work = pairs x 2 x {H} haplotypes"}
     else:
         # LOP3+POPC kernel: INT-pipe bound. Algorithmic work = ceil(2N/32) AND+POPC word-ops per pair;
         # peak = 16 POPC lanes/clk/SM x 148 SMs x max SM clock (to be replaced by the measured issue rate).
@@ -346,14 +354,15 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int8 x int8 -> int32 (tcgen05) + f64 statistics" if st.kernel_used == tb.KERNEL_UMMA else "u32 popcount + f64 statistics",
+        "dtype": ("e2m1 x e2m1 -> f32 exact (tcgen05 kind::mxf4) + f64 statistics" if fp4 else
+                  "int8 x int8 -> int32 (tcgen05) + f64 statistics" if tensor else "u32 popcount + f64 statistics"),
         "data": "synthetic",
         "config": {
             "workload": (f"tomahawk calc -p all-pairs, synthetic {n_samples} samples ({H} haplotypes) x {n_variants} SNVs, "
                          f"R2>={args.min_r2}" + (f" (weak scaling: {args.variants} x sqrt({world}) variants)" if world > 1 else "")),
             "baseline_config": "BASELINE.json configs[1]",
             "pairs_per_step": pairs_total, "haplotype_cmp_per_s": value * H, "records_per_step": records,
-            "kernel": "umma" if st.kernel_used == tb.KERNEL_UMMA else "popc",
+            "kernel": "umma_fp4" if fp4 else "umma_i8" if tensor else "popc",
             "l2": "256 MiB device memset between steps (flush) and operands > L2",
             "seed": args.seed, "gen_seconds": round(t_gen, 2),
             "ms_count_kernel_per_step": float(np.mean(cnt_ms)), "ms_stats_kernel_per_step": float(np.mean(sts_ms)),

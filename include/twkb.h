@@ -48,7 +48,8 @@ extern "C" {
  * phased data without missing genotypes and the LOP3+POPC kernel otherwise. */
 #define TWKB_KERNEL_AUTO 0
 #define TWKB_KERNEL_POPC 1
-#define TWKB_KERNEL_UMMA 2
+#define TWKB_KERNEL_UMMA 2     /* tcgen05 kind::i8, int8 0/1 operands, int32 accumulate        */
+#define TWKB_KERNEL_UMMA_FP4 3 /* tcgen05 kind::mxf4, e2m1 0/1 operands, exact fp32 accumulate */
 
 /* 1:1 with the fields of twk_ld_settings that `calc` reads (include/core.h:909-924;
  * defaults lib/core.cpp:297-306 -- see twkb_settings_init), plus device placement.

@@ -29,6 +29,8 @@ CASES = {
     "phased_miss_quirks": (dict(n_samples=1000, n_variants=300, seed=107, missing_rate=0.05), ["-p", "-r", "0.05"], dict(force_phased=1, minR2=0.05)),
     "window": (dict(n_samples=500, n_variants=1700, seed=108), ["-p", "-r", "0.1", "-w", "60000"], dict(force_phased=1, minR2=0.1, window=1, l_window=60000)),
     # the reference CLI only exposes -r and -P (lib/calc.h:99-220); maxR2/D' keep their defaults
+    # auto mode (neither -p nor -u): a pair is unphased iff either variant has missing alleles (Q4)
+    "auto_mixed": (dict(n_samples=60, n_variants=300, seed=110, missing_rate=0.01), ["-r", "0.05"], dict(minR2=0.05)),
     "minp_filter": (dict(n_samples=600, n_variants=250, seed=109), ["-p", "-r", "0.05", "-P", "1e-3"],
                     dict(force_phased=1, minR2=0.05, minP=1e-3)),
 }
@@ -36,7 +38,10 @@ CASES = {
 
 def main():
     assert lc.have_reference(), "build the reference first: bash oracle/build_ref.sh"
+    only = set(sys.argv[1:])
     for name, (skw, cli, prm) in CASES.items():
+        if only and name not in only:
+            continue
         s = tf.synth_genotypes(**skw)
         twk = os.path.join(TMP, f"g_{name}.twk")
         tf.write_twk(twk, s)
@@ -55,6 +60,8 @@ def main():
             cli=np.array(" ".join(cli)), params=np.array(repr(prm)),
         )
         print(name, "records", len(recs), "pairs", info["pairs"])
+    if only and "fisher" not in only:
+        return
     # Fisher known answers straight from the reference's kt_fisher_exact
     rng = np.random.default_rng(7)
     tabs = []

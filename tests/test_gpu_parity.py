@@ -83,7 +83,7 @@ def test_golden_reference_vectors(name, kernel):
     s, ref, prm, pairs, cli = load_golden(name)
     eng, got, st = gpu_run(s, prm, kernel)
     assert st.pairs_visited == pairs
-    if "unphased" in name:
+    if "unphased" in name or name == "auto_mixed":
         check_unphased(s, got, ref, prm)
     else:
         assert_records_bitexact(got, ref, p_rtol=1e-9)
@@ -178,16 +178,73 @@ def test_unphased_tables_bit_exact_all_pairs(missing):
     eng.close()
 
 
-# ------------------------------------------------------------------- both count kernels
+# ------------------------------------------------------------------- all count kernels
 def test_tensor_and_popc_kernels_agree_bit_for_bit():
+    """POPC, int8 (kind::i8) and e2m1 (kind::mxf4, the AUTO choice) kernels: identical bytes."""
     s = tf.synth_genotypes(2504, 1100, seed=71)
     prm = dict(force_phased=1, minR2=0.02)
-    e1, r1, s1 = gpu_run(s, prm, tb.KERNEL_POPC)
-    e2, r2, s2 = gpu_run(s, prm, tb.KERNEL_AUTO)
-    assert s1.kernel_used == tb.KERNEL_POPC
-    a, b = tf.canonical(r1, False), tf.canonical(r2, False)
-    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
-    e1.close(); e2.close()
+    out = {}
+    for k in (tb.KERNEL_POPC, tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4, tb.KERNEL_AUTO):
+        e, r, st = gpu_run(s, prm, k)
+        assert st.kernel_used == (tb.KERNEL_UMMA_FP4 if k == tb.KERNEL_AUTO else k)
+        out[k] = tf.canonical(r, False)
+        e.close()
+    for k in out:
+        assert np.array_equal(out[tb.KERNEL_POPC].view(np.uint8), out[k].view(np.uint8)), k
+
+
+def _dense_matrix(n_samples, n_variants, seed, chain=False):
+    """Adversarial inputs for the exactness of the e2m1 kernel's fp32 accumulation: nearly every
+    haplotype carries the alt allele (counts close to 2N), or -- chain=True -- every variant is its
+    predecessor with 2 % of the haplotypes flipped (half-dense rows in strong LD, so records
+    survive an R2 cut and counts are ~N)."""
+    rng = np.random.default_rng(seed)
+    nb = 2 * n_samples
+    words = (nb + 127) // 128 * 2
+    data = np.zeros((n_variants, words), np.uint64)
+    ac = np.zeros(n_variants, np.uint32)
+    prev = None
+    for v in range(n_variants):
+        bits = np.zeros(words * 64, np.uint8)
+        if chain and prev is not None:
+            bits[:nb] = prev[:nb] ^ (rng.random(nb) < 0.02)
+        else:
+            bits[:nb] = rng.random(nb) < (0.5 if chain or v % 3 == 0 else 0.97)
+        bits[0] = 0
+        prev = bits
+        ac[v] = bits.sum()
+        data[v] = np.packbits(bits, bitorder="little").view(np.uint64)
+    meta = np.zeros(n_variants, tb.VARIANT_DTYPE)
+    meta["pos"] = 100 * (1 + np.arange(n_variants)); meta["ac"] = ac; meta["hwe"] = 1.0; meta["gt_phase"] = 1
+    return data, meta
+
+
+@pytest.mark.parametrize("n_samples,n_variants,minR2,kernels", [
+    (2504, 700, 0.0, (tb.KERNEL_POPC, tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4)),
+    (60000, 600, 0.0, (tb.KERNEL_POPC, tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4)),      # counts up to ~116,000
+    (500000, 520, 0.3, (tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4)),                     # 1M haplotypes, counts ~500,000
+])
+def test_e2m1_accumulation_exact_on_dense_data(n_samples, n_variants, minR2, kernels):
+    data, meta = _dense_matrix(n_samples, n_variants, seed=n_samples, chain=n_samples >= 500000)
+    out = []
+    for k in kernels:
+        eng = tb.Engine(force_phased=1, minR2=minR2, kernel=k)
+        eng.load(n_samples, data, None, meta)
+        out.append(tf.canonical(eng.compute(), False))
+        assert eng.stats().kernel_used == k
+        eng.close()
+    assert len(out[0]) > 0
+    for o in out[1:]:
+        assert np.array_equal(out[0].view(np.uint8), o.view(np.uint8))
+    # ground truth for a few pairs straight from the bits
+    bits = np.unpackbits(data[:8].view(np.uint8), axis=1, bitorder="little")[:, :2 * n_samples].astype(np.int64)
+    n11 = bits @ bits.T
+    r = out[-1]
+    step = 100
+    ia, ib = (r["packA"] >> 2) // step - 1, (r["packB"] >> 2) // step - 1
+    sel = (ia < 8) & (ib < 8)
+    assert sel.any()
+    assert np.array_equal(r["cnt"][sel][:, 3], n11[ia[sel], ib[sel]].astype(np.float64))
 
 
 # ----------------------------------------------------------- multi-part = whole (no GPU-GPU traffic)

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtwkb.so")
 
 RECORD_BYTES = 106
-KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA = 0, 1, 2
+KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_UMMA_FP4 = 0, 1, 2, 3
 
 ERRORS = {
     -1: "TWKB_EINVAL", -2: "TWKB_ENODEVICE", -3: "TWKB_ECUDA", -4: "TWKB_ENOMEM",

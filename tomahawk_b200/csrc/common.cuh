@@ -45,7 +45,8 @@ struct DevParams {
     uint32_t unphased;            // 1: unphased math for every pair
     uint32_t diag;                // 1: row range == col range, only i<j
     uint32_t lgamma_len;
-    uint32_t pad;
+    uint32_t pair_filter;         // auto mode passes: 0 all pairs, 1 only pairs without a variant
+                                  // with missing alleles, 2 only pairs with one (ld_engine.cpp:2775)
 };
 
 // Window-mode block structure (reference .twk blocks):

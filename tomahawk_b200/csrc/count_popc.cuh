@@ -66,6 +66,7 @@ struct CountArgs {
     uint32_t row_begin, row_end; // variant index limits of this problem (rows)
     uint32_t col_begin, col_end; // (cols)
     uint32_t screen_off;         // 1: every enumerated pair becomes a candidate (debug/test)
+    uint32_t debug_flags;        // profiling aids (env TWKB_DEBUG_FLAGS); 0 in production
 };
 
 // Window-mode pair rule of the reference:
@@ -125,6 +126,10 @@ __device__ __noinline__ void emit_pair(const CountArgs& args, const DevParams& p
     if (ok) {
         const DevVariant vj = args.meta[j];
         ok = (vi.ac + vj.ac > 2);  // ld_engine.cpp:1918
+        if (prm.pair_filter) {
+            const bool miss = ((vi.flags | vj.flags) & VF_HAS_MISSING) != 0;
+            ok = ok && (prm.pair_filter == 1u ? !miss : miss);
+        }
         if (ok && prm.window) ok = window_pair_allowed(i, j, vi, vj, args.meta, args.blocks, prm.l_window);
         if (ok) {
             if (MODE == MODE_PHASED_NOMISS) {

@@ -48,9 +48,12 @@ struct UmmaOperand {
     bool valid = false;
     uint8_t* d_bytes = nullptr;  // [Mpad][Kbytes]
     size_t capacity = 0;
-    uint32_t Kbytes = 0;
+    uint32_t Kbytes = 0;         // bytes per operand row
+    uint32_t Kelems = 0;         // padded haplotypes per row (= Kbytes for int8, 2*Kbytes for e2m1)
     uint32_t Mpad = 0;
-    CUtensorMap tmap;
+    bool fp4 = false;            // e2m1 nibbles instead of int8 bytes
+    CUtensorMap tmap;            // box 128 B x 128 rows (A, and B of the int8 kernels)
+    CUtensorMap tmap_b;          // box 128 B x B rows of the persistent kernel
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -457,13 +460,31 @@ count_umma2_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
 }
 
 // =====================================================================================
-// Persistent 2-CTA variant: one CTA pair per TPC loops over 256 x 256 tiles. The operand
-// ring is 6 stages deep (192 KB of the SM's shared memory in flight hides the ~1-2 us
-// L2 latency that starves the 3-stage kernels), TMEM holds two 256-column accumulators,
-// and the epilogue warps drain tile n while the tensor pipe already works on tile n+1.
-constexpr int UMMA3_STAGES = 6;
+// Persistent 2-CTA variant: one CTA pair per TPC loops over 256 x TILE_N tiles. The operand
+// ring is 6 stages deep (~190 KB of the SM's shared memory in flight hides the ~1-2 us
+// L2 latency that starves the 3-stage kernels), TMEM holds two accumulators, and the
+// epilogue warps drain tile n while the tensor pipe already works on tile n+1.
+//
+// Two operand encodings share the kernel (template parameter FP4):
+//   FP4 = false  int8 0/1 operands, tcgen05.mma kind::i8, int32 accumulators, 256x256 tiles;
+//   FP4 = true   e2m1 0/1 operands (nibble 0x2 = 1.0), tcgen05.mma kind::mxf4 block-scaled
+//                with every UE8M0 scale factor = 2^0, fp32 accumulators. The products are
+//                0 or 1 and every partial sum is an integer < 2^24, so the fp32 accumulation
+//                is exact (enforced by the host: 2N < 2^24, and proven bit for bit against
+//                the POPC kernel by the tests). Twice the MACs per instruction and half the
+//                operand bytes of int8. The scale factors occupy TMEM columns [480,512), so
+//                the two accumulators are 240 columns wide: 256 x 240 tiles.
+template <bool FP4>
+struct Umma3Cfg {
+    static constexpr uint32_t TILE_N = FP4 ? 240u : 256u;
+    static constexpr uint32_t B_ROWS = TILE_N / 2;                          // B rows staged per CTA
+    static constexpr uint32_t STAGE_BYTES = (128u + B_ROWS) * UMMA_BLOCK_K; // per CTA
+    static constexpr int STAGES = 6;
+    static constexpr uint32_t SF_COL = 480u;                                // FP4 only
+    static constexpr size_t SMEM_BYTES =
+        1024 + (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(DevVariant) + 2 * 256 * sizeof(float2) + 256;
+};
 constexpr uint32_t UMMA3_TMEM_COLS = 512;
-constexpr size_t UMMA3_SMEM_BYTES = 1024 + (size_t)UMMA3_STAGES * UMMA2_STAGE_BYTES + 2 * 256 * sizeof(DevVariant) + 256;
 
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target_cta) {
     uint32_t remote;
@@ -472,16 +493,51 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t targe
 }
 __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// Block-scaled e2m1 MMA (K = 64 per instruction), scale factors read from TMEM.
+__device__ __forceinline__ void umma_mxf4_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t tmem_sfa, uint32_t tmem_sfb) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+// Instruction descriptor of the block-scaled kinds (cute::UMMA::InstrDescriptorBlockScaled):
+// A/B format E2M1 (1 @ bits 7, 10), K-major, N>>3 @ 17, scale format UE8M0 (1 @ 23), M>>4 @ 24,
+// scale-factor ids 0, K = 64.
+__host__ __device__ constexpr uint32_t umma_idesc_mxf4(uint32_t M, uint32_t N) {
+    return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
+}
+// 32 lanes x 32 columns of one constant.
+__device__ __forceinline__ void tmem_fill_32x32(uint32_t taddr, uint32_t v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+        "r"(v)
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <bool FP4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA_THREADS, 1)
-count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, DevParams prm, uint32_t num_kblocks, uint32_t n_tiles) {
+count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, CountArgs args,
+                   DevParams prm, uint32_t num_kblocks, uint32_t n_tiles) {
+    using Cfg = Umma3Cfg<FP4>;
+    constexpr uint32_t TILE_N = Cfg::TILE_N;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
-    DevVariant* s_meta = reinterpret_cast<DevVariant*>(smem + (size_t)UMMA3_STAGES * UMMA2_STAGE_BYTES);  // [2][256]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_meta + 2 * 256);
-    uint64_t* empty_bar = full_bar + UMMA3_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + UMMA3_STAGES;  // [2]
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2], the leader's copy is the one used
+    DevVariant* s_meta = reinterpret_cast<DevVariant*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);  // [2][256]
+    float2* s_colf = reinterpret_cast<float2*>(s_meta + 2 * 256);                                  // [2][256] {ac_j, s_j}
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_colf + 2 * 256);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2], the leader's copy is the one used
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -491,7 +547,7 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < UMMA3_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
@@ -507,6 +563,13 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (FP4) {
+        // every scale factor = UE8M0 127 = 2^0, for all 128 lanes of both CTAs
+        if (warp >= 4) tmem_fill_32x32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + Cfg::SF_COL, 0x7F7F7F7Fu);
+        tcgen05_fence_before();
+        cluster_sync_all();
+        tcgen05_fence_after();
+    }
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -515,37 +578,49 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
             for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters) {
                 const uint2 tile = args.tiles[t];
                 for (uint32_t kb = 0; kb < num_kblocks; ++kb, ++it) {
-                    const int s = it % UMMA3_STAGES;
-                    if (it >= (uint32_t)UMMA3_STAGES) mbar_wait(&empty_bar[s], ((it / UMMA3_STAGES) - 1) & 1);
-                    uint8_t* sA = stage_base + (size_t)s * UMMA2_STAGE_BYTES;
+                    const int s = it % STAGES;
+                    if (it >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+                    uint8_t* sA = stage_base + (size_t)s * Cfg::STAGE_BYTES;
                     uint8_t* sB = sA + 128 * UMMA_BLOCK_K;
-                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * UMMA2_STAGE_BYTES);
-                    tma_load_2d_2sm(sA, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(tile.x + 128 * rank));
-                    tma_load_2d_2sm(sB, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(tile.y + 128 * rank));
+                    if (args.debug_flags & 1u) {  // profiling aid: no operand traffic after the first ring fill (results invalid)
+                        if (it >= (uint32_t)STAGES) {
+                            if (leader) mbar_arrive_expect_tx(&full_bar[s], 0);
+                            continue;
+                        }
+                    }
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+                    tma_load_2d_2sm(sA, &tmap_a, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(tile.x + 128 * rank));
+                    tma_load_2d_2sm(sB, &tmap_b, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(tile.y + Cfg::B_ROWS * rank));
                 }
             }
         }
     } else if (warp == 1) {
         // ========================= MMA issuer (leader only) =========================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_i8(256, 256);
+            constexpr uint32_t idesc = FP4 ? umma_idesc_mxf4(256, TILE_N) : umma_idesc_i8(256, TILE_N);
             uint32_t it = 0, n = 0;
             for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters, ++n) {
                 const uint32_t acc = n & 1;
                 if (n >= 2) mbar_wait(&tmem_empty_bar[acc], ((n >> 1) - 1) & 1);  // epilogue drained tile n-2
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * 256;
+                const uint32_t d_tmem = tmem_base + acc * TILE_N;
                 for (uint32_t kb = 0; kb < num_kblocks; ++kb, ++it) {
-                    const int s = it % UMMA3_STAGES;
-                    mbar_wait(&full_bar[s], (it / UMMA3_STAGES) & 1);
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(stage_base + (size_t)s * UMMA2_STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
                     const uint32_t b_addr = a_addr + 128 * UMMA_BLOCK_K;
                     const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(b_addr);
+                    // 32 bytes of K per instruction in both encodings (32 int8 / 64 e2m1)
 #pragma unroll
-                    for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k)
-                        umma_i8_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
-                                    (kb | k) != 0 ? 1u : 0u);
+                    for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k) {
+                        if (FP4)
+                            umma_mxf4_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
+                                          (kb | k) != 0 ? 1u : 0u, tmem_base + Cfg::SF_COL, tmem_base + Cfg::SF_COL + 8);
+                        else
+                            umma_i8_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
+                                        (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit_2sm(&empty_bar[s]);
                 }
                 umma_commit_2sm(&tmem_full_bar[acc]);
@@ -553,32 +628,74 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
         }
     } else if (warp >= 4) {
         // ================================ epilogue ================================
+        // Fast path, 5 fp32 instructions per pair: with X = n11*T - acA*acB, DA = acA(T-acA),
+        // DB = acB(T-acB) the pair can only reach R2 >= minR2 if |X| >= sqrt(minR2*DA*DB). Per
+        // row s_i = sqrt(DA) and per column s_j = sqrt(thr*DB), thr = minR2*(1-1e-12)*(1-2e-5),
+        // are precomputed; m = max_j(|X| + 1e-6*acA*acB - s_i*s_j) over the 32 columns of a
+        // chunk (the 1e-6 term and the 2e-5 relative slack dominate every fp32 rounding error
+        // of the expression, so the test is conservative). Only chunks in which some lane has
+        // m >= -1 (3 % of the chunks at R2 >= 0.1) take the exact per-column path below.
+        // Invalid rows / columns carry s = +inf (-> -inf or NaN, both ignored by fmaxf).
         const int q = warp & 3;
         const uint32_t M = prm.n_variants;
         const float Tf = (float)(2u * prm.n_samples);
         const float thr = (float)prm.screenR2 * (1.0f - 1.0e-5f);
+        const float thr_fast = (float)prm.screenR2 * (1.0f - 2.0e-5f);
         const bool no_screen = args.screen_off || !(prm.minR2 > 0.0);
         const int te = threadIdx.x - 128;
+        const float f_inf = __int_as_float(0x7f800000);
         uint32_t n = 0;
         for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters, ++n) {
             const uint32_t acc = n & 1;
             const uint2 tile = args.tiles[t];
             const uint32_t i0 = tile.x, j0 = tile.y;
             DevVariant* meta_j = s_meta + acc * 256;
-            meta_j[te] = args.meta[j0 + te];
-            meta_j[te + 128] = args.meta[j0 + te + 128];
+            float2* colf = s_colf + acc * 256;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int jl = te + 128 * h;
+                const uint32_t j = j0 + jl;
+                const DevVariant vj = j < args.Mpad ? args.meta[j] : DevVariant{0, 0, 0, 0};
+                meta_j[jl] = vj;
+                const bool j_ok = jl < (int)TILE_N && j >= args.col_begin && j < args.col_end && j < M;
+                const float acB = (float)vj.ac;
+                colf[jl] = make_float2(acB, j_ok ? sqrtf(thr_fast * (acB * (Tf - acB))) : f_inf);
+            }
             const uint32_t i = i0 + 128 * rank + 32 * q + lane;
             const DevVariant vi = args.meta[i];
             const bool i_ok = i >= args.row_begin && i < args.row_end && i < M;
             const float acA = (float)vi.ac;
             const float dA = acA * (Tf - acA);
+            const float sA = i_ok ? sqrtf(dA) : f_inf;
             epilogue_bar_sync();  // column metadata of this tile visible to the 4 epilogue warps
             mbar_wait(&tmem_full_bar[acc], (n >> 1) & 1);
             tcgen05_fence_after();
 #pragma unroll 1
-            for (int chunk = 0; chunk < (int)(UMMA2_TILE / 32); ++chunk) {
+            for (int chunk = 0; chunk < (int)((TILE_N + 31) / 32); ++chunk) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * 256 + (uint32_t)(chunk * 32), r);
+                // (FP4: the last chunk reads 16 columns past the accumulator; they are ignored below)
+                tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * TILE_N + (uint32_t)(chunk * 32), r);
+                if (!no_screen) {
+                    float m = -f_inf;
+                    const float4* cf4 = reinterpret_cast<const float4*>(colf + chunk * 32);
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; ++c2) {
+                        const float4 cb = cf4[c2];  // {ac_j, s_j} of two columns
+                        {
+                            const float n11 = FP4 ? __uint_as_float(r[2 * c2]) : (float)r[2 * c2];
+                            const float pab = acA * cb.x;
+                            const float x = fmaf(n11, Tf, -pab);
+                            m = fmaxf(m, fmaf(-sA, cb.y, fmaf(pab, 1.0e-6f, fabsf(x))));
+                        }
+                        {
+                            const float n11 = FP4 ? __uint_as_float(r[2 * c2 + 1]) : (float)r[2 * c2 + 1];
+                            const float pab = acA * cb.z;
+                            const float x = fmaf(n11, Tf, -pab);
+                            m = fmaxf(m, fmaf(-sA, cb.w, fmaf(pab, 1.0e-6f, fabsf(x))));
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, m >= -1.0f)) continue;
+                }
                 uint32_t passmask = 0;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -586,8 +703,9 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
                     const uint32_t j = j0 + jl;
                     const DevVariant vj = meta_j[jl];
                     bool pass = i_ok && j >= args.col_begin && j < args.col_end && j < M && (!prm.diag || i < j) && (vi.ac + vj.ac > 2);
+                    if (TILE_N % 32 != 0) pass = pass && (jl < (int)TILE_N);
                     if (!no_screen) {
-                        const float n11 = (float)r[c];
+                        const float n11 = FP4 ? __uint_as_float(r[c]) : (float)r[c];
                         const float acB = (float)vj.ac;
                         const float pab = acA * acB;
                         const float x = fabsf(fmaf(n11, Tf, -pab));
@@ -604,7 +722,7 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
                     for (int c = 0; c < 32; ++c) {
                         if ((colmask >> c) & 1u) {
                             PairAcc<1> pa;
-                            pa.v[0][0] = r[c];
+                            pa.v[0][0] = FP4 ? (uint32_t)__uint_as_float(r[c]) : r[c];
                             emit_pair<MODE_PHASED_NOMISS>(args, prm, i, j0 + chunk * 32 + c, vi, pa, lane, (passmask >> c) & 1u);
                         }
                     }
@@ -621,6 +739,33 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, Dev
     if (warp == 2) {
         tcgen05_fence_after();
         tmem_dealloc_2sm(tmem_base, UMMA3_TMEM_COLS);
+    }
+}
+
+// One e2m1 nibble (0x2 = 1.0, 0x0 = 0.0) per haplotype from the reference-layout rows.
+__global__ void expand_bits_to_e2m1_kernel(const uint64_t* __restrict__ rows, size_t stride64, uint32_t n_variants,
+                                           uint32_t n_bits, uint8_t* __restrict__ out, uint32_t Kbytes, uint32_t Mpad) {
+    const uint32_t w = blockIdx.y * blockDim.x + threadIdx.x;  // 64-haplotype group = 32 output bytes
+    const uint32_t v = blockIdx.x;
+    if (w * 32 >= Kbytes || v >= Mpad) return;
+    uint64_t x = 0;
+    if (v < n_variants && (size_t)w < stride64 && (uint64_t)w * 64 < n_bits) {
+        x = rows[(size_t)v * stride64 + w];
+        if ((uint64_t)w * 64 + 64 > n_bits) x &= (1ull << (n_bits - w * 64)) - 1ull;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)v * Kbytes + (size_t)w * 32);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        uint32_t b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t y = (uint32_t)(x >> (32 * q + 8 * r)) & 0xFFu;  // bit t -> nibble t
+            y = (y | (y << 12)) & 0x000F000Fu;
+            y = (y | (y << 6)) & 0x03030303u;
+            y = (y | (y << 3)) & 0x11111111u;
+            b[r] = y << 1;
+        }
+        dst[q] = make_uint4(b[0], b[1], b[2], b[3]);
     }
 }
 
@@ -648,41 +793,6 @@ inline bool umma_supported() {
     return get_tmap_encoder() != nullptr;
 }
 
-// Builds (once per matrix) the byte-expanded operand and its tensor map.
-inline int umma_prepare(UmmaOperand& op, const uint64_t* d_rows, size_t stride64, uint32_t n_variants, uint32_t Mpad,
-                        uint32_t n_samples, cudaStream_t stream, std::string& err, uint64_t* launches) {
-    if (op.valid) return 0;
-    const uint32_t n_bits = 2 * n_samples;
-    const uint32_t Kbytes = (n_bits + UMMA_BLOCK_K - 1) / UMMA_BLOCK_K * UMMA_BLOCK_K;
-    const size_t need = (size_t)Mpad * Kbytes;
-    if (op.capacity < need) {
-        if (op.d_bytes) cudaFree(op.d_bytes);
-        op.d_bytes = nullptr;
-        op.capacity = 0;
-        cudaError_t e = cudaMalloc((void**)&op.d_bytes, need);
-        if (e != cudaSuccess) { err = std::string("cudaMalloc(int8 operand): ") + cudaGetErrorString(e); return -3; }
-        op.capacity = need;
-    }
-    op.Kbytes = Kbytes;
-    op.Mpad = Mpad;
-    dim3 grid(Mpad, (Kbytes / 64 + 127) / 128), block(128);
-    expand_bits_to_bytes_kernel<<<grid, block, 0, stream>>>(d_rows, stride64, n_variants, n_bits, op.d_bytes, Kbytes, Mpad);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { err = std::string("expand kernel: ") + cudaGetErrorString(e); return -3; }
-    if (launches) *launches += 1;
-    PFN_tmapEncodeTiled enc = get_tmap_encoder();
-    if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return -3; }
-    cuuint64_t gdim[2] = {Kbytes, Mpad};
-    cuuint64_t gstride[1] = {Kbytes};
-    cuuint32_t box[2] = {UMMA_BLOCK_K, UMMA_TILE_M};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&op.tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, op.d_bytes, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return -3; }
-    op.valid = true;
-    return 0;
-}
-
 // 3 (default) = persistent CTA-pair kernel, 2 = one 256x256 tile per CTA pair,
 // 1 = single-CTA kernel (128x128 tiles). The older variants are kept for A/B profiling.
 inline int umma_cta_group() {
@@ -692,24 +802,90 @@ inline int umma_cta_group() {
     }
     return 3;
 }
-inline uint32_t umma_tile() { return umma_cta_group() >= 2 ? UMMA2_TILE : UMMA_TILE_M; }
+// e2m1 operands are served by the persistent kernel only; fp32 accumulation of 0/1 products is
+// exact while every count stays below 2^24.
+inline bool umma_fp4_possible(uint32_t n_samples) { return umma_cta_group() == 3 && 2ull * n_samples < (1ull << 24); }
+inline void umma_tile(bool fp4, uint32_t& TI, uint32_t& TJ) {
+    if (umma_cta_group() < 2) { TI = TJ = UMMA_TILE_M; return; }
+    TI = UMMA2_TILE;
+    TJ = fp4 ? Umma3Cfg<true>::TILE_N : UMMA2_TILE;
+}
+
+static inline int umma_encode_map(CUtensorMap* map, uint8_t* base, uint32_t Kbytes, uint32_t Mpad, uint32_t box_rows, std::string& err) {
+    PFN_tmapEncodeTiled enc = get_tmap_encoder();
+    if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return -3; }
+    cuuint64_t gdim[2] = {Kbytes, Mpad};
+    cuuint64_t gstride[1] = {Kbytes};
+    cuuint32_t box[2] = {UMMA_BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed: " + std::to_string((int)r); return -3; }
+    return 0;
+}
+
+// Builds (once per matrix and encoding) the expanded operand and its tensor maps.
+inline int umma_prepare(UmmaOperand& op, bool fp4, const uint64_t* d_rows, size_t stride64, uint32_t n_variants, uint32_t Mpad,
+                        uint32_t n_samples, cudaStream_t stream, std::string& err, uint64_t* launches) {
+    if (op.valid && op.fp4 == fp4) return 0;
+    op.valid = false;
+    const uint32_t n_bits = 2 * n_samples;
+    // one pipeline stage = 128 bytes of K = 128 int8 or 256 e2m1 elements
+    const uint32_t k_per_stage = fp4 ? 2 * UMMA_BLOCK_K : UMMA_BLOCK_K;
+    const uint32_t Kelems = (n_bits + k_per_stage - 1) / k_per_stage * k_per_stage;
+    const uint32_t Kbytes = fp4 ? Kelems / 2 : Kelems;
+    const size_t need = (size_t)Mpad * Kbytes;
+    if (op.capacity < need) {
+        if (op.d_bytes) cudaFree(op.d_bytes);
+        op.d_bytes = nullptr;
+        op.capacity = 0;
+        cudaError_t e = cudaMalloc((void**)&op.d_bytes, need);
+        if (e != cudaSuccess) { err = std::string("cudaMalloc(tensor-core operand): ") + cudaGetErrorString(e); return -3; }
+        op.capacity = need;
+    }
+    op.Kbytes = Kbytes;
+    op.Kelems = Kelems;
+    op.Mpad = Mpad;
+    op.fp4 = fp4;
+    if (fp4) {
+        dim3 grid(Mpad, (Kbytes / 32 + 127) / 128), block(128);
+        expand_bits_to_e2m1_kernel<<<grid, block, 0, stream>>>(d_rows, stride64, n_variants, n_bits, op.d_bytes, Kbytes, Mpad);
+    } else {
+        dim3 grid(Mpad, (Kbytes / 64 + 127) / 128), block(128);
+        expand_bits_to_bytes_kernel<<<grid, block, 0, stream>>>(d_rows, stride64, n_variants, n_bits, op.d_bytes, Kbytes, Mpad);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("expand kernel: ") + cudaGetErrorString(e); return -3; }
+    if (launches) *launches += 1;
+    int rc = umma_encode_map(&op.tmap, op.d_bytes, Kbytes, Mpad, UMMA_TILE_M, err);
+    if (rc) return rc;
+    rc = umma_encode_map(&op.tmap_b, op.d_bytes, Kbytes, Mpad, fp4 ? Umma3Cfg<true>::B_ROWS : UMMA_TILE_M, err);
+    if (rc) return rc;
+    op.valid = true;
+    return 0;
+}
+
+template <bool FP4>
+inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
+    static bool configured = false;
+    static int n_sm = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(count_umma3_kernel<FP4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Umma3Cfg<FP4>::SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    const uint32_t n_clusters = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, n_sm / 2));
+    count_umma3_kernel<FP4><<<2 * n_clusters, UMMA_THREADS, Umma3Cfg<FP4>::SMEM_BYTES, stream>>>(
+        op.tmap, op.tmap_b, args, prm, op.Kbytes / UMMA_BLOCK_K, n_tiles);
+    return cudaGetLastError();
+}
 
 inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
-    if (umma_cta_group() == 3) {
-        static bool configured3 = false;
-        static int n_sm = 0;
-        if (!configured3) {
-            cudaError_t e = cudaFuncSetAttribute(count_umma3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA3_SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            configured3 = true;
-        }
-        const uint32_t n_clusters = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, n_sm / 2));
-        count_umma3_kernel<<<2 * n_clusters, UMMA_THREADS, UMMA3_SMEM_BYTES, stream>>>(op.tmap, args, prm, op.Kbytes / UMMA_BLOCK_K, n_tiles);
-        return cudaGetLastError();
-    }
+    if (umma_cta_group() == 3) return op.fp4 ? umma3_launch<true>(op, args, prm, n_tiles, stream) : umma3_launch<false>(op, args, prm, n_tiles, stream);
     if (umma_cta_group() == 2) {
         static bool configured2 = false;
         if (!configured2) {

@@ -386,8 +386,8 @@ static cudaError_t launch_popc(Context* ctx, const CountArgs& args, const DevPar
     return cudaGetLastError();
 }
 
-static void tile_dims(int mode, bool umma, uint32_t& TI, uint32_t& TJ) {
-    if (umma) { TI = TJ = umma_tile(); return; }
+static void tile_dims(int mode, bool umma, bool fp4, uint32_t& TI, uint32_t& TJ) {
+    if (umma) { umma_tile(fp4, TI, TJ); return; }
     switch (mode) {
         case MODE_PHASED_NOMISS: TI = popc_tile_i<0>(); TJ = popc_tile_j<0>(); break;
         case MODE_PHASED_MISS: TI = popc_tile_i<1>(); TJ = popc_tile_j<1>(); break;
@@ -457,21 +457,33 @@ static int flush_records(Context* ctx, uint64_t n_records, twkb_sink_fn sink, vo
 // One pass over a sub-problem with the planes of `mode`.
 // pair_filter: 0 = all pairs, 1 = only pairs with no missing variant, 2 = only pairs with one
 // (auto mode passes; see compute()).
-static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bool screen_off, twkb_sink_fn sink,
-                    void* user, std::vector<Candidate>* dump) {
+static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_filter, bool resident, bool screen_off,
+                    twkb_sink_fn sink, void* user, std::vector<Candidate>* dump) {
     int rc = ensure_planes(ctx, mode);
     if (rc) return rc;
-    bool use_umma = false;
+    bool use_umma = false, use_fp4 = false;
     if (mode == MODE_PHASED_NOMISS && ctx->st.kernel != TWKB_KERNEL_POPC && !dump) use_umma = umma_supported();
-    if (ctx->st.kernel == TWKB_KERNEL_UMMA && !use_umma && !dump) {
-        ctx->err = "TWKB_KERNEL_UMMA requested but the tensor-core kernel only serves phased data without missing genotypes";
+    if ((ctx->st.kernel == TWKB_KERNEL_UMMA || ctx->st.kernel == TWKB_KERNEL_UMMA_FP4) && !use_umma && !dump) {
+        ctx->err = "tensor-core kernel requested but it only serves phased data without missing genotypes";
         return TWKB_EINVAL;
     }
-    uint32_t TI, TJ;
-    tile_dims(mode, use_umma, TI, TJ);
     if (use_umma) {
-        rc = umma_prepare(ctx->umma, ctx->d_raw_data.p, ctx->raw_stride, ctx->n_variants, ctx->Mpad, ctx->n_samples, ctx->stream,
-                          ctx->err, &ctx->stats.other_launches);
+        // operand encoding: e2m1 (kind::mxf4, 2x the MAC rate of int8) whenever its fp32
+        // accumulation is exact (2N < 2^24), int8 otherwise or on request
+        use_fp4 = ctx->st.kernel != TWKB_KERNEL_UMMA && umma_fp4_possible(ctx->n_samples);
+        if (const char* e = getenv("TWKB_UMMA_KIND")) {
+            if (e[0] == 'i') use_fp4 = false;
+        }
+        if (ctx->st.kernel == TWKB_KERNEL_UMMA_FP4 && !use_fp4) {
+            ctx->err = "TWKB_KERNEL_UMMA_FP4 needs 2N < 2^24 and the persistent kernel";
+            return TWKB_EINVAL;
+        }
+    }
+    uint32_t TI, TJ;
+    tile_dims(mode, use_umma, use_fp4, TI, TJ);
+    if (use_umma) {
+        rc = umma_prepare(ctx->umma, use_fp4, ctx->d_raw_data.p, ctx->raw_stride, ctx->n_variants, ctx->Mpad, ctx->n_samples,
+                          ctx->stream, ctx->err, &ctx->stats.other_launches);
         if (rc) return rc;
     }
     // The tile plan depends only on the sub-problem, the tile shape, the window and the
@@ -493,7 +505,7 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
     }
     const std::vector<uint2>& tiles = ctx->plan_tiles;
     if (ctx->st.part_count > 1 && !ctx->st.window) ctx->stats.pairs_visited = ctx->plan_pairs;
-    ctx->stats.kernel_used = use_umma ? TWKB_KERNEL_UMMA : TWKB_KERNEL_POPC;
+    ctx->stats.kernel_used = use_umma ? (use_fp4 ? TWKB_KERNEL_UMMA_FP4 : TWKB_KERNEL_UMMA) : TWKB_KERNEL_POPC;
     ctx->stats.n_planes = ctx->np;
     const uint64_t tile_pairs = (uint64_t)TI * TJ;
     rc = ensure_work_buffers(ctx, tile_pairs);
@@ -501,6 +513,7 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
     if (tiles.empty()) return TWKB_OK;
 
     DevParams prm = make_params(ctx, pb);
+    prm.pair_filter = pair_filter;
     CountArgs args{};
     args.planes = ctx->d_planes.p;
     args.K32 = ctx->K32;
@@ -514,6 +527,7 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
     args.row_begin = pb.row_begin; args.row_end = pb.row_end;
     args.col_begin = pb.col_begin; args.col_end = pb.col_end;
     args.screen_off = screen_off ? 1u : 0u;
+    if (const char* e = getenv("TWKB_DEBUG_FLAGS")) args.debug_flags = (uint32_t)atoi(e);
 
     // Batch size: the candidate buffer must hold a whole batch. Start from the
     // worst case when nothing can be screened out, else optimistic and adapt.
@@ -555,7 +569,7 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, bool resident, bo
             batch = std::max<uint64_t>(1, nb / 2);
             continue;
         }
-        if (use_umma) ctx->stats.mma_macs += (uint64_t)nb * tile_pairs * ctx->umma.Kbytes;
+        if (use_umma) ctx->stats.mma_macs += (uint64_t)nb * tile_pairs * ctx->umma.Kelems;
         else ctx->stats.word_ops += (uint64_t)nb * tile_pairs * ctx->K32 * ctx->np * ctx->np;
         ctx->stats.pairs_screened += ncand;
         t += nb;
@@ -631,10 +645,14 @@ static int compute_impl(Context* ctx, bool resident, twkb_sink_fn sink, void* us
     }
     if (ctx->st.force_phased || ctx->st.forced_unphased || !ctx->any_missing) {
         // -p, -u, or auto mode on complete data (auto => phased for every pair, ld_engine.cpp:2775-2790)
-        rc = run_pass(ctx, pb, wanted_mode(ctx, ctx->st.forced_unphased), resident, screen_off, sink, user, dump);
+        rc = run_pass(ctx, pb, wanted_mode(ctx, ctx->st.forced_unphased), 0, resident, screen_off, sink, user, dump);
     } else {
-        ctx->err = "auto mode (neither -p nor -u) on data with missing genotypes is not implemented; pass -p or -u";
-        rc = TWKB_EINVAL;
+        // Auto mode (ld_engine.cpp:2737-2838): a pair takes the unphased path iff either variant
+        // has missing alleles (an != 0), else the phased path; gt_phase is never consulted (Q4).
+        // Two passes over the same tile plan family: the rows of complete variants carry no mask
+        // bits, so the no-missing phased planes (and the tensor-core kernel) are exact for pass 1.
+        rc = run_pass(ctx, pb, MODE_PHASED_NOMISS, 1, resident, screen_off, sink, user, dump);
+        if (rc == TWKB_OK) rc = run_pass(ctx, pb, MODE_UNPHASED_MISS, 2, resident, screen_off, sink, user, dump);
     }
     if (rc == TWKB_OK) {
         CUDA_TRY(cudaEventRecord(ctx->ev_end, ctx->stream));
