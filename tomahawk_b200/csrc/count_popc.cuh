@@ -110,12 +110,68 @@ __device__ __forceinline__ bool screen_unphased(const uint32_t* t, const DevPara
 
 template <int NP> struct PairAcc { uint32_t v[NP][NP]; };
 
+// Exact per-pair decision for a pair inside the problem's ranges: pair rules of the reference
+// (ac_i+ac_j<=2 skip, auto-mode pass filter, window rule Q7), the exact 2x2 / 3x3 table from the
+// plane products, and the fp64 R2 screen. c[] / mode are the candidate fields.
+template <int MODE>
+__device__ __forceinline__ bool pair_decide(const CountArgs& args, const DevParams& prm, uint32_t i, uint32_t j, const DevVariant& vi,
+                                            const DevVariant& vj, const PairAcc<PopcCfg<MODE>::NP>& pa, uint32_t (&c)[9],
+                                            uint32_t& mode) {
+    constexpr int NP = PopcCfg<MODE>::NP;
+    bool ok = (vi.ac + vj.ac > 2);  // ld_engine.cpp:1918
+    if (prm.pair_filter) {
+        const bool miss = ((vi.flags | vj.flags) & VF_HAS_MISSING) != 0;
+        ok = ok && (prm.pair_filter == 1u ? !miss : miss);
+    }
+    if (ok && prm.window) ok = window_pair_allowed(i, j, vi, vj, args.meta, args.blocks, prm.l_window);
+    if (!ok) return false;
+    if (MODE == MODE_PHASED_NOMISS) {
+        // ld_engine.cpp:244-246 / :682-685
+        const uint32_t n11 = pa.v[0][0];
+        c[3] = n11;
+        c[1] = vi.ac - n11;
+        c[2] = vj.ac - n11;
+        c[0] = 2u * prm.n_samples - ((vi.ac + vj.ac) - n11);
+        ok = args.screen_off || screen_phased(c[0], c[1], c[2], c[3], prm);
+    } else if (MODE == MODE_PHASED_MISS) {
+        // planes (alt&valid, valid): the four masked counts of ld_engine.cpp:555-581
+        const uint32_t n11 = pa.v[0][0], nA = pa.v[0][NP - 1], nB = pa.v[NP - 1][0], nV = pa.v[NP - 1][NP - 1];
+        c[3] = n11;
+        c[1] = nA - n11;
+        c[2] = nB - n11;
+        c[0] = nV - nA - nB + n11;
+        ok = args.screen_off || screen_phased(c[0], c[1], c[2], c[3], prm);
+    } else {
+        // unphased: plane 0 = het, 1 = hom, (2 = valid); 3x3 table of ld_engine.cpp:835-844
+        uint32_t hetA_v, homA_v, hetB_v, homB_v, vv;
+        if (MODE == MODE_UNPHASED_NOMISS) {
+            const uint32_t* pp = args.plane_popc;
+            hetA_v = pp[i]; homA_v = pp[args.Mpad + i];
+            hetB_v = pp[j]; homB_v = pp[args.Mpad + j];
+            vv = prm.n_samples;
+        } else {
+            hetA_v = pa.v[0][NP - 1]; homA_v = pa.v[1 % NP][NP - 1];
+            hetB_v = pa.v[NP - 1][0]; homB_v = pa.v[NP - 1][1 % NP];
+            vv = pa.v[NP - 1][NP - 1];
+        }
+        const uint32_t c11 = pa.v[0][0], c12 = pa.v[0][1 % NP], c21 = pa.v[1 % NP][0], c22 = pa.v[1 % NP][1 % NP];
+        mode = 1;
+        c[4] = c11; c[5] = c12; c[7] = c21; c[8] = c22;
+        c[3] = hetA_v - c11 - c12;  // A het, B 0/0
+        c[6] = homA_v - c21 - c22;  // A 1/1, B 0/0
+        c[1] = hetB_v - c11 - c21;  // A 0/0, B het
+        c[2] = homB_v - c12 - c22;  // A 0/0, B 1/1
+        c[0] = vv - (c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7] + c[8]);
+        ok = args.screen_off || screen_unphased(c, prm);
+    }
+    return ok;
+}
+
 // Per-pair epilogue: pair rules of the reference, exact table, screen, compaction.
 // Called convergently by all 32 lanes of a warp.
 template <int MODE>
 __device__ __noinline__ void emit_pair(const CountArgs& args, const DevParams& prm, uint32_t i, uint32_t j,
                                        DevVariant vi, PairAcc<PopcCfg<MODE>::NP> pa, int lane, bool pre_ok = true) {
-    constexpr int NP = PopcCfg<MODE>::NP;
     const uint32_t M = prm.n_variants;
     bool ok = pre_ok && i >= args.row_begin && i < args.row_end && j >= args.col_begin && j < args.col_end && i < M && j < M;
     if (prm.diag) ok = ok && (i < j);
@@ -125,53 +181,7 @@ __device__ __noinline__ void emit_pair(const CountArgs& args, const DevParams& p
     uint32_t mode = 0;
     if (ok) {
         const DevVariant vj = args.meta[j];
-        ok = (vi.ac + vj.ac > 2);  // ld_engine.cpp:1918
-        if (prm.pair_filter) {
-            const bool miss = ((vi.flags | vj.flags) & VF_HAS_MISSING) != 0;
-            ok = ok && (prm.pair_filter == 1u ? !miss : miss);
-        }
-        if (ok && prm.window) ok = window_pair_allowed(i, j, vi, vj, args.meta, args.blocks, prm.l_window);
-        if (ok) {
-            if (MODE == MODE_PHASED_NOMISS) {
-                // ld_engine.cpp:244-246 / :682-685
-                const uint32_t n11 = pa.v[0][0];
-                c[3] = n11;
-                c[1] = vi.ac - n11;
-                c[2] = vj.ac - n11;
-                c[0] = 2u * prm.n_samples - ((vi.ac + vj.ac) - n11);
-                ok = args.screen_off || screen_phased(c[0], c[1], c[2], c[3], prm);
-            } else if (MODE == MODE_PHASED_MISS) {
-                // planes (alt&valid, valid): the four masked counts of ld_engine.cpp:555-581
-                const uint32_t n11 = pa.v[0][0], nA = pa.v[0][NP - 1], nB = pa.v[NP - 1][0], nV = pa.v[NP - 1][NP - 1];
-                c[3] = n11;
-                c[1] = nA - n11;
-                c[2] = nB - n11;
-                c[0] = nV - nA - nB + n11;
-                ok = args.screen_off || screen_phased(c[0], c[1], c[2], c[3], prm);
-            } else {
-                // unphased: plane 0 = het, 1 = hom, (2 = valid); 3x3 table of ld_engine.cpp:835-844
-                uint32_t hetA_v, homA_v, hetB_v, homB_v, vv;
-                if (MODE == MODE_UNPHASED_NOMISS) {
-                    const uint32_t* pp = args.plane_popc;
-                    hetA_v = pp[i]; homA_v = pp[args.Mpad + i];
-                    hetB_v = pp[j]; homB_v = pp[args.Mpad + j];
-                    vv = prm.n_samples;
-                } else {
-                    hetA_v = pa.v[0][NP - 1]; homA_v = pa.v[1 % NP][NP - 1];
-                    hetB_v = pa.v[NP - 1][0]; homB_v = pa.v[NP - 1][1 % NP];
-                    vv = pa.v[NP - 1][NP - 1];
-                }
-                const uint32_t c11 = pa.v[0][0], c12 = pa.v[0][1 % NP], c21 = pa.v[1 % NP][0], c22 = pa.v[1 % NP][1 % NP];
-                mode = 1;
-                c[4] = c11; c[5] = c12; c[7] = c21; c[8] = c22;
-                c[3] = hetA_v - c11 - c12;  // A het, B 0/0
-                c[6] = homA_v - c21 - c22;  // A 1/1, B 0/0
-                c[1] = hetB_v - c11 - c21;  // A 0/0, B het
-                c[2] = homB_v - c12 - c22;  // A 0/0, B 1/1
-                c[0] = vv - (c[1] + c[2] + c[3] + c[4] + c[5] + c[6] + c[7] + c[8]);
-                ok = args.screen_off || screen_unphased(c, prm);
-            }
-        }
+        ok = pair_decide<MODE>(args, prm, i, j, vi, vj, pa, c, mode);
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, ok);
     if (ballot == 0) return;

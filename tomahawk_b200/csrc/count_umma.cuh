@@ -482,7 +482,7 @@ struct Umma3Cfg {
     static constexpr int STAGES = 6;
     static constexpr uint32_t SF_COL = 480u;                                // FP4 only
     static constexpr size_t SMEM_BYTES =
-        1024 + (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(DevVariant) + 2 * 256 * sizeof(float2) + 256;
+        1024 + (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(DevVariant) + 2 * 256 * sizeof(float2) + 1024 * 16 /*survivor ring*/ + 256;
 };
 constexpr uint32_t UMMA3_TMEM_COLS = 512;
 
@@ -522,8 +522,383 @@ __device__ __forceinline__ void tmem_fill_32x32(uint32_t taddr, uint32_t v) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// Epilogue of the persistent kernel: 8 warps, two per TMEM lane quarter (a warp may only read
+// the quarter warp_id % 4), each draining half of the columns of accumulator n & 1 of tile n
+// while the tensor pipe works on tile n + 1.
+//
+// Fast path, 5 fp32 instructions per pair: with X = n11*T - acA*acB, DA = acA(T-acA),
+// DB = acB(T-acB) the pair can only reach R2 >= minR2 if |X| >= sqrt(minR2*DA*DB). Per row
+// s_i = sqrt(DA) and per column s_j = sqrt(thr*DB), thr = minR2*(1-1e-12)*(1-2e-5), are
+// precomputed; m = max_j(|X| + 1e-6*acA*acB - s_i*s_j) over the 32 columns of a chunk (the 1e-6
+// term and the 2e-5 relative slack dominate every fp32 rounding error of the expression, so
+// the test is conservative). Only chunks in which some lane has m >= -1 (a few % of the chunks
+// at R2 >= 0.1) take the exact per-column path. Invalid rows / columns carry s = +inf
+// (-> -inf or NaN, both ignored by fmaxf).
+//
+// The epilogue is a chain of latencies (metadata loads, TMEM loads, votes), not of issue
+// slots, so everything that can be taken off the per-tile critical path is: the metadata of
+// tile n + 1 is fetched while tile n is drained, the TMEM load of chunk c + 1 is in flight
+// while chunk c is screened, and the release of the accumulator is a CTA-scope arrive.
+constexpr int UMMA3_EPI_WARPS = 8;
+constexpr int UMMA3_THREADS = 128 + 32 * UMMA3_EPI_WARPS;
+
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// The "+r" operands tie the wait to the registers of the load it completes.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ DevVariant lds_variant(uint32_t saddr) {
+    DevVariant v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.pos), "=r"(v.ac), "=r"(v.rid), "=r"(v.flags) : "r"(saddr));
+    return v;
+}
+// arrive on an mbarrier of another CTA of the cluster (CTA-scope release: no gpu-wide fence)
+__device__ __forceinline__ void mbar_arrive_remote_cta(uint64_t* bar, uint32_t target_cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(target_cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void epilogue_bar_sync8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct EpiRow {  // per-thread row constants of one tile
+    uint32_t i;
+    DevVariant vi;
+    bool i_ok;
+    float acA, dA, sA;
+};
+
+// Direct path of a 32-column chunk (the instantiation without a screen, minR2 = 0, where every
+// pair is a candidate): per-column pair rules, exact decision, then ONE atomic per chunk (warp
+// scan) and the candidate stores.
 template <bool FP4>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA_THREADS, 1)
+__device__ __forceinline__ void umma_direct_chunk(const CountArgs& args, const DevParams& prm, const uint32_t (&r)[32], const EpiRow& row,
+                                                  uint32_t meta_saddr, uint32_t j0, int chunk, float Tf, float thr, bool no_screen,
+                                                  int lane) {
+    constexpr uint32_t TILE_N = Umma3Cfg<FP4>::TILE_N;
+    const uint32_t M = prm.n_variants;
+    uint32_t passmask = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const int jl = chunk * 32 + c;
+        const uint32_t j = j0 + jl;
+        const DevVariant vj = lds_variant(meta_saddr + (uint32_t)jl * 16u);
+        bool pass = row.i_ok && j >= args.col_begin && j < args.col_end && j < M && (!prm.diag || row.i < j) && (row.vi.ac + vj.ac > 2);
+        if (TILE_N % 32 != 0) pass = pass && (jl < (int)TILE_N);
+        if (!no_screen) {
+            const float n11 = FP4 ? __uint_as_float(r[c]) : (float)r[c];
+            const float acB = (float)vj.ac;
+            const float pab = row.acA * acB;
+            const float x = fabsf(fmaf(n11, Tf, -pab));
+            const float slack = 4.0f + 4.0e-7f * fmaxf(n11 * Tf, pab);
+            const float lhs = (x + slack) * (x + slack);
+            const float rhs = thr * (row.dA * (acB * (Tf - acB)));
+            pass = pass && (lhs >= rhs);
+        }
+        passmask |= (pass ? 1u : 0u) << c;
+    }
+    if (!__any_sync(0xffffffffu, passmask != 0u)) return;
+    // exact decision for the flagged pairs of this lane (a handful at most)
+    uint32_t keep = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        if ((passmask >> c) & 1u) {
+            const int jl = chunk * 32 + c;
+            const DevVariant vj = lds_variant(meta_saddr + (uint32_t)jl * 16u);
+            PairAcc<1> pa;
+            pa.v[0][0] = FP4 ? (uint32_t)__uint_as_float(r[c]) : r[c];
+            uint32_t cc[9], mode = 0;
+            if (pair_decide<MODE_PHASED_NOMISS>(args, prm, row.i, j0 + jl, row.vi, vj, pa, cc, mode)) keep |= 1u << c;
+        }
+    }
+    // warp-aggregated compaction: one atomic per chunk
+    const uint32_t cnt = __popc(keep);
+    uint32_t scan = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, scan, d);
+        if (lane >= d) scan += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, scan, 31);
+    if (total == 0) return;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(args.cand_count, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0) + (scan - cnt);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        if ((keep >> c) & 1u) {
+            const unsigned long long slot = base + __popc(keep & ((1u << c) - 1u));
+            if (slot < args.cand_capacity) {
+                const int jl = chunk * 32 + c;
+                const DevVariant vj = lds_variant(meta_saddr + (uint32_t)jl * 16u);
+                const uint32_t n11 = FP4 ? (uint32_t)__uint_as_float(r[c]) : r[c];
+                uint4* dst = reinterpret_cast<uint4*>(args.cands + slot);
+                dst[0] = make_uint4(row.i, j0 + jl, 2u * prm.n_samples - ((row.vi.ac + vj.ac) - n11), row.vi.ac - n11);
+                dst[1] = make_uint4(vj.ac - n11, n11, 0u, 0u);
+                dst[2] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    }
+}
+
+// ---- survivor queue of the persistent kernel -------------------------------------------------
+// The pairs the fast screen flags are rare (1e-5 of the pairs at C2) but spread over every
+// tile, and their exact decision needs global round trips (metadata, the candidate-slot
+// atomic): ~2-5 us, a whole tile time, if an epilogue warp does it inline. Instead the epilogue
+// warps push (i, j, n11) into a shared-memory ring (~0.3 us) and the otherwise idle warp 3
+// drains it: exact pair rules + fp64 screen, warp-aggregated global atomic, candidate stores.
+constexpr uint32_t UMMA3_QCAP = 1024;  // entries (16 KB)
+struct __align__(16) QEntry { uint32_t i, j, n11, seq; };
+struct SurvivorQueue {
+    QEntry* ring;        // [UMMA3_QCAP]
+    uint32_t* ctrl;      // [0] tail (reservations), [1] head (consumed), [2] finished producer warps
+};
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void queue_push(const SurvivorQueue& q, uint32_t i, uint32_t j, uint32_t n11) {
+    const uint32_t slot = atomicAdd(&q.ctrl[0], 1u);
+    while (slot - ld_volatile_shared(&q.ctrl[1]) >= UMMA3_QCAP) __nanosleep(64);  // ring full: wait for the drain warp
+    QEntry* e = q.ring + (slot % UMMA3_QCAP);
+    e->i = i; e->j = j; e->n11 = n11;
+    __threadfence_block();
+    st_volatile_shared(&e->seq, slot / UMMA3_QCAP + 1u);  // publishes the entry
+}
+
+// Warp 3: drains the ring until all epilogue warps have finished and the ring is empty.
+__device__ __noinline__ void umma_drain_loop(const CountArgs& args, const DevParams& prm, SurvivorQueue q, int lane) {
+    const uint32_t M = prm.n_variants;
+    uint32_t head = 0;
+    for (;;) {
+        uint32_t tail = ld_volatile_shared(&q.ctrl[0]);
+        if (tail == head) {
+            if (ld_volatile_shared(&q.ctrl[2]) == (uint32_t)UMMA3_EPI_WARPS) {
+                tail = ld_volatile_shared(&q.ctrl[0]);  // pushes precede the producer's "finished" mark
+                if (tail == head) break;
+            } else {
+                __nanosleep(200);
+                continue;
+            }
+        }
+        const uint32_t n = min(tail - head, 32u);
+        const bool have = (uint32_t)lane < n;
+        uint32_t i = 0, j = 0, n11 = 0;
+        if (have) {
+            const uint32_t slot = head + (uint32_t)lane;
+            QEntry* e = q.ring + (slot % UMMA3_QCAP);
+            while (ld_volatile_shared(&e->seq) != slot / UMMA3_QCAP + 1u) __nanosleep(32);  // reserved, not yet written
+            __threadfence_block();
+            i = e->i; j = e->j; n11 = e->n11;
+        }
+        __syncwarp();
+        head += n;
+        __threadfence_block();
+        if (lane == 0) st_volatile_shared(&q.ctrl[1], head);  // the slots may be reused
+        bool ok = have && i >= args.row_begin && i < args.row_end && j >= args.col_begin && j < args.col_end && i < M && j < M;
+        if (prm.diag) ok = ok && (i < j);
+        uint32_t c[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) c[k] = 0;
+        uint32_t mode = 0;
+        if (ok) {
+            const DevVariant vi = args.meta[i], vj = args.meta[j];
+            PairAcc<1> pa;
+            pa.v[0][0] = n11;
+            ok = pair_decide<MODE_PHASED_NOMISS>(args, prm, i, j, vi, vj, pa, c, mode);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+        if (ballot == 0) continue;
+        const int leader = __ffs(ballot) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(args.cand_count, (unsigned long long)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ok) {
+            const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1));
+            if (slot < args.cand_capacity) {
+                uint4* dst = reinterpret_cast<uint4*>(args.cands + slot);
+                dst[0] = make_uint4(i, j, c[0], c[1]);
+                dst[1] = make_uint4(c[2], c[3], 0u, 0u);
+                dst[2] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    }
+}
+
+// One 32-column chunk held in r[]. SCREEN: fast screen, flagged pairs go to the survivor queue.
+// !SCREEN (minR2 = 0, nothing can be screened out): the direct path for every chunk.
+template <bool FP4, bool SCREEN>
+__device__ __forceinline__ void umma_epilogue_chunk(const CountArgs& args, const DevParams& prm, uint32_t (&r)[32], const EpiRow& row,
+                                                    uint32_t meta_saddr, uint32_t colf_saddr, uint32_t j0, int chunk, float Tf,
+                                                    float thr, int lane, const SurvivorQueue& q) {
+    if (SCREEN) {
+        float m = __int_as_float(0xff800000);
+#pragma unroll
+        for (int c2 = 0; c2 < 16; ++c2) {
+            const float4 cb = lds_f4(colf_saddr + (uint32_t)(chunk * 32 + 2 * c2) * 8u);  // {ac_j, s_j} of two columns
+            {
+                const float n11 = FP4 ? __uint_as_float(r[2 * c2]) : (float)r[2 * c2];
+                const float pab = row.acA * cb.x;
+                const float x = fmaf(n11, Tf, -pab);
+                m = fmaxf(m, fmaf(-row.sA, cb.y, fmaf(pab, 1.0e-6f, fabsf(x))));
+            }
+            {
+                const float n11 = FP4 ? __uint_as_float(r[2 * c2 + 1]) : (float)r[2 * c2 + 1];
+                const float pab = row.acA * cb.z;
+                const float x = fmaf(n11, Tf, -pab);
+                m = fmaxf(m, fmaf(-row.sA, cb.w, fmaf(pab, 1.0e-6f, fabsf(x))));
+            }
+        }
+        if (!__any_sync(0xffffffffu, m >= -1.0f)) return;
+        // which pairs: the same margins once more, kept as a bit mask (rare path)
+        uint32_t mask = 0;
+#pragma unroll
+        for (int c2 = 0; c2 < 16; ++c2) {
+            const float4 cb = lds_f4(colf_saddr + (uint32_t)(chunk * 32 + 2 * c2) * 8u);
+            {
+                const float n11 = FP4 ? __uint_as_float(r[2 * c2]) : (float)r[2 * c2];
+                const float pab = row.acA * cb.x;
+                const float x = fmaf(n11, Tf, -pab);
+                mask |= (fmaf(-row.sA, cb.y, fmaf(pab, 1.0e-6f, fabsf(x))) >= -1.0f ? 1u : 0u) << (2 * c2);
+            }
+            {
+                const float n11 = FP4 ? __uint_as_float(r[2 * c2 + 1]) : (float)r[2 * c2 + 1];
+                const float pab = row.acA * cb.z;
+                const float x = fmaf(n11, Tf, -pab);
+                mask |= (fmaf(-row.sA, cb.w, fmaf(pab, 1.0e-6f, fabsf(x))) >= -1.0f ? 1u : 0u) << (2 * c2 + 1);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if ((mask >> c) & 1u) queue_push(q, row.i, j0 + (uint32_t)(chunk * 32 + c), FP4 ? (uint32_t)__uint_as_float(r[c]) : r[c]);
+    } else {
+        umma_direct_chunk<FP4>(args, prm, r, row, meta_saddr, j0, chunk, Tf, thr, true, lane);
+    }
+}
+
+template <bool FP4, bool SCREEN>
+__device__ __forceinline__ void umma_epilogue_loop(const CountArgs& args, const DevParams& prm, DevVariant* s_meta, float2* s_colf,
+                                                   uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint32_t tmem_base,
+                                                   uint32_t cluster_id, uint32_t n_clusters, uint32_t n_tiles, uint32_t row_off,
+                                                   uint32_t leader_cta, int warp, int lane, const SurvivorQueue& queue) {
+    constexpr uint32_t TILE_N = Umma3Cfg<FP4>::TILE_N;
+    constexpr int N_CHUNKS = (int)((TILE_N + 31) / 32);       // 8
+    constexpr int CHUNKS_PER_WARP = N_CHUNKS / (UMMA3_EPI_WARPS / 4);  // 4
+    static_assert(CHUNKS_PER_WARP % 2 == 0, "the chunk loop is unrolled by two");
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int half = (warp - 4) >> 2;       // which half of the columns
+    const int te = threadIdx.x - 128;       // 0..255: column whose metadata this thread prepares
+    const uint32_t M = prm.n_variants;
+    const float Tf = (float)(2u * prm.n_samples);
+    const float thr = (float)prm.screenR2 * (1.0f - 1.0e-5f);
+    const float thr_fast = (float)prm.screenR2 * (1.0f - 2.0e-5f);
+    const float f_inf = __int_as_float(0x7f800000);
+    const uint32_t meta_s0 = smem_u32(s_meta), colf_s0 = smem_u32(s_colf);
+
+    auto store_column = [&](uint32_t buf, uint32_t j0, DevVariant vj) {
+        const uint32_t j = j0 + (uint32_t)te;
+        s_meta[buf * 256 + te] = vj;
+        const bool j_ok = te < (int)TILE_N && j >= args.col_begin && j < args.col_end && j < M;
+        const float acB = (float)vj.ac;
+        s_colf[buf * 256 + te] = make_float2(acB, j_ok ? sqrtf(thr_fast * (acB * (Tf - acB))) : f_inf);
+    };
+    auto load_column = [&](uint32_t j0) {
+        const uint32_t j = j0 + (uint32_t)te;
+        return j < args.Mpad ? args.meta[j] : DevVariant{0, 0, 0, 0};
+    };
+
+    uint32_t t = cluster_id;
+    uint2 tile = make_uint2(0, 0);
+    DevVariant vi_cur{0, 0, 0, 0};
+    if (t < n_tiles) {
+        tile = args.tiles[t];
+        store_column(0, tile.y, load_column(tile.y));
+        vi_cur = args.meta[tile.x + row_off + 32 * q + lane];
+    }
+    for (uint32_t n = 0; t < n_tiles; t += n_clusters, ++n) {
+        const uint32_t acc = n & 1;
+        const uint32_t j0 = tile.y;
+        EpiRow row;
+        row.i = tile.x + row_off + 32 * q + lane;
+        row.vi = vi_cur;
+        row.i_ok = row.i >= args.row_begin && row.i < args.row_end && row.i < M;
+        row.acA = (float)row.vi.ac;
+        row.dA = row.acA * (Tf - row.acA);
+        row.sA = row.i_ok ? sqrtf(row.dA) : f_inf;
+        // buffer `acc` (written during the previous iteration) becomes visible; every warp is
+        // done with tile n - 1, so buffer acc ^ 1 may be rewritten below
+        epilogue_bar_sync8();
+        // metadata of the next tile: the loads stay in flight across the drain of this one
+        const uint32_t t_next = t + n_clusters;
+        const bool has_next = t_next < n_tiles;
+        uint2 tile_next = make_uint2(0, 0);
+        DevVariant vj_next{0, 0, 0, 0}, vi_next{0, 0, 0, 0};
+        if (has_next) {
+            tile_next = args.tiles[t_next];
+            vj_next = load_column(tile_next.y);
+            vi_next = args.meta[tile_next.x + row_off + 32 * q + lane];
+        }
+        mbar_wait(&tmem_full_bar[acc], (n >> 1) & 1);
+        tcgen05_fence_after();
+        if (!(args.debug_flags & 2u)) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * TILE_N;
+            const uint32_t meta_sa = meta_s0 + acc * 256u * 16u, colf_sa = colf_s0 + acc * 256u * 8u;
+            const int c_begin = half * CHUNKS_PER_WARP;
+            uint32_t r0[32], r1[32];
+            // (FP4: the last chunk reads 16 columns past the accumulator; they carry s_j = +inf)
+            tmem_ld_32x32_nowait(taddr + (uint32_t)(c_begin * 32), r0);
+            tmem_ld_wait(r0);
+#pragma unroll 1
+            for (int c = c_begin; c < c_begin + CHUNKS_PER_WARP; c += 2) {
+                tmem_ld_32x32_nowait(taddr + (uint32_t)((c + 1) * 32), r1);
+                umma_epilogue_chunk<FP4, SCREEN>(args, prm, r0, row, meta_sa, colf_sa, j0, c, Tf, thr, lane, queue);
+                tmem_ld_wait(r1);
+                if (c + 2 < c_begin + CHUNKS_PER_WARP) tmem_ld_32x32_nowait(taddr + (uint32_t)((c + 2) * 32), r0);
+                umma_epilogue_chunk<FP4, SCREEN>(args, prm, r1, row, meta_sa, colf_sa, j0, c + 1, Tf, thr, lane, queue);
+                tmem_ld_wait(r0);
+            }
+        }
+        // this warp has read everything it needs from accumulator `acc`
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_cta(&tmem_empty_bar[acc], leader_cta);
+        if (has_next) store_column(acc ^ 1u, tile_next.y, vj_next);
+        tile = tile_next;
+        vi_cur = vi_next;
+    }
+    // every push of this warp is written; tell the drain warp
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) atomicAdd(&queue.ctrl[2], 1u);
+}
+
+template <bool FP4, bool SCREEN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA3_THREADS, 1)
 count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, CountArgs args,
                    DevParams prm, uint32_t num_kblocks, uint32_t n_tiles) {
     using Cfg = Umma3Cfg<FP4>;
@@ -534,11 +909,14 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint8_t* stage_base = smem;
     DevVariant* s_meta = reinterpret_cast<DevVariant*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);  // [2][256]
     float2* s_colf = reinterpret_cast<float2*>(s_meta + 2 * 256);                                  // [2][256] {ac_j, s_j}
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_colf + 2 * 256);
+    QEntry* s_ring = reinterpret_cast<QEntry*>(s_colf + 2 * 256);                                  // [UMMA3_QCAP]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ring + UMMA3_QCAP);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2], the leader's copy is the one used
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint32_t* q_ctrl = tmem_slot + 1;              // [3] tail, head, finished producers
+    const SurvivorQueue queue{s_ring, q_ctrl};
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -554,10 +932,12 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs
+            mbar_init(&tmem_empty_bar[a], 2 * UMMA3_EPI_WARPS);  // epilogue warps of both CTAs
         }
         mbar_fence_init();
+        q_ctrl[0] = 0; q_ctrl[1] = 0; q_ctrl[2] = 0;
     }
+    for (uint32_t e = threadIdx.x; e < UMMA3_QCAP; e += blockDim.x) s_ring[e].seq = 0;
     if (warp == 2) tmem_alloc_2sm(tmem_slot, UMMA3_TMEM_COLS);
     tcgen05_fence_before();
     cluster_sync_all();
@@ -565,7 +945,7 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     if (FP4) {
         // every scale factor = UE8M0 127 = 2^0, for all 128 lanes of both CTAs
-        if (warp >= 4) tmem_fill_32x32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + Cfg::SF_COL, 0x7F7F7F7Fu);
+        if (warp >= 4 && warp < 8) tmem_fill_32x32(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + Cfg::SF_COL, 0x7F7F7F7Fu);
         tcgen05_fence_before();
         cluster_sync_all();
         tcgen05_fence_after();
@@ -627,112 +1007,10 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ================================ epilogue ================================
-        // Fast path, 5 fp32 instructions per pair: with X = n11*T - acA*acB, DA = acA(T-acA),
-        // DB = acB(T-acB) the pair can only reach R2 >= minR2 if |X| >= sqrt(minR2*DA*DB). Per
-        // row s_i = sqrt(DA) and per column s_j = sqrt(thr*DB), thr = minR2*(1-1e-12)*(1-2e-5),
-        // are precomputed; m = max_j(|X| + 1e-6*acA*acB - s_i*s_j) over the 32 columns of a
-        // chunk (the 1e-6 term and the 2e-5 relative slack dominate every fp32 rounding error
-        // of the expression, so the test is conservative). Only chunks in which some lane has
-        // m >= -1 (3 % of the chunks at R2 >= 0.1) take the exact per-column path below.
-        // Invalid rows / columns carry s = +inf (-> -inf or NaN, both ignored by fmaxf).
-        const int q = warp & 3;
-        const uint32_t M = prm.n_variants;
-        const float Tf = (float)(2u * prm.n_samples);
-        const float thr = (float)prm.screenR2 * (1.0f - 1.0e-5f);
-        const float thr_fast = (float)prm.screenR2 * (1.0f - 2.0e-5f);
-        const bool no_screen = args.screen_off || !(prm.minR2 > 0.0);
-        const int te = threadIdx.x - 128;
-        const float f_inf = __int_as_float(0x7f800000);
-        uint32_t n = 0;
-        for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters, ++n) {
-            const uint32_t acc = n & 1;
-            const uint2 tile = args.tiles[t];
-            const uint32_t i0 = tile.x, j0 = tile.y;
-            DevVariant* meta_j = s_meta + acc * 256;
-            float2* colf = s_colf + acc * 256;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int jl = te + 128 * h;
-                const uint32_t j = j0 + jl;
-                const DevVariant vj = j < args.Mpad ? args.meta[j] : DevVariant{0, 0, 0, 0};
-                meta_j[jl] = vj;
-                const bool j_ok = jl < (int)TILE_N && j >= args.col_begin && j < args.col_end && j < M;
-                const float acB = (float)vj.ac;
-                colf[jl] = make_float2(acB, j_ok ? sqrtf(thr_fast * (acB * (Tf - acB))) : f_inf);
-            }
-            const uint32_t i = i0 + 128 * rank + 32 * q + lane;
-            const DevVariant vi = args.meta[i];
-            const bool i_ok = i >= args.row_begin && i < args.row_end && i < M;
-            const float acA = (float)vi.ac;
-            const float dA = acA * (Tf - acA);
-            const float sA = i_ok ? sqrtf(dA) : f_inf;
-            epilogue_bar_sync();  // column metadata of this tile visible to the 4 epilogue warps
-            mbar_wait(&tmem_full_bar[acc], (n >> 1) & 1);
-            tcgen05_fence_after();
-#pragma unroll 1
-            for (int chunk = 0; chunk < (int)((TILE_N + 31) / 32); ++chunk) {
-                uint32_t r[32];
-                // (FP4: the last chunk reads 16 columns past the accumulator; they are ignored below)
-                tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + acc * TILE_N + (uint32_t)(chunk * 32), r);
-                if (!no_screen) {
-                    float m = -f_inf;
-                    const float4* cf4 = reinterpret_cast<const float4*>(colf + chunk * 32);
-#pragma unroll
-                    for (int c2 = 0; c2 < 16; ++c2) {
-                        const float4 cb = cf4[c2];  // {ac_j, s_j} of two columns
-                        {
-                            const float n11 = FP4 ? __uint_as_float(r[2 * c2]) : (float)r[2 * c2];
-                            const float pab = acA * cb.x;
-                            const float x = fmaf(n11, Tf, -pab);
-                            m = fmaxf(m, fmaf(-sA, cb.y, fmaf(pab, 1.0e-6f, fabsf(x))));
-                        }
-                        {
-                            const float n11 = FP4 ? __uint_as_float(r[2 * c2 + 1]) : (float)r[2 * c2 + 1];
-                            const float pab = acA * cb.z;
-                            const float x = fmaf(n11, Tf, -pab);
-                            m = fmaxf(m, fmaf(-sA, cb.w, fmaf(pab, 1.0e-6f, fabsf(x))));
-                        }
-                    }
-                    if (!__any_sync(0xffffffffu, m >= -1.0f)) continue;
-                }
-                uint32_t passmask = 0;
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int jl = chunk * 32 + c;
-                    const uint32_t j = j0 + jl;
-                    const DevVariant vj = meta_j[jl];
-                    bool pass = i_ok && j >= args.col_begin && j < args.col_end && j < M && (!prm.diag || i < j) && (vi.ac + vj.ac > 2);
-                    if (TILE_N % 32 != 0) pass = pass && (jl < (int)TILE_N);
-                    if (!no_screen) {
-                        const float n11 = FP4 ? __uint_as_float(r[c]) : (float)r[c];
-                        const float acB = (float)vj.ac;
-                        const float pab = acA * acB;
-                        const float x = fabsf(fmaf(n11, Tf, -pab));
-                        const float slack = 4.0f + 4.0e-7f * fmaxf(n11 * Tf, pab);
-                        const float lhs = (x + slack) * (x + slack);
-                        const float rhs = thr * (dA * (acB * (Tf - acB)));
-                        pass = pass && (lhs >= rhs);
-                    }
-                    passmask |= (pass ? 1u : 0u) << c;
-                }
-                const uint32_t colmask = __reduce_or_sync(0xffffffffu, passmask);
-                if (colmask) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        if ((colmask >> c) & 1u) {
-                            PairAcc<1> pa;
-                            pa.v[0][0] = FP4 ? (uint32_t)__uint_as_float(r[c]) : r[c];
-                            emit_pair<MODE_PHASED_NOMISS>(args, prm, i, j0 + chunk * 32 + c, vi, pa, lane, (passmask >> c) & 1u);
-                        }
-                    }
-                }
-            }
-            // this warp has read everything it needs from accumulator `acc`
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
-        }
+        umma_epilogue_loop<FP4, SCREEN>(args, prm, s_meta, s_colf, tmem_full_bar, tmem_empty_bar, tmem_base, cluster_id, n_clusters, n_tiles,
+                                128u * rank, 0u, warp, lane, queue);
+    } else if (warp == 3) {
+        umma_drain_loop(args, prm, queue, lane);
     }
     tcgen05_fence_before();
     cluster_sync_all();
@@ -865,12 +1143,12 @@ inline int umma_prepare(UmmaOperand& op, bool fp4, const uint64_t* d_rows, size_
     return 0;
 }
 
-template <bool FP4>
+template <bool FP4, bool SCREEN>
 inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
     static bool configured = false;
     static int n_sm = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(count_umma3_kernel<FP4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(count_umma3_kernel<FP4, SCREEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Umma3Cfg<FP4>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -879,13 +1157,20 @@ inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const De
         configured = true;
     }
     const uint32_t n_clusters = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, n_sm / 2));
-    count_umma3_kernel<FP4><<<2 * n_clusters, UMMA_THREADS, Umma3Cfg<FP4>::SMEM_BYTES, stream>>>(
+    count_umma3_kernel<FP4, SCREEN><<<2 * n_clusters, UMMA3_THREADS, Umma3Cfg<FP4>::SMEM_BYTES, stream>>>(
         op.tmap, op.tmap_b, args, prm, op.Kbytes / UMMA_BLOCK_K, n_tiles);
     return cudaGetLastError();
 }
 
 inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
-    if (umma_cta_group() == 3) return op.fp4 ? umma3_launch<true>(op, args, prm, n_tiles, stream) : umma3_launch<false>(op, args, prm, n_tiles, stream);
+    if (umma_cta_group() == 3)
+    {
+        // the instantiation with the fast screen + survivor queue, or (minR2 = 0 / screen off:
+        // every pair is a candidate) the one that compacts every chunk directly
+        const bool screen = !args.screen_off && prm.minR2 > 0.0;
+        if (op.fp4) return screen ? umma3_launch<true, true>(op, args, prm, n_tiles, stream) : umma3_launch<true, false>(op, args, prm, n_tiles, stream);
+        return screen ? umma3_launch<false, true>(op, args, prm, n_tiles, stream) : umma3_launch<false, false>(op, args, prm, n_tiles, stream);
+    }
     if (umma_cta_group() == 2) {
         static bool configured2 = false;
         if (!configured2) {
