@@ -133,10 +133,11 @@ def test_phased_vs_oracle(name, skw, prm, kernel):
     (dict(n_samples=500, n_variants=300, seed=52), dict(forced_unphased=1, minR2=0.0)),
     (dict(n_samples=37, n_variants=200, seed=53, missing_rate=0.3), dict(forced_unphased=1, minR2=0.2)),
 ])
-def test_unphased_vs_oracle(skw, prm):
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_unphased_vs_oracle(skw, prm, kernel):
     s = tf.synth_genotypes(**skw)
     ref, visited = lc.calc(s, lc.default_params(**prm))
-    eng, got, st = gpu_run(s, prm)
+    eng, got, st = gpu_run(s, prm, kernel)
     assert st.pairs_visited == visited
     check_unphased(s, got, ref, prm)
     eng.close()
@@ -191,6 +192,49 @@ def test_tensor_and_popc_kernels_agree_bit_for_bit():
         e.close()
     for k in out:
         assert np.array_equal(out[tb.KERNEL_POPC].view(np.uint8), out[k].view(np.uint8)), k
+
+
+PLANES_CASES = [
+    # masked phased 2x2 (2 operand rows per variant), unphased 3x3 without / with missing (2 / 3 rows)
+    ("phased_miss", dict(n_samples=1024, n_variants=1300, seed=72, missing_rate=0.07), dict(force_phased=1, minR2=0.02)),
+    ("phased_miss_all", dict(n_samples=640, n_variants=333, seed=73, missing_rate=0.2), dict(force_phased=1, minR2=0.0)),
+    ("unphased_nomiss", dict(n_samples=1000, n_variants=1100, seed=74), dict(forced_unphased=1, minR2=0.05)),
+    ("unphased_miss", dict(n_samples=1250, n_variants=1000, seed=75, missing_rate=0.05), dict(forced_unphased=1, minR2=0.1)),
+    ("unphased_miss_all", dict(n_samples=77, n_variants=250, seed=76, missing_rate=0.3), dict(forced_unphased=1, minR2=0.0)),
+    ("unphased_window", dict(n_samples=300, n_variants=2100, seed=77, missing_rate=0.05), dict(forced_unphased=1, minR2=0.1, window=1, l_window=30000)),
+    ("auto_mixed", dict(n_samples=60, n_variants=900, seed=78, missing_rate=0.01), dict(minR2=0.05)),  # ~half the variants complete
+]
+
+
+@pytest.mark.parametrize("name,skw,prm", PLANES_CASES, ids=[c[0] for c in PLANES_CASES])
+def test_planes_tensor_kernels_agree_with_popc_bit_for_bit(name, skw, prm):
+    """Masked-phased and unphased tables on the tensor pipe (NP operand rows per variant, e2m1)
+    must give the very bytes of the LOP3+POPC kernel: same counts -> same candidates -> same records."""
+    s = tf.synth_genotypes(**skw)
+    out, used = {}, {}
+    for k in (tb.KERNEL_POPC, tb.KERNEL_AUTO):
+        e, r, st = gpu_run(s, prm, k)
+        out[k], used[k] = tf.canonical(r, False), st.kernel_used
+        e.close()
+    assert used[tb.KERNEL_POPC] == tb.KERNEL_POPC
+    assert used[tb.KERNEL_AUTO] == tb.KERNEL_UMMA_FP4
+    assert len(out[tb.KERNEL_POPC]) > 0
+    assert np.array_equal(out[tb.KERNEL_POPC].view(np.uint8), out[tb.KERNEL_AUTO].view(np.uint8))
+
+
+def test_planes_tensor_parts_union_equals_whole():
+    s = tf.synth_genotypes(400, 700, seed=79, missing_rate=0.05)
+    prm = dict(forced_unphased=1, minR2=0.05)
+    e, whole, _ = gpu_run(s, prm, tb.KERNEL_AUTO)
+    e.close()
+    parts = []
+    for r in range(3):
+        e, got, st = gpu_run(s, prm, tb.KERNEL_AUTO, part_index=r, part_count=3)
+        assert st.kernel_used == tb.KERNEL_UMMA_FP4
+        parts.append(got)
+        e.close()
+    union = tf.canonical(np.concatenate(parts), False)
+    assert np.array_equal(union.view(np.uint8), tf.canonical(whole, False).view(np.uint8))
 
 
 def _dense_matrix(n_samples, n_variants, seed, chain=False):

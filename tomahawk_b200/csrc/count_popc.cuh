@@ -168,10 +168,10 @@ __device__ __forceinline__ bool pair_decide(const CountArgs& args, const DevPara
 }
 
 // Per-pair epilogue: pair rules of the reference, exact table, screen, compaction.
-// Called convergently by all 32 lanes of a warp.
+// Called convergently by all 32 lanes of a warp; vj is only read by lanes with pre_ok.
 template <int MODE>
-__device__ __noinline__ void emit_pair(const CountArgs& args, const DevParams& prm, uint32_t i, uint32_t j,
-                                       DevVariant vi, PairAcc<PopcCfg<MODE>::NP> pa, int lane, bool pre_ok = true) {
+__device__ __forceinline__ void emit_pair_with(const CountArgs& args, const DevParams& prm, uint32_t i, uint32_t j, const DevVariant& vi,
+                                               const DevVariant& vj, const PairAcc<PopcCfg<MODE>::NP>& pa, int lane, bool pre_ok) {
     const uint32_t M = prm.n_variants;
     bool ok = pre_ok && i >= args.row_begin && i < args.row_end && j >= args.col_begin && j < args.col_end && i < M && j < M;
     if (prm.diag) ok = ok && (i < j);
@@ -179,10 +179,7 @@ __device__ __noinline__ void emit_pair(const CountArgs& args, const DevParams& p
 #pragma unroll
     for (int k = 0; k < 9; ++k) c[k] = 0;
     uint32_t mode = 0;
-    if (ok) {
-        const DevVariant vj = args.meta[j];
-        ok = pair_decide<MODE>(args, prm, i, j, vi, vj, pa, c, mode);
-    }
+    if (ok) ok = pair_decide<MODE>(args, prm, i, j, vi, vj, pa, c, mode);
     const unsigned ballot = __ballot_sync(0xffffffffu, ok);
     if (ballot == 0) return;
     const int leader = __ffs(ballot) - 1;
@@ -198,6 +195,16 @@ __device__ __noinline__ void emit_pair(const CountArgs& args, const DevParams& p
             dst[2] = make_uint4(c[6], c[7], c[8], mode);
         }
     }
+}
+
+template <int MODE>
+__device__ __noinline__ void emit_pair(const CountArgs& args, const DevParams& prm, uint32_t i, uint32_t j,
+                                       DevVariant vi, PairAcc<PopcCfg<MODE>::NP> pa, int lane, bool pre_ok = true) {
+    const uint32_t M = prm.n_variants;
+    const bool in = pre_ok && i < M && j < M;
+    DevVariant vj{0, 0, 0, 0};
+    if (in) vj = args.meta[j];
+    emit_pair_with<MODE>(args, prm, i, j, vi, vj, pa, lane, in);
 }
 
 template <int MODE>

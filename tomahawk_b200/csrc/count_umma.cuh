@@ -54,6 +54,9 @@ struct UmmaOperand {
     bool fp4 = false;            // e2m1 nibbles instead of int8 bytes
     CUtensorMap tmap;            // box 128 B x 128 rows (A, and B of the int8 kernels)
     CUtensorMap tmap_b;          // box 128 B x B rows of the persistent kernel
+    int mode = 0;                // CountMode the operand was built for (planes kernels: 1..3)
+    uint8_t* d_bytes_b = nullptr;  // planes kernels: the plane-major B copy [RB][Kbytes]
+    size_t capacity_b = 0;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -897,7 +900,245 @@ __device__ __forceinline__ void umma_epilogue_loop(const CountArgs& args, const 
     if (lane == 0) atomicAdd(&queue.ctrl[2], 1u);
 }
 
-template <bool FP4, bool SCREEN>
+// ---- multi-plane tables on the tensor pipe (masked phased 2x2, unphased 3x3) ----------------
+// The NP^2 joint plane counts of a pair (count_popc.cuh: PopcCfg<MODE>::NP planes per variant) are
+// NP^2 entries of the SAME product A.B^T when every variant contributes NP operand rows, one per
+// plane ([alt&valid; valid], [het; hom], [het&valid; hom&valid; valid] -- SURVEY.md 8d "GEMM view").
+// The MMA pipeline is the e2m1 persistent kernel unchanged (256 x 240 tiles); only the row order of
+// the two operand copies and the epilogue differ:
+//   A copy: 32-row groups of G = 32/NP variants, row = 32*(v/G) + NP*(v%G) + plane (NP = 3 leaves two
+//           zero rows per group), so the NP accumulator rows of a variant are NP adjacent TMEM
+//           lanes of one warp: a tile holds TI = 8*G variants (128 / 80);
+//   B copy: plane-major per tile of NV = 240/NP variants, row = 240*(v/NV) + NV*plane + v%NV, so a
+//           thread reads the NP column planes of 8 consecutive variants with NP tcgen05.ld.x8.
+// Epilogue: lane (variant vl, plane pa) gathers the NP x NP table of (vl, column c) with NP^2 warp
+// shuffles per column; the lane with pa == c % NP runs the exact per-pair rules + fp64 screen of
+// the POPC kernel (pair_decide) and survivors are appended with one atomic per warp ballot. The
+// tensor work per pair is NP^2 times that of the 1-plane kernel, so this epilogue is hidden.
+template <int MODE>
+struct PlanesCfg {
+    static constexpr int NP = PopcCfg<MODE>::NP;
+    static constexpr uint32_t G = 32u / (NP > 0 ? NP : 1);
+    static constexpr uint32_t TI = 8u * G;
+    static constexpr uint32_t NV = 240u / (NP > 0 ? NP : 1);
+    static constexpr uint32_t TJ = NV;
+    static constexpr int CW = 8;
+    static constexpr int N_CHUNKS = (int)(NV / CW);
+    static_assert(NV % CW == 0, "column chunks");
+};
+
+__device__ __forceinline__ void tmem_ld_32x32_x8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
+
+// x[pl] for a lane-constant pl (NP - 1 selects; the register indices stay static)
+template <int NP>
+__device__ __forceinline__ uint32_t sel_by_lane(uint32_t pl, const uint32_t (&x)[NP]) {
+    if (NP == 2) return pl ? x[1] : x[0];
+    return pl == 0 ? x[0] : (pl == 1 ? x[1] : x[NP - 1]);
+}
+
+// Conservative fp32 form of the exact fp64 screens of count_popc.cuh (screen_phased /
+// screen_unphased), division free: every quantity is scaled by T^2 (phased) or (2T)^2 (unphased),
+// the operands are integers < 2^25 and every rounding error (<= 2^-24 relative per operation) is
+// covered by the explicit slack terms, so a pair the exact screen keeps is always flagged. Flagged
+// pairs (~0.5 % at R2 >= 0.1) then take the exact path.
+template <int MODE>
+__device__ __forceinline__ bool planes_fast_screen(const PairAcc<PopcCfg<MODE>::NP>& pa, uint32_t n_samples, uint32_t hetA, uint32_t homA,
+                                                   uint32_t hetB, uint32_t homB, float thr) {
+    constexpr int NP = PopcCfg<MODE>::NP;
+    if (MODE == MODE_PHASED_MISS) {
+        const float n11 = (float)pa.v[0][0], nA = (float)pa.v[0][1], nB = (float)pa.v[1][0], nV = (float)pa.v[1][1];
+        const float p1 = n11 * nV, p2 = nA * nB;
+        const float x = fabsf(p1 - p2) + (2.5e-7f * (p1 + p2) + 1.0f);
+        const float den = (nA * (nV - nA)) * (nB * (nV - nB));  // nV - nA: exact integers
+        return (x * x) * (1.0f + 1.0e-5f) >= thr * den;
+    } else {
+        uint32_t hA, oA, hB, oB, vv;
+        if (MODE == MODE_UNPHASED_NOMISS) { hA = hetA; oA = homA; hB = hetB; oB = homB; vv = n_samples; }
+        else { hA = pa.v[0][NP - 1]; oA = pa.v[1 % NP][NP - 1]; hB = pa.v[NP - 1][0]; oB = pa.v[NP - 1][1 % NP]; vv = pa.v[NP - 1][NP - 1]; }
+        const uint32_t c11 = pa.v[0][0], c12 = pa.v[0][1 % NP], c21 = pa.v[1 % NP][0], c22 = pa.v[1 % NP][1 % NP];
+        // t0 = both 0/0, t1 = (0/0, het), t3 = (het, 0/0), t4 = (het, het); n11 = 2 t0 + t1 + t3
+        const uint32_t t0 = vv - hA - oA - hB - oB + c11 + c12 + c21 + c22;
+        const uint32_t t1 = hB - c11 - c21, t3 = hA - c11 - c12;
+        const uint32_t n11 = 2u * t0 + t1 + t3;
+        const uint32_t S = 2u * vv;
+        const uint32_t a = S - hA - 2u * oA, c = S - hB - 2u * oB;  // 2T * P, 2T * Q
+        const float Sf = (float)S, af = (float)a, cf = (float)c;
+        const float pq = af * cf, eps = 1.0e-5f * (Sf * Sf);
+        const float l1 = (float)n11 * Sf, h1 = (float)(n11 + c11) * Sf;
+        const float lo = (l1 - pq) - eps, hi = (h1 - pq) + eps;
+        const float dmax = fmaxf(fabsf(lo), fabsf(hi)) + (2.5e-7f * (h1 + pq) + 3.0e-12f * (Sf * Sf) + 1.0f);
+        const float den = (af * (float)(S - a)) * (cf * (float)(S - c));
+        return (dmax * dmax) * (1.0f + 1.0e-5f) >= thr * den;
+    }
+}
+
+// Exact path of one round: kept out of line (long fp64 code, rarely taken).
+template <int MODE>
+__device__ __noinline__ void umma_planes_exact(const CountArgs& args, const DevParams& prm, uint32_t i, uint32_t j, DevVariant vi,
+                                               DevVariant vj, PairAcc<PopcCfg<MODE>::NP> pa, int lane, bool active) {
+    emit_pair_with<MODE>(args, prm, i, j, vi, vj, pa, lane, active);
+}
+
+template <int MODE>
+__device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args, const DevParams& prm, DevVariant* s_meta, uint2* s_colx,
+                                                          uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint32_t tmem_base,
+                                                          uint32_t cluster_id, uint32_t n_clusters, uint32_t n_tiles, uint32_t rank,
+                                                          uint32_t leader_cta, int warp, int lane) {
+    using PC = PlanesCfg<MODE>;
+    constexpr int NP = PC::NP;
+    constexpr int CW = PC::CW;
+    constexpr int ROUNDS = (CW + NP - 1) / NP;
+    constexpr uint32_t TILE_N = 240u;
+    const int q = warp & 3;            // TMEM lane quarter
+    const int half = (warp - 4) >> 2;  // which half of the column chunks
+    const int te = threadIdx.x - 128;  // 0..255: column whose metadata this thread stages
+    const uint32_t vl = (uint32_t)lane / NP, pl = (uint32_t)lane % NP;
+    const bool lane_ok = vl < PC::G;
+    const int base_lane = lane - (int)pl;
+    const uint32_t meta_s0 = smem_u32(s_meta);
+    const int c_begin = half ? (PC::N_CHUNKS + 1) / 2 : 0;
+    const int c_end = half ? PC::N_CHUNKS : (PC::N_CHUNKS + 1) / 2;
+    const bool no_screen = args.screen_off || !(prm.minR2 > 0.0);
+    const float thr = (float)prm.minR2 * (1.0f - 1.0e-5f);
+    const uint32_t* pp = args.plane_popc;
+
+    struct Col { DevVariant v; uint2 x; };
+    auto load_column = [&](uint32_t j0) {
+        const uint32_t j = j0 + (uint32_t)te;
+        Col c{DevVariant{0, 0, 0, 0}, make_uint2(0, 0)};
+        if (te < (int)PC::NV && j < args.Mpad) {
+            c.v = args.meta[j];
+            if (MODE == MODE_UNPHASED_NOMISS) c.x = make_uint2(pp[j], pp[args.Mpad + j]);
+        }
+        return c;
+    };
+    auto store_column = [&](uint32_t buf, const Col& c) {
+        s_meta[buf * 256u + te] = c.v;
+        if (MODE == MODE_UNPHASED_NOMISS) s_colx[buf * 256u + te] = c.x;
+    };
+    struct Row { DevVariant v; uint32_t het, hom; };
+    auto load_row = [&](uint32_t i0) {
+        const uint32_t i = i0 + (4u * rank + (uint32_t)q) * PC::G + vl;
+        Row r{DevVariant{0, 0, 0, 0}, 0, 0};
+        if (lane_ok && i < args.Mpad) {
+            r.v = args.meta[i];
+            if (MODE == MODE_UNPHASED_NOMISS) { r.het = pp[i]; r.hom = pp[args.Mpad + i]; }
+        }
+        return r;
+    };
+
+    uint32_t t = cluster_id;
+    uint2 tile = make_uint2(0, 0);
+    Row row_cur{DevVariant{0, 0, 0, 0}, 0, 0};
+    if (t < n_tiles) {
+        tile = args.tiles[t];
+        store_column(0, load_column(tile.y));
+        row_cur = load_row(tile.x);
+    }
+    for (uint32_t n = 0; t < n_tiles; t += n_clusters, ++n) {
+        const uint32_t acc = n & 1;
+        const uint32_t j0 = tile.y;
+        const uint32_t i = tile.x + (4u * rank + (uint32_t)q) * PC::G + vl;
+        const Row row = row_cur;
+        epilogue_bar_sync8();  // metadata buffer `acc` visible; buffer acc ^ 1 free
+        const uint32_t t_next = t + n_clusters;
+        const bool has_next = t_next < n_tiles;
+        uint2 tile_next = make_uint2(0, 0);
+        Col col_next{DevVariant{0, 0, 0, 0}, make_uint2(0, 0)};
+        Row row_next{DevVariant{0, 0, 0, 0}, 0, 0};
+        if (has_next) {
+            tile_next = args.tiles[t_next];
+            col_next = load_column(tile_next.y);
+            row_next = load_row(tile_next.x);
+        }
+        mbar_wait(&tmem_full_bar[acc], (n >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * TILE_N;
+        const uint32_t meta_sa = meta_s0 + acc * 256u * 16u;
+        const uint2* colx = s_colx + acc * 256u;
+        uint32_t r[NP][CW], rn[NP][CW];
+#pragma unroll
+        for (int pb = 0; pb < NP; ++pb) tmem_ld_32x32_x8_nowait(taddr + (uint32_t)pb * PC::NV + (uint32_t)(c_begin * CW), r[pb]);
+#pragma unroll 1
+        for (int ch = c_begin; ch < c_end; ++ch) {
+#pragma unroll
+            for (int pb = 0; pb < NP; ++pb) tmem_ld_wait8(r[pb]);
+            if (ch + 1 < c_end) {  // next chunk in flight while this one is screened
+#pragma unroll
+                for (int pb = 0; pb < NP; ++pb) tmem_ld_32x32_x8_nowait(taddr + (uint32_t)pb * PC::NV + (uint32_t)((ch + 1) * CW), rn[pb]);
+            }
+#pragma unroll
+            for (int g = 0; g < ROUNDS; ++g) {
+                // lane (vl, pl) takes column NP*g + pl: step s moves, from the lane holding plane row
+                // a = (pl + s) % NP of this variant, its NP column-plane values of that column
+                uint32_t recv[NP][NP];
+#pragma unroll
+                for (int sft = 0; sft < NP; ++sft) {
+#pragma unroll
+                    for (int b = 0; b < NP; ++b) {
+                        uint32_t cand[NP];  // what this lane sends to destination plane-lane d = (pl - sft) mod NP
+#pragma unroll
+                        for (int d = 0; d < NP; ++d) {
+                            const int col = NP * g + d;
+                            cand[(d + sft) % NP] = r[b][col < CW ? col : CW - 1];
+                        }
+                        const uint32_t send = sel_by_lane<NP>(pl, cand);
+                        recv[sft][b] = __shfl_sync(0xffffffffu, send, base_lane + (int)((pl + (uint32_t)sft) % NP));
+                    }
+                }
+                PairAcc<NP> pa;
+#pragma unroll
+                for (int a = 0; a < NP; ++a) {
+#pragma unroll
+                    for (int b = 0; b < NP; ++b) {
+                        uint32_t cand[NP];  // recv[(a - pl) mod NP][b]
+#pragma unroll
+                        for (int d = 0; d < NP; ++d) cand[d] = recv[(a - d + NP) % NP][b];
+                        pa.v[a][b] = (uint32_t)__uint_as_float(sel_by_lane<NP>(pl, cand));
+                    }
+                }
+                const uint32_t cl = (uint32_t)(NP * g) + pl;  // column of this lane inside the chunk
+                const bool active = lane_ok && cl < (uint32_t)CW;
+                const uint32_t jl = (uint32_t)(ch * CW) + (active ? cl : 0u);
+                bool flag = active;
+                if (!no_screen) {
+                    uint2 cx = make_uint2(0, 0);
+                    if (MODE == MODE_UNPHASED_NOMISS) cx = colx[jl];
+                    flag = active && planes_fast_screen<MODE>(pa, prm.n_samples, row.het, row.hom, cx.x, cx.y, thr);
+                }
+                if (__any_sync(0xffffffffu, flag)) {
+                    const DevVariant vj = lds_variant(meta_sa + jl * 16u);
+                    umma_planes_exact<MODE>(args, prm, i, j0 + jl, row.v, vj, pa, lane, flag);
+                }
+            }
+            if (ch + 1 < c_end) {
+#pragma unroll
+                for (int pb = 0; pb < NP; ++pb)
+#pragma unroll
+                    for (int c = 0; c < CW; ++c) r[pb][c] = rn[pb][c];
+            }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote_cta(&tmem_empty_bar[acc], leader_cta);
+        if (has_next) store_column(acc ^ 1u, col_next);
+        tile = tile_next;
+        row_cur = row_next;
+    }
+}
+
+template <bool FP4, bool SCREEN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA3_THREADS, 1)
 count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, CountArgs args,
                    DevParams prm, uint32_t num_kblocks, uint32_t n_tiles) {
@@ -969,8 +1210,11 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         }
                     }
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
-                    tma_load_2d_2sm(sA, &tmap_a, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(tile.x + 128 * rank));
-                    tma_load_2d_2sm(sB, &tmap_b, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(tile.y + Cfg::B_ROWS * rank));
+                    // operand rows of this CTA's halves of the tile (planes: the re-ordered copies)
+                    const uint32_t a_row = MODE == MODE_PHASED_NOMISS ? tile.x : (tile.x / PlanesCfg<MODE>::TI) * 256u;
+                    const uint32_t b_row = MODE == MODE_PHASED_NOMISS ? tile.y : (tile.y / PlanesCfg<MODE>::TJ) * 240u;
+                    tma_load_2d_2sm(sA, &tmap_a, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(a_row + 128 * rank));
+                    tma_load_2d_2sm(sB, &tmap_b, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(b_row + Cfg::B_ROWS * rank));
                 }
             }
         }
@@ -1007,10 +1251,14 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        umma_epilogue_loop<FP4, SCREEN>(args, prm, s_meta, s_colf, tmem_full_bar, tmem_empty_bar, tmem_base, cluster_id, n_clusters, n_tiles,
-                                128u * rank, 0u, warp, lane, queue);
+        if constexpr (MODE == MODE_PHASED_NOMISS)
+            umma_epilogue_loop<FP4, SCREEN>(args, prm, s_meta, s_colf, tmem_full_bar, tmem_empty_bar, tmem_base, cluster_id, n_clusters,
+                                            n_tiles, 128u * rank, 0u, warp, lane, queue);
+        else
+            umma_planes_epilogue_loop<MODE>(args, prm, s_meta, reinterpret_cast<uint2*>(s_colf), tmem_full_bar, tmem_empty_bar, tmem_base,
+                                            cluster_id, n_clusters, n_tiles, rank, 0u, warp, lane);
     } else if (warp == 3) {
-        umma_drain_loop(args, prm, queue, lane);
+        if constexpr (MODE == MODE_PHASED_NOMISS) umma_drain_loop(args, prm, queue, lane);
     }
     tcgen05_fence_before();
     cluster_sync_all();
@@ -1105,8 +1353,9 @@ static inline int umma_encode_map(CUtensorMap* map, uint8_t* base, uint32_t Kbyt
 // Builds (once per matrix and encoding) the expanded operand and its tensor maps.
 inline int umma_prepare(UmmaOperand& op, bool fp4, const uint64_t* d_rows, size_t stride64, uint32_t n_variants, uint32_t Mpad,
                         uint32_t n_samples, cudaStream_t stream, std::string& err, uint64_t* launches) {
-    if (op.valid && op.fp4 == fp4) return 0;
+    if (op.valid && op.fp4 == fp4 && op.mode == 0) return 0;
     op.valid = false;
+    op.mode = 0;
     const uint32_t n_bits = 2 * n_samples;
     // one pipeline stage = 128 bytes of K = 128 int8 or 256 e2m1 elements
     const uint32_t k_per_stage = fp4 ? 2 * UMMA_BLOCK_K : UMMA_BLOCK_K;
@@ -1143,12 +1392,104 @@ inline int umma_prepare(UmmaOperand& op, bool fp4, const uint64_t* d_rows, size_
     return 0;
 }
 
-template <bool FP4, bool SCREEN>
+// e2m1 operand copies of the planes kernels from the word-major bit planes plane[p][k][v]
+// (pack.cuh): word k of plane p of variant v -> 32 nibbles at byte 16k of the variant's rows
+// in the A order (32-row groups) and in the B order (plane-major tiles); see PlanesCfg.
+template <int NP>
+__global__ void expand_planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, uint32_t K32, uint32_t Mpad, uint32_t n_variants,
+                                             uint8_t* __restrict__ outA, uint8_t* __restrict__ outB, uint32_t Kbytes) {
+    constexpr uint32_t G = 32u / NP, NV = 240u / NP;
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = blockIdx.y;
+    if (v >= n_variants || k >= K32) return;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const uint32_t x = planes[((size_t)p * K32 + k) * Mpad + v];
+        uint32_t b[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            uint32_t y = (x >> (8 * r)) & 0xFFu;  // bit t -> nibble t, 1 -> 0x2 (e2m1 1.0)
+            y = (y | (y << 12)) & 0x000F000Fu;
+            y = (y | (y << 6)) & 0x03030303u;
+            y = (y | (y << 3)) & 0x11111111u;
+            b[r] = y << 1;
+        }
+        const uint4 val = make_uint4(b[0], b[1], b[2], b[3]);
+        const size_t rowA = (size_t)(v / G) * 32u + (v % G) * NP + p;
+        const size_t rowB = (size_t)(v / NV) * 240u + (size_t)p * NV + (v % NV);
+        *reinterpret_cast<uint4*>(outA + rowA * Kbytes + (size_t)k * 16u) = val;
+        *reinterpret_cast<uint4*>(outB + rowB * Kbytes + (size_t)k * 16u) = val;
+    }
+}
+
+inline void planes_tile(int mode, uint32_t& TI, uint32_t& TJ) {
+    const uint32_t np = mode == MODE_UNPHASED_MISS ? 3u : 2u;
+    TI = 8u * (32u / np);
+    TJ = 240u / np;
+}
+
+// Builds (once per matrix and mode) the two e2m1 operand copies of a planes kernel.
+inline int umma_prepare_planes(UmmaOperand& op, int mode, const uint32_t* d_planes, uint32_t K32, uint32_t Mpad, uint32_t n_variants,
+                               cudaStream_t stream, std::string& err, uint64_t* launches) {
+    if (op.valid && op.mode == mode) return 0;
+    op.valid = false;
+    uint32_t TI, TJ;
+    planes_tile(mode, TI, TJ);
+    const uint32_t Kbytes = K32 * 16u;  // K32 is a multiple of 16 words -> whole 128-byte K blocks
+    const size_t rowsA = (size_t)((n_variants + TI - 1) / TI) * 256u, rowsB = (size_t)((n_variants + TJ - 1) / TJ) * 240u;
+    const size_t needA = rowsA * Kbytes, needB = rowsB * Kbytes;
+    auto grow = [&](uint8_t*& ptr, size_t& cap, size_t need) -> bool {
+        if (cap >= need) return true;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        if (cudaMalloc((void**)&ptr, need) != cudaSuccess) return false;
+        cap = need;
+        return true;
+    };
+    if (!grow(op.d_bytes, op.capacity, needA) || !grow(op.d_bytes_b, op.capacity_b, needB)) {
+        err = std::string("cudaMalloc(tensor-core plane operands): ") + cudaGetErrorString(cudaGetLastError());
+        return -3;
+    }
+    cudaMemsetAsync(op.d_bytes, 0, needA, stream);
+    cudaMemsetAsync(op.d_bytes_b, 0, needB, stream);
+    dim3 grid((n_variants + 127) / 128, K32), block(128);
+    if (mode == MODE_UNPHASED_MISS)
+        expand_planes_to_e2m1_kernel<3><<<grid, block, 0, stream>>>(d_planes, K32, Mpad, n_variants, op.d_bytes, op.d_bytes_b, Kbytes);
+    else
+        expand_planes_to_e2m1_kernel<2><<<grid, block, 0, stream>>>(d_planes, K32, Mpad, n_variants, op.d_bytes, op.d_bytes_b, Kbytes);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("expand planes kernel: ") + cudaGetErrorString(e); return -3; }
+    if (launches) *launches += 3;
+    op.Kbytes = Kbytes;
+    op.Kelems = 2 * Kbytes;
+    op.Mpad = Mpad;
+    op.fp4 = true;
+    op.mode = mode;
+    PFN_tmapEncodeTiled enc = get_tmap_encoder();
+    if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return -3; }
+    auto encode = [&](CUtensorMap* map, uint8_t* base, size_t rows, uint32_t box_rows) -> bool {
+        cuuint64_t gdim[2] = {Kbytes, rows};
+        cuuint64_t gstride[1] = {Kbytes};
+        cuuint32_t box[2] = {UMMA_BLOCK_K, box_rows};
+        cuuint32_t estr[2] = {1, 1};
+        return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!encode(&op.tmap, op.d_bytes, rowsA, 128) || !encode(&op.tmap_b, op.d_bytes_b, rowsB, Umma3Cfg<true>::B_ROWS)) {
+        err = "cuTensorMapEncodeTiled failed (plane operands)";
+        return -3;
+    }
+    op.valid = true;
+    return 0;
+}
+
+template <bool FP4, bool SCREEN, int MODE>
 inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
     static bool configured = false;
     static int n_sm = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(count_umma3_kernel<FP4, SCREEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(count_umma3_kernel<FP4, SCREEN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Umma3Cfg<FP4>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         int dev = 0;
@@ -1157,7 +1498,7 @@ inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const De
         configured = true;
     }
     const uint32_t n_clusters = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, n_sm / 2));
-    count_umma3_kernel<FP4, SCREEN><<<2 * n_clusters, UMMA3_THREADS, Umma3Cfg<FP4>::SMEM_BYTES, stream>>>(
+    count_umma3_kernel<FP4, SCREEN, MODE><<<2 * n_clusters, UMMA3_THREADS, Umma3Cfg<FP4>::SMEM_BYTES, stream>>>(
         op.tmap, op.tmap_b, args, prm, op.Kbytes / UMMA_BLOCK_K, n_tiles);
     return cudaGetLastError();
 }
@@ -1168,8 +1509,12 @@ inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const Dev
         // the instantiation with the fast screen + survivor queue, or (minR2 = 0 / screen off:
         // every pair is a candidate) the one that compacts every chunk directly
         const bool screen = !args.screen_off && prm.minR2 > 0.0;
-        if (op.fp4) return screen ? umma3_launch<true, true>(op, args, prm, n_tiles, stream) : umma3_launch<true, false>(op, args, prm, n_tiles, stream);
-        return screen ? umma3_launch<false, true>(op, args, prm, n_tiles, stream) : umma3_launch<false, false>(op, args, prm, n_tiles, stream);
+        if (op.mode == MODE_PHASED_MISS) return umma3_launch<true, false, MODE_PHASED_MISS>(op, args, prm, n_tiles, stream);
+        if (op.mode == MODE_UNPHASED_NOMISS) return umma3_launch<true, false, MODE_UNPHASED_NOMISS>(op, args, prm, n_tiles, stream);
+        if (op.mode == MODE_UNPHASED_MISS) return umma3_launch<true, false, MODE_UNPHASED_MISS>(op, args, prm, n_tiles, stream);
+        if (op.fp4)
+            return screen ? umma3_launch<true, true, 0>(op, args, prm, n_tiles, stream) : umma3_launch<true, false, 0>(op, args, prm, n_tiles, stream);
+        return screen ? umma3_launch<false, true, 0>(op, args, prm, n_tiles, stream) : umma3_launch<false, false, 0>(op, args, prm, n_tiles, stream);
     }
     if (umma_cta_group() == 2) {
         static bool configured2 = false;
@@ -1193,8 +1538,9 @@ inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const Dev
 
 inline void umma_release(UmmaOperand& op) {
     if (op.d_bytes) cudaFree(op.d_bytes);
-    op.d_bytes = nullptr;
-    op.capacity = 0;
+    if (op.d_bytes_b) cudaFree(op.d_bytes_b);
+    op.d_bytes = op.d_bytes_b = nullptr;
+    op.capacity = op.capacity_b = 0;
     op.valid = false;
 }
 

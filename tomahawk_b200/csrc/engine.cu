@@ -461,13 +461,22 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_fil
                     twkb_sink_fn sink, void* user, std::vector<Candidate>* dump) {
     int rc = ensure_planes(ctx, mode);
     if (rc) return rc;
+    // Kernel choice. Tensor pipe (tcgen05) whenever the counts of the mode are a 0/1 contraction
+    // whose fp32 accumulation is exact (2N < 2^24): 1 plane -> count_umma3_kernel<.,.,0>, masked
+    // phased / unphased tables -> the planes variants (NP operand rows per variant). The LOP3+POPC
+    // kernel serves explicit requests, the candidate dump of the tests, and 2N >= 2^24 with masks.
     bool use_umma = false, use_fp4 = false;
-    if (mode == MODE_PHASED_NOMISS && ctx->st.kernel != TWKB_KERNEL_POPC && !dump) use_umma = umma_supported();
+    const bool planes_mode = mode != MODE_PHASED_NOMISS;
+    if (ctx->st.kernel != TWKB_KERNEL_POPC && !dump && umma_supported()) {
+        if (!planes_mode) use_umma = true;
+        else use_umma = ctx->st.kernel != TWKB_KERNEL_UMMA && umma_fp4_possible(ctx->n_samples) && !getenv("TWKB_PLANES_POPC");
+    }
     if ((ctx->st.kernel == TWKB_KERNEL_UMMA || ctx->st.kernel == TWKB_KERNEL_UMMA_FP4) && !use_umma && !dump) {
-        ctx->err = "tensor-core kernel requested but it only serves phased data without missing genotypes";
+        ctx->err = planes_mode ? "the int8 tensor-core kernel only serves phased data without missing genotypes (use AUTO or UMMA_FP4)"
+                               : "tensor-core kernel requested but unavailable";
         return TWKB_EINVAL;
     }
-    if (use_umma) {
+    if (use_umma && !planes_mode) {
         // operand encoding: e2m1 (kind::mxf4, 2x the MAC rate of int8) whenever its fp32
         // accumulation is exact (2N < 2^24), int8 otherwise or on request
         use_fp4 = ctx->st.kernel != TWKB_KERNEL_UMMA && umma_fp4_possible(ctx->n_samples);
@@ -479,11 +488,17 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_fil
             return TWKB_EINVAL;
         }
     }
+    if (use_umma && planes_mode) use_fp4 = true;
     uint32_t TI, TJ;
-    tile_dims(mode, use_umma, use_fp4, TI, TJ);
+    if (use_umma && planes_mode) planes_tile(mode, TI, TJ);
+    else tile_dims(mode, use_umma, use_fp4, TI, TJ);
     if (use_umma) {
-        rc = umma_prepare(ctx->umma, use_fp4, ctx->d_raw_data.p, ctx->raw_stride, ctx->n_variants, ctx->Mpad, ctx->n_samples,
-                          ctx->stream, ctx->err, &ctx->stats.other_launches);
+        if (planes_mode)
+            rc = umma_prepare_planes(ctx->umma, mode, ctx->d_planes.p, ctx->K32, ctx->Mpad, ctx->n_variants, ctx->stream, ctx->err,
+                                     &ctx->stats.other_launches);
+        else
+            rc = umma_prepare(ctx->umma, use_fp4, ctx->d_raw_data.p, ctx->raw_stride, ctx->n_variants, ctx->Mpad, ctx->n_samples,
+                              ctx->stream, ctx->err, &ctx->stats.other_launches);
         if (rc) return rc;
     }
     // The tile plan depends only on the sub-problem, the tile shape, the window and the
@@ -569,7 +584,7 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_fil
             batch = std::max<uint64_t>(1, nb / 2);
             continue;
         }
-        if (use_umma) ctx->stats.mma_macs += (uint64_t)nb * tile_pairs * ctx->umma.Kelems;
+        if (use_umma) ctx->stats.mma_macs += (uint64_t)nb * (planes_mode ? 256ull * 240ull : tile_pairs) * ctx->umma.Kelems;
         else ctx->stats.word_ops += (uint64_t)nb * tile_pairs * ctx->K32 * ctx->np * ctx->np;
         ctx->stats.pairs_screened += ncand;
         t += nb;
