@@ -207,6 +207,7 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- workload: weak scaling keeps pairs per GPU constant => M grows with sqrt(N)
