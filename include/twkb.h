@@ -81,7 +81,13 @@ typedef struct twkb_settings {
     int32_t kernel;          /* TWKB_KERNEL_*                                     */
     int32_t twk_block_size;  /* .twk block length that defines window-mode tiles
                                 (500, lib/importer.h:36)                          */
-    int32_t reserved[5];
+    int32_t sparse_max_words; /* rare-variant (list) path: a variant whose haplotype row has at
+                                most this many non-zero 32-bit words is kept as a word list
+                                and served by the sparse kernel (reference: twk_igt_list +
+                                PhasedListVector). 0 = automatic (ceil(2N/32)/64 when
+                                2N >= 32768, phased data without missing genotypes, no -c
+                                chunking), > 0 explicit, < 0 never                       */
+    int32_t reserved[4];
 } twkb_settings;
 
 /* Subset of twk1_t (include/core.h:291-295) the LD path reads. */
@@ -115,6 +121,10 @@ typedef struct twkb_stats {
     uint64_t mma_macs;        /* int8 multiply-accumulates issued (UMMA kernel)        */
     double ms_device_total;   /* CUDA-event time from the first launch of the call to
                                  the completion of its last kernel / copy             */
+    uint64_t sparse_variants; /* variants served by the list (sparse) kernel           */
+    uint64_t sparse_launches; /* sparse-kernel launches                                */
+    uint64_t sparse_word_ops; /* AND+POPC word operations issued by the sparse kernel  */
+    double ms_sparse_kernel;  /* CUDA-event time summed over sparse-kernel launches    */
 } twkb_stats;
 
 /* Receives `n` packed 106-byte records (forward orientation: A is the variant

@@ -291,6 +291,81 @@ def test_e2m1_accumulation_exact_on_dense_data(n_samples, n_variants, minR2, ker
     assert np.array_equal(r["cnt"][sel][:, 3], n11[ia[sel], ib[sel]].astype(np.float64))
 
 
+# ------------------------------------------------------------ rare-variant (list) kernel
+def _cands_sorted(eng):
+    c = eng.debug_candidates(True)
+    return c[np.lexsort((c["j"], c["i"]))]
+
+
+@pytest.mark.parametrize("T", [3, 12, 10_000])
+def test_sparse_kernel_counts_bit_exact_all_pairs(T):
+    """Variants with <= T non-zero words go through the list kernel (count_sparse.cuh), the rest
+    through the dense kernels on the [dense | sparse]-ordered resident matrix: every pair exactly
+    once, oriented by file order, with the very counts of the all-dense run."""
+    s = tf.synth_genotypes(1500, 900, seed=91, rare_fraction=0.7)
+    e0, _, _ = gpu_run(s, dict(force_phased=1, minR2=0.5), sparse_max_words=-1)
+    e1, _, st = gpu_run(s, dict(force_phased=1, minR2=0.5), sparse_max_words=T)
+    assert st.sparse_variants > 100 and st.sparse_launches > 0
+    if T >= 10_000:
+        assert st.sparse_variants == s.n_variants   # everything sparse: no dense phase at all
+    else:
+        assert st.sparse_variants < s.n_variants
+    a, b = _cands_sorted(e0), _cands_sorted(e1)
+    assert len(a) == len(b)
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    e0.close(); e1.close()
+
+
+SPARSE_CASES = [
+    ("r2_002", dict(n_samples=2504, n_variants=2300, seed=92, rare_fraction=0.8), dict(force_phased=1, minR2=0.02), 20),
+    ("r2_0_all_pairs", dict(n_samples=700, n_variants=500, seed=93, rare_fraction=0.6), dict(force_phased=1, minR2=0.0), 5),
+    ("window", dict(n_samples=900, n_variants=3100, seed=94, rare_fraction=0.8), dict(force_phased=1, minR2=0.05, window=1, l_window=40000), 6),
+    ("auto_mode_complete_data", dict(n_samples=1000, n_variants=1200, seed=95, rare_fraction=0.5), dict(minR2=0.05), 6),
+]
+
+
+@pytest.mark.parametrize("name,skw,prm,T", SPARSE_CASES, ids=[c[0] for c in SPARSE_CASES])
+def test_sparse_path_records_identical_to_dense(name, skw, prm, T):
+    s = tf.synth_genotypes(**skw)
+    e, ref, st0 = gpu_run(s, prm, tb.KERNEL_POPC, sparse_max_words=-1)
+    e.close()
+    e, got, st = gpu_run(s, prm, tb.KERNEL_AUTO, sparse_max_words=T)
+    e.close()
+    assert st.sparse_variants > 0.1 * s.n_variants and st.sparse_word_ops > 0
+    assert st.kernel_used == tb.KERNEL_UMMA_FP4          # dense x dense stays on the tensor pipe
+    assert st.pairs_visited == st0.pairs_visited
+    assert len(ref) > 0
+    assert np.array_equal(tf.canonical(got, False).view(np.uint8), tf.canonical(ref, False).view(np.uint8))
+
+
+def test_sparse_path_parts_union_equals_whole():
+    s = tf.synth_genotypes(800, 2600, seed=96, rare_fraction=0.75)
+    prm = dict(force_phased=1, minR2=0.05)
+    e, whole, st = gpu_run(s, prm, tb.KERNEL_POPC, sparse_max_words=-1)
+    e.close()
+    chunks, visited = [], 0
+    for r in range(3):
+        e, recs, stp = gpu_run(s, prm, tb.KERNEL_AUTO, sparse_max_words=6, part_index=r, part_count=3)
+        assert stp.sparse_variants > 0
+        chunks.append(recs)
+        visited += stp.pairs_visited
+        e.close()
+    assert visited == st.pairs_visited
+    allr = np.concatenate(chunks)
+    assert len(keyset(allr)) == len(allr)
+    assert np.array_equal(tf.canonical(allr, False).view(np.uint8), tf.canonical(whole, False).view(np.uint8))
+
+
+def test_sparse_path_rejects_mode_change_without_reload():
+    s = tf.synth_genotypes(300, 400, seed=97, rare_fraction=0.8)
+    e, _, st = gpu_run(s, dict(force_phased=1, minR2=0.1), tb.KERNEL_AUTO, sparse_max_words=4)
+    assert st.sparse_variants > 0
+    e.update(force_phased=0, forced_unphased=1)
+    with pytest.raises(tb.TwkbError):
+        e.compute()
+    e.close()
+
+
 # ----------------------------------------------------------- multi-part = whole (no GPU-GPU traffic)
 @pytest.mark.parametrize("parts", [2, 3])
 def test_parts_union_equals_whole(parts):

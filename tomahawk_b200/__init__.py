@@ -47,7 +47,8 @@ class Settings(ctypes.Structure):
         ("minP", ctypes.c_double), ("minR2", ctypes.c_double), ("maxR2", ctypes.c_double),
         ("minDprime", ctypes.c_double), ("maxDprime", ctypes.c_double),
         ("device", ctypes.c_int32), ("part_index", ctypes.c_int32), ("part_count", ctypes.c_int32),
-        ("kernel", ctypes.c_int32), ("twk_block_size", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5),
+        ("kernel", ctypes.c_int32), ("twk_block_size", ctypes.c_int32), ("sparse_max_words", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 4),
     ]
 
 
@@ -59,6 +60,8 @@ class Stats(ctypes.Structure):
         ("ms_h2d", ctypes.c_double), ("bytes_h2d", ctypes.c_uint64), ("bytes_d2h", ctypes.c_uint64),
         ("kernel_used", ctypes.c_int32), ("n_planes", ctypes.c_int32), ("word_ops", ctypes.c_uint64),
         ("mma_macs", ctypes.c_uint64), ("ms_device_total", ctypes.c_double),
+        ("sparse_variants", ctypes.c_uint64), ("sparse_launches", ctypes.c_uint64), ("sparse_word_ops", ctypes.c_uint64),
+        ("ms_sparse_kernel", ctypes.c_double),
     ]
 
     def as_dict(self):

@@ -16,6 +16,7 @@
 #include "../../include/twkb.h"
 #include "common.cuh"
 #include "count_popc.cuh"
+#include "count_sparse.cuh"
 #include "count_umma.cuh"
 #include "hostio.h"
 #include "pack.cuh"
@@ -81,6 +82,24 @@ struct Context {
     uint32_t lgamma_len = 0;
     std::vector<twkb_variant> h_meta;
     UmmaOperand umma;  // int8-expanded operand of the tensor-core kernel
+
+    // Rare-variant (list) class. When active the resident matrix is ordered
+    // [dense variants | sparse variants], both in file order; every index the kernels see is a
+    // resident index, h_orig maps it back to the file order that orients a pair (A = lower).
+    bool permuted = false;
+    uint32_t nD = 0, nS = 0, sparse_T = 0;
+    std::vector<uint32_t> h_orig;            // resident -> original index (identity when !permuted)
+    std::vector<twkb_variant> h_meta_orig;   // metadata in file order (block structure, visited pairs)
+    DevBuf<uint32_t> d_orig, d_sp_off;
+    DevBuf<uint2> d_sp_ent;
+    uint64_t sp_entries = 0;
+    std::vector<uint2> sp_plan_tiles;
+    uint64_t sp_plan_pairs = 0;
+    std::string sp_plan_key;
+    DevBuf<uint2> d_sp_tiles;
+    double est_cand_per_sp_tile = -1.0;
+    std::vector<uint32_t> h_sp_off;               // [nS + 1] CSR offsets
+    std::vector<uint64_t> sp_tile_words_prefix;   // prefix sum of word operations per sparse tile
 
     // window-mode block structure
     DevBuf<uint32_t> d_blk_of, d_blk_first, d_blk_last, d_blk_prune;
@@ -204,15 +223,16 @@ static int ensure_planes(Context* ctx, int mode) {
 // ld_balancing.h:189-196.
 static int build_blocks(Context* ctx) {
     const uint32_t M = ctx->n_variants;
+    const std::vector<twkb_variant>& mo = ctx->h_meta_orig;  // blocks are defined on the file order
     const uint32_t bs = ctx->st.twk_block_size > 0 ? (uint32_t)ctx->st.twk_block_size : 500u;
-    std::vector<uint32_t> blk_of(ctx->Mpad, 0);
+    std::vector<uint32_t> blk_of_orig(M, 0);
     ctx->h_blk_first.clear();
     ctx->h_blk_last.clear();
     for (uint32_t v = 0; v < M;) {
         uint32_t e = v + 1;
-        while (e < M && e - v < bs && ctx->h_meta[e].rid == ctx->h_meta[v].rid) ++e;
+        while (e < M && e - v < bs && mo[e].rid == mo[v].rid) ++e;
         const uint32_t b = (uint32_t)ctx->h_blk_first.size();
-        for (uint32_t x = v; x < e; ++x) blk_of[x] = b;
+        for (uint32_t x = v; x < e; ++x) blk_of_orig[x] = b;
         ctx->h_blk_first.push_back(v);
         ctx->h_blk_last.push_back(e - 1);
         v = e;
@@ -221,21 +241,27 @@ static int build_blocks(Context* ctx) {
     const uint32_t w = (uint32_t)ctx->st.l_window;
     ctx->h_blk_prune.assign(nb, nb);
     for (uint32_t bi = 0; bi < nb; ++bi) {
-        const uint32_t last_pos = ctx->h_meta[ctx->h_blk_last[bi]].pos;
+        const uint32_t last_pos = mo[ctx->h_blk_last[bi]].pos;
         for (uint32_t bj = bi + 1; bj < nb; ++bj) {
-            if ((uint32_t)(ctx->h_meta[ctx->h_blk_first[bj]].pos - last_pos) > w) {
+            if ((uint32_t)(mo[ctx->h_blk_first[bj]].pos - last_pos) > w) {
                 ctx->h_blk_prune[bi] = bj;
                 break;
             }
         }
     }
+    // device copies in resident indices (identical to the file order unless the matrix is
+    // ordered [dense | sparse])
+    std::vector<uint32_t> inv(M), blk_of(ctx->Mpad, 0), d_first(nb), d_last(nb);
+    for (uint32_t x = 0; x < M; ++x) inv[ctx->h_orig[x]] = x;
+    for (uint32_t x = 0; x < M; ++x) blk_of[x] = blk_of_orig[ctx->h_orig[x]];
+    for (uint32_t b = 0; b < nb; ++b) { d_first[b] = inv[ctx->h_blk_first[b]]; d_last[b] = inv[ctx->h_blk_last[b]]; }
     CUDA_TRY(ctx->d_blk_of.alloc(ctx->Mpad));
     CUDA_TRY(ctx->d_blk_first.alloc(nb));
     CUDA_TRY(ctx->d_blk_last.alloc(nb));
     CUDA_TRY(ctx->d_blk_prune.alloc(nb));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_of.p, blk_of.data(), ctx->Mpad * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_first.p, ctx->h_blk_first.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_last.p, ctx->h_blk_last.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_first.p, d_first.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_last.p, d_last.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_blk_prune.p, ctx->h_blk_prune.data(), nb * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return TWKB_OK;
@@ -252,10 +278,10 @@ static uint64_t visited_pairs(const Context* ctx, const Problem& pb) {
     const uint32_t w = (uint32_t)ctx->st.l_window;
     for (uint32_t bi = 0; bi < nb; ++bi) {
         const uint64_t ni = ctx->h_blk_last[bi] - ctx->h_blk_first[bi] + 1;
-        const twkb_variant& vf = ctx->h_meta[ctx->h_blk_first[bi]];
+        const twkb_variant& vf = ctx->h_meta_orig[ctx->h_blk_first[bi]];
         for (uint32_t bj = bi; bj < ctx->h_blk_prune[bi] || bj == bi; ++bj) {
             if (bj >= nb) break;
-            const twkb_variant& vl = ctx->h_meta[ctx->h_blk_last[bj]];
+            const twkb_variant& vl = ctx->h_meta_orig[ctx->h_blk_last[bj]];
             const bool aborted = vf.rid == vl.rid && (uint32_t)(vl.pos - vf.pos) > w;
             if (!aborted) {
                 const uint64_t nj = ctx->h_blk_last[bj] - ctx->h_blk_first[bj] + 1;
@@ -373,6 +399,51 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
     if (pairs_out) *pairs_out = pairs;
 }
 
+// Tiles of the sparse kernel (count_sparse.cuh): SP_ROWS sparse rows x SP_TJ columns, covering every
+// pair with a sparse member exactly once -- sparse row r with every dense column (resident index
+// < nD) and every LATER sparse column. Window mode drops tiles whose column parts are all out of
+// reach of all rows (both classes keep the file order, so first/last bound the positions).
+static void build_sparse_tiles(const Context* ctx, std::vector<uint2>& tiles, uint64_t* pairs_out) {
+    tiles.clear();
+    const uint32_t M = ctx->n_variants, nD = ctx->nD;
+    const bool window = ctx->st.window;
+    const uint32_t w = (uint32_t)ctx->st.l_window;
+    const int parts = std::max(1, ctx->st.part_count), part = ctx->st.part_index;
+    uint64_t group = 0, pairs = 0;
+    for (uint32_t r0 = nD; r0 < M; r0 += SP_ROWS) {
+        const uint32_t r1 = std::min<uint32_t>(r0 + SP_ROWS, M);
+        const twkb_variant &a0 = ctx->h_meta[r0], &a1 = ctx->h_meta[r1 - 1];
+        for (uint32_t j0 = 0; j0 < M; j0 += SP_TJ) {
+            const uint32_t j1 = std::min<uint32_t>(j0 + SP_TJ, M);
+            const uint32_t da = j0, db = std::min(j1, nD);        // dense columns of the tile
+            const uint32_t sa = std::max(j0, r0 + 1), sb = j1;   // sparse columns later than the first row
+            const bool has_d = da < db, has_s = sa < sb;
+            if (!has_d && !has_s) continue;
+            if (window) {
+                auto far = [&](uint32_t ca, uint32_t cb) {
+                    const twkb_variant &b0 = ctx->h_meta[ca], &b1 = ctx->h_meta[cb - 1];
+                    if (!(a0.rid == a1.rid && b0.rid == b1.rid && a0.rid == b0.rid)) return false;
+                    if (b0.pos >= a1.pos && (uint32_t)(b0.pos - a1.pos) > w) return true;
+                    if (a0.pos >= b1.pos && (uint32_t)(a0.pos - b1.pos) > w) return true;
+                    return false;
+                };
+                if ((!has_d || far(da, db)) && (!has_s || far(sa, sb))) continue;
+            }
+            if ((group % parts) == (uint64_t)part) {
+                tiles.push_back(make_uint2(r0, j0));
+                uint64_t n = has_d ? (uint64_t)(r1 - r0) * (db - da) : 0;
+                for (uint32_t r = r0; r < r1; ++r) {
+                    const uint32_t lo = std::max(j0, r + 1);
+                    if (lo < j1) n += j1 - lo;
+                }
+                pairs += n;
+            }
+            ++group;
+        }
+    }
+    if (pairs_out) *pairs_out = pairs;
+}
+
 template <int MODE>
 static cudaError_t launch_popc(Context* ctx, const CountArgs& args, const DevParams& prm, uint32_t n_tiles) {
     static bool configured = false;
@@ -454,11 +525,104 @@ static int flush_records(Context* ctx, uint64_t n_records, twkb_sink_fn sink, vo
     return TWKB_OK;
 }
 
+// Batch loop shared by the dense and the sparse phase of a pass: launches `launch(t, nb)` over
+// the tile list in batches the candidate buffer can hold (retry with fewer tiles on overflow),
+// runs the statistics kernel on the survivors of every batch and drains the record buffer.
+struct BatchPlan {
+    size_t n_tiles = 0;
+    uint64_t tile_pairs = 0;      // pairs per tile (worst-case candidates)
+    bool no_screen = false;
+    bool sparse = false;
+    double* est_cand_per_tile = nullptr;
+};
+template <typename LaunchFn, typename AccountFn>
+static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, LaunchFn launch, AccountFn account, bool resident,
+                       twkb_sink_fn sink, void* user, std::vector<Candidate>* dump, uint64_t& rec_on_device) {
+    // Batch size: the candidate buffer must hold a whole batch. Start from the
+    // worst case when nothing can be screened out, else optimistic and adapt.
+    uint64_t batch = bp.no_screen ? std::max<uint64_t>(1, ctx->cand_cap / bp.tile_pairs)
+                                  : std::max<uint64_t>(1, ctx->cand_cap / bp.tile_pairs * 64);
+    if (!bp.no_screen && *bp.est_cand_per_tile >= 0.0)  // the previous run over this matrix measured the survivor rate
+        batch = std::max<uint64_t>(batch, (uint64_t)(0.25 * ctx->cand_cap / std::max(1.0, *bp.est_cand_per_tile)));
+    if (const char* e = getenv("TWKB_BATCH_TILES")) batch = std::max<uint64_t>(1, (uint64_t)atoll(e));
+    int rc = TWKB_OK;
+    size_t t = 0;
+    while (t < bp.n_tiles) {
+        const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, bp.n_tiles - t);
+        CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        CUDA_TRY(launch(t, nb));
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (bp.sparse) { ctx->stats.ms_sparse_kernel += ms; ctx->stats.sparse_launches += 1; }
+        else { ctx->stats.ms_count_kernel += ms; ctx->stats.count_launches += 1; }
+        const uint64_t ncand = ctx->h_counters[0];
+        if (ncand > ctx->cand_cap) {  // overflow: redo this batch with fewer tiles
+            if (nb == 1) { ctx->err = "candidate buffer smaller than one tile"; return TWKB_ENOMEM; }
+            batch = std::max<uint64_t>(1, nb / 2);
+            continue;
+        }
+        account(t, nb);
+        ctx->stats.pairs_screened += ncand;
+        t += nb;
+        if (dump) {
+            const size_t old = dump->size();
+            dump->resize(old + ncand);
+            CUDA_TRY(cudaMemcpy(dump->data() + old, ctx->d_cands.p, ncand * sizeof(Candidate), cudaMemcpyDeviceToHost));
+            continue;
+        }
+        if (ncand) {
+            if (rec_on_device + ncand > ctx->rec_cap) {
+                if (!resident) {
+                    rc = flush_records(ctx, rec_on_device, sink, user);
+                    if (rc) return rc;
+                }
+                ctx->stats.records_out += rec_on_device;
+                rec_on_device = 0;
+                CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p + 1, 0, sizeof(unsigned long long), ctx->stream));
+            }
+            CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
+            stats_kernel<<<(unsigned)((ncand + 127) / 128), 128, 0, ctx->stream>>>(
+                ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm, ctx->d_lgamma.p, ctx->d_records.p, ctx->rec_cap,
+                ctx->d_counters.p + 1);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_counters + 1, ctx->d_counters.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
+            ctx->stats.ms_stats_kernel += ms;
+            ctx->stats.stats_launches += 1;
+            rec_on_device = ctx->h_counters[1];
+        }
+        // adapt: aim for a half-full candidate buffer
+        if (!bp.no_screen && !getenv("TWKB_BATCH_TILES")) {
+            const double per_tile = std::max(1.0, (double)ncand / nb);
+            batch = std::max<uint64_t>(1, (uint64_t)(0.5 * ctx->cand_cap / per_tile));
+            *bp.est_cand_per_tile = std::max(*bp.est_cand_per_tile, per_tile);
+        }
+    }
+    return TWKB_OK;
+}
+
 // One pass over a sub-problem with the planes of `mode`.
 // pair_filter: 0 = all pairs, 1 = only pairs with no missing variant, 2 = only pairs with one
 // (auto mode passes; see compute()).
-static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_filter, bool resident, bool screen_off,
+static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_filter, bool resident, bool screen_off,
                     twkb_sink_fn sink, void* user, std::vector<Candidate>* dump) {
+    // Rare-variant class active: the dense kernels see the [0, nD) x [0, nD) triangle only, the
+    // sparse kernel every pair with a sparse member (second phase below).
+    const bool sparse_phase = ctx->permuted && ctx->nS > 0;
+    if (sparse_phase && (mode != MODE_PHASED_NOMISS || ctx->st.n_chunks != 1)) {
+        ctx->err = "the resident matrix is ordered [dense | sparse] for the rare-variant path (sparse_max_words); "
+                   "reload it to run unphased / chunked (-c) computations";
+        return TWKB_ESTATE;
+    }
+    Problem pb = pb_in;
+    if (sparse_phase) pb = Problem{0, ctx->nD, 0, ctx->nD, true};
+    const uint32_t n_dense = sparse_phase ? ctx->nD : ctx->n_variants;
     int rc = ensure_planes(ctx, mode);
     if (rc) return rc;
     // Kernel choice. Tensor pipe (tcgen05) whenever the counts of the mode are a 0/1 contraction
@@ -492,13 +656,13 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_fil
     uint32_t TI, TJ;
     if (use_umma && planes_mode) planes_tile(mode, TI, TJ);
     else tile_dims(mode, use_umma, use_fp4, TI, TJ);
-    if (use_umma) {
+    if (use_umma && n_dense >= 2) {
         if (planes_mode)
             rc = umma_prepare_planes(ctx->umma, mode, ctx->d_planes.p, ctx->K32, ctx->Mpad, ctx->n_variants, ctx->stream, ctx->err,
                                      &ctx->stats.other_launches);
-        else
-            rc = umma_prepare(ctx->umma, use_fp4, ctx->d_raw_data.p, ctx->raw_stride, ctx->n_variants, ctx->Mpad, ctx->n_samples,
-                              ctx->stream, ctx->err, &ctx->stats.other_launches);
+        else  // only the dense variants are expanded: the operand is nD rows, not M
+            rc = umma_prepare(ctx->umma, use_fp4, ctx->d_raw_data.p, ctx->raw_stride, n_dense, (n_dense + 255) / 256 * 256,
+                              ctx->n_samples, ctx->stream, ctx->err, &ctx->stats.other_launches);
         if (rc) return rc;
     }
     // The tile plan depends only on the sub-problem, the tile shape, the window and the
@@ -510,7 +674,8 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_fil
     if (ctx->plan_key != keybuf) {
         uint32_t super = 16u;  // super-tile edge (in tiles) of the L2-friendly order
         if (const char* e = getenv("TWKB_SUPER")) super = (uint32_t)std::max(1, atoi(e));
-        build_tiles(ctx, pb, TI, TJ, super, ctx->plan_tiles, &ctx->plan_pairs);
+        if (n_dense >= 2) build_tiles(ctx, pb, TI, TJ, super, ctx->plan_tiles, &ctx->plan_pairs);
+        else { ctx->plan_tiles.clear(); ctx->plan_pairs = 0; }
         CUDA_TRY(ctx->d_tiles.alloc(std::max<size_t>(ctx->plan_tiles.size(), 1)));
         if (!ctx->plan_tiles.empty())
             CUDA_TRY(cudaMemcpyAsync(ctx->d_tiles.p, ctx->plan_tiles.data(), ctx->plan_tiles.size() * sizeof(uint2),
@@ -518,14 +683,35 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_fil
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         ctx->plan_key = keybuf;
     }
+    if (sparse_phase) {
+        std::snprintf(keybuf, sizeof(keybuf), "%llu|w%d:%d:%d|p%d/%d", (unsigned long long)ctx->matrix_epoch, (int)ctx->st.window,
+                      ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
+        if (ctx->sp_plan_key != keybuf) {
+            build_sparse_tiles(ctx, ctx->sp_plan_tiles, &ctx->sp_plan_pairs);
+            ctx->sp_tile_words_prefix.assign(ctx->sp_plan_tiles.size() + 1, 0);
+            for (size_t i = 0; i < ctx->sp_plan_tiles.size(); ++i) {
+                const uint2 tl = ctx->sp_plan_tiles[i];
+                const uint32_t s0 = tl.x - ctx->nD, s1 = std::min<uint32_t>(s0 + SP_ROWS, ctx->nS);
+                const uint64_t cols = std::min<uint32_t>(tl.y + SP_TJ, ctx->n_variants) - tl.y;
+                ctx->sp_tile_words_prefix[i + 1] = ctx->sp_tile_words_prefix[i] + (uint64_t)(ctx->h_sp_off[s1] - ctx->h_sp_off[s0]) * cols;
+            }
+            CUDA_TRY(ctx->d_sp_tiles.alloc(std::max<size_t>(ctx->sp_plan_tiles.size(), 1)));
+            if (!ctx->sp_plan_tiles.empty())
+                CUDA_TRY(cudaMemcpyAsync(ctx->d_sp_tiles.p, ctx->sp_plan_tiles.data(), ctx->sp_plan_tiles.size() * sizeof(uint2),
+                                         cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            ctx->sp_plan_key = keybuf;
+        }
+    }
     const std::vector<uint2>& tiles = ctx->plan_tiles;
-    if (ctx->st.part_count > 1 && !ctx->st.window) ctx->stats.pairs_visited = ctx->plan_pairs;
+    if (ctx->st.part_count > 1 && !ctx->st.window) ctx->stats.pairs_visited = ctx->plan_pairs + (sparse_phase ? ctx->sp_plan_pairs : 0);
     ctx->stats.kernel_used = use_umma ? (use_fp4 ? TWKB_KERNEL_UMMA_FP4 : TWKB_KERNEL_UMMA) : TWKB_KERNEL_POPC;
     ctx->stats.n_planes = ctx->np;
+    ctx->stats.sparse_variants = sparse_phase ? ctx->nS : 0;
     const uint64_t tile_pairs = (uint64_t)TI * TJ;
-    rc = ensure_work_buffers(ctx, tile_pairs);
+    rc = ensure_work_buffers(ctx, std::max<uint64_t>(tile_pairs, (uint64_t)SP_ROWS * SP_TJ));
     if (rc) return rc;
-    if (tiles.empty()) return TWKB_OK;
+    if (tiles.empty() && !(sparse_phase && !ctx->sp_plan_tiles.empty())) return TWKB_OK;
 
     DevParams prm = make_params(ctx, pb);
     prm.pair_filter = pair_filter;
@@ -544,85 +730,59 @@ static int run_pass(Context* ctx, const Problem& pb, int mode, uint32_t pair_fil
     args.screen_off = screen_off ? 1u : 0u;
     if (const char* e = getenv("TWKB_DEBUG_FLAGS")) args.debug_flags = (uint32_t)atoi(e);
 
-    // Batch size: the candidate buffer must hold a whole batch. Start from the
-    // worst case when nothing can be screened out, else optimistic and adapt.
     const bool no_screen = screen_off || !(ctx->st.minR2 > 0.0);
-    uint64_t batch = no_screen ? std::max<uint64_t>(1, ctx->cand_cap / tile_pairs) : std::max<uint64_t>(1, ctx->cand_cap / tile_pairs * 64);
-    if (!no_screen && ctx->est_cand_per_tile >= 0.0)  // the previous run over this matrix measured the survivor rate
-        batch = std::max<uint64_t>(batch, (uint64_t)(0.25 * ctx->cand_cap / std::max(1.0, ctx->est_cand_per_tile)));
-    if (const char* e = getenv("TWKB_BATCH_TILES")) batch = std::max<uint64_t>(1, (uint64_t)atoll(e));
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     uint64_t rec_on_device = 0;
-    size_t t = 0;
-    while (t < tiles.size()) {
-        const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, tiles.size() - t);
-        CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(unsigned long long), ctx->stream));
-        args.tiles = ctx->d_tiles.p + t;
-        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-        cudaError_t le;
-        if (use_umma) {
-            le = umma_launch(ctx->umma, args, prm, nb, ctx->stream);
-        } else {
+
+    // ---- phase 1: dense x dense tiles
+    if (!tiles.empty()) {
+        BatchPlan bp;
+        bp.n_tiles = tiles.size();
+        bp.tile_pairs = tile_pairs;
+        bp.no_screen = no_screen;
+        bp.est_cand_per_tile = &ctx->est_cand_per_tile;
+        auto launch = [&](size_t t, uint32_t nb) -> cudaError_t {
+            args.tiles = ctx->d_tiles.p + t;
+            if (use_umma) return umma_launch(ctx->umma, args, prm, nb, ctx->stream);
             switch (mode) {
-                case MODE_PHASED_NOMISS: le = launch_popc<0>(ctx, args, prm, nb); break;
-                case MODE_PHASED_MISS: le = launch_popc<1>(ctx, args, prm, nb); break;
-                case MODE_UNPHASED_NOMISS: le = launch_popc<2>(ctx, args, prm, nb); break;
-                default: le = launch_popc<3>(ctx, args, prm, nb); break;
+                case MODE_PHASED_NOMISS: return launch_popc<0>(ctx, args, prm, nb);
+                case MODE_PHASED_MISS: return launch_popc<1>(ctx, args, prm, nb);
+                case MODE_UNPHASED_NOMISS: return launch_popc<2>(ctx, args, prm, nb);
+                default: return launch_popc<3>(ctx, args, prm, nb);
             }
-        }
-        CUDA_TRY(le);
-        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        ctx->stats.ms_count_kernel += ms;
-        ctx->stats.count_launches += 1;
-        const uint64_t ncand = ctx->h_counters[0];
-        if (ncand > ctx->cand_cap) {  // overflow: redo this batch with fewer tiles
-            if (nb == 1) { ctx->err = "candidate buffer smaller than one tile"; return TWKB_ENOMEM; }
-            batch = std::max<uint64_t>(1, nb / 2);
-            continue;
-        }
-        if (use_umma) ctx->stats.mma_macs += (uint64_t)nb * (planes_mode ? 256ull * 240ull : tile_pairs) * ctx->umma.Kelems;
-        else ctx->stats.word_ops += (uint64_t)nb * tile_pairs * ctx->K32 * ctx->np * ctx->np;
-        ctx->stats.pairs_screened += ncand;
-        t += nb;
-        if (dump) {
-            const size_t old = dump->size();
-            dump->resize(old + ncand);
-            CUDA_TRY(cudaMemcpy(dump->data() + old, ctx->d_cands.p, ncand * sizeof(Candidate), cudaMemcpyDeviceToHost));
-            continue;
-        }
-        if (ncand) {
-            if (rec_on_device + ncand > ctx->rec_cap) {
-                if (!resident) {
-                    rc = flush_records(ctx, rec_on_device, sink, user);
-                    if (rc) return rc;
-                }
-                ctx->stats.records_out += rec_on_device;
-                rec_on_device = 0;
-                CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p + 1, 0, sizeof(unsigned long long), ctx->stream));
-            }
-            CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
-            stats_kernel<<<(unsigned)((ncand + 127) / 128), 128, 0, ctx->stream>>>(
-                ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm, ctx->d_lgamma.p, ctx->d_records.p, ctx->rec_cap,
-                ctx->d_counters.p + 1);
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
-            CUDA_TRY(cudaMemcpyAsync(ctx->h_counters + 1, ctx->d_counters.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
-            ctx->stats.ms_stats_kernel += ms;
-            ctx->stats.stats_launches += 1;
-            rec_on_device = ctx->h_counters[1];
-        }
-        // adapt: aim for a half-full candidate buffer
-        if (!no_screen && !getenv("TWKB_BATCH_TILES")) {
-            const double per_tile = std::max(1.0, (double)ncand / nb);
-            batch = std::max<uint64_t>(1, (uint64_t)(0.5 * ctx->cand_cap / per_tile));
-            ctx->est_cand_per_tile = std::max(ctx->est_cand_per_tile, per_tile);
-        }
+        };
+        auto account = [&](size_t, uint32_t nb) {
+            if (use_umma) ctx->stats.mma_macs += (uint64_t)nb * (planes_mode ? 256ull * 240ull : tile_pairs) * ctx->umma.Kelems;
+            else ctx->stats.word_ops += (uint64_t)nb * tile_pairs * ctx->K32 * ctx->np * ctx->np;
+        };
+        rc = run_batches(ctx, bp, prm, launch, account, resident, sink, user, dump, rec_on_device);
+        if (rc) return rc;
+    }
+    // ---- phase 2: every pair with a sparse member (list kernel)
+    if (sparse_phase && !ctx->sp_plan_tiles.empty()) {
+        DevParams sprm = prm;
+        sprm.diag = 0;  // the kernel applies its own "each pair once" rule
+        CountArgs sargs = args;
+        sargs.row_begin = 0; sargs.row_end = ctx->n_variants;
+        sargs.col_begin = 0; sargs.col_end = ctx->n_variants;
+        SparseArgs sp{ctx->d_sp_off.p, ctx->d_sp_ent.p, ctx->d_orig.p, ctx->nD, ctx->nS};
+        BatchPlan bp;
+        bp.n_tiles = ctx->sp_plan_tiles.size();
+        bp.tile_pairs = (uint64_t)SP_ROWS * SP_TJ;
+        bp.no_screen = no_screen;
+        bp.sparse = true;
+        bp.est_cand_per_tile = &ctx->est_cand_per_sp_tile;
+        auto launch = [&](size_t t, uint32_t nb) -> cudaError_t {
+            sargs.tiles = ctx->d_sp_tiles.p + t;
+            if (no_screen) count_sparse_kernel<false><<<nb, SP_THREADS, 0, ctx->stream>>>(sargs, sp, sprm);
+            else count_sparse_kernel<true><<<nb, SP_THREADS, 0, ctx->stream>>>(sargs, sp, sprm);
+            return cudaGetLastError();
+        };
+        // word operations actually issued: entries of the tile's rows x columns of the tile
+        std::vector<uint64_t>& pre = ctx->sp_tile_words_prefix;
+        auto account = [&](size_t t, uint32_t nb) { ctx->stats.sparse_word_ops += pre[t + nb] - pre[t]; };
+        rc = run_batches(ctx, bp, sprm, launch, account, resident, sink, user, dump, rec_on_device);
+        if (rc) return rc;
     }
     if (!dump) {
         if (!resident) {
@@ -680,6 +840,85 @@ static int compute_impl(Context* ctx, bool resident, twkb_sink_fn sink, void* us
     return rc;
 }
 
+// Rare-variant classification (reference: twk_igt_list::Build keeps, per variant, the offsets of
+// the registers that hold an alt allele, include/core.h:601-632, and PhasedListVector walks the
+// list of the sparser variant, ld_engine.cpp:185-267). Variants whose row has <= T non-zero
+// 32-bit words become the sparse class: the resident rows are re-ordered [dense | sparse] (file
+// order inside each class) and the sparse rows get a CSR list of (word, value) entries.
+static int classify_sparse(Context* ctx) {
+    const uint32_t M = ctx->n_variants;
+    ctx->permuted = false;
+    ctx->nD = M;
+    ctx->nS = 0;
+    ctx->sparse_T = 0;
+    ctx->sp_entries = 0;
+    ctx->sp_plan_key.clear();
+    ctx->est_cand_per_sp_tile = -1.0;
+    ctx->h_orig.resize(M);
+    for (uint32_t x = 0; x < M; ++x) ctx->h_orig[x] = x;
+    const twkb_settings& st = ctx->st;
+    const uint32_t n_bits = 2 * ctx->n_samples;
+    const uint32_t K32raw = (n_bits + 31) / 32;
+    int64_t T = 0;
+    if (st.sparse_max_words > 0) T = st.sparse_max_words;
+    else if (st.sparse_max_words == 0 && st.kernel == TWKB_KERNEL_AUTO && n_bits >= 32768u) T = K32raw / 64;
+    if (st.sparse_max_words >= 0) {
+        if (const char* e = getenv("TWKB_SPARSE_T")) T = atoll(e);
+    }
+    if (T <= 0 || ctx->any_missing || st.forced_unphased || st.n_chunks != 1 || M < 2) return TWKB_OK;
+    DevBuf<uint32_t> d_nnz;
+    CUDA_TRY(d_nnz.alloc(M));
+    row_nnz32_kernel<<<(M + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_raw_data.p, ctx->raw_stride, M, n_bits, d_nnz.p);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> nnz(M);
+    CUDA_TRY(cudaMemcpyAsync(nnz.data(), d_nnz.p, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    d_nnz.release();
+    ctx->stats.other_launches += 1;
+    uint32_t nS = 0;
+    for (uint32_t v = 0; v < M; ++v) nS += (nnz[v] <= (uint64_t)T) ? 1u : 0u;
+    // an automatic threshold only pays when a real share of the variants is rare
+    if (nS == 0 || (st.sparse_max_words == 0 && !getenv("TWKB_SPARSE_T") && nS < std::max<uint32_t>(256u, M / 20))) return TWKB_OK;
+    const uint32_t nD = M - nS;
+    uint32_t d = 0, sidx = nD;
+    ctx->h_sp_off.assign(nS + 1, 0);
+    for (uint32_t v = 0; v < M; ++v) {
+        if (nnz[v] <= (uint64_t)T) {
+            ctx->h_sp_off[sidx - nD + 1] = ctx->h_sp_off[sidx - nD] + nnz[v];
+            ctx->h_orig[sidx++] = v;
+        } else {
+            ctx->h_orig[d++] = v;
+        }
+    }
+    ctx->sp_entries = ctx->h_sp_off[nS];
+    // resident order -> device, rows gathered into the new order
+    std::vector<uint32_t> orig_pad(ctx->Mpad);
+    for (uint32_t x = 0; x < ctx->Mpad; ++x) orig_pad[x] = x < M ? ctx->h_orig[x] : x;
+    CUDA_TRY(ctx->d_orig.alloc(ctx->Mpad));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_orig.p, orig_pad.data(), (size_t)ctx->Mpad * 4, cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf<uint64_t> gathered;
+    CUDA_TRY(gathered.alloc((size_t)M * ctx->raw_stride));
+    gather_rows_kernel<<<M, 128, 0, ctx->stream>>>(ctx->d_raw_data.p, gathered.p, ctx->d_orig.p, ctx->raw_stride, M);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    std::swap(ctx->d_raw_data.p, gathered.p);
+    std::swap(ctx->d_raw_data.n, gathered.n);
+    gathered.release();
+    // CSR entries
+    CUDA_TRY(ctx->d_sp_off.alloc(nS + 1));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_sp_off.p, ctx->h_sp_off.data(), (size_t)(nS + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx->d_sp_ent.alloc(std::max<uint64_t>(ctx->sp_entries, 1)));
+    build_sparse_entries_kernel<<<(nS + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_raw_data.p, ctx->raw_stride, nD, nS, n_bits, ctx->d_sp_off.p,
+                                                                        ctx->d_sp_ent.p);
+    CUDA_TRY(cudaGetLastError());
+    ctx->stats.other_launches += 2;
+    ctx->permuted = true;
+    ctx->nD = nD;
+    ctx->nS = nS;
+    ctx->sparse_T = (uint32_t)T;
+    return TWKB_OK;
+}
+
 static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* data, const uint64_t* mask,
                        size_t stride, const twkb_variant* meta, bool device_src) {
     if (!data || !meta || n_samples == 0 || n_variants == 0) { ctx->err = "null/empty matrix"; return TWKB_EINVAL; }
@@ -695,7 +934,7 @@ static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, co
     ctx->n_variants = n_variants;
     ctx->Mpad = (n_variants + 255) / 256 * 256;
     ctx->raw_stride = stride;
-    ctx->h_meta.assign(meta, meta + n_variants);
+    ctx->h_meta_orig.assign(meta, meta + n_variants);
     ctx->any_missing = false;
     for (uint32_t v = 0; v < n_variants; ++v)
         if (meta[v].gt_missing || meta[v].an) ctx->any_missing = true;
@@ -711,6 +950,14 @@ static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, co
         CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_mask.p, mask, words * 8, kind, ctx->stream));
         if (!device_src) ctx->stats.bytes_h2d += words * 8;
     }
+    // rare-variant class: may re-order the resident rows [dense | sparse]
+    {
+        const int rc_sp = classify_sparse(ctx);
+        if (rc_sp) return rc_sp;
+    }
+    ctx->h_meta.resize(n_variants);
+    for (uint32_t x = 0; x < n_variants; ++x) ctx->h_meta[x] = meta[ctx->h_orig[x]];
+    meta = ctx->h_meta.data();  // resident order from here on
     // device metadata
     std::vector<DevVariant> dm(ctx->Mpad);
     std::memset(dm.data(), 0, dm.size() * sizeof(DevVariant));
@@ -808,6 +1055,7 @@ void twkb_destroy(void* c) {
     ctx->d_meta.release(); ctx->d_lgamma.release(); ctx->d_blk_of.release(); ctx->d_blk_first.release();
     ctx->d_blk_last.release(); ctx->d_blk_prune.release(); ctx->d_tiles.release(); ctx->d_cands.release();
     ctx->d_counters.release(); ctx->d_records.release();
+    ctx->d_orig.release(); ctx->d_sp_off.release(); ctx->d_sp_ent.release(); ctx->d_sp_tiles.release();
     umma_release(ctx->umma);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
     if (ctx->h_stage[1]) cudaFreeHost(ctx->h_stage[1]);
@@ -870,6 +1118,8 @@ int twkb_debug_candidates(void* c, int screen_off, uint32_t* out, uint64_t capac
     std::vector<Candidate> dump;
     int rc = compute_impl(ctx, true, nullptr, nullptr, screen_off != 0, &dump);
     if (rc) return rc;
+    if (ctx->permuted)  // candidates carry resident indices; callers see the file order
+        for (Candidate& cd : dump) { cd.i = ctx->h_orig[cd.i]; cd.j = ctx->h_orig[cd.j]; }
     *n_out = dump.size();
     if (out) {
         if (dump.size() > capacity) { ctx->err = "debug buffer too small"; return TWKB_ENOMEM; }
@@ -1004,6 +1254,7 @@ int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_vari
     if (ctx.st.part_count <= 0) { ctx.st.part_count = 1; ctx.st.part_index = 0; }
     ctx.n_variants = n_variants;
     ctx.h_meta.assign(meta, meta + n_variants);
+    ctx.h_meta_orig = ctx.h_meta;
     Problem pb;
     rc = select_problem(&ctx, pb);
     if (rc) return rc;
