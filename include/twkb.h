@@ -182,9 +182,20 @@ int twkb_debug_candidates(void* ctx, int screen_off, uint32_t* out, uint64_t cap
 int twkb_calc_file(const twkb_settings* s, const char* in_path, const char* out_path, twkb_stats* stats_out,
                    char* errbuf, size_t errbuf_len);
 
+/* Same with the `-I` interval strings of `calc` (twk_ld_settings::ival_strings, include/core.h:923;
+ * grammar "chr", "chr:pos", "chr:from-to", lib/intervals.cpp:91-136). The reference works at .twk
+ * BLOCK granularity (lib/ld/ld.cpp:257-365): every variant of every block overlapping an interval
+ * takes part. With settings->emulate_quirks the reference's loading rule is reproduced exactly
+ * (n consecutive blocks from the first overlapping one); without it, the distinct union. */
+int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const char* out_path,
+                             const char* const* intervals, int32_t n_intervals, twkb_stats* stats_out, char* errbuf,
+                             size_t errbuf_len);
+
 /* .twk reader (twk_reader::Open + twk1_blk_iterator::NextBlock + twk_igt_vec::Build):
  * unpacks every block into the row layout twkb_load_matrix takes. */
 int twkb_twk_open(const char* path, int n_threads, void** handle, char* errbuf, size_t errbuf_len);
+int twkb_twk_open_intervals(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
+                            int32_t emulate_quirks, void** handle, char* errbuf, size_t errbuf_len);
 int twkb_twk_dims(void* handle, uint32_t* n_samples, uint32_t* n_variants, size_t* row_stride_words,
                   int32_t* any_missing, uint32_t* n_blocks);
 int twkb_twk_copy(void* handle, uint64_t* data_bits, uint64_t* mask_bits /* nullable */, twkb_variant* meta);

@@ -31,6 +31,12 @@ CASES = {
     # the reference CLI only exposes -r and -P (lib/calc.h:99-220); maxR2/D' keep their defaults
     # auto mode (neither -p nor -u): a pair is unphased iff either variant has missing alleles (Q4)
     "auto_mixed": (dict(n_samples=60, n_variants=300, seed=110, missing_rate=0.01), ["-r", "0.05"], dict(minR2=0.05)),
+    # -I: block-granular selection (lib/ld/ld.cpp:257-365). One interval -> the overlapping blocks;
+    # two disjoint intervals -> the reference reads n consecutive blocks from the first overlap.
+    "interval_one": (dict(n_samples=300, n_variants=2300, seed=111), ["-p", "-r", "0.1", "-I", "1:60000-110000"],
+                     dict(force_phased=1, minR2=0.1)),
+    "interval_two": (dict(n_samples=300, n_variants=2300, seed=112), ["-p", "-r", "0.1", "-I", "1:60000-110000", "-I", "1:200000-210000"],
+                     dict(force_phased=1, minR2=0.1)),
     "minp_filter": (dict(n_samples=600, n_variants=250, seed=109), ["-p", "-r", "0.05", "-P", "1e-3"],
                     dict(force_phased=1, minR2=0.05, minP=1e-3)),
 }
@@ -49,7 +55,16 @@ def main():
         recs = tf.canonical(tf.read_two(os.path.join(TMP, f"g_{name}.two")), forward_only=True)
         # pairs visited: the reference's own figure when its (racy) stderr summary parses,
         # else the restatement's count (identical whenever both are available)
-        _, visited = lc.calc(s, lc.default_params(**prm))
+        if "-I" in cli:
+            # the restatement takes the variant set the reference loaded (its own LOG line)
+            import re
+            m = re.search(r"([\d,]+) variants from ([\d,]+) blocks", info["stderr"])
+            nv = int(m.group(1).replace(",", ""))
+            first = int(np.searchsorted(s.pos, (recs["packA"] >> 2).min())) // 500 * 500
+            sub = tf.Synth(alleles=s.alleles[first:first + nv], pos=s.pos[first:first + nv], rid=s.rid[first:first + nv], n_samples=s.n_samples)
+            _, visited = lc.calc(sub, lc.default_params(**prm))
+        else:
+            _, visited = lc.calc(s, lc.default_params(**prm))
         if "pairs" in info:
             assert info["pairs"] == visited, (info["pairs"], visited)
         info["pairs"] = visited

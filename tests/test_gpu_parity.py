@@ -414,6 +414,23 @@ def test_calc_file_end_to_end_matches_reference_golden(tmpdir_repo):
     assert not ld.Compute(st, os.path.join(tmpdir_repo, "missing.twk"), os.path.join(tmpdir_repo, "x"))
 
 
+@pytest.mark.parametrize("name", ["interval_one", "interval_two"])
+def test_calc_file_interval_mode_matches_reference_golden(name, tmpdir_repo):
+    """`calc -I`: block-granular interval selection + LD, file to file, against the reference's records."""
+    s, ref, prm, pairs, cli = load_golden(name)
+    t = cli.split()
+    ivals = [t[i + 1] for i in range(len(t)) if t[i] == "-I"]
+    twk = os.path.join(tmpdir_repo, f"{name}_gpu.twk")
+    tf.write_twk(twk, s)
+    ld = tb.twk_ld()
+    assert ld.Compute(tb.default_settings(**prm), twk, os.path.join(tmpdir_repo, f"{name}_gpu_out"), ival_strings=ivals)
+    back = tf.read_two(os.path.join(tmpdir_repo, f"{name}_gpu_out.two"))
+    assert len(back) == 2 * len(ref)
+    assert_records_bitexact(tf.canonical(back, forward_only=True), ref, p_rtol=1e-9)
+    assert ld.last_stats.pairs_visited == pairs
+    assert not ld.Compute(tb.default_settings(**prm), twk, os.path.join(tmpdir_repo, "x"), ival_strings=["nochr:1-2"])
+
+
 # ---------------------------------------------------------- properties at larger sizes
 def test_properties_at_scale():
     """20,000 x 5,008 haplotypes (2e8 pairs): too big for the scalar oracle, so check

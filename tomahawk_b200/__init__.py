@@ -85,8 +85,8 @@ _lib = None
 EXPORTS = [
     "twkb_settings_init", "twkb_create", "twkb_destroy", "twkb_last_error", "twkb_update_settings",
     "twkb_load_matrix", "twkb_load_matrix_device", "twkb_compute", "twkb_compute_resident", "twkb_get_stats",
-    "twkb_debug_candidates", "twkb_calc_file", "twkb_version",
-    "twkb_twk_open", "twkb_twk_dims", "twkb_twk_copy", "twkb_twk_close",
+    "twkb_debug_candidates", "twkb_calc_file", "twkb_calc_file_intervals", "twkb_version",
+    "twkb_twk_open", "twkb_twk_open_intervals", "twkb_twk_dims", "twkb_twk_copy", "twkb_twk_close",
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
 ]
 
@@ -120,6 +120,11 @@ def lib():
         L.twkb_calc_file.argtypes = [ctypes.POINTER(Settings), ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(Stats),
                                      ctypes.c_char_p, ctypes.c_size_t]
         L.twkb_twk_open.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+        L.twkb_calc_file_intervals.argtypes = [ctypes.POINTER(Settings), ctypes.c_char_p, ctypes.c_char_p,
+                                               ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32, ctypes.POINTER(Stats),
+                                               ctypes.c_char_p, ctypes.c_size_t]
+        L.twkb_twk_open_intervals.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32,
+                                              ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
         L.twkb_twk_dims.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
                                     ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32)]
         L.twkb_twk_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
@@ -135,15 +140,26 @@ def lib():
     return _lib
 
 
+def _c_strings(strings):
+    if not strings:
+        return None
+    arr = (ctypes.c_char_p * len(strings))()
+    arr[:] = [x.encode() for x in strings]
+    return arr
+
+
 class TwkFile:
     """A .twk file unpacked by the host reader (twkb_twk_*)."""
 
-    def __init__(self, path: str, n_threads: int = 4):
+    def __init__(self, path: str, n_threads: int = 4, intervals=(), emulate_quirks: bool = True):
+        """``intervals``: the ``-I`` strings of ``calc`` (block-granular selection, lib/ld/ld.cpp:257-365)."""
         L = lib()
         self._L = L
         self._h = ctypes.c_void_p()
         err = ctypes.create_string_buffer(512)
-        rc = L.twkb_twk_open(path.encode(), n_threads, ctypes.byref(self._h), err, 512)
+        iv = _c_strings(intervals)
+        rc = L.twkb_twk_open_intervals(path.encode(), n_threads, iv, len(intervals), int(emulate_quirks),
+                                       ctypes.byref(self._h), err, 512)
         if rc != 0:
             raise TwkbError(rc, err.value.decode())
         ns, nv, st, am, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t(), ctypes.c_int32(), ctypes.c_uint32()
@@ -325,13 +341,14 @@ class twk_ld:
     def __init__(self):
         self.last_stats = None
 
-    def Compute(self, settings: Settings, in_path: str, out_path: str) -> bool:
+    def Compute(self, settings: Settings, in_path: str, out_path: str, ival_strings=()) -> bool:
         import sys
 
         L = lib()
         st = Stats()
         err = ctypes.create_string_buffer(1024)
-        rc = L.twkb_calc_file(ctypes.byref(settings), in_path.encode(), out_path.encode(), ctypes.byref(st), err, 1024)
+        rc = L.twkb_calc_file_intervals(ctypes.byref(settings), in_path.encode(), out_path.encode(),
+                                        _c_strings(ival_strings), len(ival_strings), ctypes.byref(st), err, 1024)
         self.last_stats = st
         if rc != 0:
             print(f"[ERROR] {err.value.decode()}", file=sys.stderr)

@@ -1132,9 +1132,14 @@ static int writer_sink(void* user, const uint8_t* recs, uint64_t n) {
     return static_cast<TwoWriter*>(user)->add(recs, n);
 }
 
-// `tomahawk calc`: twk_ld::Compute (reference lib/ld/ld.cpp:477-671) end to end.
 int twkb_calc_file(const twkb_settings* s, const char* in_path, const char* out_path, twkb_stats* stats_out, char* errbuf,
                    size_t errbuf_len) {
+    return twkb_calc_file_intervals(s, in_path, out_path, nullptr, 0, stats_out, errbuf, errbuf_len);
+}
+
+// `tomahawk calc`: twk_ld::Compute (reference lib/ld/ld.cpp:477-671) end to end.
+int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const char* out_path, const char* const* intervals,
+                             int32_t n_intervals, twkb_stats* stats_out, char* errbuf, size_t errbuf_len) {
     auto fail = [&](int code, const std::string& m) {
         if (errbuf && errbuf_len) {
             std::snprintf(errbuf, errbuf_len, "%s", m.c_str());
@@ -1145,7 +1150,12 @@ int twkb_calc_file(const twkb_settings* s, const char* in_path, const char* out_
     if (std::strlen(in_path) == 0) return fail(TWKB_EINVAL, "No file-name provided...");  // ld.cpp:480
     std::string err;
     TwkFile twk;
-    int rc = read_twk(in_path, std::max(1, s->n_threads), twk, err);
+    std::vector<std::string> ivals;
+    for (int32_t i = 0; i < n_intervals; ++i) {
+        if (!intervals || !intervals[i]) return fail(TWKB_EINVAL, "null interval string");
+        ivals.emplace_back(intervals[i]);
+    }
+    int rc = read_twk(in_path, std::max(1, s->n_threads), twk, err, ivals.empty() ? nullptr : &ivals, s->emulate_quirks != 0);
     if (rc) return fail(rc, err);
     void* c = nullptr;
     rc = twkb_create(s, &c);
@@ -1184,10 +1194,20 @@ static int copy_err(char* errbuf, size_t n, const std::string& m, int code) {
 }
 
 int twkb_twk_open(const char* path, int n_threads, void** handle, char* errbuf, size_t errbuf_len) {
+    return twkb_twk_open_intervals(path, n_threads, nullptr, 0, 1, handle, errbuf, errbuf_len);
+}
+
+int twkb_twk_open_intervals(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
+                            int32_t emulate_quirks, void** handle, char* errbuf, size_t errbuf_len) {
     if (!path || !handle) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
+    std::vector<std::string> ivals;
+    for (int32_t i = 0; i < n_intervals; ++i) {
+        if (!intervals || !intervals[i]) return copy_err(errbuf, errbuf_len, "null interval string", TWKB_EINVAL);
+        ivals.emplace_back(intervals[i]);
+    }
     TwkFile* f = new TwkFile();
     std::string err;
-    const int rc = read_twk(path, std::max(1, n_threads), *f, err);
+    const int rc = read_twk(path, std::max(1, n_threads), *f, err, ivals.empty() ? nullptr : &ivals, emulate_quirks != 0);
     if (rc) { delete f; return copy_err(errbuf, errbuf_len, err, rc); }
     *handle = f;
     return TWKB_OK;

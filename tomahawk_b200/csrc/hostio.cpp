@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cctype>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <mutex>
@@ -62,13 +64,114 @@ inline void or_range(uint64_t* row, uint64_t start, uint64_t end, uint64_t patte
     row[w1] |= pattern & m1;
 }
 
-struct BlockRef { uint64_t foff; uint32_t n, first_variant; int32_t rid; };
+struct BlockRef { uint64_t foff; uint32_t n, first_variant; int32_t rid; uint32_t minpos, maxpos; };
+
+struct Contig { std::string name; int64_t n_bases; };
+struct Ival { uint32_t start, stop; };
+
+// Grammar of the reference's interval strings (include/tomahawk.h:57-59): a number is
+// digits, an optional decimal part and an optional one-digit exponent; values go through
+// atof and are truncated to u32 (lib/intervals.cpp:103-104).
+bool is_name(const std::string& s) {
+    if (s.empty()) return false;
+    for (char ch : s)
+        if (!(std::isalnum((unsigned char)ch) || ch == '-' || ch == '_')) return false;
+    return true;
+}
+bool is_number(const std::string& s) {
+    size_t i = 0;
+    while (i < s.size() && std::isdigit((unsigned char)s[i])) ++i;
+    if (i == 0) return false;
+    if (i < s.size() && s[i] == '.') {
+        const size_t j = ++i;
+        while (i < s.size() && std::isdigit((unsigned char)s[i])) ++i;
+        if (i == j) return false;
+    }
+    if (i < s.size() && (s[i] == 'e' || s[i] == 'E')) {
+        if (i + 2 != s.size() || !std::isdigit((unsigned char)s[i + 1])) return false;
+        i += 2;
+    }
+    return i == s.size();
+}
+
+// twk_intervals::ParseIntervalString + Dedupe + Build (lib/intervals.cpp:35-136) and the block
+// loading rule of twk_ld_impl::LoadTargetBlocks (lib/ld/ld.cpp:279-365): `calc -I` works at
+// .twk BLOCK granularity -- every variant of every block that overlaps an interval takes part.
+// Returns the index-entry numbers to load, in load order.
+int select_interval_blocks(const std::vector<std::string>& strings, const std::vector<Contig>& contigs,
+                           const std::vector<BlockRef>& blocks, bool emulate_quirks, std::vector<uint32_t>& sel,
+                           std::string& err) {
+    std::vector<std::vector<Ival>> ivecs(contigs.size());
+    auto contig_of = [&](const std::string& name) -> int {
+        for (size_t c = 0; c < contigs.size(); ++c)
+            if (contigs[c].name == name) return (int)c;
+        return -1;
+    };
+    for (const std::string& s : strings) {
+        const size_t colon = s.find(':');
+        const std::string name = s.substr(0, colon);
+        if (colon != std::string::npos && s.find(':', colon + 1) != std::string::npos) { err = "Illegal format: " + s; return TWKB_EINVAL; }
+        if (!is_name(name)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
+        const int c = contig_of(name);
+        if (colon == std::string::npos) {  // contig only: [0, n_bases]
+            if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
+            ivecs[c].push_back({0u, (uint32_t)contigs[c].n_bases});
+            continue;
+        }
+        const std::string rest = s.substr(colon + 1);
+        // a '-' can only separate the two numbers (names were cut at the colon)
+        const size_t dash = rest.find('-');
+        if (dash == std::string::npos) {  // contig:pos -> [pos, pos + 1]
+            if (!is_number(rest)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
+            if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
+            const uint32_t p = (uint32_t)std::atof(rest.c_str());
+            ivecs[c].push_back({p, p + 1});
+        } else {
+            const std::string a = rest.substr(0, dash), b = rest.substr(dash + 1);
+            if (!is_number(a) || !is_number(b)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
+            if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
+            ivecs[c].push_back({(uint32_t)std::atof(a.c_str()), (uint32_t)std::atof(b.c_str())});
+        }
+    }
+    std::vector<uint32_t> overlap;
+    for (size_t c = 0; c < ivecs.size(); ++c) {
+        std::vector<Ival>& v = ivecs[c];
+        if (v.empty()) continue;
+        std::stable_sort(v.begin(), v.end(), [](const Ival& x, const Ival& y) { return x.start != y.start ? x.start < y.start : x.stop < y.stop; });
+        std::vector<Ival> merged{v[0]};
+        for (size_t j = 1; j < v.size(); ++j) {  // Dedupe, lib/intervals.cpp:35-52
+            if (v[j].start < merged.back().stop && v[j].stop >= merged.back().start) merged.back().stop = v[j].stop;
+            else merged.push_back(v[j]);
+        }
+        for (const Ival& iv : merged)  // Index::FindOverlap, lib/index.cpp:125-134 (minpos/maxpos are 1-based)
+            for (size_t b = 0; b < blocks.size(); ++b)
+                if (blocks[b].rid == (int32_t)c && blocks[b].minpos <= iv.stop && blocks[b].maxpos >= iv.start) overlap.push_back((uint32_t)b);
+    }
+    if (overlap.empty()) { err = "Found no blocks overlapping the provided range(s)..."; return TWKB_EINVAL; }
+    sel.clear();
+    if (emulate_quirks) {
+        // The reference seeks to the FIRST overlapping block and reads overlap.size() consecutive
+        // blocks from there (ld.cpp:323-333), whatever the other entries were: identical to the
+        // union for one interval, a run of neighbours for several disjoint ones.
+        for (uint32_t k = 0; k < overlap.size(); ++k) {
+            const uint64_t b = (uint64_t)overlap[0] + k;
+            if (b >= blocks.size()) { err = "Failed to load block " + std::to_string(k) + "..."; return TWKB_EIO; }
+            sel.push_back((uint32_t)b);
+        }
+    } else {
+        sel = overlap;
+        std::sort(sel.begin(), sel.end());
+        sel.erase(std::unique(sel.begin(), sel.end()), sel.end());
+    }
+    return TWKB_OK;
+}
 
 }  // namespace
 
 // lib/twk_reader.cpp:49-125 (Open), :8-44 (NextBlock), lib/core.cpp:75-101 (twk1_t),
 // include/core.h:195-215 (run words), lib/core.cpp:365-383 (bitvector + mask).
-int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err) {
+int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err, const std::vector<std::string>* intervals,
+             bool emulate_quirks) {
     FILE* fp = std::fopen(path.c_str(), "rb");
     if (!fp) { err = "Failed to open \"" + path + "\"!"; return TWKB_EIO; }
     std::fseek(fp, 0, SEEK_END);
@@ -86,6 +189,7 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     const uint64_t h_unc = c.get<uint64_t>(), h_cmp = c.get<uint64_t>();
     if (!c.ok || (uint64_t)(c.end - c.p) < h_cmp) { err = "truncated header"; return TWKB_EIO; }
     std::vector<uint8_t> hdr;
+    std::vector<Contig> contigs;
     if (!zstd_inflate(c.p, h_cmp, h_unc, hdr, err)) return TWKB_EIO;
     {
         Cursor h{hdr.data(), hdr.data() + hdr.size()};
@@ -97,6 +201,17 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
         out.n_contigs = h.get<uint32_t>();
         if (!h.ok) { err = "corrupt VcfHeader"; return TWKB_EIO; }
         out.header_tail.assign(reinterpret_cast<const char*>(tail), hdr.data() + hdr.size() - tail);
+        for (uint32_t i = 0; i < out.n_contigs && h.ok; ++i) {  // VcfContig, include/header.h:115-128
+            h.get<uint32_t>();                                    // idx
+            Contig ct;
+            ct.name = h.str();
+            h.str();                                              // description
+            ct.n_bases = h.get<int64_t>();
+            const uint32_t n_extra = h.get<uint32_t>();
+            for (uint32_t x = 0; x < n_extra && h.ok; ++x) { h.str(); h.str(); }
+            contigs.push_back(ct);
+        }
+        if (!h.ok) contigs.clear();  // names are only needed for -I
     }
     // footer: ... u64 offset_of_index, 32-byte EOF
     uint64_t idx_off = 0;
@@ -110,7 +225,7 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     if (!zstd_inflate(f.p, i_cmp, i_unc, idx, err)) { err = "Failed to decompress index!"; return TWKB_EIO; }
     Cursor ix{idx.data(), idx.data() + idx.size()};
     if (ix.get<uint64_t>() != kIndexMarker) { err = "bad index marker"; return TWKB_EIO; }
-    const uint64_t n_ent = ix.get<uint64_t>();
+    uint64_t n_ent = ix.get<uint64_t>();
     ix.get<uint64_t>();  // m
     ix.get<uint64_t>();  // m_ent
     std::vector<BlockRef> blocks(n_ent);
@@ -118,14 +233,29 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     for (uint64_t i = 0; i < n_ent; ++i) {  // IndexEntry, lib/index.cpp:8-18
         const int32_t rid = ix.get<int32_t>();
         const uint32_t n = ix.get<uint32_t>();
-        ix.get<uint32_t>(); ix.get<uint32_t>(); ix.get<uint32_t>(); ix.get<uint32_t>();
+        const uint32_t minpos = ix.get<uint32_t>(), maxpos = ix.get<uint32_t>();
+        ix.get<uint32_t>(); ix.get<uint32_t>();
         const uint64_t foff = ix.get<uint64_t>();
         ix.get<uint64_t>();
-        blocks[i] = {foff, n, (uint32_t)total, rid};
+        blocks[i] = {foff, n, (uint32_t)total, rid, minpos, maxpos};
         total += n;
     }
     if (!ix.ok || total == 0 || total > 0xffffffffull) { err = "No valid data available..."; return TWKB_EIO; }
-    out.n_blocks = (uint32_t)n_ent;
+    if (intervals && !intervals->empty()) {  // calc -I: keep the overlapping blocks only
+        std::vector<uint32_t> sel;
+        const int rc = select_interval_blocks(*intervals, contigs, blocks, emulate_quirks, sel, err);
+        if (rc) return rc;
+        std::vector<BlockRef> kept;
+        total = 0;
+        for (uint32_t b : sel) {
+            kept.push_back(blocks[b]);
+            kept.back().first_variant = (uint32_t)total;
+            total += blocks[b].n;
+        }
+        blocks.swap(kept);
+    }
+    n_ent = blocks.size();
+    out.n_blocks = (uint32_t)blocks.size();
     out.n_variants = (uint32_t)total;
     const uint64_t H = 2ull * out.n_samples;
     out.stride = ((H + 63) / 64 + 1) / 2 * 2;

@@ -39,7 +39,10 @@ struct TwkFile {
 };
 
 // Reads and unpacks `path` with up to n_threads host threads. Returns 0 or TWKB_EIO.
-int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err);
+// `intervals` (nullable): the -I strings of `calc` ("chr", "chr:pos", "chr:from-to"); only the
+// .twk blocks that overlap them are loaded (reference lib/ld/ld.cpp:257-365, lib/intervals.cpp).
+int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err,
+             const std::vector<std::string>* intervals = nullptr, bool emulate_quirks = true);
 
 // Streaming .two writer: takes forward records, writes forward and reverse
 // blocks of <= b_size records, the index and the EOF marker.
