@@ -199,6 +199,9 @@ int twkb_twk_open_intervals(const char* path, int n_threads, const char* const* 
 int twkb_twk_dims(void* handle, uint32_t* n_samples, uint32_t* n_variants, size_t* row_stride_words,
                   int32_t* any_missing, uint32_t* n_blocks);
 int twkb_twk_copy(void* handle, uint64_t* data_bits, uint64_t* mask_bits /* nullable */, twkb_variant* meta);
+/* Borrow the unpacked rows instead of copying them (valid until twkb_twk_close; mask_bits is set
+ * to NULL when no variant has missing genotypes). */
+int twkb_twk_view(void* handle, const uint64_t** data_bits, const uint64_t** mask_bits, const twkb_variant** meta);
 void twkb_twk_close(void* handle);
 
 /* .two writer (twk_two_writer_t + twk_ld_engine::CompressFwd/Rev + IndexOutput): takes

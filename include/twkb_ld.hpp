@@ -1,0 +1,243 @@
+// twkb_ld.hpp -- C++ host mirror of the reference's LD driver, header-only, on top of the
+// C-ABI of twkb.h (libtwkb.so). It keeps the reference's interface for this path:
+//
+//   reference                                            | here (namespace twkb_host)
+//   -----------------------------------------------------+------------------------------
+//   struct twk_ld_settings      include/core.h:909-924   | struct twk_ld_settings (same field
+//     defaults                  lib/core.cpp:297-306     |   names, meaning and defaults)
+//     GetString()               lib/core.cpp:308-332     |   GetString()
+//   class twk_ld                include/ld.h:40-69       | class twk_ld
+//     bool Compute(const twk_ld_settings&)  ld.h:53      |   bool Compute(const twk_ld_settings&)
+//     bool Compute()            lib/ld/ld.cpp:477-671    |   bool Compute()
+//
+// Error behaviour follows the reference: a message "[date][ERROR] ..." on stderr and a `false`
+// result; the stages log "[date][LOG]..." lines like lib/ld/ld.cpp does. There is no CPU compute
+// path: without an sm_100 device Compute() fails with the library's TWKB_ENODEVICE message.
+//
+// B200 additions to the settings: `devices` (CUDA ordinals; one host thread and one device
+// context per entry, the tile grid dealt between them -- the replacement of the reference's
+// n_threads worker slaves, lib/ld/ld.cpp:623-644) and `kernel` (TWKB_KERNEL_*).
+#ifndef TWKB_LD_HPP_
+#define TWKB_LD_HPP_
+
+#include <sys/time.h>
+
+#include <chrono>
+#include <cstdio>
+#include <ctime>
+#include <iostream>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "twkb.h"
+
+namespace twkb_host {
+
+inline std::string datetime() {  // "YYYY-MM-DD HH:MM:SS,mmm", lib/utility.cpp:60-86
+    struct timeval tv;
+    gettimeofday(&tv, nullptr);
+    struct tm tmv;
+    localtime_r(&tv.tv_sec, &tmv);
+    char buf[64], out[80];
+    std::strftime(buf, sizeof(buf), "%Y-%m-%d %H:%M:%S", &tmv);
+    std::snprintf(out, sizeof(out), "%s,%03d", buf, (int)(tv.tv_usec / 1000));
+    return out;
+}
+inline std::string timestamp(const std::string& type) { return "[" + datetime() + "][" + type + "] "; }
+inline std::string timestamp(const std::string& type, const std::string& type2) {
+    return "[" + datetime() + "][" + type + "][" + type2 + "] ";
+}
+inline std::string pretty(uint64_t v) {  // utility::ToPrettyString: thousands separators
+    std::string s = std::to_string(v), o;
+    for (size_t i = 0; i < s.size(); ++i) {
+        o += s[i];
+        const size_t left = s.size() - 1 - i;
+        if (left && left % 3 == 0) o += ',';
+    }
+    return o;
+}
+
+struct twk_ld_settings {
+    bool square = true, window = false, low_memory = false, bitmaps = false, single = false;
+    bool force_phased = false, forced_unphased = false, force_cross_intervals = false;
+    int32_t c_level = 1, bl_size = 500, b_size = 10000, l_window = 1000000;
+    int32_t n_threads = (int32_t)std::thread::hardware_concurrency(), cycle_threshold = 0, ldd_load_type = 7;
+    int32_t l_surrounding = 500000;
+    std::string in, out = "-";
+    double minP = 1, minR2 = 0.1, maxR2 = 100, minDprime = 0, maxDprime = 100;
+    int32_t n_chunks = 1, c_chunk = 0;
+    std::vector<std::string> ival_strings;
+    // --- B200 additions ---
+    std::vector<int32_t> devices{0};
+    int32_t kernel = TWKB_KERNEL_AUTO;
+    bool emulate_quirks = true;
+    bool silent = false;  // suppress the LOG lines (errors are always printed)
+
+    std::string GetString() const {
+        auto tf = [](bool b) { return std::string(b ? "TRUE" : "FALSE"); };
+        std::string s = "square=" + tf(square) + ",window=" + tf(window) + ",low_memory=" + tf(low_memory) + ",bitmaps=" + tf(bitmaps) +
+                        ",single=" + tf(single) + ",force_phased=" + tf(force_phased) + ",force_unphased=" + tf(forced_unphased) +
+                        ",compression_level=" + std::to_string(c_level) + ",block_size=" + std::to_string(bl_size) +
+                        ",output_block_size=" + std::to_string(b_size) +
+                        (window ? std::string(",window_size=") + std::to_string(l_window) : "") +
+                        ",l_surrounding=" + std::to_string(l_surrounding) + ",minP=" + std::to_string(minP) +
+                        ",minR2=" + std::to_string(minR2) + ",maxR2=" + std::to_string(maxR2) + ",minDprime=" + std::to_string(minDprime) +
+                        ",maxDprime=" + std::to_string(maxDprime) + ",n_chunks=" + std::to_string(n_chunks) +
+                        ",c_chunk=" + std::to_string(c_chunk) + ",n_threads=" + std::to_string(n_threads) +
+                        ",ldd_type=" + std::to_string((int)ldd_load_type) + ",cycle_threshold=" + std::to_string(cycle_threshold);
+        s += ",devices=";
+        for (size_t i = 0; i < devices.size(); ++i) s += (i ? "+" : "") + std::to_string(devices[i]);
+        return s;
+    }
+
+    void ToC(twkb_settings* c) const {
+        twkb_settings_init(c);
+        c->square = square; c->window = window; c->low_memory = low_memory; c->bitmaps = bitmaps; c->single = single;
+        c->force_phased = force_phased; c->forced_unphased = forced_unphased; c->emulate_quirks = emulate_quirks;
+        c->c_level = c_level; c->bl_size = bl_size; c->b_size = b_size; c->l_window = l_window;
+        c->n_threads = n_threads > 0 ? n_threads : 1; c->l_surrounding = l_surrounding;
+        c->n_chunks = n_chunks; c->c_chunk = c_chunk;
+        c->minP = minP; c->minR2 = minR2; c->maxR2 = maxR2; c->minDprime = minDprime; c->maxDprime = maxDprime;
+        c->kernel = kernel;
+    }
+};
+
+class twk_ld {
+public:
+    twk_ld() = default;
+    void operator=(const twk_ld_settings& s) { settings = s; }
+
+    bool Compute(const twk_ld_settings& s) {
+        settings = s;
+        return Compute();
+    }
+
+    // twk_ld::Compute, lib/ld/ld.cpp:477-671: open, select blocks, load, compute, write.
+    bool Compute() {
+        stats = twkb_stats{};
+        if (settings.in.empty()) return error("No file-name provided...");
+        if (settings.window && settings.n_chunks != 1) return error("Cannot use chunking in window mode!");
+        if (settings.devices.empty()) return error("No device selected...");
+        // the reference's default "-" streams blocks to stdout; the block writer of this path needs a file
+        if (settings.out.empty() || settings.out == "-") return error("Writing to stdout is not supported: give -o <output.two>");
+        log("READER") << "Opening " << settings.in << "..." << std::endl;
+        char errbuf[1024] = {0};
+        std::vector<const char*> iv;
+        for (const std::string& x : settings.ival_strings) iv.push_back(x.c_str());
+        void* twk = nullptr;
+        int rc = twkb_twk_open_intervals(settings.in.c_str(), settings.n_threads > 0 ? settings.n_threads : 1, iv.empty() ? nullptr : iv.data(),
+                                         (int32_t)iv.size(), settings.emulate_quirks ? 1 : 0, &twk, errbuf, sizeof(errbuf));
+        if (rc) return error(errbuf[0] ? errbuf : "Failed to open file: " + settings.in + "...");
+        uint32_t n_samples = 0, n_variants = 0, n_blocks = 0;
+        size_t stride = 0;
+        int32_t any_missing = 0;
+        twkb_twk_dims(twk, &n_samples, &n_variants, &stride, &any_missing, &n_blocks);
+        const uint64_t* data = nullptr;
+        const uint64_t* mask = nullptr;
+        const twkb_variant* meta = nullptr;
+        twkb_twk_view(twk, &data, &mask, &meta);
+        log() << "Samples: " << pretty(n_samples) << "..." << std::endl;
+        log() << pretty(n_variants) << " variants from " << pretty(n_blocks) << " blocks..." << std::endl;
+        log("PARAMS") << settings.GetString() << std::endl;
+
+        // output name: a ".two" suffix is forced (ld.cpp:589-598)
+        std::string out = settings.out;
+        {
+            const size_t slash = out.find_last_of('/'), dot = out.find_last_of('.');
+            const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash);
+            std::string ext = has_ext ? out.substr(dot + 1) : "";
+            for (char& ch : ext) ch = (char)std::tolower((unsigned char)ch);
+            if (ext != "two") out = (has_ext ? out.substr(0, dot) : out) + ".two";
+        }
+        log("WRITER") << "Opening " << out << "..." << std::endl;
+        void* writer = nullptr;
+        rc = twkb_two_open(out.c_str(), twk, command_line.c_str(), settings.c_level, settings.b_size, &writer, errbuf, sizeof(errbuf));
+        if (rc) {
+            twkb_twk_close(twk);
+            return error(errbuf[0] ? errbuf : "Failed to open file: " + out + "...");
+        }
+
+        const int n_dev = (int)settings.devices.size();
+        log("THREAD") << "Spawning " << n_dev << " device context(s)..." << std::endl;
+        Shared shared;
+        shared.writer = writer;
+        std::vector<std::string> errors(n_dev);
+        std::vector<twkb_stats> st(n_dev);
+        std::vector<int> rcs(n_dev, 0);
+        const auto t0 = std::chrono::steady_clock::now();
+        auto worker = [&](int k) {
+            twkb_settings cs;
+            settings.ToC(&cs);
+            cs.device = settings.devices[k];
+            cs.part_index = k;
+            cs.part_count = n_dev;
+            void* ctx = nullptr;
+            int r = twkb_create(&cs, &ctx);
+            if (r) { errors[k] = twkb_last_error(nullptr); rcs[k] = r; return; }
+            r = twkb_load_matrix(ctx, n_samples, n_variants, data, mask, stride, meta);
+            if (r == TWKB_OK) r = twkb_compute(ctx, &twk_ld::sink, &shared);
+            if (r) { errors[k] = twkb_last_error(ctx); rcs[k] = r; }
+            else twkb_get_stats(ctx, &st[k]);
+            twkb_destroy(ctx);
+        };
+        std::vector<std::thread> pool;
+        for (int k = 1; k < n_dev; ++k) pool.emplace_back(worker, k);
+        worker(0);
+        for (std::thread& t : pool) t.join();
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        bool ok = true;
+        for (int k = 0; k < n_dev; ++k)
+            if (rcs[k]) { error("device " + std::to_string(settings.devices[k]) + ": " + errors[k]); ok = false; }
+        rc = twkb_two_close(writer);
+        twkb_twk_close(twk);
+        if (!ok) return false;
+        if (rc) return error("Failed to write final block!");
+        for (int k = 0; k < n_dev; ++k) {
+            stats.pairs_visited += st[k].pairs_visited; stats.pairs_screened += st[k].pairs_screened;
+            stats.records_out += st[k].records_out; stats.count_launches += st[k].count_launches;
+            stats.stats_launches += st[k].stats_launches; stats.other_launches += st[k].other_launches;
+            stats.sparse_launches += st[k].sparse_launches;
+            stats.ms_count_kernel += st[k].ms_count_kernel; stats.ms_stats_kernel += st[k].ms_stats_kernel;
+            stats.bytes_h2d += st[k].bytes_h2d; stats.bytes_d2h += st[k].bytes_d2h;
+            stats.kernel_used = st[k].kernel_used;
+        }
+        stats.seconds_total = secs;
+        // twk_ld_progress::PrintFinal, lib/ld/ld_progress.h:89-96 (genotypes = pairs x samples)
+        log("PROGRESS") << "Finished in " << secs << "s. Variants: " << pretty(stats.pairs_visited)
+                        << ", genotypes: " << pretty(stats.pairs_visited * n_samples) << ", output: " << pretty(stats.records_out) << std::endl;
+        log("PROGRESS") << pretty((uint64_t)(stats.pairs_visited / (secs > 0 ? secs : 1e-9))) << " variants/s and "
+                        << pretty((uint64_t)(stats.pairs_visited * (double)n_samples / (secs > 0 ? secs : 1e-9))) << " genotypes/s" << std::endl;
+        log("PROGRESS") << "All done..." << std::endl;
+        return true;
+    }
+
+    twk_ld_settings settings;
+    twkb_stats stats{};            // aggregated over the device contexts of the last Compute()
+    std::string command_line = "twkb_calc";  // recorded in the .two header (##tomahawk_calcCommand)
+
+private:
+    struct Shared { std::mutex mu; void* writer = nullptr; };
+    static int sink(void* user, const uint8_t* recs, uint64_t n) {
+        Shared* s = static_cast<Shared*>(user);
+        std::lock_guard<std::mutex> g(s->mu);
+        return twkb_two_add(s->writer, recs, n);
+    }
+    bool error(const std::string& m) const {
+        std::cerr << timestamp("ERROR") << m << std::endl;
+        return false;
+    }
+    struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+    std::ostream& log(const char* sub = nullptr) {
+        static NullBuf nb;
+        static std::ostream null_stream(&nb);
+        if (settings.silent) return null_stream;
+        std::cerr << (sub ? timestamp("LOG", sub) : timestamp("LOG"));
+        return std::cerr;
+    }
+};
+
+}  // namespace twkb_host
+
+#endif  // TWKB_LD_HPP_

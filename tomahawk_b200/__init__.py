@@ -86,7 +86,7 @@ EXPORTS = [
     "twkb_settings_init", "twkb_create", "twkb_destroy", "twkb_last_error", "twkb_update_settings",
     "twkb_load_matrix", "twkb_load_matrix_device", "twkb_compute", "twkb_compute_resident", "twkb_get_stats",
     "twkb_debug_candidates", "twkb_calc_file", "twkb_calc_file_intervals", "twkb_version",
-    "twkb_twk_open", "twkb_twk_open_intervals", "twkb_twk_dims", "twkb_twk_copy", "twkb_twk_close",
+    "twkb_twk_open", "twkb_twk_open_intervals", "twkb_twk_dims", "twkb_twk_copy", "twkb_twk_view", "twkb_twk_close",
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
 ]
 

@@ -1237,6 +1237,15 @@ int twkb_twk_copy(void* handle, uint64_t* data_bits, uint64_t* mask_bits, twkb_v
     return TWKB_OK;
 }
 
+int twkb_twk_view(void* handle, const uint64_t** data_bits, const uint64_t** mask_bits, const twkb_variant** meta) {
+    if (!handle) return TWKB_EINVAL;
+    const TwkFile* f = static_cast<TwkFile*>(handle);
+    if (data_bits) *data_bits = f->data.data();
+    if (mask_bits) *mask_bits = f->any_missing ? f->mask.data() : nullptr;
+    if (meta) *meta = f->meta.data();
+    return TWKB_OK;
+}
+
 void twkb_twk_close(void* handle) { delete static_cast<TwkFile*>(handle); }
 
 int twkb_two_open(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t b_size,
