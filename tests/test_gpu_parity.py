@@ -356,6 +356,73 @@ def test_sparse_path_parts_union_equals_whole():
     assert np.array_equal(tf.canonical(allr, False).view(np.uint8), tf.canonical(whole, False).view(np.uint8))
 
 
+def _biobank_matrix(n_samples, n_variants, seed):
+    """BASELINE configs[4] in miniature: 1M-haplotype rows, 80 % of the variants rare (MAF < 1 %:
+    60 % with <= 400 carriers -- the list class under the automatic threshold -- and 20 % with up to
+    10,000), 20 % common; neighbours share carriers (LD) so that records survive an R2 cut."""
+    rng = np.random.default_rng(seed)
+    nb = 2 * n_samples
+    words = (nb + 127) // 128 * 2
+    data = np.zeros((n_variants, words), np.uint64)
+    ac = np.zeros(n_variants, np.uint32)
+    prev_idx = None
+    for v in range(n_variants):
+        u = rng.random()
+        if u < 0.8:
+            k = int(rng.integers(2, 400)) if u < 0.6 else int(rng.integers(400, 10000))
+            if prev_idx is not None and rng.random() < 0.6:     # copy most carriers of the previous rare variant
+                keep = prev_idx[rng.random(len(prev_idx)) < 0.9]
+                idx = np.unique(np.concatenate([keep, rng.integers(1, nb, max(1, k // 10))]))
+            else:
+                idx = np.unique(rng.integers(1, nb, k))
+            prev_idx = idx
+            row = np.zeros(words * 8, np.uint8)
+            np.bitwise_or.at(row, idx >> 3, (1 << (idx & 7)).astype(np.uint8))
+            data[v] = row.view(np.uint64)
+            ac[v] = len(idx)
+        else:
+            bits = np.zeros(words * 64, np.uint8)
+            bits[1:nb] = rng.random(nb - 1) < rng.uniform(0.05, 0.5)
+            ac[v] = bits.sum()
+            data[v] = np.packbits(bits, bitorder="little").view(np.uint64)
+    meta = np.zeros(n_variants, tb.VARIANT_DTYPE)
+    meta["pos"] = 100 * (1 + np.arange(n_variants)); meta["ac"] = ac; meta["hwe"] = 1.0; meta["gt_phase"] = 1
+    return data, meta
+
+
+def test_biobank_scale_window_sparse_auto_threshold():
+    """1,000,000 haplotypes, -w window, rare-variant class chosen by the AUTOMATIC threshold
+    (sparse_max_words = 0 -> ceil(2N/32)/64 = 488 words): records identical to the all-dense run,
+    counts checked against the bits, and the list kernel must do far less work than dense rows."""
+    n_samples, n_variants = 500_000, 1200
+    data, meta = _biobank_matrix(n_samples, n_variants, seed=5)
+    prm = dict(force_phased=1, minR2=0.2, window=1, l_window=50_000)
+    out, sts = [], []
+    for smw in (-1, 0):
+        eng = tb.Engine(kernel=tb.KERNEL_AUTO, sparse_max_words=smw, **prm)
+        eng.load(n_samples, data, None, meta)
+        out.append(tf.canonical(eng.compute(), False))
+        sts.append(eng.stats())
+        eng.close()
+    dense, auto = sts
+    assert dense.sparse_variants == 0 and auto.sparse_variants > 0.3 * n_variants
+    assert auto.kernel_used == tb.KERNEL_UMMA_FP4 and auto.sparse_launches > 0
+    assert auto.pairs_visited == dense.pairs_visited
+    assert len(out[0]) > 100
+    assert np.array_equal(out[0].view(np.uint8), out[1].view(np.uint8))
+    # the list kernel touches only the non-zero words of the rare rows
+    K32 = (2 * n_samples + 31) // 32
+    assert auto.sparse_word_ops < 0.05 * auto.sparse_variants * n_variants * K32
+    r = out[1]
+    assert np.all(r["cnt"].sum(axis=1) == 2 * n_samples)
+    ia, ib = (r["packA"] >> 2) // 100 - 1, (r["packB"] >> 2) // 100 - 1
+    assert np.all(r["cnt"][:, 1] + r["cnt"][:, 3] == meta["ac"][ia])
+    assert np.all(r["cnt"][:, 2] + r["cnt"][:, 3] == meta["ac"][ib])
+    for k in np.linspace(0, len(r) - 1, 40).astype(int):      # ALTALT straight from the bits
+        n11 = int(np.unpackbits((data[ia[k]] & data[ib[k]]).view(np.uint8)).sum())
+        assert r["cnt"][k, 3] == n11
+
+
 def test_sparse_path_rejects_mode_change_without_reload():
     s = tf.synth_genotypes(300, 400, seed=97, rare_fraction=0.8)
     e, _, st = gpu_run(s, dict(force_phased=1, minR2=0.1), tb.KERNEL_AUTO, sparse_max_words=4)
