@@ -87,7 +87,10 @@ typedef struct twkb_settings {
                                 PhasedListVector). 0 = automatic (ceil(2N/32)/64 when
                                 2N >= 32768, phased data without missing genotypes, no -c
                                 chunking), > 0 explicit, < 0 never                       */
-    int32_t reserved[4];
+    int32_t host_unpack;     /* twkb_calc_file: 0 (default) = the .twk run-length records are decoded
+                                on the device (twkb_load_runs); 1 = unpack the rows on the host
+                                (twkb_load_matrix), the reference's twk_igt_vec::Build arrangement */
+    int32_t reserved[3];
 } twkb_settings;
 
 /* Subset of twk1_t (include/core.h:291-295) the LD path reads. */
@@ -101,6 +104,18 @@ typedef struct twkb_variant {
     uint8_t gt_phase;   /* all genotypes phased                        */
     uint8_t pad[6];
 } twkb_variant;
+
+/* Where the run-length genotype words of one variant sit inside a byte buffer (a .twk block body,
+ * lib/core.cpp:75-101). A run word is twk1_igt_t<uint8_t|uint16_t|uint32_t> (include/core.h:188-256):
+ * miss = 0: len << 2 | alleleA << 1 | alleleB; miss = 1: len << 4 | alleleA << 2 | alleleB with
+ * allele codes 0 ref, 1 alt, 2 missing (lib/genotype_encoder.h:11-17); len counts samples. */
+typedef struct twkb_run_desc {
+    uint64_t offset; /* byte offset of the first run word (any alignment) */
+    uint32_t n_runs;
+    uint8_t width;   /* bytes per run word: 1, 2 or 4 */
+    uint8_t miss;    /* 1 = 2-bit allele codes */
+    uint8_t pad[2];
+} twkb_run_desc;
 
 /* Counters of one twkb_compute call (reference: twk_ld_progress n_var/n_out). */
 typedef struct twkb_stats {
@@ -125,6 +140,11 @@ typedef struct twkb_stats {
     uint64_t sparse_launches; /* sparse-kernel launches                                */
     uint64_t sparse_word_ops; /* AND+POPC word operations issued by the sparse kernel  */
     double ms_sparse_kernel;  /* CUDA-event time summed over sparse-kernel launches    */
+    double ms_decode_kernel;  /* CUDA-event time of decode_runs_kernel (twkb_load_runs)  */
+    /* twkb_calc_file only: wall clock of its phases */
+    double seconds_file_read;  /* .twk read + zstd inflate (+ host unpack when host_unpack) */
+    double seconds_file_load;  /* upload + device decode / transpose                        */
+    double seconds_file_total; /* open to the closed .two file                               */
 } twkb_stats;
 
 /* Receives `n` packed 106-byte records (forward orientation: A is the variant
@@ -155,6 +175,18 @@ int twkb_load_matrix(void* ctx, uint32_t n_samples, uint32_t n_variants, const u
  * (e.g. received by an NCCL broadcast). Pointers are CUDA device pointers. */
 int twkb_load_matrix_device(void* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* d_data_bits,
                             const uint64_t* d_mask_bits, size_t row_stride_words, const twkb_variant* meta);
+
+/* Upload run-length encoded genotypes and decode them ON THE DEVICE into the same resident rows
+ * (+ mask rows) twkb_load_matrix would have uploaded -- the device counterpart of
+ * twk_igt_vec::Build (lib/core.cpp:349-383). run_bytes is host memory (copied); desc[v] locates
+ * variant v's run words in it. Fails with TWKB_EINVAL if the runs of a variant do not cover
+ * exactly n_samples samples. */
+int twkb_load_runs(void* ctx, uint32_t n_samples, uint32_t n_variants, const uint8_t* run_bytes, size_t n_run_bytes,
+                   const twkb_run_desc* desc, const twkb_variant* meta);
+
+/* Test hook: copy the resident reference-layout rows (file order unless the rare-variant class
+ * re-ordered them) back to the host. mask_bits may be NULL. */
+int twkb_debug_rows(void* ctx, uint64_t* data_bits, uint64_t* mask_bits, size_t row_stride_words);
 
 /* Run the LD computation over this context's share of the pair grid. */
 int twkb_compute(void* ctx, twkb_sink_fn sink, void* user);
@@ -202,6 +234,13 @@ int twkb_twk_copy(void* handle, uint64_t* data_bits, uint64_t* mask_bits /* null
 /* Borrow the unpacked rows instead of copying them (valid until twkb_twk_close; mask_bits is set
  * to NULL when no variant has missing genotypes). */
 int twkb_twk_view(void* handle, const uint64_t** data_bits, const uint64_t** mask_bits, const twkb_variant** meta);
+/* Runs mode: inflate the blocks but leave the genotypes run-length encoded (no host unpack);
+ * twkb_twk_runs_view then yields what twkb_load_runs takes. twkb_twk_copy / twkb_twk_view fail with
+ * TWKB_ESTATE on such a handle; twkb_twk_dims and twkb_two_open work on both kinds. */
+int twkb_twk_open_runs(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
+                       int32_t emulate_quirks, void** handle, char* errbuf, size_t errbuf_len);
+int twkb_twk_runs_view(void* handle, const uint8_t** run_bytes, size_t* n_run_bytes, const twkb_run_desc** desc,
+                       const twkb_variant** meta);
 void twkb_twk_close(void* handle);
 
 /* .two writer (twk_two_writer_t + twk_ld_engine::CompressFwd/Rev + IndexOutput): takes
@@ -209,6 +248,7 @@ void twkb_twk_close(void* handle);
  * twk_handle supplies the VcfHeader that is copied into the .two header. */
 int twkb_two_open(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t b_size,
                   void** writer, char* errbuf, size_t errbuf_len);
+int twkb_two_set_threads(void* writer, int32_t n_threads); /* zstd block compression threads (default 1) */
 int twkb_two_add(void* writer, const uint8_t* records, uint64_t n);
 int twkb_two_close(void* writer); /* finishes the file and frees the writer */
 

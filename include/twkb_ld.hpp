@@ -73,6 +73,7 @@ struct twk_ld_settings {
     std::vector<int32_t> devices{0};
     int32_t kernel = TWKB_KERNEL_AUTO;
     bool emulate_quirks = true;
+    bool host_unpack = false;  // true: unpack the .twk rows on the host instead of decoding the runs on the device
     bool silent = false;  // suppress the LOG lines (errors are always printed)
 
     std::string GetString() const {
@@ -101,6 +102,7 @@ struct twk_ld_settings {
         c->n_chunks = n_chunks; c->c_chunk = c_chunk;
         c->minP = minP; c->minR2 = minR2; c->maxR2 = maxR2; c->minDprime = minDprime; c->maxDprime = maxDprime;
         c->kernel = kernel;
+        c->host_unpack = host_unpack ? 1 : 0;
     }
 };
 
@@ -127,8 +129,11 @@ public:
         std::vector<const char*> iv;
         for (const std::string& x : settings.ival_strings) iv.push_back(x.c_str());
         void* twk = nullptr;
-        int rc = twkb_twk_open_intervals(settings.in.c_str(), settings.n_threads > 0 ? settings.n_threads : 1, iv.empty() ? nullptr : iv.data(),
-                                         (int32_t)iv.size(), settings.emulate_quirks ? 1 : 0, &twk, errbuf, sizeof(errbuf));
+        // default: blocks are inflated on the host, the run-length genotypes are decoded on the device
+        const bool runs = !settings.host_unpack;
+        int rc = (runs ? twkb_twk_open_runs : twkb_twk_open_intervals)(
+            settings.in.c_str(), settings.n_threads > 0 ? settings.n_threads : 1, iv.empty() ? nullptr : iv.data(),
+            (int32_t)iv.size(), settings.emulate_quirks ? 1 : 0, &twk, errbuf, sizeof(errbuf));
         if (rc) return error(errbuf[0] ? errbuf : "Failed to open file: " + settings.in + "...");
         uint32_t n_samples = 0, n_variants = 0, n_blocks = 0;
         size_t stride = 0;
@@ -137,7 +142,11 @@ public:
         const uint64_t* data = nullptr;
         const uint64_t* mask = nullptr;
         const twkb_variant* meta = nullptr;
-        twkb_twk_view(twk, &data, &mask, &meta);
+        const uint8_t* run_bytes = nullptr;
+        size_t n_run_bytes = 0;
+        const twkb_run_desc* run_desc = nullptr;
+        if (runs) twkb_twk_runs_view(twk, &run_bytes, &n_run_bytes, &run_desc, &meta);
+        else twkb_twk_view(twk, &data, &mask, &meta);
         log() << "Samples: " << pretty(n_samples) << "..." << std::endl;
         log() << pretty(n_variants) << " variants from " << pretty(n_blocks) << " blocks..." << std::endl;
         log("PARAMS") << settings.GetString() << std::endl;
@@ -158,6 +167,7 @@ public:
             twkb_twk_close(twk);
             return error(errbuf[0] ? errbuf : "Failed to open file: " + out + "...");
         }
+        twkb_two_set_threads(writer, settings.n_threads > 0 ? settings.n_threads : 1);
 
         const int n_dev = (int)settings.devices.size();
         log("THREAD") << "Spawning " << n_dev << " device context(s)..." << std::endl;
@@ -176,7 +186,8 @@ public:
             void* ctx = nullptr;
             int r = twkb_create(&cs, &ctx);
             if (r) { errors[k] = twkb_last_error(nullptr); rcs[k] = r; return; }
-            r = twkb_load_matrix(ctx, n_samples, n_variants, data, mask, stride, meta);
+            r = runs ? twkb_load_runs(ctx, n_samples, n_variants, run_bytes, n_run_bytes, run_desc, meta)
+                     : twkb_load_matrix(ctx, n_samples, n_variants, data, mask, stride, meta);
             if (r == TWKB_OK) r = twkb_compute(ctx, &twk_ld::sink, &shared);
             if (r) { errors[k] = twkb_last_error(ctx); rcs[k] = r; }
             else twkb_get_stats(ctx, &st[k]);

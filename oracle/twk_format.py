@@ -98,7 +98,7 @@ def _header_bytes(n_samples: int, contigs, literals: str) -> bytes:
     return bytes(b)
 
 
-def _rle_variant(al: np.ndarray, has_missing: bool):
+def _rle_variant(al: np.ndarray, has_missing: bool, force_ptype: int | None = None):
     """Run-length encode one variant's 2N allele codes -> (ptype, runs ndarray).
 
     Run word = len << (2+2*miss) | refA << (1+miss) | refB (include/core.h:195-198).
@@ -114,11 +114,13 @@ def _rle_variant(al: np.ndarray, has_missing: bool):
     codes = code[starts]
     lbits = 2 + 2 * int(has_missing)
     for ptype, dt in ((1, np.uint8), (2, np.uint16), (4, np.uint32)):
+        if force_ptype is not None and ptype != force_ptype:
+            continue
         maxlen = (1 << (8 * ptype - lbits)) - 1
         # split long runs into pieces of <= maxlen
         pieces = (lens + maxlen - 1) // maxlen
         total = int(pieces.sum())
-        if ptype < 4 and total > 2 * len(lens) + 8:
+        if force_ptype is None and ptype < 4 and total > 2 * len(lens) + 8:
             continue  # too much splitting; use a wider primitive
         rl = np.repeat(lens, pieces)
         rc = np.repeat(codes, pieces)
@@ -130,6 +132,64 @@ def _rle_variant(al: np.ndarray, has_missing: bool):
         runs = ((full.astype(np.uint64) << lbits) | rc.astype(np.uint64)).astype(dt)
         return ptype, runs
     raise AssertionError
+
+
+def encode_runs(s: Synth, widths=None, seed: int = 0):
+    """Run-length records of every variant of ``s`` laid out back to back at arbitrary (odd)
+    offsets: (raw uint8, desc) as twkb_load_runs takes them. ``widths``: run-word widths to draw
+    from per variant (default: the writer's own choice)."""
+    rng = np.random.default_rng(seed)
+    an = s.an
+    chunks, desc, off = [], [], 0
+    for v in range(s.n_variants):
+        pad = int(rng.integers(0, 4))
+        chunks.append(np.zeros(pad, dtype=np.uint8))
+        off += pad
+        miss = bool(an[v] != 0)
+        ptype, runs = _rle_variant(s.alleles[v], miss, None if widths is None else int(rng.choice(widths)))
+        b = np.frombuffer(runs.astype(runs.dtype.newbyteorder("<")).tobytes(), dtype=np.uint8)
+        desc.append((off, len(runs), ptype, int(miss)))
+        chunks.append(b)
+        off += len(b)
+    raw = np.concatenate(chunks) if chunks else np.zeros(0, dtype=np.uint8)
+    d = np.zeros(len(desc), dtype=[("offset", "<u8"), ("n_runs", "<u4"), ("width", "u1"), ("miss", "u1"), ("pad", "u1", (2,))])
+    for k, (o, n, w, m) in enumerate(desc):
+        d[k]["offset"], d[k]["n_runs"], d[k]["width"], d[k]["miss"] = o, n, w, m
+    return raw, d
+
+
+def decode_runs(raw: np.ndarray, desc: np.ndarray, n_samples: int, with_mask: bool):
+    """CPU restatement of twk_igt_vec::Build (reference lib/core.cpp:349-383) over located run
+    words: returns (data, mask) uint64 rows [n_variants, stride] in the layout pack_bits() makes.
+    ``desc`` has fields offset / n_runs / width / miss (tomahawk_b200.RUN_DESC_DTYPE).
+    Test oracle of the device decoder (decode.cuh); raises if a variant's runs do not cover
+    exactly n_samples samples."""
+    H = 2 * n_samples
+    stride = ((H + 63) // 64 + 1) // 2 * 2
+    M = len(desc)
+    data = np.zeros((M, stride * 64), dtype=np.uint8)
+    mask = np.zeros((M, stride * 64), dtype=np.uint8) if with_mask else None
+    for v in range(M):
+        d = desc[v]
+        w = int(d["width"])
+        words = np.frombuffer(raw[int(d["offset"]): int(d["offset"]) + int(d["n_runs"]) * w].tobytes(),
+                              dtype={1: "<u1", 2: "<u2", 4: "<u4"}[w]).astype(np.uint64)
+        miss = int(d["miss"])
+        lens = (words >> np.uint64(2 + 2 * miss)).astype(np.int64)
+        a = ((words >> np.uint64(1 + miss)) & np.uint64((1 << (1 + miss)) - 1)).astype(np.int64)
+        b = (words & np.uint64((1 << (1 + miss)) - 1)).astype(np.int64)
+        if int(lens.sum()) != n_samples:
+            raise ValueError(f"variant {v}: runs cover {int(lens.sum())} of {n_samples} samples")
+        ea = np.repeat(a, lens)
+        eb = np.repeat(b, lens)
+        data[v, 0:H:2] = ea == 1   # lib/core.cpp:371-376
+        data[v, 1:H:2] = eb == 1
+        if mask is not None:
+            m = (ea == 2) | (eb == 2)  # :379-380: both bits of the sample
+            mask[v, 0:H:2] = m
+            mask[v, 1:H:2] = m
+    pack = lambda bits: np.packbits(bits, axis=1, bitorder="little").view("<u8")
+    return pack(data), (pack(mask) if mask is not None else None)
 
 
 def write_twk(path: str, s: Synth, block_size: int = 500, c_level: int = 1, contigs=None):

@@ -554,3 +554,82 @@ def test_edge_cases():
     with pytest.raises(tb.TwkbError):
         e.compute()
     e.close()
+
+
+# ---------------------------------------------------------- device-side .twk decode
+@pytest.mark.parametrize("kw,widths", [
+    (dict(n_samples=2504, n_variants=1500, seed=31), None),
+    (dict(n_samples=333, n_variants=700, seed=32, missing_rate=0.07), [1, 2, 4]),
+    (dict(n_samples=31, n_variants=41, seed=33, missing_rate=0.2), [1, 2, 4]),
+    (dict(n_samples=1, n_variants=9, seed=34), [1]),
+    (dict(n_samples=40000, n_variants=64, seed=35), [4]),        # interiors > 64 words: warp-cooperative stores
+    (dict(n_samples=40000, n_variants=64, seed=36, missing_rate=0.01), [2, 4]),
+])
+def test_device_run_decode_rows_bit_identical(kw, widths):
+    """decode_runs_kernel == twk_igt_vec::Build (lib/core.cpp:349-383): the resident rows and mask
+    rows after twkb_load_runs equal the host-packed ones word for word."""
+    s = tf.synth_genotypes(**kw)
+    if kw["n_samples"] == 40000:   # long alt/alt and missing runs
+        s.alleles[3, 1000:60000] = 1
+        s.alleles[5, :] = 1
+        if kw.get("missing_rate"):
+            s.alleles[7, 20000:70000] = 2
+    raw, desc = tf.encode_runs(s, widths, seed=kw["seed"])
+    want_data, want_mask = tf.pack_bits(s)
+    meta = lc.variant_meta(s)
+    eng = tb.Engine(force_phased=1, sparse_max_words=-1)
+    eng.load_runs(s.n_samples, raw, desc, meta)
+    data, mask = eng.rows(s.n_variants, want_data.shape[1], with_mask=True)
+    assert np.array_equal(data, want_data)
+    assert np.array_equal(mask, want_mask if want_mask is not None else np.zeros_like(want_data))
+    eng.close()
+
+
+def test_device_run_decode_records_equal_matrix_load():
+    s = tf.synth_genotypes(700, 900, seed=37, missing_rate=0.05)
+    prm = dict(forced_unphased=1, minR2=0.05)
+    _, want, st0 = gpu_run(s, prm, tb.KERNEL_AUTO)
+    raw, desc = tf.encode_runs(s, [1, 2, 4], seed=1)
+    eng = tb.Engine(kernel=tb.KERNEL_AUTO, **prm)
+    eng.load_runs(s.n_samples, raw, desc, lc.variant_meta(s))
+    got = eng.compute()
+    assert eng.stats().pairs_visited == st0.pairs_visited
+    assert np.array_equal(tf.canonical(got, forward_only=False).view(np.uint8), tf.canonical(want, forward_only=False).view(np.uint8))
+
+
+def test_device_run_decode_rejects_bad_runs():
+    s = tf.synth_genotypes(100, 20, seed=38)
+    raw, desc = tf.encode_runs(s, [2])
+    meta = lc.variant_meta(s)
+    eng = tb.Engine(force_phased=1)
+    bad = desc.copy()
+    bad["n_runs"][4] -= 1                     # runs no longer cover all samples
+    with pytest.raises(tb.TwkbError, match="variant 4"):
+        eng.load_runs(s.n_samples, raw, bad, meta)
+    bad = desc.copy()
+    bad["offset"][6] = len(raw)               # points past the buffer
+    with pytest.raises(tb.TwkbError, match="truncated"):
+        eng.load_runs(s.n_samples, raw, bad, meta)
+    bad = desc.copy()
+    bad["width"][0] = 3
+    with pytest.raises(tb.TwkbError):
+        eng.load_runs(s.n_samples, raw, bad, meta)
+    eng.load_runs(s.n_samples, raw, desc, meta)   # the context is still usable
+    assert eng.stats() is not None
+
+
+@pytest.mark.parametrize("name", ["phased_r01", "unphased_miss", "auto_mixed"])
+def test_calc_file_device_decode_equals_host_unpack(name, tmpdir_repo):
+    """twkb_calc_file: device-side decode (default) and host unpack (host_unpack=1) write the same records."""
+    s, ref, prm, pairs, cli = load_golden(name)
+    twk = os.path.join(tmpdir_repo, f"dd_{name}.twk")
+    tf.write_twk(twk, s)
+    outs = []
+    for host_unpack in (0, 1):
+        ld = tb.twk_ld()
+        out = os.path.join(tmpdir_repo, f"dd_{name}_{host_unpack}")
+        assert ld.Compute(tb.default_settings(host_unpack=host_unpack, n_threads=4, **prm), twk, out)
+        assert ld.last_stats.pairs_visited == pairs
+        outs.append(tf.canonical(tf.read_two(out + ".two"), forward_only=False))
+    assert np.array_equal(outs[0].view(np.uint8), outs[1].view(np.uint8))
+    assert len(outs[0]) == 2 * len(ref)

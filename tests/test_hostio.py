@@ -186,3 +186,73 @@ def test_interval_selection_matches_live_reference(tmpdir_repo):
         if len(recs):
             assert (recs["packA"] >> 2).min() >= meta["pos"][0] and (recs["packA"] >> 2).max() <= meta["pos"][-1]
         f.close()
+
+
+# ---- runs mode (device-side decode): the reader only locates the run words ----
+@pytest.mark.parametrize("kw", [
+    dict(n_samples=2504, n_variants=1203, seed=1),                     # u16 and u8 run words
+    dict(n_samples=333, n_variants=777, seed=2, missing_rate=0.07),    # 2-bit allele codes
+    dict(n_samples=31, n_variants=40, seed=3, missing_rate=0.2),
+    dict(n_samples=70000, n_variants=30, seed=6),                      # u32 run words
+])
+def test_twk_reader_runs_mode_locates_the_same_genotypes(kw, tmpdir_repo):
+    s = tf.synth_genotypes(**kw)
+    path = os.path.join(tmpdir_repo, "runs.twk")
+    n_blocks = tf.write_twk(path, s)
+    f = tb.TwkFile(path, n_threads=3, runs=True)
+    assert (f.n_samples, f.n_variants, f.n_blocks) == (s.n_samples, s.n_variants, n_blocks)
+    raw, desc, meta = f.runs()
+    want_data, want_mask = tf.pack_bits(s)
+    assert f.any_missing == (want_mask is not None)
+    data, mask = tf.decode_runs(raw, desc, s.n_samples, with_mask=want_mask is not None)
+    assert np.array_equal(data, want_data)
+    if want_mask is not None:
+        assert np.array_equal(mask, want_mask)
+    want_meta = lc.variant_meta(s)
+    for k in ("rid", "pos", "ac", "an", "hwe", "gt_missing", "gt_phase"):
+        assert np.array_equal(meta[k], want_meta[k]), k
+    assert set(np.unique(desc["width"])) <= {1, 2, 4}
+    with pytest.raises(tb.TwkbError):   # a runs handle has no unpacked rows
+        f.matrix()
+    f.close()
+
+
+def test_twk_reader_runs_mode_interval_selection(tmpdir_repo):
+    s = tf.synth_genotypes(200, 2000, seed=8)
+    path = os.path.join(tmpdir_repo, "runs_iv.twk")
+    tf.write_twk(path, s)
+    iv = [f"1:{int(s.pos[700])}-{int(s.pos[1200])}"]
+    rows = tb.TwkFile(path, intervals=iv)
+    runs = tb.TwkFile(path, intervals=iv, runs=True)
+    assert rows.n_variants == runs.n_variants == 1000
+    data, _, meta = rows.matrix()
+    raw, desc, meta_r = runs.runs()
+    got, _ = tf.decode_runs(raw, desc, s.n_samples, with_mask=False)
+    assert np.array_equal(got, data)
+    assert np.array_equal(meta["pos"], meta_r["pos"])
+
+
+def _two_body(path):
+    """File bytes after the (date-stamped) header block."""
+    raw = open(path, "rb").read()
+    cmp_len = int(np.frombuffer(raw[12:20], dtype="<u8")[0])
+    return raw[20 + cmp_len:]
+
+
+@pytest.mark.parametrize("threads", [2, 5])
+def test_two_writer_parallel_compression_is_byte_identical(threads, tmpdir_repo):
+    s, recs, prm, pairs, _ = load_golden("phased_r0")
+    twk_path = os.path.join(tmpdir_repo, "pw.twk")
+    tf.write_twk(twk_path, s)
+    twk = tb.TwkFile(twk_path)
+    outs = []
+    for nt in (1, threads):
+        out = os.path.join(tmpdir_repo, f"pw_{nt}.two")
+        w = tb.TwoWriter(out, twk, "pytest", c_level=1, b_size=300, n_threads=nt)
+        for k in range(0, len(recs), 7000):
+            w.add(recs[k:k + 7000])
+        w.close()
+        outs.append(out)
+    assert _two_body(outs[0]) == _two_body(outs[1])
+    back = tf.read_two(outs[1])
+    assert len(back) == 2 * len(recs)

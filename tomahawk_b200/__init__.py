@@ -48,7 +48,7 @@ class Settings(ctypes.Structure):
         ("minDprime", ctypes.c_double), ("maxDprime", ctypes.c_double),
         ("device", ctypes.c_int32), ("part_index", ctypes.c_int32), ("part_count", ctypes.c_int32),
         ("kernel", ctypes.c_int32), ("twk_block_size", ctypes.c_int32), ("sparse_max_words", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 4),
+        ("host_unpack", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
     ]
 
 
@@ -61,7 +61,8 @@ class Stats(ctypes.Structure):
         ("kernel_used", ctypes.c_int32), ("n_planes", ctypes.c_int32), ("word_ops", ctypes.c_uint64),
         ("mma_macs", ctypes.c_uint64), ("ms_device_total", ctypes.c_double),
         ("sparse_variants", ctypes.c_uint64), ("sparse_launches", ctypes.c_uint64), ("sparse_word_ops", ctypes.c_uint64),
-        ("ms_sparse_kernel", ctypes.c_double),
+        ("ms_sparse_kernel", ctypes.c_double), ("ms_decode_kernel", ctypes.c_double),
+        ("seconds_file_read", ctypes.c_double), ("seconds_file_load", ctypes.c_double), ("seconds_file_total", ctypes.c_double),
     ]
 
     def as_dict(self):
@@ -77,6 +78,7 @@ TWO_DTYPE = np.dtype(
      ("cnt", "<f8", (4,)), ("D", "<f8"), ("Dprime", "<f8"), ("R", "<f8"), ("R2", "<f8"), ("P", "<f8"),
      ("ChiSqFisher", "<f8"), ("ChiSqModel", "<f8")]
 )
+RUN_DESC_DTYPE = np.dtype([("offset", "<u8"), ("n_runs", "<u4"), ("width", "u1"), ("miss", "u1"), ("pad", "u1", (2,))])
 CAND_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("c", "<u4", (9,)), ("mode", "<u4")])
 SINK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint64)
 
@@ -88,6 +90,7 @@ EXPORTS = [
     "twkb_debug_candidates", "twkb_calc_file", "twkb_calc_file_intervals", "twkb_version",
     "twkb_twk_open", "twkb_twk_open_intervals", "twkb_twk_dims", "twkb_twk_copy", "twkb_twk_view", "twkb_twk_close",
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
+    "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
 ]
 
 
@@ -112,6 +115,14 @@ def lib():
         for name in ("twkb_load_matrix", "twkb_load_matrix_device"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        L.twkb_load_runs.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
+                                     ctypes.c_void_p, ctypes.c_void_p]
+        L.twkb_debug_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.twkb_twk_open_runs.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32,
+                                         ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+        L.twkb_twk_runs_view.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
+        L.twkb_two_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int32]
         L.twkb_compute.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
         L.twkb_compute_resident.argtypes = [ctypes.c_void_p]
         L.twkb_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
@@ -151,15 +162,17 @@ def _c_strings(strings):
 class TwkFile:
     """A .twk file unpacked by the host reader (twkb_twk_*)."""
 
-    def __init__(self, path: str, n_threads: int = 4, intervals=(), emulate_quirks: bool = True):
-        """``intervals``: the ``-I`` strings of ``calc`` (block-granular selection, lib/ld/ld.cpp:257-365)."""
+    def __init__(self, path: str, n_threads: int = 4, intervals=(), emulate_quirks: bool = True, runs: bool = False):
+        """``intervals``: the ``-I`` strings of ``calc`` (block-granular selection, lib/ld/ld.cpp:257-365).
+        ``runs``: keep the genotypes run-length encoded for the device decoder (:meth:`runs`)."""
         L = lib()
         self._L = L
         self._h = ctypes.c_void_p()
+        self.runs_mode = runs
         err = ctypes.create_string_buffer(512)
         iv = _c_strings(intervals)
-        rc = L.twkb_twk_open_intervals(path.encode(), n_threads, iv, len(intervals), int(emulate_quirks),
-                                       ctypes.byref(self._h), err, 512)
+        opener = L.twkb_twk_open_runs if runs else L.twkb_twk_open_intervals
+        rc = opener(path.encode(), n_threads, iv, len(intervals), int(emulate_quirks), ctypes.byref(self._h), err, 512)
         if rc != 0:
             raise TwkbError(rc, err.value.decode())
         ns, nv, st, am, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t(), ctypes.c_int32(), ctypes.c_uint32()
@@ -167,7 +180,21 @@ class TwkFile:
         self.n_samples, self.n_variants, self.stride = ns.value, nv.value, st.value
         self.any_missing, self.n_blocks = bool(am.value), nb.value
 
+    def runs(self):
+        """(run_bytes uint8[n], desc RUN_DESC_DTYPE[n_variants], meta) -- views into the handle's buffers,
+        valid until close(); what Engine.load_runs takes."""
+        b, n, d, m = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_void_p(), ctypes.c_void_p()
+        rc = self._L.twkb_twk_runs_view(self._h, ctypes.byref(b), ctypes.byref(n), ctypes.byref(d), ctypes.byref(m))
+        if rc != 0:
+            raise TwkbError(rc, "handle was not opened in runs mode")
+        raw = np.ctypeslib.as_array(ctypes.cast(b, ctypes.POINTER(ctypes.c_uint8)), shape=(n.value,))
+        desc = np.frombuffer((ctypes.c_uint8 * (16 * self.n_variants)).from_address(d.value), dtype=RUN_DESC_DTYPE)
+        meta = np.frombuffer((ctypes.c_uint8 * (32 * self.n_variants)).from_address(m.value), dtype=VARIANT_DTYPE)
+        return raw, desc, meta
+
     def matrix(self):
+        if self.runs_mode:
+            raise TwkbError(-5, "handle holds run-length records; use runs()")
         data = np.zeros((self.n_variants, self.stride), dtype=np.uint64)
         mask = np.zeros_like(data) if self.any_missing else None
         meta = np.zeros(self.n_variants, dtype=VARIANT_DTYPE)
@@ -189,7 +216,8 @@ class TwkFile:
 class TwoWriter:
     """Streaming .two writer (twkb_two_*): forward records in, forward + reverse blocks out."""
 
-    def __init__(self, path: str, twk: TwkFile, command_line: str = "", c_level: int = 1, b_size: int = 10000):
+    def __init__(self, path: str, twk: TwkFile, command_line: str = "", c_level: int = 1, b_size: int = 10000,
+                 n_threads: int = 1):
         L = lib()
         self._L = L
         self._w = ctypes.c_void_p()
@@ -197,6 +225,7 @@ class TwoWriter:
         rc = L.twkb_two_open(path.encode(), twk._h, command_line.encode(), c_level, b_size, ctypes.byref(self._w), err, 512)
         if rc != 0:
             raise TwkbError(rc, err.value.decode())
+        L.twkb_two_set_threads(self._w, n_threads)
 
     def add(self, records: np.ndarray):
         records = np.ascontiguousarray(records)
@@ -283,6 +312,22 @@ class Engine:
         self._check(self._L.twkb_load_matrix(self._ctx, n_samples, data.shape[0], data.ctypes.data,
                                              mask.ctypes.data if mask is not None else None, data.shape[1],
                                              meta.ctypes.data))
+
+    def load_runs(self, n_samples: int, run_bytes: np.ndarray, desc: np.ndarray, meta: np.ndarray):
+        """Run-length records (twk1_igt_t words located by ``desc``) -> resident rows, decoded on the device."""
+        run_bytes = np.ascontiguousarray(run_bytes, dtype=np.uint8)
+        desc = np.ascontiguousarray(desc)
+        meta = np.ascontiguousarray(meta)
+        assert desc.dtype.itemsize == 16 and meta.dtype.itemsize == 32 and len(desc) == len(meta)
+        self._check(self._L.twkb_load_runs(self._ctx, n_samples, len(desc), run_bytes.ctypes.data, run_bytes.size,
+                                           desc.ctypes.data, meta.ctypes.data))
+
+    def rows(self, n_variants: int, stride: int, with_mask: bool = False):
+        """Test hook: the resident reference-layout rows copied back to the host."""
+        data = np.zeros((n_variants, stride), dtype=np.uint64)
+        mask = np.zeros_like(data) if with_mask else None
+        self._check(self._L.twkb_debug_rows(self._ctx, data.ctypes.data, mask.ctypes.data if with_mask else None, stride))
+        return data, mask
 
     def load_device(self, n_samples, n_variants, d_data_ptr, d_mask_ptr, stride, meta):
         meta = np.ascontiguousarray(meta)

@@ -18,6 +18,7 @@
 #include "count_popc.cuh"
 #include "count_sparse.cuh"
 #include "count_umma.cuh"
+#include "decode.cuh"
 #include "hostio.h"
 #include "pack.cuh"
 #include "stats.cuh"
@@ -123,6 +124,7 @@ struct Context {
     unsigned long long* h_counters = nullptr;  // pinned
 
     twkb_stats stats{};
+    double ms_decode = 0.0;  // decode_runs_kernel time of the last twkb_load_runs
 
     int fail(const std::string& m) {
         err = m;
@@ -804,6 +806,7 @@ static int compute_impl(Context* ctx, bool resident, twkb_sink_fn sink, void* us
     ctx->stats = twkb_stats{};
     ctx->stats.ms_h2d = ms_h2d;
     ctx->stats.bytes_h2d = b_h2d;
+    ctx->stats.ms_decode_kernel = ctx->ms_decode;
     CUDA_TRY(cudaEventRecord(ctx->ev_begin, ctx->stream));
     Problem pb;
     int rc = select_problem(ctx, pb);
@@ -919,9 +922,9 @@ static int classify_sparse(Context* ctx) {
     return TWKB_OK;
 }
 
-static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* data, const uint64_t* mask,
-                       size_t stride, const twkb_variant* meta, bool device_src) {
-    if (!data || !meta || n_samples == 0 || n_variants == 0) { ctx->err = "null/empty matrix"; return TWKB_EINVAL; }
+// First half of every load: shape, file-order metadata, missing-data flag.
+static int load_begin(Context* ctx, uint32_t n_samples, uint32_t n_variants, size_t stride, const twkb_variant* meta) {
+    if (!meta || n_samples == 0 || n_variants == 0) { ctx->err = "null/empty matrix"; return TWKB_EINVAL; }
     if (stride * 64 < 2 * (size_t)n_samples) { ctx->err = "row_stride_words too small for n_samples"; return TWKB_EINVAL; }
     if (2 * (uint64_t)n_samples >= (1ull << 31)) { ctx->err = "n_samples too large"; return TWKB_EINVAL; }
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -938,18 +941,13 @@ static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, co
     ctx->any_missing = false;
     for (uint32_t v = 0; v < n_variants; ++v)
         if (meta[v].gt_missing || meta[v].an) ctx->any_missing = true;
-    if (ctx->any_missing && !mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
-    const size_t words = (size_t)n_variants * stride;
-    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-    CUDA_TRY(ctx->d_raw_data.alloc(words));
-    const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_data.p, data, words * 8, kind, ctx->stream));
-    ctx->stats.bytes_h2d = device_src ? 0 : words * 8;
-    if (ctx->any_missing) {
-        CUDA_TRY(ctx->d_raw_mask.alloc(words));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_mask.p, mask, words * 8, kind, ctx->stream));
-        if (!device_src) ctx->stats.bytes_h2d += words * 8;
-    }
+    return TWKB_OK;
+}
+
+// Second half: d_raw_data (+ d_raw_mask) hold the reference-layout rows, however they got there
+// (ev0 was recorded before the upload started).
+static int load_finish(Context* ctx, const twkb_variant* meta) {
+    const uint32_t n_samples = ctx->n_samples, n_variants = ctx->n_variants;
     // rare-variant class: may re-order the resident rows [dense | sparse]
     {
         const int rc_sp = classify_sparse(ctx);
@@ -989,7 +987,87 @@ static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, co
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->stats.ms_h2d = ms;
+    ctx->stats.ms_decode_kernel = ctx->ms_decode;
     return TWKB_OK;
+}
+
+static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* data, const uint64_t* mask,
+                       size_t stride, const twkb_variant* meta, bool device_src) {
+    if (!data) { ctx->err = "null/empty matrix"; return TWKB_EINVAL; }
+    int rc = load_begin(ctx, n_samples, n_variants, stride, meta);
+    if (rc) return rc;
+    ctx->ms_decode = 0.0;
+    if (ctx->any_missing && !mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
+    const size_t words = (size_t)n_variants * stride;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_TRY(ctx->d_raw_data.alloc(words));
+    const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_data.p, data, words * 8, kind, ctx->stream));
+    ctx->stats.bytes_h2d = device_src ? 0 : words * 8;
+    if (ctx->any_missing) {
+        CUDA_TRY(ctx->d_raw_mask.alloc(words));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_mask.p, mask, words * 8, kind, ctx->stream));
+        if (!device_src) ctx->stats.bytes_h2d += words * 8;
+    }
+    return load_finish(ctx, meta);
+}
+
+// twkb_load_runs: run-length records -> resident rows, decoded by decode_runs_kernel.
+static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint8_t* bytes, size_t n_bytes,
+                     const twkb_run_desc* desc, const twkb_variant* meta) {
+    if (!bytes || !desc) { ctx->err = "null run buffer"; return TWKB_EINVAL; }
+    const uint64_t H = 2ull * n_samples;
+    const size_t stride = ((H + 63) / 64 + 1) / 2 * 2;  // 128-bit aligned rows, as twk_igt_vec (include/core.h:52-60)
+    int rc = load_begin(ctx, n_samples, n_variants, stride, meta);
+    if (rc) return rc;
+    for (uint32_t v = 0; v < n_variants; ++v) {
+        const twkb_run_desc& d = desc[v];
+        if ((d.width != 1 && d.width != 2 && d.width != 4) || d.miss > 1 || d.offset > n_bytes ||
+            (uint64_t)d.n_runs * d.width > n_bytes - d.offset) {
+            ctx->err = "illegal gt primitive type / truncated runs (variant " + std::to_string(v) + ")";
+            return TWKB_EINVAL;
+        }
+    }
+    const size_t words = (size_t)n_variants * stride;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    DevBuf<uint8_t> d_bytes;
+    DevBuf<twkb_run_desc> d_desc;
+    DevBuf<uint32_t> d_err;
+    CUDA_TRY(d_bytes.alloc(n_bytes + 16));
+    CUDA_TRY(d_desc.alloc(n_variants));
+    CUDA_TRY(d_err.alloc(2));
+    CUDA_TRY(ctx->d_raw_data.alloc(words));
+    if (ctx->any_missing) CUDA_TRY(ctx->d_raw_mask.alloc(words));
+    CUDA_TRY(cudaMemcpyAsync(d_bytes.p, bytes, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_desc.p, desc, (size_t)n_variants * sizeof(twkb_run_desc), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_raw_data.p, 0, words * 8, ctx->stream));
+    if (ctx->any_missing) CUDA_TRY(cudaMemsetAsync(ctx->d_raw_mask.p, 0, words * 8, ctx->stream));
+    const uint32_t h_err0[2] = {0u, 0xffffffffu};
+    CUDA_TRY(cudaMemcpyAsync(d_err.p, h_err0, sizeof(h_err0), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
+    decode_runs_kernel<<<(n_variants + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, ctx->stream>>>(
+        d_bytes.p, d_desc.p, n_variants, (uint32_t)H, reinterpret_cast<uint32_t*>(ctx->d_raw_data.p),
+        ctx->any_missing ? reinterpret_cast<uint32_t*>(ctx->d_raw_mask.p) : nullptr, stride * 2, d_err.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
+    uint32_t h_err[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h_err, d_err.p, sizeof(h_err), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    d_bytes.release();
+    d_desc.release();
+    d_err.release();
+    {
+        float ms_dec = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms_dec, ctx->ev2, ctx->ev3));
+        ctx->ms_decode = ms_dec;
+    }
+    ctx->stats.other_launches += 1;
+    ctx->stats.bytes_h2d = n_bytes + (size_t)n_variants * sizeof(twkb_run_desc);
+    if (h_err[0]) {
+        ctx->err = "run lengths do not cover all samples (variant " + std::to_string(h_err[1]) + ")";
+        return TWKB_EINVAL;
+    }
+    return load_finish(ctx, meta);
 }
 
 }  // namespace twkb
@@ -1096,6 +1174,29 @@ int twkb_load_matrix_device(void* c, uint32_t n_samples, uint32_t n_variants, co
     return load_common(static_cast<Context*>(c), n_samples, n_variants, d_data_bits, d_mask_bits, row_stride_words, meta, true);
 }
 
+int twkb_load_runs(void* c, uint32_t n_samples, uint32_t n_variants, const uint8_t* run_bytes, size_t n_run_bytes,
+                   const twkb_run_desc* desc, const twkb_variant* meta) {
+    if (!c) return TWKB_EINVAL;
+    return load_runs(static_cast<Context*>(c), n_samples, n_variants, run_bytes, n_run_bytes, desc, meta);
+}
+
+int twkb_debug_rows(void* c, uint64_t* data_bits, uint64_t* mask_bits, size_t row_stride_words) {
+    if (!c || !data_bits) return TWKB_EINVAL;
+    Context* ctx = static_cast<Context*>(c);
+    if (!ctx->loaded) { ctx->err = "twkb_debug_rows before a load"; return TWKB_ESTATE; }
+    if (row_stride_words < ctx->raw_stride) { ctx->err = "row_stride_words too small"; return TWKB_EINVAL; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t w = ctx->raw_stride * 8;
+    CUDA_TRY(cudaMemcpy2D(data_bits, row_stride_words * 8, ctx->d_raw_data.p, w, w, ctx->n_variants, cudaMemcpyDeviceToHost));
+    if (mask_bits) {
+        if (ctx->any_missing)
+            CUDA_TRY(cudaMemcpy2D(mask_bits, row_stride_words * 8, ctx->d_raw_mask.p, w, w, ctx->n_variants, cudaMemcpyDeviceToHost));
+        else
+            for (uint32_t v = 0; v < ctx->n_variants; ++v) std::memset(mask_bits + (size_t)v * row_stride_words, 0, w);
+    }
+    return TWKB_OK;
+}
+
 int twkb_compute(void* c, twkb_sink_fn sink, void* user) {
     if (!c) return TWKB_EINVAL;
     return compute_impl(static_cast<Context*>(c), false, sink, user, false, nullptr);
@@ -1155,14 +1256,24 @@ int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const 
         if (!intervals || !intervals[i]) return fail(TWKB_EINVAL, "null interval string");
         ivals.emplace_back(intervals[i]);
     }
-    int rc = read_twk(in_path, std::max(1, s->n_threads), twk, err, ivals.empty() ? nullptr : &ivals, s->emulate_quirks != 0);
+    const bool runs = s->host_unpack == 0;  // default: the device decodes the run-length records
+    const auto t_open = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
+    int rc = read_twk(in_path, std::max(1, s->n_threads), twk, err, ivals.empty() ? nullptr : &ivals, s->emulate_quirks != 0, runs);
     if (rc) return fail(rc, err);
+    const double sec_read = since(t_open);
     void* c = nullptr;
     rc = twkb_create(s, &c);
     if (rc) return fail(rc, twkb_last_error(nullptr));
     Context* ctx = static_cast<Context*>(c);
-    rc = twkb_load_matrix(c, twk.n_samples, twk.n_variants, twk.data.data(), twk.any_missing ? twk.mask.data() : nullptr,
-                          twk.stride, twk.meta.data());
+    const auto t_load = std::chrono::steady_clock::now();
+    if (runs)
+        rc = twkb_load_runs(c, twk.n_samples, twk.n_variants, twk.raw.data(), twk.raw.size(), twk.run_desc.data(), twk.meta.data());
+    else
+        rc = twkb_load_matrix(c, twk.n_samples, twk.n_variants, twk.data.data(), twk.any_missing ? twk.mask.data() : nullptr,
+                              twk.stride, twk.meta.data());
+    if (rc == TWKB_OK && runs) { std::vector<uint8_t>().swap(twk.raw); }  // the runs now live on the device
+    const double sec_load = since(t_load);
     if (rc) { err = ctx->err; twkb_destroy(c); return fail(rc, err); }
     // output name: the reference forces a ".two" suffix (ld.cpp:589-598)
     std::string out = out_path;
@@ -1178,11 +1289,17 @@ int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const 
     std::string cmd = std::string("tomahawk_b200 calc -i ") + in_path + " -o " + out_path;
     rc = writer.open(out, twk, cmd, s->c_level, s->b_size, err);
     if (rc) { twkb_destroy(c); return fail(rc, err); }
+    writer.set_threads(std::max(1, s->n_threads));
     rc = twkb_compute(c, writer_sink, &writer);
     if (rc) { err = ctx->err.empty() ? writer.error() : ctx->err; twkb_destroy(c); return fail(rc, err); }
     rc = writer.finish();
     if (rc) { err = writer.error(); twkb_destroy(c); return fail(rc, err); }
-    if (stats_out) *stats_out = ctx->stats;
+    if (stats_out) {
+        *stats_out = ctx->stats;
+        stats_out->seconds_file_read = sec_read;
+        stats_out->seconds_file_load = sec_load;
+        stats_out->seconds_file_total = since(t_open);
+    }
     twkb_destroy(c);
     return TWKB_OK;
 }
@@ -1213,6 +1330,34 @@ int twkb_twk_open_intervals(const char* path, int n_threads, const char* const* 
     return TWKB_OK;
 }
 
+int twkb_twk_open_runs(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
+                       int32_t emulate_quirks, void** handle, char* errbuf, size_t errbuf_len) {
+    if (!path || !handle) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
+    std::vector<std::string> ivals;
+    for (int32_t i = 0; i < n_intervals; ++i) {
+        if (!intervals || !intervals[i]) return copy_err(errbuf, errbuf_len, "null interval string", TWKB_EINVAL);
+        ivals.emplace_back(intervals[i]);
+    }
+    TwkFile* f = new TwkFile();
+    std::string err;
+    const int rc = read_twk(path, std::max(1, n_threads), *f, err, ivals.empty() ? nullptr : &ivals, emulate_quirks != 0, true);
+    if (rc) { delete f; return copy_err(errbuf, errbuf_len, err, rc); }
+    *handle = f;
+    return TWKB_OK;
+}
+
+int twkb_twk_runs_view(void* handle, const uint8_t** run_bytes, size_t* n_run_bytes, const twkb_run_desc** desc,
+                       const twkb_variant** meta) {
+    if (!handle) return TWKB_EINVAL;
+    const TwkFile* f = static_cast<TwkFile*>(handle);
+    if (!f->runs_mode) return TWKB_ESTATE;
+    if (run_bytes) *run_bytes = f->raw.data();
+    if (n_run_bytes) *n_run_bytes = f->raw.size();
+    if (desc) *desc = f->run_desc.data();
+    if (meta) *meta = f->meta.data();
+    return TWKB_OK;
+}
+
 int twkb_twk_dims(void* handle, uint32_t* n_samples, uint32_t* n_variants, size_t* row_stride_words, int32_t* any_missing,
                   uint32_t* n_blocks) {
     if (!handle) return TWKB_EINVAL;
@@ -1228,6 +1373,7 @@ int twkb_twk_dims(void* handle, uint32_t* n_samples, uint32_t* n_variants, size_
 int twkb_twk_copy(void* handle, uint64_t* data_bits, uint64_t* mask_bits, twkb_variant* meta) {
     if (!handle) return TWKB_EINVAL;
     const TwkFile* f = static_cast<TwkFile*>(handle);
+    if (f->runs_mode) return TWKB_ESTATE;
     if (data_bits) std::memcpy(data_bits, f->data.data(), f->data.size() * 8);
     if (mask_bits) {
         if (f->any_missing) std::memcpy(mask_bits, f->mask.data(), f->mask.size() * 8);
@@ -1240,6 +1386,7 @@ int twkb_twk_copy(void* handle, uint64_t* data_bits, uint64_t* mask_bits, twkb_v
 int twkb_twk_view(void* handle, const uint64_t** data_bits, const uint64_t** mask_bits, const twkb_variant** meta) {
     if (!handle) return TWKB_EINVAL;
     const TwkFile* f = static_cast<TwkFile*>(handle);
+    if (f->runs_mode) return TWKB_ESTATE;
     if (data_bits) *data_bits = f->data.data();
     if (mask_bits) *mask_bits = f->any_missing ? f->mask.data() : nullptr;
     if (meta) *meta = f->meta.data();
@@ -1256,6 +1403,12 @@ int twkb_two_open(const char* path, void* twk_handle, const char* command_line, 
     const int rc = w->open(path, *static_cast<TwkFile*>(twk_handle), command_line ? command_line : "", c_level, b_size, err);
     if (rc) { delete w; return copy_err(errbuf, errbuf_len, err, rc); }
     *writer = w;
+    return TWKB_OK;
+}
+
+int twkb_two_set_threads(void* writer, int32_t n_threads) {
+    if (!writer) return TWKB_EINVAL;
+    static_cast<TwoWriter*>(writer)->set_threads(n_threads);
     return TWKB_OK;
 }
 

@@ -171,7 +171,7 @@ int select_interval_blocks(const std::vector<std::string>& strings, const std::v
 // lib/twk_reader.cpp:49-125 (Open), :8-44 (NextBlock), lib/core.cpp:75-101 (twk1_t),
 // include/core.h:195-215 (run words), lib/core.cpp:365-383 (bitvector + mask).
 int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err, const std::vector<std::string>* intervals,
-             bool emulate_quirks) {
+             bool emulate_quirks, bool keep_runs) {
     FILE* fp = std::fopen(path.c_str(), "rb");
     if (!fp) { err = "Failed to open \"" + path + "\"!"; return TWKB_EIO; }
     std::fseek(fp, 0, SEEK_END);
@@ -259,9 +259,25 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     out.n_variants = (uint32_t)total;
     const uint64_t H = 2ull * out.n_samples;
     out.stride = ((H + 63) / 64 + 1) / 2 * 2;
-    out.data.assign((size_t)total * out.stride, 0);
+    out.runs_mode = keep_runs;
     out.meta.assign(total, twkb_variant{});
+    // Runs mode: every block is inflated straight into its slot of out.raw (sizes from the block
+    // headers), the variant headers are parsed in place and the run words stay where they are.
+    std::vector<uint64_t> raw_off(n_ent + 1, 0);
+    if (keep_runs) {
+        for (uint64_t b = 0; b < n_ent; ++b) {
+            if (blocks[b].foff + 9 > file.size()) { err = "block offset beyond file"; return TWKB_EIO; }
+            uint32_t unc = 0;
+            std::memcpy(&unc, file.data() + blocks[b].foff + 1, 4);
+            raw_off[b + 1] = raw_off[b] + ((uint64_t)unc + 15) / 16 * 16;
+        }
+        out.raw.assign(raw_off[n_ent] + 16, 0);
+        out.run_desc.assign(total, twkb_run_desc{});
+    } else {
+        out.data.assign((size_t)total * out.stride, 0);
+    }
     std::vector<std::vector<uint64_t>> block_masks(n_ent);  // only for blocks that have missing data
+    std::atomic<bool> any_miss_flag{false};
     std::atomic<uint64_t> next{0};
     std::atomic<bool> failed{false};
     std::string first_err;
@@ -281,8 +297,17 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
             if (bc.get<uint8_t>() != 1) { fail("bad block marker"); return; }
             const uint32_t unc = bc.get<uint32_t>(), cmp = bc.get<uint32_t>();
             std::string e;
-            if ((uint64_t)(bc.end - bc.p) < cmp || !zstd_inflate(bc.p, cmp, unc, raw, e)) { fail("Failed to load block " + std::to_string(b)); return; }
-            Cursor r{raw.data(), raw.data() + raw.size()};
+            const uint8_t* raw_base = nullptr;
+            if (keep_runs) {
+                uint8_t* dst = out.raw.data() + raw_off[b];
+                const size_t got = (uint64_t)(bc.end - bc.p) < cmp ? (size_t)-1 : ZSTD_decompress(dst, unc, bc.p, cmp);
+                if (got == (size_t)-1 || ZSTD_isError(got) || got != unc) { fail("Failed to load block " + std::to_string(b)); return; }
+                raw_base = dst;
+            } else {
+                if ((uint64_t)(bc.end - bc.p) < cmp || !zstd_inflate(bc.p, cmp, unc, raw, e)) { fail("Failed to load block " + std::to_string(b)); return; }
+                raw_base = raw.data();
+            }
+            Cursor r{raw_base, raw_base + unc};
             const uint32_t n = r.get<uint32_t>();
             r.get<uint32_t>();  // m
             r.get<uint32_t>();  // rid
@@ -306,6 +331,16 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
                 if (!r.ok || (ptype != 1 && ptype != 2 && ptype != 4) || (size_t)(r.end - r.p) < (size_t)n_runs * ptype) {
                     fail("illegal gt primitive type / truncated runs");
                     return;
+                }
+                if (keep_runs) {  // the device walks the runs (decode.cuh); only locate them
+                    twkb_run_desc& rd = out.run_desc[br.first_variant + v];
+                    rd.offset = (uint64_t)(r.p - out.raw.data());
+                    rd.n_runs = n_runs;
+                    rd.width = (uint8_t)ptype;
+                    rd.miss = (uint8_t)miss;
+                    if (mv.gt_missing || miss || mv.an) any_miss_flag.store(true, std::memory_order_relaxed);
+                    r.p += (size_t)n_runs * ptype;
+                    continue;
                 }
                 uint64_t* row = out.data.data() + (size_t)(br.first_variant + v) * out.stride;
                 uint64_t* mrow = nullptr;
@@ -338,10 +373,10 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     worker();
     for (auto& th : pool) th.join();
     if (failed.load()) { err = first_err; return TWKB_EIO; }
-    out.any_missing = false;
+    out.any_missing = any_miss_flag.load();
     for (auto& m : block_masks) if (!m.empty()) out.any_missing = true;
     for (auto& mv : out.meta) if (mv.an || mv.gt_missing) out.any_missing = true;
-    if (out.any_missing) {
+    if (out.any_missing && !keep_runs) {
         out.mask.assign((size_t)total * out.stride, 0);
         for (uint64_t b = 0; b < n_ent; ++b)
             if (!block_masks[b].empty())
@@ -392,43 +427,64 @@ int TwoWriter::open(const std::string& path, const TwkFile& src, const std::stri
     return TWKB_OK;
 }
 
-// one zstd block: u8 1, u32 unc, u32 cmp, payload (include/writer.h:70-87)
-int TwoWriter::write_block(const std::vector<uint8_t>& raw, uint32_t* b_cmp) {
-    zbuf_.resize(ZSTD_compressBound(raw.size()));
-    const size_t zn = ZSTD_compress(zbuf_.data(), zbuf_.size(), raw.data(), raw.size(), c_level_);
-    if (ZSTD_isError(zn)) { err_ = "failed compression"; return TWKB_EIO; }
-    const uint8_t marker = 1;
-    const uint32_t unc = (uint32_t)raw.size(), cmp = (uint32_t)zn;
-    if (std::fwrite(&marker, 1, 1, fp_) != 1 || std::fwrite(&unc, 4, 1, fp_) != 1 || std::fwrite(&cmp, 4, 1, fp_) != 1 ||
-        std::fwrite(zbuf_.data(), 1, zn, fp_) != zn) {
-        err_ = "write failed";
-        return TWKB_EIO;
+// Compresses every pending block (up to threads_ at a time; blocks are independent zstd frames)
+// and writes them in queue order. One block on disk: u8 1, u32 unc, u32 cmp, payload
+// (include/writer.h:70-87); the index entry gets its offsets here.
+int TwoWriter::drain() {
+    if (pending_.empty()) return TWKB_OK;
+    std::atomic<size_t> next{0};
+    std::atomic<bool> bad{false};
+    auto work = [&]() {
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= pending_.size()) return;
+            Pending& pb = pending_[k];
+            pb.z.resize(ZSTD_compressBound(pb.raw.size()));
+            pb.zn = ZSTD_compress(pb.z.data(), pb.z.size(), pb.raw.data(), pb.raw.size(), c_level_);
+            if (ZSTD_isError(pb.zn)) bad.store(true);
+        }
+    };
+    const int nt = (int)std::min<size_t>((size_t)threads_, pending_.size());
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    if (bad.load()) { err_ = "failed compression"; return TWKB_EIO; }
+    for (Pending& pb : pending_) {
+        const uint8_t marker = 1;
+        const uint32_t unc = (uint32_t)pb.raw.size(), cmp = (uint32_t)pb.zn;
+        pb.ent.foff = (uint64_t)std::ftell(fp_);
+        if (std::fwrite(&marker, 1, 1, fp_) != 1 || std::fwrite(&unc, 4, 1, fp_) != 1 || std::fwrite(&cmp, 4, 1, fp_) != 1 ||
+            std::fwrite(pb.z.data(), 1, pb.zn, fp_) != pb.zn) {
+            err_ = "write failed";
+            return TWKB_EIO;
+        }
+        pb.ent.fend = (uint64_t)std::ftell(fp_);
+        pb.ent.b_cmp = cmp;
+        index_.push_back(pb.ent);
     }
-    *b_cmp = cmp;
+    pending_.clear();
     return TWKB_OK;
 }
 
-// lib/ld/ld_engine.cpp:1742-1802 (CompressFwd/CompressRev)
+// lib/ld/ld_engine.cpp:1742-1802 (CompressFwd/CompressRev): the block is queued; drain() writes it.
 int TwoWriter::flush_side(Side& s) {
     if (s.n == 0) return TWKB_OK;
-    scratch_.resize(8 + s.buf.size());
+    pending_.emplace_back();
+    Pending& pb = pending_.back();
+    pb.raw.resize(8 + s.buf.size());
     const uint32_t n = s.n, m = b_size_ + 100;  // twk1_two_block_t {n, m}, lib/core.cpp:626-631
-    std::memcpy(scratch_.data(), &n, 4);
-    std::memcpy(scratch_.data() + 4, &m, 4);
-    std::memcpy(scratch_.data() + 8, s.buf.data(), s.buf.size());
-    s.ent.foff = (uint64_t)std::ftell(fp_);
-    uint32_t cmp = 0;
-    const int rc = write_block(scratch_, &cmp);
-    if (rc) return rc;
-    s.ent.fend = (uint64_t)std::ftell(fp_);
-    s.ent.n = n;
-    s.ent.b_unc = TWKB_RECORD_BYTES * n + 8;
-    s.ent.b_cmp = cmp;
-    index_.push_back(s.ent);
+    std::memcpy(pb.raw.data(), &n, 4);
+    std::memcpy(pb.raw.data() + 4, &m, 4);
+    std::memcpy(pb.raw.data() + 8, s.buf.data(), s.buf.size());
+    pb.ent = s.ent;
+    pb.ent.n = n;
+    pb.ent.b_unc = TWKB_RECORD_BYTES * n + 8;
     n_written_ += n;
     s.buf.clear();
     s.n = 0;
     s.ent.rid = -1; s.ent.ridB = -1; s.ent.minpos = 0; s.ent.n = 0; s.ent.foff = 0; s.ent.fend = 0;
+    if (pending_.size() >= (size_t)std::max(2, 4 * threads_)) return drain();
     return TWKB_OK;
 }
 
@@ -475,6 +531,8 @@ int TwoWriter::finish() {
     int rc = flush_side(fwd_);
     if (rc) return rc;
     rc = flush_side(rev_);
+    if (rc) return rc;
+    rc = drain();
     if (rc) return rc;
     std::vector<uint8_t> idx;
     auto put = [&](const void* p, size_t n) { idx.insert(idx.end(), (const uint8_t*)p, (const uint8_t*)p + n); };

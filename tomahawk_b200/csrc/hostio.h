@@ -36,16 +36,25 @@ struct TwkFile {
     std::string header_tail;  // serialized samples + contigs, copied through verbatim
     uint32_t n_contigs = 0;
     uint32_t n_blocks = 0;
+    // Runs mode (keep_runs): the rows are NOT unpacked on the host. `raw` holds the inflated .twk
+    // blocks back to back and run_desc[v] locates the run-length words of variant v inside it
+    // (twk1_igt_t, include/core.h:188-256); the device decodes them (decode.cuh, twkb_load_runs).
+    bool runs_mode = false;
+    std::vector<uint8_t> raw;
+    std::vector<twkb_run_desc> run_desc;
 };
 
 // Reads and unpacks `path` with up to n_threads host threads. Returns 0 or TWKB_EIO.
 // `intervals` (nullable): the -I strings of `calc` ("chr", "chr:pos", "chr:from-to"); only the
 // .twk blocks that overlap them are loaded (reference lib/ld/ld.cpp:257-365, lib/intervals.cpp).
+// keep_runs: leave the genotypes run-length encoded for the device decoder (see TwkFile::raw).
 int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err,
-             const std::vector<std::string>* intervals = nullptr, bool emulate_quirks = true);
+             const std::vector<std::string>* intervals = nullptr, bool emulate_quirks = true, bool keep_runs = false);
 
 // Streaming .two writer: takes forward records, writes forward and reverse
-// blocks of <= b_size records, the index and the EOF marker.
+// blocks of <= b_size records, the index and the EOF marker. Finished blocks queue up and are
+// zstd-compressed by up to `threads` host threads at a time, then written in order: the file is
+// byte-identical to the single-threaded one.
 class TwoWriter {
 public:
     TwoWriter() = default;
@@ -54,6 +63,7 @@ public:
              std::string& err);
     int add(const uint8_t* records, uint64_t n);  // forward records, TWKB_RECORD_BYTES each
     int finish();
+    void set_threads(int n) { threads_ = n < 1 ? 1 : n; }
     uint64_t records_written() const { return n_written_; }
     const std::string& error() const { return err_; }
 
@@ -68,8 +78,13 @@ private:
         uint32_t n = 0;
         IndexEntry ent{};
     };
+    struct Pending {  // a finished block waiting for compression
+        std::vector<uint8_t> raw, z;
+        size_t zn = 0;
+        IndexEntry ent{};
+    };
     int flush_side(Side& s);
-    int write_block(const std::vector<uint8_t>& raw, uint32_t* b_cmp);
+    int drain();  // compress (in parallel) and write every pending block
 
     FILE* fp_ = nullptr;
     int c_level_ = 1;
@@ -77,7 +92,8 @@ private:
     uint32_t n_contigs_ = 0;
     Side fwd_, rev_;
     std::vector<IndexEntry> index_;
-    std::vector<uint8_t> scratch_, zbuf_;
+    std::vector<Pending> pending_;
+    int threads_ = 1;
     uint64_t n_written_ = 0;
     std::string err_;
 };
