@@ -674,7 +674,10 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
                   pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, (int)ctx->st.window,
                   ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
     if (ctx->plan_key != keybuf) {
-        uint32_t super = 16u;  // super-tile edge (in tiles) of the L2-friendly order
+        // super-tile edge (in tiles) of the L2-friendly order: 32 x 32 tiles of e2m1 operand rows are
+        // a 40 MB working set (C2), half the DRAM re-reads of 16 x 16 (B200 sweep 16/24/32/48:
+        // 28.42 / 28.15 / 28.12 / 28.12 ms per C2 launch)
+        uint32_t super = 32u;
         if (const char* e = getenv("TWKB_SUPER")) super = (uint32_t)std::max(1, atoi(e));
         if (n_dense >= 2) build_tiles(ctx, pb, TI, TJ, super, ctx->plan_tiles, &ctx->plan_pairs);
         else { ctx->plan_tiles.clear(); ctx->plan_pairs = 0; }
@@ -1029,6 +1032,14 @@ static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, cons
         }
     }
     const size_t words = (size_t)n_variants * stride;
+    const bool trace = getenv("TWKB_TRACE") != nullptr;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        std::fprintf(stderr, "[twkb trace] load_runs %-14s %8.3f ms\n", what,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count());
+    };
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     DevBuf<uint8_t> d_bytes;
     DevBuf<twkb_run_desc> d_desc;
@@ -1038,7 +1049,9 @@ static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, cons
     CUDA_TRY(d_err.alloc(2));
     CUDA_TRY(ctx->d_raw_data.alloc(words));
     if (ctx->any_missing) CUDA_TRY(ctx->d_raw_mask.alloc(words));
+    mark("alloc");
     CUDA_TRY(cudaMemcpyAsync(d_bytes.p, bytes, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    mark("h2d runs");
     CUDA_TRY(cudaMemcpyAsync(d_desc.p, desc, (size_t)n_variants * sizeof(twkb_run_desc), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_raw_data.p, 0, words * 8, ctx->stream));
     if (ctx->any_missing) CUDA_TRY(cudaMemsetAsync(ctx->d_raw_mask.p, 0, words * 8, ctx->stream));
@@ -1050,12 +1063,14 @@ static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, cons
         ctx->any_missing ? reinterpret_cast<uint32_t*>(ctx->d_raw_mask.p) : nullptr, stride * 2, d_err.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
+    mark("decode");
     uint32_t h_err[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(h_err, d_err.p, sizeof(h_err), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     d_bytes.release();
     d_desc.release();
     d_err.release();
+    mark("free");
     {
         float ms_dec = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms_dec, ctx->ev2, ctx->ev3));
@@ -1067,7 +1082,9 @@ static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, cons
         ctx->err = "run lengths do not cover all samples (variant " + std::to_string(h_err[1]) + ")";
         return TWKB_EINVAL;
     }
-    return load_finish(ctx, meta);
+    rc = load_finish(ctx, meta);
+    mark("finish");
+    return rc;
 }
 
 }  // namespace twkb
@@ -1272,7 +1289,7 @@ int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const 
     else
         rc = twkb_load_matrix(c, twk.n_samples, twk.n_variants, twk.data.data(), twk.any_missing ? twk.mask.data() : nullptr,
                               twk.stride, twk.meta.data());
-    if (rc == TWKB_OK && runs) { std::vector<uint8_t>().swap(twk.raw); }  // the runs now live on the device
+    if (rc == TWKB_OK && runs) twk.raw.release();  // the runs now live on the device
     const double sec_load = since(t_load);
     if (rc) { err = ctx->err; twkb_destroy(c); return fail(rc, err); }
     // output name: the reference forces a ".two" suffix (ld.cpp:589-598)
@@ -1442,7 +1459,7 @@ int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_vari
     if (rc) return rc;
     std::vector<uint2> tiles;
     uint64_t pairs = 0;
-    build_tiles(&ctx, pb, tile_i, tile_j, 16, tiles, &pairs);
+    build_tiles(&ctx, pb, tile_i, tile_j, 32, tiles, &pairs);
     *n_tiles = tiles.size();
     if (n_pairs) *n_pairs = pairs;
     if (out_ij) {

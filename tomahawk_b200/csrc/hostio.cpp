@@ -5,11 +5,17 @@
 #include <algorithm>
 #include <atomic>
 #include <cctype>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <mutex>
 #include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace twkb {
 
@@ -172,18 +178,25 @@ int select_interval_blocks(const std::vector<std::string>& strings, const std::v
 // include/core.h:195-215 (run words), lib/core.cpp:365-383 (bitvector + mask).
 int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err, const std::vector<std::string>* intervals,
              bool emulate_quirks, bool keep_runs) {
-    FILE* fp = std::fopen(path.c_str(), "rb");
-    if (!fp) { err = "Failed to open \"" + path + "\"!"; return TWKB_EIO; }
-    std::fseek(fp, 0, SEEK_END);
-    const long fsz = std::ftell(fp);
-    std::fseek(fp, 0, SEEK_SET);
-    std::vector<uint8_t> file((size_t)std::max<long>(fsz, 0));
-    if (fsz <= 0 || std::fread(file.data(), 1, file.size(), fp) != file.size()) {
-        std::fclose(fp);
-        err = "Failed to read \"" + path + "\"";
-        return TWKB_EIO;
+    // the file is mapped, not copied: the worker threads fault its pages in as they inflate blocks
+    struct Mapped {
+        const uint8_t* p = nullptr;
+        size_t n = 0;
+        ~Mapped() { if (p) munmap(const_cast<uint8_t*>(p), n); }
+        const uint8_t* data() const { return p; }
+        size_t size() const { return n; }
+    } file;
+    {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) { err = "Failed to open \"" + path + "\"!"; return TWKB_EIO; }
+        struct stat sb;
+        if (fstat(fd, &sb) != 0 || sb.st_size <= 0) { ::close(fd); err = "Failed to read \"" + path + "\""; return TWKB_EIO; }
+        void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        ::close(fd);
+        if (m == MAP_FAILED) { err = "Failed to read \"" + path + "\""; return TWKB_EIO; }
+        file.p = static_cast<const uint8_t*>(m);
+        file.n = (size_t)sb.st_size;
     }
-    std::fclose(fp);
     if (file.size() < 9 + 16 + 8 + 32 || std::memcmp(file.data(), kTwkMagic, 9) != 0) { err = "Failed to read MAGIC!"; return TWKB_EIO; }
     Cursor c{file.data() + 9, file.data() + file.size()};
     const uint64_t h_unc = c.get<uint64_t>(), h_cmp = c.get<uint64_t>();
@@ -271,7 +284,7 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
             std::memcpy(&unc, file.data() + blocks[b].foff + 1, 4);
             raw_off[b + 1] = raw_off[b] + ((uint64_t)unc + 15) / 16 * 16;
         }
-        out.raw.assign(raw_off[n_ent] + 16, 0);
+        if (!out.raw.alloc(raw_off[n_ent] + 16)) { err = "out of memory"; return TWKB_ENOMEM; }
         out.run_desc.assign(total, twkb_run_desc{});
     } else {
         out.data.assign((size_t)total * out.stride, 0);
@@ -388,7 +401,61 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
 
 // ------------------------------------------------------------------ .two writer
 TwoWriter::~TwoWriter() {
+    stop_writer();
     if (fp_) std::fclose(fp_);
+}
+
+void TwoWriter::set_threads(int n) {
+    threads_ = n < 1 ? 1 : n;
+    if (threads_ > 1 && !writer_.joinable()) writer_ = std::thread(&TwoWriter::writer_loop, this);
+}
+
+// Writer thread: takes record batches off the queue in arrival order.
+void TwoWriter::writer_loop() {
+    for (;;) {
+        std::vector<uint8_t> batch;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || !queue_.empty(); });
+            if (queue_.empty()) return;  // stop requested and everything written
+            batch.swap(queue_.front());
+            queue_.pop_front();
+        }
+        const int rc = add_sync(batch.data(), batch.size() / TWKB_RECORD_BYTES);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            queued_bytes_ -= batch.size();
+            if (rc && !async_rc_) async_rc_ = rc;
+        }
+        cv_.notify_all();
+    }
+}
+
+int TwoWriter::stop_writer() {
+    if (!writer_.joinable()) return async_rc_;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    writer_.join();
+    return async_rc_;
+}
+
+int TwoWriter::add(const uint8_t* records, uint64_t n) {
+    if (!writer_.joinable()) return add_sync(records, n);
+    if (n == 0) return async_rc_;
+    const size_t bytes = (size_t)n * TWKB_RECORD_BYTES;
+    std::vector<uint8_t> copy(records, records + bytes);
+    std::unique_lock<std::mutex> lk(mu_);
+    // back-pressure: at most ~512 MB of records waiting for the writer
+    cv_.wait(lk, [&] { return async_rc_ != 0 || queued_bytes_ < ((size_t)512 << 20); });
+    if (async_rc_) return async_rc_;
+    queued_bytes_ += bytes;
+    queue_.emplace_back(std::move(copy));
+    lk.unlock();
+    cv_.notify_all();
+    return TWKB_OK;
 }
 
 static void put_str(std::vector<uint8_t>& b, const std::string& s) {
@@ -432,6 +499,8 @@ int TwoWriter::open(const std::string& path, const TwkFile& src, const std::stri
 // (include/writer.h:70-87); the index entry gets its offsets here.
 int TwoWriter::drain() {
     if (pending_.empty()) return TWKB_OK;
+    const bool trace = std::getenv("TWKB_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     std::atomic<size_t> next{0};
     std::atomic<bool> bad{false};
     auto work = [&]() {
@@ -450,6 +519,7 @@ int TwoWriter::drain() {
     work();
     for (auto& th : pool) th.join();
     if (bad.load()) { err_ = "failed compression"; return TWKB_EIO; }
+    const auto t1 = std::chrono::steady_clock::now();
     for (Pending& pb : pending_) {
         const uint8_t marker = 1;
         const uint32_t unc = (uint32_t)pb.raw.size(), cmp = (uint32_t)pb.zn;
@@ -463,6 +533,10 @@ int TwoWriter::drain() {
         pb.ent.b_cmp = cmp;
         index_.push_back(pb.ent);
     }
+    if (trace)
+        std::fprintf(stderr, "[twkb trace] writer drain: %zu blocks, compress %.1f ms (%d threads), write %.1f ms\n", pending_.size(),
+                     std::chrono::duration<double, std::milli>(t1 - t0).count(), nt,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     pending_.clear();
     return TWKB_OK;
 }
@@ -488,39 +562,63 @@ int TwoWriter::flush_side(Side& s) {
     return TWKB_OK;
 }
 
-// lib/ld/ld_engine.cpp:1268-1298: flush rule, index bookkeeping, forward + swapped copy.
-int TwoWriter::add(const uint8_t* records, uint64_t n) {
-    for (uint64_t r = 0; r < n; ++r) {
+// lib/ld/ld_engine.cpp:1268-1298: flush rule, index bookkeeping, forward + swapped copy. The
+// reference tests every record; a run of records with the same (ridA, ridB) that fits the open
+// block changes nothing but maxpos, so such runs are appended in bulk.
+int TwoWriter::add_sync(const uint8_t* records, uint64_t n) {
+    auto rids = [&](uint64_t r, int32_t& a, int32_t& b) {
+        std::memcpy(&a, records + r * TWKB_RECORD_BYTES + 2, 4);
+        std::memcpy(&b, records + r * TWKB_RECORD_BYTES + 6, 4);
+    };
+    uint64_t r = 0;
+    while (r < n) {
         const uint8_t* rec = records + r * TWKB_RECORD_BYTES;
         int32_t ridA, ridB;
         uint32_t packA, packB;
-        std::memcpy(&ridA, rec + 2, 4);
-        std::memcpy(&ridB, rec + 6, 4);
+        rids(r, ridA, ridB);
         std::memcpy(&packA, rec + 10, 4);
         std::memcpy(&packB, rec + 14, 4);
-        const uint32_t posA = packA >> 2, posB = packB >> 2;
         if (fwd_.n == b_size_ || fwd_.ent.rid != ridA || rev_.ent.rid != ridB) {
             int rc = flush_side(fwd_);
             if (rc) return rc;
             rc = flush_side(rev_);
             if (rc) return rc;
-            fwd_.ent.rid = ridA; fwd_.ent.ridB = ridB; fwd_.ent.minpos = posA; fwd_.ent.maxpos = posA;
-            rev_.ent.rid = ridB; rev_.ent.ridB = ridA; rev_.ent.minpos = posB; rev_.ent.maxpos = posB;
+            fwd_.ent.rid = ridA; fwd_.ent.ridB = ridB; fwd_.ent.minpos = packA >> 2; fwd_.ent.maxpos = packA >> 2;
+            rev_.ent.rid = ridB; rev_.ent.ridB = ridA; rev_.ent.minpos = packB >> 2; rev_.ent.maxpos = packB >> 2;
         }
         if (fwd_.ent.ridB != ridB) fwd_.ent.ridB = -1;
         if (rev_.ent.ridB != ridA) rev_.ent.ridB = -1;
-        fwd_.ent.maxpos = posA;
-        rev_.ent.maxpos = posB;
-        fwd_.buf.insert(fwd_.buf.end(), rec, rec + TWKB_RECORD_BYTES);
-        ++fwd_.n;
-        // reverse copy: only (rid, pos) are swapped, counts and flags stay A-major (:1292-1298)
+        // the run [r, e): same contig pair, fits the open block
+        uint64_t e = r + 1;
+        const uint64_t room = r + (b_size_ - fwd_.n);
+        while (e < n && e < room) {
+            int32_t a2, b2;
+            rids(e, a2, b2);
+            if (a2 != ridA || b2 != ridB) break;
+            ++e;
+        }
+        const uint64_t cnt = e - r;
+        const uint8_t* last = records + (e - 1) * TWKB_RECORD_BYTES;
+        uint32_t lastA, lastB;
+        std::memcpy(&lastA, last + 10, 4);
+        std::memcpy(&lastB, last + 14, 4);
+        fwd_.ent.maxpos = lastA >> 2;
+        rev_.ent.maxpos = lastB >> 2;
+        fwd_.buf.insert(fwd_.buf.end(), rec, rec + cnt * TWKB_RECORD_BYTES);
+        fwd_.n += (uint32_t)cnt;
+        // reverse copies: only (rid, pos) are swapped, counts and flags stay A-major (:1292-1298)
         const size_t o = rev_.buf.size();
-        rev_.buf.insert(rev_.buf.end(), rec, rec + TWKB_RECORD_BYTES);
-        std::memcpy(rev_.buf.data() + o + 2, &ridB, 4);
-        std::memcpy(rev_.buf.data() + o + 6, &ridA, 4);
-        std::memcpy(rev_.buf.data() + o + 10, &packB, 4);
-        std::memcpy(rev_.buf.data() + o + 14, &packA, 4);
-        ++rev_.n;
+        rev_.buf.insert(rev_.buf.end(), rec, rec + cnt * TWKB_RECORD_BYTES);
+        for (uint64_t k = 0; k < cnt; ++k) {
+            uint8_t* d = rev_.buf.data() + o + k * TWKB_RECORD_BYTES;
+            const uint8_t* src = rec + k * TWKB_RECORD_BYTES;
+            std::memcpy(d + 2, src + 6, 4);
+            std::memcpy(d + 6, src + 2, 4);
+            std::memcpy(d + 10, src + 14, 4);
+            std::memcpy(d + 14, src + 10, 4);
+        }
+        rev_.n += (uint32_t)cnt;
+        r = e;
     }
     return TWKB_OK;
 }
@@ -528,7 +626,9 @@ int TwoWriter::add(const uint8_t* records, uint64_t n) {
 // include/writer.h:293-313 + lib/index.cpp:242-251
 int TwoWriter::finish() {
     if (!fp_) return TWKB_EIO;
-    int rc = flush_side(fwd_);
+    int rc = stop_writer();
+    if (rc) return rc;
+    rc = flush_side(fwd_);
     if (rc) return rc;
     rc = flush_side(rev_);
     if (rc) return rc;

@@ -5,8 +5,13 @@
 // zstd stays on the host (BASELINE.json north_star).
 #pragma once
 #include <cstdint>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/twkb.h"
@@ -22,6 +27,30 @@ size_t ZSTD_compressBound(size_t srcSize);
 unsigned ZSTD_isError(size_t code);
 const char* ZSTD_getErrorName(size_t code);
 }
+
+// Uninitialised byte buffer (malloc): the pages are first touched by the threads that fill them.
+struct ByteBuf {
+    uint8_t* p = nullptr;
+    size_t n = 0;
+    ByteBuf() = default;
+    ByteBuf(const ByteBuf&) = delete;
+    ByteBuf& operator=(const ByteBuf&) = delete;
+    ~ByteBuf() { release(); }
+    bool alloc(size_t bytes) {
+        release();
+        p = static_cast<uint8_t*>(std::malloc(bytes ? bytes : 1));
+        n = p ? bytes : 0;
+        return p != nullptr;
+    }
+    void release() {
+        std::free(p);
+        p = nullptr;
+        n = 0;
+    }
+    uint8_t* data() { return p; }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+};
 
 // A whole .twk file unpacked into the matrix layout twkb_load_matrix takes.
 struct TwkFile {
@@ -40,7 +69,7 @@ struct TwkFile {
     // blocks back to back and run_desc[v] locates the run-length words of variant v inside it
     // (twk1_igt_t, include/core.h:188-256); the device decodes them (decode.cuh, twkb_load_runs).
     bool runs_mode = false;
-    std::vector<uint8_t> raw;
+    ByteBuf raw;
     std::vector<twkb_run_desc> run_desc;
 };
 
@@ -54,7 +83,9 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
 // Streaming .two writer: takes forward records, writes forward and reverse
 // blocks of <= b_size records, the index and the EOF marker. Finished blocks queue up and are
 // zstd-compressed by up to `threads` host threads at a time, then written in order: the file is
-// byte-identical to the single-threaded one.
+// byte-identical to the single-threaded one. With more than one thread add() only queues a copy
+// of the records and a writer thread does the splitting, compression and file I/O, so the
+// caller (the device batch loop) never waits for zstd; errors surface at the next add()/finish().
 class TwoWriter {
 public:
     TwoWriter() = default;
@@ -63,7 +94,7 @@ public:
              std::string& err);
     int add(const uint8_t* records, uint64_t n);  // forward records, TWKB_RECORD_BYTES each
     int finish();
-    void set_threads(int n) { threads_ = n < 1 ? 1 : n; }
+    void set_threads(int n);
     uint64_t records_written() const { return n_written_; }
     const std::string& error() const { return err_; }
 
@@ -85,6 +116,9 @@ private:
     };
     int flush_side(Side& s);
     int drain();  // compress (in parallel) and write every pending block
+    int add_sync(const uint8_t* records, uint64_t n);
+    void writer_loop();
+    int stop_writer();
 
     FILE* fp_ = nullptr;
     int c_level_ = 1;
@@ -94,6 +128,14 @@ private:
     std::vector<IndexEntry> index_;
     std::vector<Pending> pending_;
     int threads_ = 1;
+    // asynchronous mode (threads_ > 1)
+    std::thread writer_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::vector<uint8_t>> queue_;
+    size_t queued_bytes_ = 0;
+    bool stop_ = false;
+    int async_rc_ = 0;
     uint64_t n_written_ = 0;
     std::string err_;
 };
