@@ -69,7 +69,20 @@ __device__ __forceinline__ double hyper_move(const LgTable& t, int n11, HyperSta
     return st.p;
 }
 
-// :231-267, two-sided P only
+// :231-267, two-sided P only.
+//
+// The reference walks the whole support from both ends, one recurrence step per table, until the
+// probability reaches that of the observed table (q): ~min(n1_, n_1) steps, almost all of them
+// over terms that are hundreds of orders of magnitude below q. Its recurrence is re-seeded from
+// the closed form at every n11 that is a multiple of 11 (:211), so a walk may START at any such
+// point and every later term is bit-identical to the reference's. Here each tail starts at the
+// multiple of 11 closest to the mode whose probability is still below FISHER_SKIP * q (found by
+// bisection on the closed form; the pmf is monotone on either side of the mode): the skipped terms
+// sum to < 2^13 * 1e-22 * q, far below one ulp of the result (P >= ~q), and the walk shrinks from
+// the support to ~20 standard deviations.
+constexpr double FISHER_SKIP = 1e-22;
+constexpr int FISHER_SKIP_MIN_RANGE = 48;  // shorter supports are walked whole
+
 __device__ double fisher_two_sided(const LgTable& t, int n11, int n12, int n21, int n22) {
     int n1_ = n11 + n12, n_1 = n11 + n21, n = n11 + n12 + n21 + n22;
     int max = (n_1 < n1_) ? n_1 : n1_;
@@ -81,18 +94,55 @@ __device__ double fisher_two_sided(const LgTable& t, int n11, int n12, int n21, 
     st.p = hyper_pmf(t, n11, n1_, n_1, n);
     const double q = st.p;
     const double qlo = dmul(0.99999999, q), qhi = dmul(1.00000001, q);
+    const bool may_skip = max - min > FISHER_SKIP_MIN_RANGE;
+    const double cut = FISHER_SKIP * q;
+    const int mode = (int)(((long long)(n1_ + 1) * (long long)(n_1 + 1)) / ((long long)n + 2));
     double p = hyper_move(t, min, st);
     double left = 0.0;
-    int i;
-    for (i = min + 1; p < qlo && i <= max; ++i) {
+    int i = min + 1;
+    if (may_skip && p < cut) {
+        // largest multiple of 11 in (min, mode] whose probability is below the cut
+        int lo = min / 11 + 1, hi = mode / 11, best = -1;
+        double best_p = 0.0;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const double pm = hyper_pmf(t, 11 * mid, n1_, n_1, n);
+            if (pm < cut) { best = mid; best_p = pm; lo = mid + 1; }
+            else hi = mid - 1;
+        }
+        if (best >= 0) {
+            st.n11 = 11 * best;
+            st.p = best_p;
+            p = best_p;
+            i = 11 * best + 1;
+        }
+    }
+    for (; p < qlo && i <= max; ++i) {
         left = dadd(left, p);
         p = hyper_move(t, i, st);
     }
     if (p < qhi) left = dadd(left, p);
     p = hyper_move(t, max, st);
     double right = 0.0;
-    int j;
-    for (j = max - 1; p < qlo && j >= 0; --j) {
+    int j = max - 1;
+    if (may_skip && p < cut) {
+        // smallest multiple of 11 in (mode, max) whose probability is below the cut
+        int lo = mode / 11 + 1, hi = (max - 1) / 11, best = -1;
+        double best_p = 0.0;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const double pm = hyper_pmf(t, 11 * mid, n1_, n_1, n);
+            if (pm < cut) { best = mid; best_p = pm; hi = mid - 1; }
+            else lo = mid + 1;
+        }
+        if (best >= 0) {
+            st.n11 = 11 * best;
+            st.p = best_p;
+            p = best_p;
+            j = 11 * best - 1;
+        }
+    }
+    for (; p < qlo && j >= 0; --j) {
         right = dadd(right, p);
         p = hyper_move(t, j, st);
     }
