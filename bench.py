@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-variants", type=int, default=REF_SAMPLE_VARIANTS)
+    ap.add_argument("--unphased", action="store_true", help="-u: 3x3 genotype tables (BASELINE configs[2] with --missing 0.05)")
+    ap.add_argument("--missing", type=float, default=0.0, help="per-genotype missing rate of the synthetic data")
+    ap.add_argument("--no-mma-ceiling", action="store_true", help="skip the MMA-only ceiling pass of the roofline block")
     return ap.parse_args()
 
 
@@ -132,18 +135,19 @@ def reference_run(args, n_variants, steps, warmup, as_baseline=False):
     from oracle import twk_format as tf
 
     cores = os.cpu_count() or 1
-    s = tf.synth_genotypes(args.samples, n_variants, seed=args.seed)
+    s = tf.synth_genotypes(args.samples, n_variants, seed=args.seed, missing_rate=args.missing)
+    mode_flag = "-u" if args.unphased else "-p"
     tmp = tempfile.mkdtemp(prefix="twkb_ref_")
     twk = os.path.join(tmp, "ref.twk")
     tf.write_twk(twk, s)
     pairs = n_variants * (n_variants - 1) // 2
-    sample = f"first {n_variants} of the workload's variants ({pairs} pairs), same N, -p -r {args.min_r2} -t {cores}"
+    sample = f"first {n_variants} of the workload's variants ({pairs} pairs), same N, {mode_flag} -r {args.min_r2} -t {cores}"
     if lc.have_reference():
         kind = "reference"
         rates, times = [], []
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            info = lc.run_reference_calc(twk, os.path.join(tmp, "ref_out"), ["-p", "-r", str(args.min_r2)], threads=cores)
+            info = lc.run_reference_calc(twk, os.path.join(tmp, "ref_out"), [mode_flag, "-r", str(args.min_r2)], threads=cores)
             dt = time.perf_counter() - t0
             if it >= warmup:
                 rates.append(info.get("pairs_per_s", pairs / dt))
@@ -157,7 +161,7 @@ def reference_run(args, n_variants, steps, warmup, as_baseline=False):
     else:
         kind = "port"
         cores = 1
-        prm = lc.default_params(force_phased=1, minR2=args.min_r2)
+        prm = lc.default_params(minR2=args.min_r2, **({"forced_unphased": 1} if args.unphased else {"force_phased": 1}))
         t0 = time.perf_counter()
         lc.calc(s, prm, cap=max(1 << 20, pairs // 4))
         dt = time.perf_counter() - t0
@@ -175,8 +179,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_gpus = max(args.gpus, 1)
 
-    workload = (f"tomahawk calc -p all-pairs, synthetic {args.samples} samples ({2 * args.samples} haplotypes) x "
-                f"{args.variants} SNVs, R2>={args.min_r2}")
+    mode_name = "-u (unphased 3x3)" if args.unphased else "-p"
+    miss_name = f", {100 * args.missing:g}% missing genotypes" if args.missing > 0 else ""
+    workload = (f"tomahawk calc {mode_name} all-pairs, synthetic {args.samples} samples ({2 * args.samples} haplotypes) x "
+                f"{args.variants} SNVs{miss_name}, R2>={args.min_r2}")
 
     if args.impl == "reference":
         if rank != 0:
@@ -216,21 +222,23 @@ def main():
     stride = synth.words_per_variant(n_samples)
     t_gen0 = time.perf_counter()
     if rank == 0:
-        s = synth.synth_genotypes(n_samples, n_variants, seed=args.seed)
-        data, _ = synth.pack_bits(s)
+        s = synth.synth_genotypes(n_samples, n_variants, seed=args.seed, missing_rate=args.missing)
+        data, mask = synth.pack_bits(s)
         meta = synth.variant_meta(s)
         del s
     else:
         data = np.zeros((n_variants, stride), dtype=np.uint64)
+        mask = np.zeros((n_variants, stride), dtype=np.uint64) if args.missing > 0 else None
         meta = np.zeros(n_variants, dtype=synth.VARIANT_DTYPE)
     t_gen = time.perf_counter() - t_gen0
 
     kernel = {"auto": tb.KERNEL_AUTO, "popc": tb.KERNEL_POPC, "umma": tb.KERNEL_UMMA, "i8": tb.KERNEL_UMMA,
               "fp4": tb.KERNEL_UMMA_FP4}[args.kernel]
-    eng = tb.Engine(force_phased=1, minR2=args.min_r2, kernel=kernel, device=local_rank,
-                    part_index=rank, part_count=world)
+    eng = tb.Engine(force_phased=0 if args.unphased else 1, forced_unphased=1 if args.unphased else 0, minR2=args.min_r2,
+                    kernel=kernel, device=local_rank, part_index=rank, part_count=world)
     # host copy in pinned memory (the e2e leg copies from here every step)
     host = torch.from_numpy(data.view(np.int64)).pin_memory()
+    host_mask = torch.from_numpy(mask.view(np.int64)).pin_memory() if mask is not None else None
     if world > 1:
         # ONE broadcast of the packed matrix (+ metadata) over NCCL/NVLink, then no collectives
         dev = host.cuda(non_blocking=True) if rank == 0 else torch.empty_like(host, device="cuda")
@@ -240,11 +248,17 @@ def main():
         meta = meta_t.cpu().numpy().view(synth.VARIANT_DTYPE)
         if rank != 0:
             host.copy_(dev.cpu())
+        dev_mask = None
+        if host_mask is not None:
+            dev_mask = host_mask.cuda(non_blocking=True) if rank == 0 else torch.empty_like(host_mask, device="cuda")
+            dist.broadcast(dev_mask, src=0)
+            if rank != 0:
+                host_mask.copy_(dev_mask.cpu())
         torch.cuda.synchronize()
-        eng.load_device(n_samples, n_variants, dev.data_ptr(), None, stride, meta)
-        del dev
+        eng.load_device(n_samples, n_variants, dev.data_ptr(), dev_mask.data_ptr() if dev_mask is not None else None, stride, meta)
+        del dev, dev_mask
     else:
-        eng.load(n_samples, host.numpy().view(np.uint64), None, meta)
+        eng.load(n_samples, host.numpy().view(np.uint64), host_mask.numpy().view(np.uint64) if host_mask is not None else None, meta)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -297,11 +311,12 @@ def main():
     e2e_ms = []
     h2d = d2h = 0
     host_np = host.numpy().view(np.uint64)
+    host_mask_np = host_mask.numpy().view(np.uint64) if host_mask is not None else None
     for it in range(1 + max(2, min(args.steps, 3))):
         flush.zero_()
         barrier()
         t1 = time.perf_counter()
-        eng.load(n_samples, host_np, None, meta)   # H2D from pinned memory + device transpose
+        eng.load(n_samples, host_np, host_mask_np, meta)   # H2D from pinned memory + device transpose
         eng.compute_discard()                      # compute + D2H of every record into pinned staging
         torch.cuda.synchronize()
         dt = time.perf_counter() - t1
@@ -332,7 +347,10 @@ def main():
         # GEMM view: 2N bit-MACs per visited pair = 2*2N flop. The tensor peak of the
         # operand type is the bf16 figure scaled by the nominal dense ratio (bf16 : int8/fp8 : fp4 =
         # 1 : 2 : 4; B200_PROFILING.md); the step is longer than a burst, so the sustained figure.
-        flop_per_pair = 2.0 * H
+        if args.unphased:   # 9 (missing) / 4 plane products over N samples
+            flop_per_pair = 2.0 * (9 if args.missing > 0 else 4) * n_samples
+        else:               # 2N bit-MACs, x4 masked counts with missing data
+            flop_per_pair = 2.0 * H * (4 if args.missing > 0 else 1)
         achieved = pairs_per_launch * flop_per_pair / avg_launch_s / 1e12
         # MEASURED_PEAKS.json holds bf16 only. The int8 / e2m1 tcgen05 kinds run at 2x / 4x the bf16 MAC
         # rate (nominal dense 2.25 : 4.5 : 9 PFLOP/s, B200_PROFILING.md). `peak` is that nominal figure of
@@ -342,15 +360,36 @@ def main():
         # this kernel holds 1.84-1.97 GHz at ~760 W); it is reported beside it for reference.
         ratio = 4.0 if fp4 else 2.0
         peak = 9000.0 if fp4 else 4500.0
-        traffic = TRAFFIC_C2_FP4 if (fp4 and world == 1 and n_variants == BASE_VARIANTS and n_samples == BASE_SAMPLES) else None
+        c2 = (fp4 and world == 1 and n_variants == BASE_VARIANTS and n_samples == BASE_SAMPLES and not args.unphased
+              and args.missing == 0)
+        traffic = TRAFFIC_C2_FP4 if c2 else None
+        # Measured ceiling of the tensor pipe for THIS kernel's instruction stream on THIS device: the same
+        # launch with operand traffic and epilogue switched off (TWKB_DEBUG_FLAGS=3: only the first ring
+        # fill is loaded, accumulators are not drained; results are discarded). What remains is the
+        # tcgen05.mma issue rate under the board's power/clock behaviour.
+        mma_only = None
+        if not args.no_mma_ceiling and not args.unphased and args.missing == 0:
+            os.environ["TWKB_DEBUG_FLAGS"] = "3"
+            try:
+                ms = []
+                for _ in range(3):
+                    flush.zero_(); torch.cuda.synchronize()
+                    eng.compute_resident()
+                    s3 = eng.stats()
+                    ms.append(s3.ms_count_kernel / max(s3.count_launches, 1))
+                mma_only = pairs_per_launch * flop_per_pair / (min(ms[1:]) * 1e-3) / 1e12
+            finally:
+                del os.environ["TWKB_DEBUG_FLAGS"]
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": "count_umma3_kernel<%s>" % ("true" if fp4 else "false"),
                     "peak_source": f"nominal dense {'e2m1 (kind::mxf4)' if fp4 else 'int8 (kind::i8)'} tcgen05 rate; no entry "
                                    f"for this operand kind in MEASURED_PEAKS.json ({peak_src})",
                     "frac_of_scaled_measured_bf16": achieved / (ratio * peaks["bf16_tflops_sustained"]),
                     "scaled_measured_bf16_peak": ratio * peaks["bf16_tflops_sustained"],
-                    "note": f"algorithmic work = pairs x 2 x {H} haplotypes (K padding to 256 and the 256x240 tile edge are not "
-                            f"counted); traffic = dram read+write bytes of one launch from the committed ncu --set full capture"}
+                    "mma_only_ceiling": mma_only, "frac_of_mma_only_ceiling": (achieved / mma_only) if mma_only else None,
+                    "note": f"algorithmic work = pairs x {flop_per_pair:g} flop (SURVEY 8d; K padding to 256 and the 256x240 tile edge "
+                            f"are not counted); traffic = dram read+write bytes of one launch from the committed ncu --set full "
+                            f"capture; mma_only_ceiling = same launch without operand loads and epilogue, measured in this run"}
     else:
         # LOP3+POPC kernel: INT-pipe bound. Algorithmic work = ceil(2N/32) AND+POPC word-ops per pair;
         # peak = 16 POPC lanes/clk/SM x 148 SMs x max SM clock (to be replaced by the measured issue rate).
@@ -371,9 +410,9 @@ def main():
                   "int8 x int8 -> int32 (tcgen05) + f64 statistics" if tensor else "u32 popcount + f64 statistics"),
         "data": "synthetic",
         "config": {
-            "workload": (f"tomahawk calc -p all-pairs, synthetic {n_samples} samples ({H} haplotypes) x {n_variants} SNVs, "
-                         f"R2>={args.min_r2}" + (f" (weak scaling: {args.variants} x sqrt({world}) variants)" if world > 1 else "")),
-            "baseline_config": "BASELINE.json configs[1]",
+            "workload": (f"tomahawk calc {mode_name} all-pairs, synthetic {n_samples} samples ({H} haplotypes) x {n_variants} SNVs"
+                         f"{miss_name}, R2>={args.min_r2}" + (f" (weak scaling: {args.variants} x sqrt({world}) variants)" if world > 1 else "")),
+            "baseline_config": "BASELINE.json configs[2]" if args.unphased else "BASELINE.json configs[1]",
             "pairs_per_step": pairs_total, "haplotype_cmp_per_s": value * H, "records_per_step": records,
             "kernel": "umma_fp4" if fp4 else "umma_i8" if tensor else "popc",
             "l2": "256 MiB device memset between steps (flush) and operands > L2",

@@ -9,7 +9,7 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 s = synth.synth_genotypes(2504, M, seed=20)
 data, mask = synth.pack_bits(s); meta = synth.variant_meta(s)
 for name, k in (("fp4", tb.KERNEL_UMMA_FP4),):
-    for flags in (0, 4, 128, 32, 64):
+    for flags in (0, 1, 2, 3):
         os.environ["TWKB_DEBUG_FLAGS"] = str(flags)
         eng = tb.Engine(force_phased=1, minR2=0.1, kernel=k)
         eng.load(2504, data, mask, meta)
