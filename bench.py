@@ -317,12 +317,15 @@ def main():
         barrier()
         t1 = time.perf_counter()
         eng.load(n_samples, host_np, host_mask_np, meta)   # H2D from pinned memory + device transpose
+        t_load = time.perf_counter() - t1
         eng.compute_discard()                      # compute + D2H of every record into pinned staging
         torch.cuda.synchronize()
         dt = time.perf_counter() - t1
         s2 = eng.stats()
         if it > 0:
             e2e_ms.append(dt * 1e3)
+            e2e_parts = {"load_wall_ms": t_load * 1e3, "load_device_ms": s2.ms_h2d, "compute_wall_ms": (dt - t_load) * 1e3,
+                         "compute_device_ms": s2.ms_device_total}
             h2d, d2h = int(s2.bytes_h2d), int(s2.bytes_d2h)
             launches_e2e = s2.count_launches + s2.stats_launches + s2.other_launches
     e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
@@ -421,7 +424,7 @@ def main():
             "wall_seconds_timed_region": wall,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": float(e2e_t[0]), "gpu_launches_per_step": int(launches_e2e)},
+                "ms_per_step": float(e2e_t[0]), "gpu_launches_per_step": int(launches_e2e), "parts_last_step": e2e_parts},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

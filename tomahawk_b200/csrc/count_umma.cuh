@@ -685,13 +685,63 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
 __device__ __forceinline__ void st_volatile_shared(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
-__device__ __forceinline__ void queue_push(const SurvivorQueue& q, uint32_t i, uint32_t j, uint32_t n11) {
-    const uint32_t slot = atomicAdd(&q.ctrl[0], 1u);
-    while (slot - ld_volatile_shared(&q.ctrl[1]) >= UMMA3_QCAP) __nanosleep(64);  // ring full: wait for the drain warp
-    QEntry* e = q.ring + (slot % UMMA3_QCAP);
-    e->i = i; e->j = j; e->n11 = n11;
-    __threadfence_block();
-    st_volatile_shared(&e->seq, slot / UMMA3_QCAP + 1u);  // publishes the entry
+// Reserves one slot per flagged lane (one atomic per warp) and waits, with a condition that is the
+// SAME in every lane, until the whole reservation fits in the ring. A per-lane wait would deadlock
+// when the ring fills: the lanes whose slots fit would be held at the loop's reconvergence point
+// behind a spinning lane, never publish, and the drain warp (which consumes in slot order) would
+// never free the slot the spinning lane waits for. Called convergently by all 32 lanes.
+__device__ __forceinline__ uint32_t queue_reserve_warp(uint32_t* ctrl, unsigned flagged, uint32_t capacity, int lane) {
+    const int leader = __ffs(flagged) - 1;
+    const uint32_t cnt = (uint32_t)__popc(flagged);
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&ctrl[0], cnt);
+    base = __shfl_sync(0xffffffffu, base, leader);
+    for (;;) {  // ring full: wait for the drain warp; lane 0 reads, so the exit is uniform by construction
+        uint32_t head = 0;
+        if (lane == 0) head = ld_volatile_shared(&ctrl[1]);
+        head = __shfl_sync(0xffffffffu, head, 0);
+        if ((base + cnt - 1u) - head < capacity) break;
+        __nanosleep(64);
+    }
+    return base + (uint32_t)__popc(flagged & ((1u << lane) - 1u));
+}
+// Warp-wide push of the flagged lanes' (i, j, n11); every lane of the warp must call it.
+__device__ __forceinline__ void queue_push_warp(const SurvivorQueue& q, bool flag, uint32_t i, uint32_t j, uint32_t n11, int lane) {
+    const unsigned fl = __ballot_sync(0xffffffffu, flag);
+    if (fl == 0) return;
+    const uint32_t slot = queue_reserve_warp(q.ctrl, fl, UMMA3_QCAP, lane);
+    if (flag) {
+        QEntry* e = q.ring + (slot % UMMA3_QCAP);
+        e->i = i; e->j = j; e->n11 = n11;
+        __threadfence_block();
+        st_volatile_shared(&e->seq, slot / UMMA3_QCAP + 1u);  // publishes the entry
+    }
+    __syncwarp();
+}
+
+// One poll of the drain warp. The control words are read by lane 0 and broadcast, and the warp is
+// re-converged first: `head`, `tail` and every decision derived from them must be identical in all
+// 32 lanes (a lane that read `tail` a few cycles later than its neighbours would consume a
+// different number of entries and wait for slots nobody will ever publish). Returns false when
+// every producer has finished and the ring is empty; sleeps when there is nothing to do yet.
+__device__ __forceinline__ bool drain_poll(uint32_t* ctrl, uint32_t head, uint32_t& tail, int lane) {
+    __syncwarp();
+    uint32_t t = 0, fin = 0;
+    if (lane == 0) {
+        t = ld_volatile_shared(&ctrl[0]);
+        if (t == head) {
+            fin = ld_volatile_shared(&ctrl[2]);
+            if (fin == (uint32_t)UMMA3_EPI_WARPS) t = ld_volatile_shared(&ctrl[0]);  // pushes precede the "finished" mark
+        }
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    fin = __shfl_sync(0xffffffffu, fin, 0);
+    tail = t;
+    if (t == head) {
+        if (fin == (uint32_t)UMMA3_EPI_WARPS) return false;
+        __nanosleep(200);
+    }
+    return true;
 }
 
 // Warp 3: drains the ring until all epilogue warps have finished and the ring is empty.
@@ -699,16 +749,9 @@ __device__ __noinline__ void umma_drain_loop(const CountArgs& args, const DevPar
     const uint32_t M = prm.n_variants;
     uint32_t head = 0;
     for (;;) {
-        uint32_t tail = ld_volatile_shared(&q.ctrl[0]);
-        if (tail == head) {
-            if (ld_volatile_shared(&q.ctrl[2]) == (uint32_t)UMMA3_EPI_WARPS) {
-                tail = ld_volatile_shared(&q.ctrl[0]);  // pushes precede the producer's "finished" mark
-                if (tail == head) break;
-            } else {
-                __nanosleep(200);
-                continue;
-            }
-        }
+        uint32_t tail;
+        if (!drain_poll(q.ctrl, head, tail, lane)) break;
+        if (tail == head) continue;
         const uint32_t n = min(tail - head, 32u);
         const bool have = (uint32_t)lane < n;
         uint32_t i = 0, j = 0, n11 = 0;
@@ -796,9 +839,12 @@ __device__ __forceinline__ void umma_epilogue_chunk(const CountArgs& args, const
                 mask |= (fmaf(-row.sA, cb.w, fmaf(pab, 1.0e-6f, fabsf(x))) >= -1.0f ? 1u : 0u) << (2 * c2 + 1);
             }
         }
+        if (__any_sync(0xffffffffu, mask != 0u)) {  // rare: some lane flagged a pair of this chunk
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-            if ((mask >> c) & 1u) queue_push(q, row.i, j0 + (uint32_t)(chunk * 32 + c), FP4 ? (uint32_t)__uint_as_float(r[c]) : r[c]);
+            for (int c = 0; c < 32; ++c)
+                queue_push_warp(q, (mask >> c) & 1u, row.i, j0 + (uint32_t)(chunk * 32 + c),
+                                FP4 ? (uint32_t)__uint_as_float(r[c]) : r[c], lane);
+        }
     } else {
         umma_direct_chunk<FP4>(args, prm, r, row, meta_saddr, j0, chunk, Tf, thr, true, lane);
     }
@@ -940,11 +986,19 @@ __device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
                  : "memory");
 }
 
-// x[pl] for a lane-constant pl (NP - 1 selects; the register indices stay static)
+// x[pl] for a lane-constant pl: NP - 1 SEL instructions on predicates that are loop invariant (is0 =
+// pl == 0, is1 = pl == 1). Written as selp so that the compiler cannot turn the lane-varying choice
+// into divergent branches (ncu of the first version: 60 BRA + 42 BSSY/BSYNC pairs per 8-column
+// chunk, a third of the epilogue's issue slots).
+__device__ __forceinline__ uint32_t selp_u32(uint32_t a, uint32_t b, uint32_t pred) {
+    uint32_t d;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.b32 %0, %1, %2, p;\n\t}" : "=r"(d) : "r"(a), "r"(b), "r"(pred));
+    return d;
+}
 template <int NP>
-__device__ __forceinline__ uint32_t sel_by_lane(uint32_t pl, const uint32_t (&x)[NP]) {
-    if (NP == 2) return pl ? x[1] : x[0];
-    return pl == 0 ? x[0] : (pl == 1 ? x[1] : x[NP - 1]);
+__device__ __forceinline__ uint32_t sel_by_lane(uint32_t is0, uint32_t is1, const uint32_t (&x)[NP]) {
+    if (NP == 2) return selp_u32(x[0], x[1], is0);
+    return selp_u32(x[0], selp_u32(x[1], x[NP - 1], is1), is0);
 }
 
 // Conservative fp32 form of the exact fp64 screens of count_popc.cuh (screen_phased /
@@ -952,33 +1006,35 @@ __device__ __forceinline__ uint32_t sel_by_lane(uint32_t pl, const uint32_t (&x)
 // the operands are integers < 2^25 and every rounding error (<= 2^-24 relative per operation) is
 // covered by the explicit slack terms, so a pair the exact screen keeps is always flagged. Flagged
 // pairs (~0.5 % at R2 >= 0.1) then take the exact path.
+// The table entries arrive as the fp32 accumulator values (exact integers < 2^24) and every sum
+// below stays an exact integer in fp32, so nothing is converted unless the pair is flagged.
 template <int MODE>
-__device__ __forceinline__ bool planes_fast_screen(const PairAcc<PopcCfg<MODE>::NP>& pa, uint32_t n_samples, uint32_t hetA, uint32_t homA,
-                                                   uint32_t hetB, uint32_t homB, float thr) {
+__device__ __forceinline__ bool planes_fast_screen(const float (&v)[PopcCfg<MODE>::NP][PopcCfg<MODE>::NP], float n_samples, float hetA,
+                                                   float homA, float hetB, float homB, float thr) {
     constexpr int NP = PopcCfg<MODE>::NP;
     if (MODE == MODE_PHASED_MISS) {
-        const float n11 = (float)pa.v[0][0], nA = (float)pa.v[0][1], nB = (float)pa.v[1][0], nV = (float)pa.v[1][1];
+        const float n11 = v[0][0], nA = v[0][1], nB = v[1][0], nV = v[1][1];
         const float p1 = n11 * nV, p2 = nA * nB;
         const float x = fabsf(p1 - p2) + (2.5e-7f * (p1 + p2) + 1.0f);
         const float den = (nA * (nV - nA)) * (nB * (nV - nB));  // nV - nA: exact integers
         return (x * x) * (1.0f + 1.0e-5f) >= thr * den;
     } else {
-        uint32_t hA, oA, hB, oB, vv;
+        float hA, oA, hB, oB, vv;
         if (MODE == MODE_UNPHASED_NOMISS) { hA = hetA; oA = homA; hB = hetB; oB = homB; vv = n_samples; }
-        else { hA = pa.v[0][NP - 1]; oA = pa.v[1 % NP][NP - 1]; hB = pa.v[NP - 1][0]; oB = pa.v[NP - 1][1 % NP]; vv = pa.v[NP - 1][NP - 1]; }
-        const uint32_t c11 = pa.v[0][0], c12 = pa.v[0][1 % NP], c21 = pa.v[1 % NP][0], c22 = pa.v[1 % NP][1 % NP];
+        else { hA = v[0][NP - 1]; oA = v[1 % NP][NP - 1]; hB = v[NP - 1][0]; oB = v[NP - 1][1 % NP]; vv = v[NP - 1][NP - 1]; }
+        const float c11 = v[0][0], c12 = v[0][1 % NP], c21 = v[1 % NP][0], c22 = v[1 % NP][1 % NP];
         // t0 = both 0/0, t1 = (0/0, het), t3 = (het, 0/0), t4 = (het, het); n11 = 2 t0 + t1 + t3
-        const uint32_t t0 = vv - hA - oA - hB - oB + c11 + c12 + c21 + c22;
-        const uint32_t t1 = hB - c11 - c21, t3 = hA - c11 - c12;
-        const uint32_t n11 = 2u * t0 + t1 + t3;
-        const uint32_t S = 2u * vv;
-        const uint32_t a = S - hA - 2u * oA, c = S - hB - 2u * oB;  // 2T * P, 2T * Q
-        const float Sf = (float)S, af = (float)a, cf = (float)c;
-        const float pq = af * cf, eps = 1.0e-5f * (Sf * Sf);
-        const float l1 = (float)n11 * Sf, h1 = (float)(n11 + c11) * Sf;
+        // (partial sums are integers in [-2 vv, 2 vv]: exact)
+        const float t0 = ((vv - hA - oA) - (hB + oB)) + ((c11 + c12) + (c21 + c22));
+        const float t1 = hB - c11 - c21, t3 = hA - c11 - c12;
+        const float n11 = 2.0f * t0 + t1 + t3;
+        const float S = 2.0f * vv;
+        const float a = S - hA - 2.0f * oA, c = S - hB - 2.0f * oB;  // 2T * P, 2T * Q
+        const float pq = a * c, eps = 1.0e-5f * (S * S);
+        const float l1 = n11 * S, h1 = (n11 + c11) * S;
         const float lo = (l1 - pq) - eps, hi = (h1 - pq) + eps;
-        const float dmax = fmaxf(fabsf(lo), fabsf(hi)) + (2.5e-7f * (h1 + pq) + 3.0e-12f * (Sf * Sf) + 1.0f);
-        const float den = (af * (float)(S - a)) * (cf * (float)(S - c));
+        const float dmax = fmaxf(fabsf(lo), fabsf(hi)) + (2.5e-7f * (h1 + pq) + 3.0e-12f * (S * S) + 1.0f);
+        const float den = (a * (S - a)) * (c * (S - c));
         return (dmax * dmax) * (1.0f + 1.0e-5f) >= thr * den;
     }
 }
@@ -990,11 +1046,81 @@ __device__ __noinline__ void umma_planes_exact(const CountArgs& args, const DevP
     emit_pair_with<MODE>(args, prm, i, j, vi, vj, pa, lane, active);
 }
 
+// ---- survivor queue of the planes kernels --------------------------------------------------------
+// Same idea as the 1-plane kernel's queue, with the pair's NP x NP plane counts as payload (48-byte
+// entries in the same 16 KB ring). With the exact decision inline, an epilogue warp ran the long
+// fp64 path in ~1/4 of its rounds whenever ANY of its 30 pairs was flagged (C3: 0.5 % of the
+// pairs), the 8 warps of a tile finished far apart and met at the per-tile barrier (ncu: 41 % of
+// the stall cycles at that barrier, 17 % of the samples inside the fp64 code). Now the epilogue
+// warps only push; warp 3 applies pair rules + exact fp64 screen and appends the candidates.
+struct __align__(16) PQEntry { uint32_t i, j, v[9], seq; };
+static_assert(sizeof(PQEntry) == 48, "planes queue entry");
+constexpr uint32_t UMMA3_PQCAP = (UMMA3_QCAP * (uint32_t)sizeof(QEntry)) / (uint32_t)sizeof(PQEntry);  // 341
+
+// Warp-aggregated push of the flagged lanes' pairs.
+template <int NP>
+__device__ __forceinline__ void planes_queue_push(PQEntry* ring, uint32_t* ctrl, bool flag, uint32_t i, uint32_t j,
+                                                  const float (&tv)[NP][NP], int lane) {
+    const unsigned fl = __ballot_sync(0xffffffffu, flag);
+    if (fl == 0) return;
+    const uint32_t slot = queue_reserve_warp(ctrl, fl, UMMA3_PQCAP, lane);
+    if (flag) {
+        PQEntry* e = ring + (slot % UMMA3_PQCAP);
+        e->i = i; e->j = j;
+#pragma unroll
+        for (int a = 0; a < NP; ++a)
+#pragma unroll
+            for (int b = 0; b < NP; ++b) e->v[a * NP + b] = (uint32_t)tv[a][b];
+        __threadfence_block();
+        st_volatile_shared(&e->seq, slot / UMMA3_PQCAP + 1u);  // publishes the entry
+    }
+    __syncwarp();
+}
+
+// Warp 3 of the planes kernels: drains the ring until all epilogue warps have finished.
+template <int MODE>
+__device__ __noinline__ void umma_planes_drain_loop(const CountArgs& args, const DevParams& prm, PQEntry* ring, uint32_t* ctrl, int lane) {
+    constexpr int NP = PopcCfg<MODE>::NP;
+    uint32_t head = 0;
+    for (;;) {
+        uint32_t tail;
+        if (!drain_poll(ctrl, head, tail, lane)) break;
+        if (tail == head) continue;
+        const uint32_t n = min(tail - head, 32u);
+        const bool have = (uint32_t)lane < n;
+        uint32_t i = 0, j = 0;
+        PairAcc<NP> pa;
+#pragma unroll
+        for (int a = 0; a < NP; ++a)
+#pragma unroll
+            for (int b = 0; b < NP; ++b) pa.v[a][b] = 0;
+        if (have) {
+            const uint32_t slot = head + (uint32_t)lane;
+            PQEntry* e = ring + (slot % UMMA3_PQCAP);
+            while (ld_volatile_shared(&e->seq) != slot / UMMA3_PQCAP + 1u) __nanosleep(32);  // reserved, not yet written
+            __threadfence_block();
+            i = e->i; j = e->j;
+#pragma unroll
+            for (int a = 0; a < NP; ++a)
+#pragma unroll
+                for (int b = 0; b < NP; ++b) pa.v[a][b] = e->v[a * NP + b];
+        }
+        __syncwarp();
+        head += n;
+        __threadfence_block();
+        if (lane == 0) st_volatile_shared(&ctrl[1], head);  // the slots may be reused
+        const bool in = have && i < prm.n_variants && j < prm.n_variants;
+        DevVariant vi{0, 0, 0, 0}, vj{0, 0, 0, 0};
+        if (in) { vi = args.meta[i]; vj = args.meta[j]; }
+        emit_pair_with<MODE>(args, prm, i, j, vi, vj, pa, lane, in);
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args, const DevParams& prm, DevVariant* s_meta, uint2* s_colx,
                                                           uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint32_t tmem_base,
                                                           uint32_t cluster_id, uint32_t n_clusters, uint32_t n_tiles, uint32_t rank,
-                                                          uint32_t leader_cta, int warp, int lane) {
+                                                          uint32_t leader_cta, int warp, int lane, PQEntry* q_ring, uint32_t* q_ctrl) {
     using PC = PlanesCfg<MODE>;
     constexpr int NP = PC::NP;
     constexpr int CW = PC::CW;
@@ -1006,6 +1132,11 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
     const uint32_t vl = (uint32_t)lane / NP, pl = (uint32_t)lane % NP;
     const bool lane_ok = vl < PC::G;
     const int base_lane = lane - (int)pl;
+    const uint32_t is0 = pl == 0 ? 1u : 0u, is1 = pl == 1 ? 1u : 0u;
+    int src_lane[NP];  // shuffle step s reads from the lane holding plane row (pl + s) % NP of this variant
+#pragma unroll
+    for (int sft = 0; sft < NP; ++sft) src_lane[sft] = base_lane + (int)((pl + (uint32_t)sft) % NP);
+    const float ns_f = (float)prm.n_samples;
     const uint32_t meta_s0 = smem_u32(s_meta);
     const int c_begin = half ? (PC::N_CHUNKS + 1) / 2 : 0;
     const int c_end = half ? PC::N_CHUNKS : (PC::N_CHUNKS + 1) / 2;
@@ -1051,6 +1182,7 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
         const uint32_t j0 = tile.y;
         const uint32_t i = tile.x + (4u * rank + (uint32_t)q) * PC::G + vl;
         const Row row = row_cur;
+        const float row_het_f = (float)row.het, row_hom_f = (float)row.hom;
         epilogue_bar_sync8();  // metadata buffer `acc` visible; buffer acc ^ 1 free
         const uint32_t t_next = t + n_clusters;
         const bool has_next = t_next < n_tiles;
@@ -1093,11 +1225,10 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
                             const int col = NP * g + d;
                             cand[(d + sft) % NP] = r[b][col < CW ? col : CW - 1];
                         }
-                        const uint32_t send = sel_by_lane<NP>(pl, cand);
-                        recv[sft][b] = __shfl_sync(0xffffffffu, send, base_lane + (int)((pl + (uint32_t)sft) % NP));
+                        recv[sft][b] = __shfl_sync(0xffffffffu, sel_by_lane<NP>(is0, is1, cand), src_lane[sft]);
                     }
                 }
-                PairAcc<NP> pa;
+                float tv[NP][NP];
 #pragma unroll
                 for (int a = 0; a < NP; ++a) {
 #pragma unroll
@@ -1105,7 +1236,7 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
                         uint32_t cand[NP];  // recv[(a - pl) mod NP][b]
 #pragma unroll
                         for (int d = 0; d < NP; ++d) cand[d] = recv[(a - d + NP) % NP][b];
-                        pa.v[a][b] = (uint32_t)__uint_as_float(sel_by_lane<NP>(pl, cand));
+                        tv[a][b] = __uint_as_float(sel_by_lane<NP>(is0, is1, cand));
                     }
                 }
                 const uint32_t cl = (uint32_t)(NP * g) + pl;  // column of this lane inside the chunk
@@ -1113,11 +1244,20 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
                 const uint32_t jl = (uint32_t)(ch * CW) + (active ? cl : 0u);
                 bool flag = active;
                 if (!no_screen) {
-                    uint2 cx = make_uint2(0, 0);
-                    if (MODE == MODE_UNPHASED_NOMISS) cx = colx[jl];
-                    flag = active && planes_fast_screen<MODE>(pa, prm.n_samples, row.het, row.hom, cx.x, cx.y, thr);
+                    float cxh = 0.0f, cxo = 0.0f;
+                    if (MODE == MODE_UNPHASED_NOMISS) { const uint2 cx = colx[jl]; cxh = (float)cx.x; cxo = (float)cx.y; }
+                    flag = active && planes_fast_screen<MODE>(tv, ns_f, row_het_f, row_hom_f, cxh, cxo, thr);
                 }
-                if (__any_sync(0xffffffffu, flag)) {
+                if (!no_screen && !(args.debug_flags & 4u)) {  // (flag 4: A/B aid, exact decision inline)
+                    // flagged pairs (a fraction of a percent) go to the drain warp
+                    planes_queue_push<NP>(q_ring, q_ctrl, flag, i, j0 + jl, tv, lane);
+                } else if (__any_sync(0xffffffffu, flag)) {
+                    // nothing can be screened out: every pair is a candidate, decided inline by all 8 warps
+                    PairAcc<NP> pa;
+#pragma unroll
+                    for (int a = 0; a < NP; ++a)
+#pragma unroll
+                        for (int b = 0; b < NP; ++b) pa.v[a][b] = (uint32_t)tv[a][b];
                     const DevVariant vj = lds_variant(meta_sa + jl * 16u);
                     umma_planes_exact<MODE>(args, prm, i, j0 + jl, row.v, vj, pa, lane, flag);
                 }
@@ -1136,6 +1276,10 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
         tile = tile_next;
         row_cur = row_next;
     }
+    // every push of this warp is written; tell the drain warp
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) atomicAdd(&q_ctrl[2], 1u);
 }
 
 template <bool FP4, bool SCREEN, int MODE>
@@ -1178,7 +1322,7 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_fence_init();
         q_ctrl[0] = 0; q_ctrl[1] = 0; q_ctrl[2] = 0;
     }
-    for (uint32_t e = threadIdx.x; e < UMMA3_QCAP; e += blockDim.x) s_ring[e].seq = 0;
+    for (uint32_t e = threadIdx.x; e < UMMA3_QCAP * 4u; e += blockDim.x) reinterpret_cast<uint32_t*>(s_ring)[e] = 0;  // seq = 0 in either entry layout
     if (warp == 2) tmem_alloc_2sm(tmem_slot, UMMA3_TMEM_COLS);
     tcgen05_fence_before();
     cluster_sync_all();
@@ -1256,9 +1400,10 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                                             n_tiles, 128u * rank, 0u, warp, lane, queue);
         else
             umma_planes_epilogue_loop<MODE>(args, prm, s_meta, reinterpret_cast<uint2*>(s_colf), tmem_full_bar, tmem_empty_bar, tmem_base,
-                                            cluster_id, n_clusters, n_tiles, rank, 0u, warp, lane);
+                                            cluster_id, n_clusters, n_tiles, rank, 0u, warp, lane, reinterpret_cast<PQEntry*>(s_ring), q_ctrl);
     } else if (warp == 3) {
         if constexpr (MODE == MODE_PHASED_NOMISS) umma_drain_loop(args, prm, queue, lane);
+        else umma_planes_drain_loop<MODE>(args, prm, reinterpret_cast<PQEntry*>(s_ring), q_ctrl, lane);
     }
     tcgen05_fence_before();
     cluster_sync_all();
