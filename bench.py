@@ -41,8 +41,8 @@ BASE_SAMPLES = 2504
 BASE_VARIANTS = 200_000
 REF_SAMPLE_VARIANTS = 30_000  # bounded CPU sample of the same workload (first M' variants)
 # dram__bytes_read.sum + dram__bytes_write.sum of one count_umma3_kernel<e2m1> launch at the full C2 size
-# (profiles/round1_ncu_c2_fp4_full.csv: 21.492 GB + 0.050 GB; the operand is 0.51 GB, re-read from L2 misses)
-TRAFFIC_C2_FP4 = 21.492050e9 + 50.211584e6
+# (profiles/round1_ncu_c2_fp4_full_v2.csv: 20.256 GB + 0.049 GB; the operand is 0.51 GB, re-read from L2 misses)
+TRAFFIC_C2_FP4 = 20.255835e9 + 48.632064e6
 
 
 def parse_args():

@@ -636,3 +636,28 @@ def test_calc_file_device_decode_equals_host_unpack(name, tmpdir_repo):
         assert len(outs[0]) == 2 * len(ref)
     else:   # unphased pairs may flip on enumerated decision boundaries
         assert abs(len(outs[0]) - 2 * len(ref)) <= max(6, 0.01 * len(ref))
+
+
+# ---------------------------------------------------------- survivor ring under pressure
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("name,skw,prm", [
+    # the in-kernel screen flags most pairs, so the shared-memory ring between the epilogue warps and
+    # the drain warp is full most of the time (the 1-plane ring holds 1024 entries, the planes ring 341)
+    ("phased_ring", dict(n_samples=800, n_variants=2600, seed=81), dict(force_phased=1, minR2=1e-4)),
+    ("unphased_nomiss_ring", dict(n_samples=900, n_variants=1500, seed=82), dict(forced_unphased=1, minR2=1e-3)),
+    ("unphased_miss_ring", dict(n_samples=1250, n_variants=1500, seed=75, missing_rate=0.05), dict(forced_unphased=1, minR2=1e-3)),
+    ("phased_miss_ring", dict(n_samples=700, n_variants=1500, seed=83, missing_rate=0.05), dict(force_phased=1, minR2=1e-3)),
+])
+def test_survivor_ring_full_is_drained_and_exact(name, skw, prm):
+    """Regression for a hang: the drain warp's control flow must stay warp-uniform and a full ring must
+    only delay the epilogue warps. Results still equal the LOP3+POPC kernel byte for byte."""
+    s = tf.synth_genotypes(**skw)
+    out = {}
+    for k in (tb.KERNEL_POPC, tb.KERNEL_AUTO):
+        e, r, st = gpu_run(s, prm, k)
+        out[k] = tf.canonical(r, False)
+        if k == tb.KERNEL_AUTO:
+            assert st.kernel_used == tb.KERNEL_UMMA_FP4
+            assert st.pairs_screened > 0.05 * st.pairs_visited   # the ring really was under pressure
+        e.close()
+    assert np.array_equal(out[tb.KERNEL_POPC].view(np.uint8), out[tb.KERNEL_AUTO].view(np.uint8))
