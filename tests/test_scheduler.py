@@ -128,3 +128,30 @@ def test_two_rank_gloo_partition():
     assert not (a & b)
     whole, _ = tb.plan_tiles(tb.default_settings(), _meta(n), 128, 128)
     assert a | b == set(map(tuple, whole.tolist()))
+
+
+@pytest.mark.parametrize("parts", [2, 8])
+def test_large_grid_parts_take_whole_super_tiles(parts):
+    """At bench scale (C2, 256 x 240 tiles) a part owns whole 32 x 32 super-tiles: disjoint cover,
+    tile counts balanced to within 2 %, and each part touches far fewer operand row groups per tile
+    than round-robin dealing of single tiles would (the L2 / DRAM locality the dealing exists for)."""
+    n, ti, tj = 200_000, 256, 240
+    meta = _meta(n)
+    whole, pairs_whole = tb.plan_tiles(tb.default_settings(), meta, ti, tj)
+    key = lambda t: (t[:, 0].astype(np.uint64) << np.uint64(32)) | t[:, 1].astype(np.uint64)
+    all_keys, counts, pairs = [], [], []
+    for r in range(parts):
+        t, p = tb.plan_tiles(tb.default_settings(part_index=r, part_count=parts), meta, ti, tj)
+        all_keys.append(key(t))
+        counts.append(len(t))
+        pairs.append(p)
+        # locality: tiles per distinct (row group, column group) the part has to stream
+        groups = len(np.unique(t[:, 0])) + len(np.unique(t[:, 1]))
+        supers = len(np.unique(key(np.stack([t[:, 0] // (32 * ti), t[:, 1] // (32 * tj)], axis=1))))
+        assert len(t) / supers > 400, "a part's tiles should fill its super-tiles"
+        assert groups <= whole[:, 0].max() // ti + whole[:, 1].max() // tj + 2
+    cat = np.concatenate(all_keys)
+    assert len(np.unique(cat)) == len(cat) == len(whole)
+    assert np.array_equal(np.sort(cat), np.sort(key(whole)))
+    assert sum(pairs) == pairs_whole == n * (n - 1) // 2
+    assert max(counts) <= 1.02 * min(counts)
