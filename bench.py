@@ -172,8 +172,32 @@ def reference_run(args, n_variants, steps, warmup, as_baseline=False):
     return {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "ms": ms, "pairs": pairs}
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line. Libraries that write to file descriptor 1 behind Python's back
+    (NCCL prints its version banner there, whatever NCCL_DEBUG_FILE says) are sent to stderr: fd 1 is
+    re-pointed at fd 2 for the whole run and the JSON line is written to a saved duplicate of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,7 +222,7 @@ def main():
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit_json(line)
         return 0
 
     import torch
@@ -435,7 +459,7 @@ def main():
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         except Exception as e:  # the baseline is a reported number, never a gate
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)[:200]}
-    print(json.dumps(line))
+    emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
