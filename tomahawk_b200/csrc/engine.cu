@@ -703,8 +703,11 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
     }
     // The tile plan depends only on the sub-problem, the tile shape, the window and the
     // partition: build it (and upload it) once and reuse it across runs.
+    // (outside window mode the plan is a function of the ranges alone, so it survives a reload of a
+    // matrix of the same shape: the end-to-end path does not rebuild and re-upload 3e5 tiles per call)
     char keybuf[256];
-    std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u|w%d:%d:%d|p%d/%d", (unsigned long long)ctx->matrix_epoch,
+    std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u|w%d:%d:%d|p%d/%d",
+                  (unsigned long long)(ctx->st.window ? ctx->matrix_epoch : 0ull),
                   pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, (int)ctx->st.window,
                   ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
     if (ctx->plan_key != keybuf) {
