@@ -15,6 +15,7 @@ import pytest
 import tomahawk_b200 as tb
 from oracle import ldcore as lc
 from oracle import twk_format as tf
+from tomahawk_b200 import synth as synth_mod
 from tests.helpers import (GOLDEN_CASES, TOL_P, TOL_STAT, assert_records_bitexact, keyset, load_golden,
                            unphased_pair_is_boundary)
 
@@ -356,38 +357,7 @@ def test_sparse_path_parts_union_equals_whole():
     assert np.array_equal(tf.canonical(allr, False).view(np.uint8), tf.canonical(whole, False).view(np.uint8))
 
 
-def _biobank_matrix(n_samples, n_variants, seed):
-    """BASELINE configs[4] in miniature: 1M-haplotype rows, 80 % of the variants rare (MAF < 1 %:
-    60 % with <= 400 carriers -- the list class under the automatic threshold -- and 20 % with up to
-    10,000), 20 % common; neighbours share carriers (LD) so that records survive an R2 cut."""
-    rng = np.random.default_rng(seed)
-    nb = 2 * n_samples
-    words = (nb + 127) // 128 * 2
-    data = np.zeros((n_variants, words), np.uint64)
-    ac = np.zeros(n_variants, np.uint32)
-    prev_idx = None
-    for v in range(n_variants):
-        u = rng.random()
-        if u < 0.8:
-            k = int(rng.integers(2, 400)) if u < 0.6 else int(rng.integers(400, 10000))
-            if prev_idx is not None and rng.random() < 0.6:     # copy most carriers of the previous rare variant
-                keep = prev_idx[rng.random(len(prev_idx)) < 0.9]
-                idx = np.unique(np.concatenate([keep, rng.integers(1, nb, max(1, k // 10))]))
-            else:
-                idx = np.unique(rng.integers(1, nb, k))
-            prev_idx = idx
-            row = np.zeros(words * 8, np.uint8)
-            np.bitwise_or.at(row, idx >> 3, (1 << (idx & 7)).astype(np.uint8))
-            data[v] = row.view(np.uint64)
-            ac[v] = len(idx)
-        else:
-            bits = np.zeros(words * 64, np.uint8)
-            bits[1:nb] = rng.random(nb - 1) < rng.uniform(0.05, 0.5)
-            ac[v] = bits.sum()
-            data[v] = np.packbits(bits, bitorder="little").view(np.uint64)
-    meta = np.zeros(n_variants, tb.VARIANT_DTYPE)
-    meta["pos"] = 100 * (1 + np.arange(n_variants)); meta["ac"] = ac; meta["hwe"] = 1.0; meta["gt_phase"] = 1
-    return data, meta
+_biobank_matrix = synth_mod.biobank_matrix
 
 
 def test_biobank_scale_window_sparse_auto_threshold():
