@@ -331,39 +331,19 @@ def main():
         step_ms_max, pairs_total = step_ms, float(pairs_rank)
     value = pairs_total / (step_ms_max * 1e-3)
 
-    # ---- e2e: host buffers -> C-ABI -> records back on the host, copies inside the timed region
+    # ---- e2e: host buffers -> C-ABI -> records back on the host, copies inside the timed region.
+    # N > 1: every rank uploads the matrix over its own PCIe link. The alternative (rank 0 uploads, one NCCL broadcast
+    # pipelined in 8 row slices, twkb_load_matrix_device) was measured and is slower on this box: e2e 41.0 vs 39.9 ms
+    # at N = 2 and 46.8 vs 45.1 ms at N = 4 (the broadcast serialises behind rank 0's single PCIe link).
     e2e_ms = []
     h2d = d2h = 0
     host_np = host.numpy().view(np.uint64)
     host_mask_np = host_mask.numpy().view(np.uint64) if host_mask is not None else None
-    # N > 1: the job's host buffers live on rank 0. Each step rank 0 copies them to its GPU from pinned
-    # memory, ONE NCCL broadcast over NVLink hands them to the other ranks (north_star: "the packed genotype
-    # matrix is broadcast once with NCCL"), and every rank loads from device memory (twkb_load_matrix_device).
-    # Eight ranks pulling the same matrix over PCIe at once would be bound by host memory bandwidth instead.
-    if dist is not None:
-        dev_e2e = torch.empty_like(host, device="cuda")
-        dev_mask_e2e = torch.empty_like(host_mask, device="cuda") if host_mask is not None else None
-        meta_host = torch.from_numpy(meta.view(np.uint8).copy()).pin_memory()
-        meta_dev = torch.empty_like(meta_host, device="cuda")
     for it in range(1 + max(2, min(args.steps, 3))):
         flush.zero_()
         barrier()
         t1 = time.perf_counter()
-        if dist is None:
-            eng.load(n_samples, host_np, host_mask_np, meta)   # H2D from pinned memory + device transpose
-        else:
-            if rank == 0:
-                dev_e2e.copy_(host, non_blocking=True)
-                meta_dev.copy_(meta_host, non_blocking=True)
-                if dev_mask_e2e is not None:
-                    dev_mask_e2e.copy_(host_mask, non_blocking=True)
-            dist.broadcast(dev_e2e, src=0)
-            dist.broadcast(meta_dev, src=0)
-            if dev_mask_e2e is not None:
-                dist.broadcast(dev_mask_e2e, src=0)
-            meta_step = meta_dev.cpu().numpy().view(synth.VARIANT_DTYPE)   # the host-side scheduler reads positions / counts
-            eng.load_device(n_samples, n_variants, dev_e2e.data_ptr(),
-                            dev_mask_e2e.data_ptr() if dev_mask_e2e is not None else None, stride, meta_step)
+        eng.load(n_samples, host_np, host_mask_np, meta)   # H2D from pinned memory + device transpose
         t_load = time.perf_counter() - t1
         eng.compute_discard()                      # compute + D2H of every record into pinned staging
         torch.cuda.synchronize()
@@ -374,8 +354,6 @@ def main():
             e2e_parts = {"load_wall_ms": t_load * 1e3, "load_device_ms": s2.ms_h2d, "compute_wall_ms": (dt - t_load) * 1e3,
                          "compute_device_ms": s2.ms_device_total}
             h2d, d2h = int(s2.bytes_h2d), int(s2.bytes_d2h)
-            if dist is not None:   # rank 0's upload of the matrix (+ mask, metadata); the other ranks receive it over NVLink
-                h2d = host.numel() * 8 * (2 if host_mask is not None else 1) + meta_host.numel()
             launches_e2e = s2.count_launches + s2.stats_launches + s2.other_launches
     e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -474,9 +452,7 @@ def main():
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": float(e2e_t[0]), "gpu_launches_per_step": int(launches_e2e), "parts_last_step": e2e_parts,
-                "path": ("host matrix on rank 0 -> H2D from pinned memory -> one NCCL broadcast -> twkb_load_matrix_device on every "
-                         "rank -> twkb_compute with a host sink" if world > 1 else
-                         "twkb_load_matrix from pinned host memory -> twkb_compute with a host sink")},
+                "path": "every rank: twkb_load_matrix from its pinned host copy -> twkb_compute with a host sink"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
