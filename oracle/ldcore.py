@@ -19,6 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 REF_CALC = os.path.join(REF_DIR, "tomahawk_calc")
 REF_VIEW = os.path.join(REF_DIR, "tomahawk_view")
+REF_SORT = os.path.join(REF_DIR, "tomahawk_sort")
 REF_FISHER = os.path.join(REF_DIR, "libref_fisher.so")
 
 VARIANT_DTYPE = np.dtype(

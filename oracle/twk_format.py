@@ -308,6 +308,25 @@ def read_two(path: str) -> np.ndarray:
     return np.concatenate(chunks)
 
 
+def read_two_index(path: str):
+    """(state, block entries, per-contig entries) of a .two file's index (lib/index.cpp:41-52, 90-99, 242-251):
+    block entry = (rid, n, minpos, maxpos, b_unc, b_cmp, foff, fend, ridB); contig entry = (rid, n, minpos,
+    maxpos, foff, fend, nn)."""
+    raw = open(path, "rb").read()
+    off = struct.unpack("<Q", raw[-40:-32])[0]
+    unc, cmp_ = struct.unpack("<QQ", raw[off + 1: off + 17])
+    idx = zstd_decompress(raw[off + 17: off + 17 + cmp_], unc)
+    marker, state, n, m, m_ent = struct.unpack("<QBQQQ", idx[:33])
+    assert marker == 1954702206512158641
+    p = 33
+    ents, meta = [], []
+    for _ in range(n):
+        ents.append(struct.unpack("<iIIIIIQQi", idx[p:p + 44])); p += 44
+    for _ in range(m_ent):
+        meta.append(struct.unpack("<iIIIQQQ", idx[p:p + 40])); p += 40
+    return state, ents, meta
+
+
 def records_from_bytes(raw: bytes | np.ndarray) -> np.ndarray:
     return np.frombuffer(bytes(raw), dtype=TWO_DTYPE)
 

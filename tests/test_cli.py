@@ -101,3 +101,39 @@ def test_cli_window_and_interval_modes(tmpdir_repo):
     r = run("calc", "-i", twk, "-o", out, *cli.split())
     assert r.returncode == 0, r.stderr
     assert_records_bitexact(tf.canonical(tf.read_two(out + ".two"), forward_only=True), ref, p_rtol=1e-9)
+
+
+# ---- twkb_sort: the reference's `sort` command line (lib/sort.h) over twkb_two_sort ----
+import tomahawk_b200 as tb  # noqa: E402
+
+SORT_CLI = os.path.join(ROOT, "tomahawk_b200", "twkb_sort")
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["-i", "", "-o", "x"], "No input value specified..."),
+    (["-i", "in.two", "-o", "x", "-m", "0"], "Cannot set memory limit <= 0..."),
+    (["-i", "in.two", "-o", "x", "-t", "0"], "Cannot set number of threads <= 0..."),
+    (["-i", "in.two", "-o", "x", "-c", "0"], "Cannot set the compression level <= 0..."),
+    (["-i", "does_not_exist.two", "-o", "x"], "Failed to open"),
+])
+def test_sort_cli_rejects_like_the_reference(args, msg):
+    r = subprocess.run([SORT_CLI, "sort"] + args, capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "[ERROR]" in r.stderr and msg in r.stderr
+
+
+def test_sort_cli_sorts_a_file(tmpdir_repo):
+    s, recs, prm, pairs, _ = load_golden("phased_r0")
+    twk_path = os.path.join(tmpdir_repo, "sc.twk")
+    tf.write_twk(twk_path, s)
+    src = os.path.join(tmpdir_repo, "sc.two")
+    w = tb.TwoWriter(src, tb.TwkFile(twk_path), "pytest", c_level=1, b_size=500)
+    w.add(recs[np.random.default_rng(3).permutation(len(recs))])
+    w.close()
+    out = os.path.join(tmpdir_repo, "sc_sorted.two")
+    r = subprocess.run([SORT_CLI, "sort", "-i", src, "-o", out, "-t", "2", "-c", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = tf.read_two(out)
+    assert len(got) == 2 * len(recs)
+    assert np.array_equal(np.lexsort((got["packB"], got["packA"], got["ridB"], got["ridA"])), np.arange(len(got)))
+    assert tf.read_two_index(out)[0] == 2

@@ -256,3 +256,91 @@ def test_two_writer_parallel_compression_is_byte_identical(threads, tmpdir_repo)
     assert _two_body(outs[0]) == _two_body(outs[1])
     back = tf.read_two(outs[1])
     assert len(back) == 2 * len(recs)
+
+
+# ---- .two sorter: twkb_two_sort against the reference's own `sort` ----
+def _unsorted_two(tmpdir, name, s, prm, contigs=None, b_size=700, seed=1):
+    ref, _ = lc.calc(s, lc.default_params(**prm))
+    twk_path = os.path.join(tmpdir, name + ".twk")
+    tf.write_twk(twk_path, s, contigs=contigs)
+    twk = tb.TwkFile(twk_path)
+    out = os.path.join(tmpdir, name + ".two")
+    w = tb.TwoWriter(out, twk, "pytest", c_level=1, b_size=b_size)
+    fwd = tf.canonical(ref, forward_only=True)
+    w.add(fwd[np.random.default_rng(seed).permutation(len(fwd))])
+    w.close()
+    return out, 2 * len(fwd)
+
+
+def _two_contigs(n_samples, n_variants, split, seed):
+    s = tf.synth_genotypes(n_samples, n_variants, seed=seed)
+    s.rid[split:] = 1
+    s.pos[split:] = (np.arange(n_variants - split) * 100).astype(np.uint32)
+    return s
+
+
+@pytest.mark.parametrize("case", ["one_contig_many_blocks", "two_contigs_cross_pairs"])
+def test_two_sorter_order_blocks_and_index(case, tmpdir_repo):
+    if case == "one_contig_many_blocks":
+        s = tf.synth_genotypes(200, 260, seed=11)          # R2 >= 0: 33,670 pairs -> 67,340 records, 7 blocks
+        src, n = _unsorted_two(tmpdir_repo, "srt1", s, dict(force_phased=1, minR2=0.0))
+    else:
+        s = _two_contigs(300, 1400, 900, seed=4)           # pairs across contigs: ridB mixed inside blocks
+        src, n = _unsorted_two(tmpdir_repo, "srt2", s, dict(force_phased=1, minR2=0.02), contigs=[("1", 10**6), ("2", 10**6)])
+    out = os.path.join(tmpdir_repo, case + "_sorted")      # ".two" is appended like the reference does
+    assert tb.sort_two(src, out, c_level=1, n_threads=3) == n
+    got = tf.read_two(out + ".two")
+    assert len(got) == n
+    # twk1_two_t::operator< (lib/core.cpp:458-468): ridA, ridB, Apos, Bpos
+    order = np.lexsort((got["packB"], got["packA"], got["ridB"], got["ridA"]))
+    assert np.array_equal(order, np.arange(n))
+    # same multiset of records as the input
+    src_recs = tf.read_two(src)
+    assert np.array_equal(np.sort(got.view(np.uint8).reshape(n, -1), axis=0), np.sort(src_recs.view(np.uint8).reshape(n, -1), axis=0))
+    state, ents, meta = tf.read_two_index(out + ".two")
+    assert state == 2                                       # TWK_IDX_SORTED
+    assert sum(e[1] for e in ents) == n and all(e[1] <= 10000 for e in ents)
+    k = 0
+    for e in ents:                                          # include/writer.h:363-374
+        blk = got[k:k + e[1]]
+        assert len(set(blk["ridA"].tolist())) == 1 and e[0] == blk["ridA"][0]
+        assert e[2] == blk["packA"][0] >> 2 and e[3] == blk["packA"][-1] >> 2
+        assert e[8] == (blk["ridB"][0] if len(set(blk["ridB"].tolist())) == 1 else -1)
+        k += e[1]
+    for rid, m in enumerate(meta):                          # IndexEntryEntry::operator+=, lib/index.cpp:70-88
+        mine = [e for e in ents if e[0] == rid]
+        if mine:
+            assert (m[0], m[1], m[2], m[3], m[6]) == (rid, sum(e[1] for e in mine), mine[0][2], mine[-1][3], len(mine))
+            assert (m[4], m[5]) == (mine[0][6], mine[-1][7])
+
+
+@pytest.mark.skipif(not os.path.exists(lc.REF_SORT), reason="oracle/_ref/tomahawk_sort not built")
+@pytest.mark.parametrize("threads", [1, 4])
+def test_two_sorter_matches_reference_sort_and_view(threads, tmpdir_repo):
+    s = _two_contigs(300, 1400, 900, seed=4)
+    src, n = _unsorted_two(tmpdir_repo, "srt3", s, dict(force_phased=1, minR2=0.02), contigs=[("1", 10**6), ("2", 10**6)])
+    theirs = os.path.join(tmpdir_repo, "srt3_ref.two")
+    r = subprocess.run([lc.REF_SORT, "sort", "-i", src, "-o", theirs, "-t", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    ours = os.path.join(tmpdir_repo, "srt3_ours.two")
+    assert tb.sort_two(src, ours, c_level=1, n_threads=threads) == n
+    a, b = tf.read_two(theirs), tf.read_two(ours)
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))            # same records in the same order
+    sa, ea, ma = tf.read_two_index(theirs)
+    sb, eb, mb = tf.read_two_index(ours)
+    assert sa == sb == 2
+    strip = lambda e: (e[0], e[1], e[2], e[3], e[4], e[8])               # offsets differ by the header's version string
+    assert [strip(e) for e in ea] == [strip(e) for e in eb]
+    assert [(m[0], m[1], m[2], m[3], m[6]) for m in ma] == [(m[0], m[1], m[2], m[3], m[6]) for m in mb]
+    for q in (["-I", "1:20000-30000"], ["-I", "2:1000-9000"], ["-I", "1:5000-6000,2:100-30000"], []):
+        outs = [subprocess.run([lc.REF_VIEW, "view", "-i", f, "-H"] + q, capture_output=True, text=True).stdout for f in (theirs, ours)]
+        assert outs[0] == outs[1] and (q == ["-I", "1:5000-6000,2:100-30000"] or len(outs[0]) > 0), q
+
+
+def test_two_sorter_rejects_bad_input(tmpdir_repo):
+    p = os.path.join(tmpdir_repo, "bad.two")
+    open(p, "wb").write(b"TWO\x01" + b"\x00" * 100)
+    with pytest.raises(tb.TwkbError):
+        tb.sort_two(p, os.path.join(tmpdir_repo, "bad_sorted"))
+    with pytest.raises(tb.TwkbError):
+        tb.sort_two(os.path.join(tmpdir_repo, "nope.two"), os.path.join(tmpdir_repo, "x"))

@@ -91,6 +91,7 @@ EXPORTS = [
     "twkb_twk_open", "twkb_twk_open_intervals", "twkb_twk_dims", "twkb_twk_copy", "twkb_twk_view", "twkb_twk_close",
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
     "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
+    "twkb_two_sort",
 ]
 
 
@@ -123,6 +124,8 @@ def lib():
         L.twkb_twk_runs_view.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
                                          ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
         L.twkb_two_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+        L.twkb_two_sort.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
+                                    ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
         L.twkb_compute.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
         L.twkb_compute_resident.argtypes = [ctypes.c_void_p]
         L.twkb_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
@@ -240,6 +243,16 @@ class TwoWriter:
             self._w = ctypes.c_void_p()
             if rc != 0:
                 raise TwkbError(rc, "twkb_two_close failed")
+
+
+def sort_two(in_path: str, out_path: str, c_level: int = 1, n_threads: int = 4) -> int:
+    """`tomahawk sort` (two_reader::Sort): writes the sorted, indexed .two file; returns the record count."""
+    n = ctypes.c_uint64(0)
+    err = ctypes.create_string_buffer(512)
+    rc = lib().twkb_two_sort(in_path.encode(), out_path.encode(), c_level, n_threads, ctypes.byref(n), err, 512)
+    if rc != 0:
+        raise TwkbError(rc, err.value.decode())
+    return int(n.value)
 
 
 def plan_tiles(settings: Settings, meta: np.ndarray, tile_i: int, tile_j: int):

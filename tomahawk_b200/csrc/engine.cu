@@ -1479,6 +1479,16 @@ int twkb_two_close(void* writer) {
     return rc;
 }
 
+int twkb_two_sort(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t* n_records,
+                  char* errbuf, size_t errbuf_len) {
+    if (!in_path || !out_path) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
+    if (std::strlen(in_path) == 0) return copy_err(errbuf, errbuf_len, "No input value specified...", TWKB_EINVAL);  // two_reader.cpp:169
+    std::string err;
+    const int rc = sort_two(in_path, out_path, c_level, n_threads, err, n_records);
+    if (rc) return copy_err(errbuf, errbuf_len, err, rc);
+    return TWKB_OK;
+}
+
 int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i, uint32_t tile_j,
                     uint32_t* out_ij, uint64_t capacity, uint64_t* n_tiles, uint64_t* n_pairs) {
     if (!s || !meta || !n_tiles || n_variants == 0 || tile_i == 0 || tile_j == 0) return TWKB_EINVAL;

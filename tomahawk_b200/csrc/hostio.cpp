@@ -667,4 +667,273 @@ int TwoWriter::finish() {
     return TWKB_OK;
 }
 
+// ------------------------------------------------------------------ .two sorter
+namespace {
+
+struct TwoIndexEntry {  // IndexEntryOutput, lib/index.cpp:41-52
+    int32_t rid;
+    uint32_t n, minpos, maxpos, b_unc, b_cmp;
+    uint64_t foff, fend;
+    int32_t ridB;
+};
+struct TwoMetaEntry {  // IndexEntryEntry, lib/index.cpp:90-99
+    int32_t rid = 0;
+    uint32_t n = 0, minpos = 0, maxpos = 0;
+    uint64_t foff = 0, fend = 0, nn = 0;
+};
+
+inline void get_rec_key(const uint8_t* rec, int32_t& ridA, int32_t& ridB, uint32_t& posA, uint32_t& posB) {
+    std::memcpy(&ridA, rec + 2, 4);
+    std::memcpy(&ridB, rec + 6, 4);
+    std::memcpy(&posA, rec + 10, 4);
+    std::memcpy(&posB, rec + 14, 4);
+}
+
+}  // namespace
+
+int sort_two(const std::string& in, const std::string& out_path, int c_level, int n_threads, std::string& err, uint64_t* n_records) {
+    n_threads = std::max(1, n_threads);
+    // ---- map the input and locate header, index and blocks (two_reader::Open, lib/two_reader.cpp:100-160)
+    const int fd = ::open(in.c_str(), O_RDONLY);
+    if (fd < 0) { err = "Failed to open \"" + in + "\"..."; return TWKB_EIO; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || sb.st_size < (off_t)(4 + 16 + 17 + 8 + 32)) { ::close(fd); err = "Failed to open \"" + in + "\"..."; return TWKB_EIO; }
+    const size_t fsz = (size_t)sb.st_size;
+    void* mp = mmap(nullptr, fsz, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if (mp == MAP_FAILED) { err = "Failed to open \"" + in + "\"..."; return TWKB_EIO; }
+    struct Unmap { void* p; size_t n; ~Unmap() { munmap(p, n); } } unmap{mp, fsz};
+    const uint8_t* file = static_cast<const uint8_t*>(mp);
+    if (std::memcmp(file, kTwoMagic, 4) != 0) { err = "Failed to read MAGIC!"; return TWKB_EIO; }
+    Cursor c{file + 4, file + fsz};
+    const uint64_t h_unc = c.get<uint64_t>(), h_cmp = c.get<uint64_t>();
+    if (!c.ok || (uint64_t)(c.end - c.p) < h_cmp) { err = "truncated header"; return TWKB_EIO; }
+    std::vector<uint8_t> hdr;
+    if (!zstd_inflate(c.p, h_cmp, h_unc, hdr, err)) return TWKB_EIO;
+    uint64_t idx_off = 0;
+    std::memcpy(&idx_off, file + fsz - 32 - 8, 8);
+    if (idx_off + 17 > fsz) { err = "Failed to seek in file!"; return TWKB_EIO; }
+    Cursor f{file + idx_off, file + fsz};
+    const uint8_t marker = f.get<uint8_t>();
+    const uint64_t i_unc = f.get<uint64_t>(), i_cmp = f.get<uint64_t>();
+    if (marker != 0 || !f.ok || (uint64_t)(f.end - f.p) < i_cmp) { err = "corrupt index footer"; return TWKB_EIO; }
+    std::vector<uint8_t> idx;
+    if (!zstd_inflate(f.p, i_cmp, i_unc, idx, err)) { err = "Failed to decompress index!"; return TWKB_EIO; }
+    Cursor ix{idx.data(), idx.data() + idx.size()};
+    if (ix.get<uint64_t>() != kIndexMarker) { err = "bad index marker"; return TWKB_EIO; }
+    ix.get<uint8_t>();  // state of the input: any
+    const uint64_t n_ent = ix.get<uint64_t>();
+    ix.get<uint64_t>();  // m
+    const uint64_t n_contigs = ix.get<uint64_t>();  // m_ent
+    std::vector<TwoIndexEntry> ents(n_ent);
+    std::vector<uint64_t> first(n_ent + 1, 0);
+    for (uint64_t i = 0; i < n_ent; ++i) {
+        TwoIndexEntry& e = ents[i];
+        e.rid = ix.get<int32_t>(); e.n = ix.get<uint32_t>(); e.minpos = ix.get<uint32_t>(); e.maxpos = ix.get<uint32_t>();
+        e.b_unc = ix.get<uint32_t>(); e.b_cmp = ix.get<uint32_t>(); e.foff = ix.get<uint64_t>(); e.fend = ix.get<uint64_t>();
+        e.ridB = ix.get<int32_t>();
+        first[i + 1] = first[i] + e.n;
+    }
+    if (!ix.ok) { err = "corrupt index"; return TWKB_EIO; }
+    const uint64_t total = first[n_ent];
+    if (total == 0) { err = "Cannot sort empty file..."; return TWKB_EINVAL; }  // two_reader.cpp:191-194
+    if (n_records) *n_records = total;
+
+    // ---- inflate every block into one record array (parallel over blocks)
+    ByteBuf recs;
+    if (!recs.alloc((size_t)total * TWKB_RECORD_BYTES)) { err = "out of memory"; return TWKB_ENOMEM; }
+    {
+        std::atomic<uint64_t> next{0};
+        std::atomic<bool> failed{false};
+        auto worker = [&]() {
+            std::vector<uint8_t> raw;
+            std::string e;
+            for (;;) {
+                const uint64_t b = next.fetch_add(1);
+                if (b >= n_ent || failed.load()) return;
+                const TwoIndexEntry& en = ents[b];
+                if (en.foff + 9 > fsz) { failed.store(true); return; }
+                Cursor bc{file + en.foff, file + fsz};
+                if (bc.get<uint8_t>() != 1) { failed.store(true); return; }
+                const uint32_t unc = bc.get<uint32_t>(), cmp = bc.get<uint32_t>();
+                if ((uint64_t)(bc.end - bc.p) < cmp || !zstd_inflate(bc.p, cmp, unc, raw, e)) { failed.store(true); return; }
+                uint32_t n = 0;
+                if (raw.size() >= 8) std::memcpy(&n, raw.data(), 4);
+                if (n != en.n || raw.size() < 8 + (size_t)n * TWKB_RECORD_BYTES) { failed.store(true); return; }
+                std::memcpy(recs.data() + first[b] * TWKB_RECORD_BYTES, raw.data() + 8, (size_t)n * TWKB_RECORD_BYTES);
+            }
+        };
+        std::vector<std::thread> pool;
+        const int nt = (int)std::min<uint64_t>((uint64_t)n_threads, n_ent);
+        for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto& th : pool) th.join();
+        if (failed.load()) { err = "Failed to load a block of \"" + in + "\""; return TWKB_EIO; }
+    }
+
+    // ---- order: twk1_two_t::operator< (lib/core.cpp:458-468): ridA, ridB, Apos, Bpos (packed positions)
+    struct Key { uint64_t hi, lo; uint32_t idx; };
+    std::vector<Key> keys((size_t)total);
+    for (uint64_t r = 0; r < total; ++r) {
+        int32_t ridA, ridB; uint32_t pA, pB;
+        get_rec_key(recs.data() + r * TWKB_RECORD_BYTES, ridA, ridB, pA, pB);
+        // the reference compares rid as int32: bias to keep the order under unsigned comparison
+        keys[r].hi = ((uint64_t)((uint32_t)ridA ^ 0x80000000u) << 32) | ((uint32_t)ridB ^ 0x80000000u);
+        keys[r].lo = ((uint64_t)pA << 32) | pB;
+        keys[r].idx = (uint32_t)r;
+    }
+    if (total > 0xffffffffull) { err = "too many records for the in-memory sorter"; return TWKB_ENOMEM; }
+    auto less = [](const Key& a, const Key& b) { return a.hi != b.hi ? a.hi < b.hi : (a.lo != b.lo ? a.lo < b.lo : a.idx < b.idx); };
+    {   // sorted runs per thread, then pairwise merges
+        const int nt = (int)std::min<uint64_t>((uint64_t)n_threads, std::max<uint64_t>(1, total / 65536));
+        std::vector<size_t> cut(nt + 1);
+        for (int t = 0; t <= nt; ++t) cut[t] = (size_t)(total * (uint64_t)t / nt);
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back([&, t]() { std::sort(keys.begin() + cut[t], keys.begin() + cut[t + 1], less); });
+        std::sort(keys.begin() + cut[0], keys.begin() + cut[1], less);
+        for (auto& th : pool) th.join();
+        for (int width = 1; width < nt; width *= 2)
+            for (int t = 0; t + width < nt; t += 2 * width)
+                std::inplace_merge(keys.begin() + cut[t], keys.begin() + cut[t + width], keys.begin() + cut[std::min(t + 2 * width, nt)], less);
+    }
+
+    // ---- output blocks: <= 10,000 records (twk_two_writer_t::n_blk_lim, include/writer.h:164), cut at every change of ridA
+    const uint32_t blk_lim = 10000;
+    struct OutBlock { uint64_t begin, end; std::vector<uint8_t> z; size_t zn = 0; TwoIndexEntry ent{}; };
+    std::vector<OutBlock> blocks;
+    {
+        uint64_t b0 = 0;
+        int32_t cur = (int32_t)((uint32_t)(keys[0].hi >> 32) ^ 0x80000000u);
+        for (uint64_t r = 1; r <= total; ++r) {
+            const int32_t ra = r < total ? (int32_t)((uint32_t)(keys[r].hi >> 32) ^ 0x80000000u) : 0;
+            if (r == total || ra != cur || r - b0 == blk_lim) {
+                blocks.push_back(OutBlock{b0, r, {}, 0, {}});
+                b0 = r;
+                cur = ra;
+            }
+        }
+    }
+    {
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        auto work = [&]() {
+            std::vector<uint8_t> raw;
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= blocks.size()) return;
+                OutBlock& ob = blocks[k];
+                const uint32_t n = (uint32_t)(ob.end - ob.begin), m = blk_lim;
+                raw.resize(8 + (size_t)n * TWKB_RECORD_BYTES);
+                std::memcpy(raw.data(), &n, 4);
+                std::memcpy(raw.data() + 4, &m, 4);
+                bool uniform = true;
+                int32_t ridA0 = 0, ridB0 = 0;
+                uint32_t pA_first = 0, pA_last = 0;
+                for (uint32_t i = 0; i < n; ++i) {
+                    const uint8_t* src = recs.data() + (size_t)keys[ob.begin + i].idx * TWKB_RECORD_BYTES;
+                    std::memcpy(raw.data() + 8 + (size_t)i * TWKB_RECORD_BYTES, src, TWKB_RECORD_BYTES);
+                    int32_t ra, rb; uint32_t pa, pb;
+                    get_rec_key(src, ra, rb, pa, pb);
+                    if (i == 0) { ridA0 = ra; ridB0 = rb; pA_first = pa; }
+                    else if (rb != ridB0) uniform = false;
+                    pA_last = pa;
+                }
+                ob.z.resize(ZSTD_compressBound(raw.size()));
+                ob.zn = ZSTD_compress(ob.z.data(), ob.z.size(), raw.data(), raw.size(), c_level);
+                if (ZSTD_isError(ob.zn)) { bad.store(true); return; }
+                // include/writer.h:363-374: minpos / maxpos are Apos (the position, flag bits dropped) of the first / last record
+                ob.ent.rid = ridA0; ob.ent.ridB = uniform ? ridB0 : -1;
+                ob.ent.n = n; ob.ent.minpos = pA_first >> 2; ob.ent.maxpos = pA_last >> 2;
+                ob.ent.b_unc = (uint32_t)raw.size(); ob.ent.b_cmp = (uint32_t)ob.zn;
+            }
+        };
+        std::vector<std::thread> pool;
+        const int nt = (int)std::min<size_t>((size_t)n_threads, blocks.size());
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        if (bad.load()) { err = "failed compression"; return TWKB_EIO; }
+    }
+
+    // ---- write: header (+ sort provenance lines, two_reader.cpp:346-349), blocks, sorted index, EOF
+    std::string out = out_path;
+    {
+        const size_t slash = out.find_last_of('/'), dot = out.find_last_of('.');
+        const bool has_ext = dot != std::string::npos && (slash == std::string::npos || dot > slash);
+        std::string ext = has_ext ? out.substr(dot + 1) : "";
+        for (auto& ch : ext) ch = (char)std::tolower((unsigned char)ch);
+        if (ext != "two") out += ".two";  // two_reader.cpp:330-333
+    }
+    FILE* fp = std::fopen(out.c_str(), "wb");
+    if (!fp) { err = "Failed top open \"" + out + "\"..."; return TWKB_EIO; }
+    {
+        Cursor h{hdr.data(), hdr.data() + hdr.size()};
+        const std::string fileformat = h.str();
+        std::string literals = h.str();
+        if (!h.ok) { std::fclose(fp); err = "corrupt VcfHeader"; return TWKB_EIO; }
+        char date[64];
+        std::time_t now = std::time(nullptr);
+        std::strftime(date, sizeof(date), "%Y-%m-%d %H:%M:%S", std::localtime(&now));
+        literals += "\n##tomahawk_sortVersion=b200-0.1.0\n##tomahawk_sortCommand=tomahawk_b200 sort -i " + in + " -o " + out_path + "; Date=" + date + "\n";
+        std::vector<uint8_t> nh;
+        put_str(nh, fileformat);
+        put_str(nh, literals);
+        nh.insert(nh.end(), h.p, h.end);
+        std::vector<uint8_t> z(ZSTD_compressBound(nh.size()));
+        const size_t zn = ZSTD_compress(z.data(), z.size(), nh.data(), nh.size(), c_level);
+        if (ZSTD_isError(zn)) { std::fclose(fp); err = "failed to compress"; return TWKB_EIO; }
+        const uint64_t unc = nh.size(), cmp = zn;
+        std::fwrite(kTwoMagic, 1, 4, fp);
+        std::fwrite(&unc, 8, 1, fp);
+        std::fwrite(&cmp, 8, 1, fp);
+        std::fwrite(z.data(), 1, zn, fp);
+    }
+    std::vector<TwoMetaEntry> meta((size_t)n_contigs);
+    for (OutBlock& ob : blocks) {
+        const uint8_t mk = 1;
+        ob.ent.foff = (uint64_t)std::ftell(fp);
+        std::fwrite(&mk, 1, 1, fp);
+        std::fwrite(&ob.ent.b_unc, 4, 1, fp);
+        std::fwrite(&ob.ent.b_cmp, 4, 1, fp);
+        if (std::fwrite(ob.z.data(), 1, ob.zn, fp) != ob.zn) { std::fclose(fp); err = "write failed"; return TWKB_EIO; }
+        ob.ent.fend = (uint64_t)std::ftell(fp);
+        if (ob.ent.rid < 0 || (uint64_t)ob.ent.rid >= n_contigs) { std::fclose(fp); err = "record with a contig id outside the header"; return TWKB_EINVAL; }
+        TwoMetaEntry& me = meta[ob.ent.rid];  // IndexEntryEntry::operator+=, lib/index.cpp:70-88
+        if (me.n == 0) { me.minpos = ob.ent.minpos; me.foff = ob.ent.foff; me.rid = ob.ent.rid; }
+        me.n += ob.ent.n;
+        me.maxpos = ob.ent.maxpos;
+        me.fend = ob.ent.fend;
+        ++me.nn;
+    }
+    std::vector<uint8_t> ob_idx;
+    auto put = [&](const void* p, size_t n) { ob_idx.insert(ob_idx.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+    const uint8_t state = 2;  // TWK_IDX_SORTED, include/index.h:105
+    uint64_t n_out = blocks.size(), m_out = 500;
+    while (m_out < n_out) m_out *= 2;
+    put(&kIndexMarker, 8); put(&state, 1); put(&n_out, 8); put(&m_out, 8); put(&n_contigs, 8);
+    for (const OutBlock& b : blocks) {
+        const TwoIndexEntry& e = b.ent;
+        put(&e.rid, 4); put(&e.n, 4); put(&e.minpos, 4); put(&e.maxpos, 4); put(&e.b_unc, 4); put(&e.b_cmp, 4);
+        put(&e.foff, 8); put(&e.fend, 8); put(&e.ridB, 4);
+    }
+    for (const TwoMetaEntry& me : meta) {
+        put(&me.rid, 4); put(&me.n, 4); put(&me.minpos, 4); put(&me.maxpos, 4); put(&me.foff, 8); put(&me.fend, 8); put(&me.nn, 8);
+    }
+    std::vector<uint8_t> z(ZSTD_compressBound(ob_idx.size()));
+    const size_t zn = ZSTD_compress(z.data(), z.size(), ob_idx.data(), ob_idx.size(), c_level);
+    if (ZSTD_isError(zn)) { std::fclose(fp); err = "failed compression"; return TWKB_EIO; }
+    const uint64_t off = (uint64_t)std::ftell(fp), unc = ob_idx.size(), cmp = zn;
+    const uint8_t mk0 = 0;
+    std::fwrite(&mk0, 1, 1, fp);
+    std::fwrite(&unc, 8, 1, fp);
+    std::fwrite(&cmp, 8, 1, fp);
+    std::fwrite(z.data(), 1, zn, fp);
+    std::fwrite(&off, 8, 1, fp);
+    std::fwrite(kEof, 1, 32, fp);
+    const bool ok = std::fflush(fp) == 0;
+    std::fclose(fp);
+    if (!ok) { err = "Failed to write final block!"; return TWKB_EIO; }
+    return TWKB_OK;
+}
+
 }  // namespace twkb

@@ -140,4 +140,14 @@ private:
     std::string err_;
 };
 
+// `tomahawk sort` for files that fit in host memory (reference two_reader::Sort,
+// lib/two_reader.cpp:162-420, which merges per-thread sorted runs through temporary files): reads
+// every block of `in`, orders the records by twk1_two_t::operator< (ridA, ridB, posA, posB;
+// lib/core.cpp:458-468) and writes `out` the way the reference's merge phase does -- blocks of
+// <= 10,000 records cut at every change of ridA, index state TWK_IDX_SORTED with per-block
+// (rid, ridB, minpos, maxpos) and the per-contig summary entries that make `view -I` seek
+// (include/writer.h:344-390, lib/index.cpp:70-88).
+int sort_two(const std::string& in, const std::string& out, int c_level, int n_threads, std::string& err,
+             uint64_t* n_records = nullptr);
+
 }  // namespace twkb
