@@ -62,10 +62,10 @@ decode_runs_kernel(const uint8_t* __restrict__ bytes, const twkb_run_desc* __res
         }
         const uint32_t len = word >> lshift;
         const uint32_t a = (word >> ashift) & amask, b = word & amask;
-        uint32_t incl = len;  // warp inclusive scan (sums stay < 2^32: 32 runs of < 2^30 samples)
+        unsigned long long incl = len;  // warp inclusive scan, 64-bit: 32 corrupt run lengths of 2^30 must not wrap
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
             if ((int)lane >= o) incl += t;
         }
         const uint64_t s_samp = base + (incl - len), e_samp = base + incl;
