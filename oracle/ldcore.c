@@ -46,7 +46,7 @@ typedef struct {
     int32_t block_size;                    /* .twk block length (500, lib/importer.h:36) */
     int32_t skip_min_cell_rule;            /* test-only: bypass the "< 5" rule (:1174-1186) so the
                                               tutorial rows, which predate it, can be replayed */
-    int32_t pad;
+    int32_t bitmaps;                       /* -p -m -M: CalculatePhasedBitmap(Window) (:2351-2524) */
 } ld_params;
 
 /* ---------------------------------------------------------------- Fisher exact
@@ -459,9 +459,19 @@ int64_t ldcore_calc(const uint64_t* data, const uint64_t* mask, size_t stride, u
             for (uint32_t i = i0; i < i1 && !aborted; ++i) {
                 for (uint32_t j = (bi == bj ? i + 1 : j0); j < j1; ++j) {
                     const ld_variant *a = &meta[i], *b = &meta[j];
-                    if (prm->window && a->rid == b->rid && (b->pos - a->pos) > (uint32_t)prm->l_window) {
-                        aborted = 1; /* ld_engine.cpp:2553-2560: abandons the whole block pair */
-                        break;
+                    /* Per-pair window rule. -p / -u (CalculatePhasedWindow :2553-2560, CalculateUnphasedWindow
+                     * :2658-2664): the first out-of-window pair abandons the whole block pair. -p -m -M
+                     * (CalculatePhasedBitmapWindow :2466-2471, :2490-2495) skips a pair only when the contigs
+                     * DIFFER and the (wrapping) position difference exceeds the window. Auto mode
+                     * (twk_ld_slave::Calculate :2737-2838) has no per-pair rule at all: only the balancer's
+                     * row prune above applies. */
+                    if (prm->window && prm->emulate_quirks && prm->force_phased && prm->bitmaps) {
+                        if (a->rid != b->rid && (b->pos - a->pos) > (uint32_t)prm->l_window) continue;
+                    } else if (prm->window && (!prm->emulate_quirks || prm->force_phased || prm->forced_unphased)) {
+                        if (a->rid == b->rid && (b->pos - a->pos) > (uint32_t)prm->l_window) {
+                            aborted = 1;
+                            break;
+                        }
                     }
                     if (a->ac + b->ac <= 2) continue; /* :1918 */
                     const uint64_t *A = data + (size_t)i * stride, *B = data + (size_t)j * stride;
@@ -479,7 +489,7 @@ int64_t ldcore_calc(const uint64_t* data, const uint64_t* mask, size_t stride, u
                         uint64_t c[4];
                         if (!a->gt_missing && !b->gt_missing) {
                             ldcore_count_phased_nomiss(A, B, words, n_samples, a->ac, b->ac, c);
-                        } else if (prm->emulate_quirks && a->ac + b->ac < thresh_miss_p) {
+                        } else if (prm->emulate_quirks && (a->ac + b->ac < thresh_miss_p || (prm->force_phased && prm->bitmaps))) {
                             /* run-length comparator (:1011-1091): same counts, mixed cells in the
                              * opposite slots (Q3) */
                             ldcore_count_phased_masked(A, mA, B, mB, n_samples, 0, c);

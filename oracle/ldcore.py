@@ -45,7 +45,7 @@ class Params(ctypes.Structure):
         ("emulate_quirks", ctypes.c_int32),
         ("block_size", ctypes.c_int32),
         ("skip_min_cell_rule", ctypes.c_int32),
-        ("pad", ctypes.c_int32),
+        ("bitmaps", ctypes.c_int32),
     ]
 
 

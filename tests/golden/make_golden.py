@@ -37,6 +37,15 @@ CASES = {
                      dict(force_phased=1, minR2=0.1)),
     "interval_two": (dict(n_samples=300, n_variants=2300, seed=112), ["-p", "-r", "0.1", "-I", "1:60000-110000", "-I", "1:200000-210000"],
                      dict(force_phased=1, minR2=0.1)),
+    # -w in AUTO mode: twk_ld_slave::Calculate (ld_engine.cpp:2737-2838) has no per-pair window test, only the
+    # balancer's row prune (ld_balancing.h:176-211) applies -- far more pairs than "-p -w"
+    "auto_window": (dict(n_samples=200, n_variants=1700, seed=121, missing_rate=0.01), ["-r", "0.05", "-w", "60000"],
+                    dict(minR2=0.05, window=1, l_window=60000)),
+    # -p -m -M -w: CalculatePhasedBitmapWindow (:2441-2524) skips a pair only when the contigs differ and the
+    # wrapping position difference exceeds the window; masked pairs always take PhasedRunlength (Q3 slots)
+    "bitmap_window": (dict(n_samples=200, n_variants=1700, seed=123, missing_rate=0.01, two_contigs=1100),
+                      ["-p", "-m", "-M", "-r", "0.05", "-w", "60000"],
+                      dict(force_phased=1, bitmaps=1, minR2=0.05, window=1, l_window=60000)),
     "minp_filter": (dict(n_samples=600, n_variants=250, seed=109), ["-p", "-r", "0.05", "-P", "1e-3"],
                     dict(force_phased=1, minR2=0.05, minP=1e-3)),
 }
@@ -48,9 +57,16 @@ def main():
     for name, (skw, cli, prm) in CASES.items():
         if only and name not in only:
             continue
+        skw = dict(skw)
+        split = skw.pop("two_contigs", None)
         s = tf.synth_genotypes(**skw)
+        contigs = None
+        if split:  # second contig restarts its positions
+            s.rid[split:] = 1
+            s.pos[split:] = (np.arange(s.n_variants - split) * 100).astype(np.uint32)
+            contigs = [("1", 10**6), ("2", 10**6)]
         twk = os.path.join(TMP, f"g_{name}.twk")
-        tf.write_twk(twk, s)
+        tf.write_twk(twk, s, contigs=contigs)
         info = lc.run_reference_calc(twk, os.path.join(TMP, f"g_{name}"), cli, threads=4)
         recs = tf.canonical(tf.read_two(os.path.join(TMP, f"g_{name}.two")), forward_only=True)
         # pairs visited: the reference's own figure when its (racy) stderr summary parses,

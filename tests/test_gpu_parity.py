@@ -27,6 +27,8 @@ KERNELS = [tb.KERNEL_POPC, tb.KERNEL_AUTO]
 def gpu_run(s, prm, kernel=tb.KERNEL_POPC, **extra):
     data, mask = tf.pack_bits(s)
     meta = lc.variant_meta(s)
+    if prm.get("bitmaps"):   # the reference takes its bitmap slaves only for -p -m -M (ld_engine.cpp:1832)
+        extra = dict(extra, low_memory=1)
     eng = tb.Engine(kernel=kernel, **prm, **extra)
     eng.load(s.n_samples, data, mask, meta)
     recs = eng.compute()
@@ -84,7 +86,7 @@ def test_golden_reference_vectors(name, kernel):
     s, ref, prm, pairs, cli = load_golden(name)
     eng, got, st = gpu_run(s, prm, kernel)
     assert st.pairs_visited == pairs
-    if "unphased" in name or name == "auto_mixed":
+    if "unphased" in name or name.startswith("auto"):
         check_unphased(s, got, ref, prm)
     else:
         assert_records_bitexact(got, ref, p_rtol=1e-9)

@@ -58,6 +58,40 @@ def test_twk_reader_rejects_garbage(tmpdir_repo):
         tb.TwkFile(os.path.join(tmpdir_repo, "does_not_exist.twk"))
 
 
+def test_twk_reader_survives_corrupt_size_fields(tmpdir_repo):
+    """Declared sizes are untrusted: a header / index / entry count that asks for 2^62 bytes must come back
+    as an error code through the C ABI, never as an exception (std::terminate) in the caller's process."""
+    import struct
+
+    s = tf.synth_genotypes(100, 700, seed=3)
+    src = os.path.join(tmpdir_repo, "corrupt_src.twk")
+    tf.write_twk(src, s)
+    raw = bytearray(open(src, "rb").read())
+    idx_off = struct.unpack("<Q", raw[-40:-32])[0]
+
+    def opened(name, b):
+        q = os.path.join(tmpdir_repo, f"corrupt_{name}.twk")
+        open(q, "wb").write(b)
+        for runs in (False, True):
+            with pytest.raises(tb.TwkbError):
+                tb.TwkFile(q, runs=runs)
+
+    b = bytearray(raw); b[9:17] = struct.pack("<Q", 1 << 62); opened("h_unc", b)                    # header: uncompressed size
+    b = bytearray(raw); b[idx_off + 1:idx_off + 9] = struct.pack("<Q", 1 << 62); opened("i_unc", b)  # index: uncompressed size
+    # a well-formed index frame whose entry count is absurd
+    i_unc, i_cmp = struct.unpack("<QQ", raw[idx_off + 1:idx_off + 17])
+    idx = bytearray(tf.zstd_decompress(bytes(raw[idx_off + 17:idx_off + 17 + i_cmp]), i_unc))
+    idx[8:16] = struct.pack("<Q", 1 << 40)
+    z = tf.zstd_compress(bytes(idx))
+    b = bytearray(raw[:idx_off]) + b"\x00" + struct.pack("<QQ", len(idx), len(z)) + z + struct.pack("<Q", idx_off) + raw[-32:]
+    opened("n_ent", b)
+    # a block whose declared uncompressed size is absurd (first block follows the header)
+    h_cmp = struct.unpack("<Q", raw[17:25])[0]
+    blk = 25 + h_cmp
+    assert raw[blk] == 1
+    b = bytearray(raw); b[blk + 1:blk + 5] = struct.pack("<I", 0xFFFFFFF0); opened("b_unc", b)
+
+
 def test_two_writer_blocks_index_and_reverse_copies(tmpdir_repo):
     s, recs, prm, pairs, _ = load_golden("phased_r0")
     twk_path = os.path.join(tmpdir_repo, "w.twk")

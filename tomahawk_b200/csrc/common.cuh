@@ -38,13 +38,14 @@ struct DevParams {
     double screenR2;       // minR2 * (1 - 1e-12): conservative in-kernel R2 pre-screen
     uint32_t n_samples;
     uint32_t n_variants;
-    uint32_t window;       // window mode on
+    uint32_t window;       // window mode: 0 off, 1 -p/-u rule, 2 auto mode (row prune only), 3 -p -m -M rule
     uint32_t l_window;
     uint32_t emulate_quirks;
     uint32_t thresh_miss_phased;  // (uint32)(0.0047*n_s + 5.2913), ld_engine.cpp:1910
     uint32_t unphased;            // 1: unphased math for every pair
     uint32_t diag;                // 1: row range == col range, only i<j
     uint32_t lgamma_len;
+    uint32_t bitmap_mode;         // -p -m -M with emulate_quirks: every masked pair takes the run-length slots (Q3)
     uint32_t pair_filter;         // auto mode passes: 0 all pairs, 1 only pairs without a variant
                                   // with missing alleles, 2 only pairs with one (ld_engine.cpp:2775)
 };

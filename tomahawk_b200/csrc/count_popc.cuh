@@ -69,13 +69,19 @@ struct CountArgs {
     uint32_t debug_flags;        // profiling aids (env TWKB_DEBUG_FLAGS); 0 in production
 };
 
-// Window-mode pair rule of the reference:
-// ld_balancing.h:189-196 prunes the rest of a block row by positions only, and
-// ld_engine.cpp:2553-2560 abandons a block pair at its first out-of-window pair.
-__device__ __forceinline__ bool window_pair_allowed(uint32_t i, uint32_t j, const DevVariant& vi, const DevVariant& vj,
+// Window-mode pair rules of the reference. DevParams::window selects:
+//   1  -p / -u (CalculatePhasedWindow ld_engine.cpp:2553-2560, CalculateUnphasedWindow :2658-2664):
+//      ld_balancing.h:189-196 prunes the rest of a block row by positions only, and the slave
+//      abandons a block pair at its first out-of-window pair;
+//   2  auto mode (twk_ld_slave::Calculate :2737-2838 has no per-pair test): the row prune only;
+//   3  -p -m -M (CalculatePhasedBitmapWindow :2466-2471, :2490-2495): the row prune, and a pair is
+//      skipped only when the contigs DIFFER and the wrapping position difference exceeds the window.
+__device__ __forceinline__ bool window_pair_allowed(uint32_t kind, uint32_t i, uint32_t j, const DevVariant& vi, const DevVariant& vj,
                                                     const DevVariant* meta, const DevBlocks& bl, uint32_t w) {
     const uint32_t bi = bl.blk_of[i], bj = bl.blk_of[j];
     if (bi != bj && bj >= bl.blk_prune[bi]) return false;
+    if (kind == 2u) return true;
+    if (kind == 3u) return !(vi.rid != vj.rid && (vj.pos - vi.pos) > w);
     const uint32_t fi = bl.blk_first[bi], lj = bl.blk_last[bj];
     const DevVariant vf = meta[fi], vl = meta[lj];
     if (vf.rid == vl.rid && (vl.pos - vf.pos) > w) return i == fi && !((vj.pos - vi.pos) > w);
@@ -123,7 +129,7 @@ __device__ __forceinline__ bool pair_decide(const CountArgs& args, const DevPara
         const bool miss = ((vi.flags | vj.flags) & VF_HAS_MISSING) != 0;
         ok = ok && (prm.pair_filter == 1u ? !miss : miss);
     }
-    if (ok && prm.window) ok = window_pair_allowed(i, j, vi, vj, args.meta, args.blocks, prm.l_window);
+    if (ok && prm.window) ok = window_pair_allowed(prm.window, i, j, vi, vj, args.meta, args.blocks, prm.l_window);
     if (!ok) return false;
     if (MODE == MODE_PHASED_NOMISS) {
         // ld_engine.cpp:244-246 / :682-685

@@ -170,6 +170,16 @@ static int validate_settings(const twkb_settings* s, std::string& why) {
     return TWKB_OK;
 }
 
+// Which per-pair window rule the reference applies for these flags (count_popc.cuh:
+// window_pair_allowed). Without emulate_quirks every mode uses the -p / -u rule.
+static uint32_t window_kind(const twkb_settings& s) {
+    if (!s.window) return 0u;
+    if (!s.emulate_quirks) return 1u;
+    if (s.force_phased && s.low_memory && s.bitmaps) return 3u;  // ld_engine.cpp:1832-1834
+    if (s.force_phased || s.forced_unphased) return 1u;
+    return 2u;  // auto mode: twk_ld_slave::Calculate, ld_engine.cpp:1842-1843
+}
+
 static DevParams make_params(const Context* ctx, const Problem& pb) {
     DevParams p{};
     const twkb_settings& s = ctx->st;
@@ -177,7 +187,8 @@ static DevParams make_params(const Context* ctx, const Problem& pb) {
     p.screenR2 = s.minR2 * (1.0 - 1e-12);
     p.n_samples = ctx->n_samples;
     p.n_variants = ctx->n_variants;
-    p.window = s.window ? 1u : 0u;
+    p.window = window_kind(s);
+    p.bitmap_mode = (s.emulate_quirks && s.force_phased && s.low_memory && s.bitmaps) ? 1u : 0u;
     p.l_window = (uint32_t)s.l_window;
     p.emulate_quirks = s.emulate_quirks ? 1u : 0u;
     p.thresh_miss_phased = (uint32_t)(0.0047 * ctx->n_samples + 5.2913);
@@ -278,13 +289,14 @@ static uint64_t visited_pairs(const Context* ctx, const Problem& pb) {
     uint64_t total = 0;
     const uint32_t nb = (uint32_t)ctx->h_blk_first.size();
     const uint32_t w = (uint32_t)ctx->st.l_window;
+    const uint32_t kind = window_kind(ctx->st);
     for (uint32_t bi = 0; bi < nb; ++bi) {
         const uint64_t ni = ctx->h_blk_last[bi] - ctx->h_blk_first[bi] + 1;
         const twkb_variant& vf = ctx->h_meta_orig[ctx->h_blk_first[bi]];
         for (uint32_t bj = bi; bj < ctx->h_blk_prune[bi] || bj == bi; ++bj) {
             if (bj >= nb) break;
             const twkb_variant& vl = ctx->h_meta_orig[ctx->h_blk_last[bj]];
-            const bool aborted = vf.rid == vl.rid && (uint32_t)(vl.pos - vf.pos) > w;
+            const bool aborted = kind == 1u && vf.rid == vl.rid && (uint32_t)(vl.pos - vf.pos) > w;
             if (!aborted) {
                 const uint64_t nj = ctx->h_blk_last[bj] - ctx->h_blk_first[bj] + 1;
                 total += (bi == bj) ? (ni * ni - ni) / 2 : ni * nj;
@@ -359,7 +371,9 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
     };
     const uint32_t ti0 = pb.row_begin / TI, ti1 = (pb.row_end + TI - 1) / TI;
     const uint32_t tj0 = pb.col_begin / TJ, tj1 = (pb.col_end + TJ - 1) / TJ;
-    const bool window = ctx->st.window;
+    // tile-level window skip: only the -p / -u rule drops every pair farther apart than the window
+    // (the auto-mode and -M rules keep them inside un-pruned block pairs; the kernels decide per pair)
+    const bool window = window_kind(ctx->st) == 1u;
     const uint32_t w = (uint32_t)ctx->st.l_window;
     const uint32_t M = ctx->n_variants;
     const int parts = std::max(1, ctx->st.part_count), part = ctx->st.part_index;
@@ -442,7 +456,7 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
 static void build_sparse_tiles(const Context* ctx, std::vector<uint2>& tiles, uint64_t* pairs_out) {
     tiles.clear();
     const uint32_t M = ctx->n_variants, nD = ctx->nD;
-    const bool window = ctx->st.window;
+    const bool window = window_kind(ctx->st) == 1u;
     const uint32_t w = (uint32_t)ctx->st.l_window;
     const int parts = std::max(1, ctx->st.part_count), part = ctx->st.part_index;
     uint64_t group = 0, pairs = 0;
@@ -708,7 +722,7 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
     char keybuf[256];
     std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u|w%d:%d:%d|p%d/%d",
                   (unsigned long long)(ctx->st.window ? ctx->matrix_epoch : 0ull),
-                  pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, (int)ctx->st.window,
+                  pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, (int)window_kind(ctx->st),
                   ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
     if (ctx->plan_key != keybuf) {
         // super-tile edge (in tiles) of the L2-friendly order: 32 x 32 tiles of e2m1 operand rows are
@@ -726,7 +740,7 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
         ctx->plan_key = keybuf;
     }
     if (sparse_phase) {
-        std::snprintf(keybuf, sizeof(keybuf), "%llu|w%d:%d:%d|p%d/%d", (unsigned long long)ctx->matrix_epoch, (int)ctx->st.window,
+        std::snprintf(keybuf, sizeof(keybuf), "%llu|w%d:%d:%d|p%d/%d", (unsigned long long)ctx->matrix_epoch, (int)window_kind(ctx->st),
                       ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
         if (ctx->sp_plan_key != keybuf) {
             build_sparse_tiles(ctx, ctx->sp_plan_tiles, &ctx->sp_plan_pairs);
@@ -1128,6 +1142,42 @@ static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, cons
 
 using namespace twkb;
 
+// No C++ exception may cross the C ABI (a corrupt file that drives an allocation to 2^62 bytes would
+// otherwise reach the caller as std::terminate): every entry point that allocates or parses runs
+// inside one of these guards and reports TWKB_ENOMEM / TWKB_EIO instead.
+template <typename F>
+static int guarded_buf(char* errbuf, size_t errbuf_len, F&& body) {
+    auto put = [&](const char* m, int code) {
+        if (errbuf && errbuf_len) std::snprintf(errbuf, errbuf_len, "%s", m);
+        return code;
+    };
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return put("out of host memory", TWKB_ENOMEM);
+    } catch (const std::exception& e) {
+        return put((std::string("internal error: ") + e.what()).c_str(), TWKB_EIO);
+    } catch (...) {
+        return put("internal error", TWKB_EIO);
+    }
+}
+template <typename F>
+static int guarded_ctx(void* c, F&& body) {
+    Context* ctx = static_cast<Context*>(c);
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "out of host memory";
+        return TWKB_ENOMEM;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = std::string("internal error: ") + e.what();
+        return TWKB_ECUDA;
+    } catch (...) {
+        if (ctx) ctx->err = "internal error";
+        return TWKB_ECUDA;
+    }
+}
+
 extern "C" {
 
 void twkb_settings_init(twkb_settings* s) {
@@ -1141,7 +1191,7 @@ const char* twkb_last_error(void* c) {
     return static_cast<Context*>(c)->err.c_str();
 }
 
-int twkb_create(const twkb_settings* s, void** out) {
+static int twkb_create_impl(const twkb_settings* s, void** out) {
     std::lock_guard<std::mutex> lock(g_create_mutex);
     if (!s || !out) { g_create_error = "null argument"; return TWKB_EINVAL; }
     std::string why;
@@ -1219,19 +1269,19 @@ int twkb_update_settings(void* c, const twkb_settings* s) {
 int twkb_load_matrix(void* c, uint32_t n_samples, uint32_t n_variants, const uint64_t* data_bits, const uint64_t* mask_bits,
                      size_t row_stride_words, const twkb_variant* meta) {
     if (!c) return TWKB_EINVAL;
-    return load_common(static_cast<Context*>(c), n_samples, n_variants, data_bits, mask_bits, row_stride_words, meta, false);
+    return guarded_ctx(c, [&] { return load_common(static_cast<Context*>(c), n_samples, n_variants, data_bits, mask_bits, row_stride_words, meta, false); });
 }
 
 int twkb_load_matrix_device(void* c, uint32_t n_samples, uint32_t n_variants, const uint64_t* d_data_bits,
                             const uint64_t* d_mask_bits, size_t row_stride_words, const twkb_variant* meta) {
     if (!c) return TWKB_EINVAL;
-    return load_common(static_cast<Context*>(c), n_samples, n_variants, d_data_bits, d_mask_bits, row_stride_words, meta, true);
+    return guarded_ctx(c, [&] { return load_common(static_cast<Context*>(c), n_samples, n_variants, d_data_bits, d_mask_bits, row_stride_words, meta, true); });
 }
 
 int twkb_load_runs(void* c, uint32_t n_samples, uint32_t n_variants, const uint8_t* run_bytes, size_t n_run_bytes,
                    const twkb_run_desc* desc, const twkb_variant* meta) {
     if (!c) return TWKB_EINVAL;
-    return load_runs(static_cast<Context*>(c), n_samples, n_variants, run_bytes, n_run_bytes, desc, meta);
+    return guarded_ctx(c, [&] { return load_runs(static_cast<Context*>(c), n_samples, n_variants, run_bytes, n_run_bytes, desc, meta); });
 }
 
 int twkb_debug_rows(void* c, uint64_t* data_bits, uint64_t* mask_bits, size_t row_stride_words) {
@@ -1253,12 +1303,12 @@ int twkb_debug_rows(void* c, uint64_t* data_bits, uint64_t* mask_bits, size_t ro
 
 int twkb_compute(void* c, twkb_sink_fn sink, void* user) {
     if (!c) return TWKB_EINVAL;
-    return compute_impl(static_cast<Context*>(c), false, sink, user, false, nullptr);
+    return guarded_ctx(c, [&] { return compute_impl(static_cast<Context*>(c), false, sink, user, false, nullptr); });
 }
 
 int twkb_compute_resident(void* c) {
     if (!c) return TWKB_EINVAL;
-    return compute_impl(static_cast<Context*>(c), true, nullptr, nullptr, false, nullptr);
+    return guarded_ctx(c, [&] { return compute_impl(static_cast<Context*>(c), true, nullptr, nullptr, false, nullptr); });
 }
 
 int twkb_get_stats(void* c, twkb_stats* out) {
@@ -1267,7 +1317,7 @@ int twkb_get_stats(void* c, twkb_stats* out) {
     return TWKB_OK;
 }
 
-int twkb_debug_candidates(void* c, int screen_off, uint32_t* out, uint64_t capacity, uint64_t* n_out) {
+static int twkb_debug_candidates_impl(void* c, int screen_off, uint32_t* out, uint64_t capacity, uint64_t* n_out) {
     if (!c || !n_out) return TWKB_EINVAL;
     Context* ctx = static_cast<Context*>(c);
     std::vector<Candidate> dump;
@@ -1293,7 +1343,7 @@ int twkb_calc_file(const twkb_settings* s, const char* in_path, const char* out_
 }
 
 // `tomahawk calc`: twk_ld::Compute (reference lib/ld/ld.cpp:477-671) end to end.
-int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const char* out_path, const char* const* intervals,
+static int twkb_calc_file_intervals_impl(const twkb_settings* s, const char* in_path, const char* out_path, const char* const* intervals,
                              int32_t n_intervals, twkb_stats* stats_out, char* errbuf, size_t errbuf_len) {
     auto fail = [&](int code, const std::string& m) {
         if (errbuf && errbuf_len) {
@@ -1368,7 +1418,7 @@ int twkb_twk_open(const char* path, int n_threads, void** handle, char* errbuf, 
     return twkb_twk_open_intervals(path, n_threads, nullptr, 0, 1, handle, errbuf, errbuf_len);
 }
 
-int twkb_twk_open_intervals(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
+static int twkb_twk_open_intervals_impl(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
                             int32_t emulate_quirks, void** handle, char* errbuf, size_t errbuf_len) {
     if (!path || !handle) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
     std::vector<std::string> ivals;
@@ -1384,7 +1434,7 @@ int twkb_twk_open_intervals(const char* path, int n_threads, const char* const* 
     return TWKB_OK;
 }
 
-int twkb_twk_open_runs(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
+static int twkb_twk_open_runs_impl(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
                        int32_t emulate_quirks, void** handle, char* errbuf, size_t errbuf_len) {
     if (!path || !handle) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
     std::vector<std::string> ivals;
@@ -1449,7 +1499,7 @@ int twkb_twk_view(void* handle, const uint64_t** data_bits, const uint64_t** mas
 
 void twkb_twk_close(void* handle) { delete static_cast<TwkFile*>(handle); }
 
-int twkb_two_open(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t b_size,
+static int twkb_two_open_impl(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t b_size,
                   void** writer, char* errbuf, size_t errbuf_len) {
     if (!path || !twk_handle || !writer) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
     TwoWriter* w = new TwoWriter();
@@ -1466,12 +1516,12 @@ int twkb_two_set_threads(void* writer, int32_t n_threads) {
     return TWKB_OK;
 }
 
-int twkb_two_add(void* writer, const uint8_t* records, uint64_t n) {
+static int twkb_two_add_impl(void* writer, const uint8_t* records, uint64_t n) {
     if (!writer || (!records && n)) return TWKB_EINVAL;
     return static_cast<TwoWriter*>(writer)->add(records, n);
 }
 
-int twkb_two_close(void* writer) {
+static int twkb_two_close_impl(void* writer) {
     if (!writer) return TWKB_EINVAL;
     TwoWriter* w = static_cast<TwoWriter*>(writer);
     const int rc = w->finish();
@@ -1479,7 +1529,7 @@ int twkb_two_close(void* writer) {
     return rc;
 }
 
-int twkb_two_sort(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t* n_records,
+static int twkb_two_sort_impl(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t* n_records,
                   char* errbuf, size_t errbuf_len) {
     if (!in_path || !out_path) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
     if (std::strlen(in_path) == 0) return copy_err(errbuf, errbuf_len, "No input value specified...", TWKB_EINVAL);  // two_reader.cpp:169
@@ -1489,7 +1539,7 @@ int twkb_two_sort(const char* in_path, const char* out_path, int32_t c_level, in
     return TWKB_OK;
 }
 
-int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i, uint32_t tile_j,
+static int twkb_plan_tiles_impl(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i, uint32_t tile_j,
                     uint32_t* out_ij, uint64_t capacity, uint64_t* n_tiles, uint64_t* n_pairs) {
     if (!s || !meta || !n_tiles || n_variants == 0 || tile_i == 0 || tile_j == 0) return TWKB_EINVAL;
     std::string why;
@@ -1514,6 +1564,53 @@ int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_vari
         for (size_t t = 0; t < tiles.size(); ++t) { out_ij[2 * t] = tiles[t].x; out_ij[2 * t + 1] = tiles[t].y; }
     }
     return TWKB_OK;
+}
+
+// ---- exception-safe entry points (see guarded_buf / guarded_ctx)
+int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const char* out_path, const char* const* intervals,
+                             int32_t n_intervals, twkb_stats* stats_out, char* errbuf, size_t errbuf_len) {
+    return guarded_buf(errbuf, errbuf_len, [&] { return twkb_calc_file_intervals_impl(s, in_path, out_path, intervals, n_intervals, stats_out, errbuf, errbuf_len); });
+}
+
+int twkb_twk_open_intervals(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
+                            int32_t emulate_quirks, void** handle, char* errbuf, size_t errbuf_len) {
+    return guarded_buf(errbuf, errbuf_len, [&] { return twkb_twk_open_intervals_impl(path, n_threads, intervals, n_intervals, emulate_quirks, handle, errbuf, errbuf_len); });
+}
+
+int twkb_twk_open_runs(const char* path, int n_threads, const char* const* intervals, int32_t n_intervals,
+                       int32_t emulate_quirks, void** handle, char* errbuf, size_t errbuf_len) {
+    return guarded_buf(errbuf, errbuf_len, [&] { return twkb_twk_open_runs_impl(path, n_threads, intervals, n_intervals, emulate_quirks, handle, errbuf, errbuf_len); });
+}
+
+int twkb_two_open(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t b_size,
+                  void** writer, char* errbuf, size_t errbuf_len) {
+    return guarded_buf(errbuf, errbuf_len, [&] { return twkb_two_open_impl(path, twk_handle, command_line, c_level, b_size, writer, errbuf, errbuf_len); });
+}
+
+int twkb_two_sort(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t* n_records,
+                  char* errbuf, size_t errbuf_len) {
+    return guarded_buf(errbuf, errbuf_len, [&] { return twkb_two_sort_impl(in_path, out_path, c_level, n_threads, n_records, errbuf, errbuf_len); });
+}
+
+int twkb_two_add(void* writer, const uint8_t* records, uint64_t n) {
+    return guarded_buf(nullptr, 0, [&] { return twkb_two_add_impl(writer, records, n); });
+}
+
+int twkb_two_close(void* writer) {
+    return guarded_buf(nullptr, 0, [&] { return twkb_two_close_impl(writer); });
+}
+
+int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i, uint32_t tile_j,
+                    uint32_t* out_ij, uint64_t capacity, uint64_t* n_tiles, uint64_t* n_pairs) {
+    return guarded_buf(nullptr, 0, [&] { return twkb_plan_tiles_impl(s, n_variants, meta, tile_i, tile_j, out_ij, capacity, n_tiles, n_pairs); });
+}
+
+int twkb_create(const twkb_settings* s, void** out) {
+    return guarded_buf(nullptr, 0, [&] { return twkb_create_impl(s, out); });
+}
+
+int twkb_debug_candidates(void* c, int screen_off, uint32_t* out, uint64_t capacity, uint64_t* n_out) {
+    return guarded_ctx(c, [&] { return twkb_debug_candidates_impl(c, screen_off, out, capacity, n_out); });
 }
 
 }  // extern "C"

@@ -47,8 +47,23 @@ struct Cursor {
     }
 };
 
+// Inflates one zstd frame whose size the file declares. The declared size is attacker-controlled
+// (a corrupt header must not become a 2^62-byte allocation): it has to agree with the size recorded in
+// the frame itself, or -- for frames written without one -- stay within zstd's maximum expansion.
 bool zstd_inflate(const uint8_t* src, size_t n_cmp, size_t n_unc, std::vector<uint8_t>& dst, std::string& err) {
-    dst.resize(n_unc ? n_unc : 1);
+    const unsigned long long fcs = ZSTD_getFrameContentSize(src, n_cmp);
+    const unsigned long long kUnknown = 0ULL - 1, kError = 0ULL - 2;  // ZSTD_CONTENTSIZE_UNKNOWN / _ERROR
+    if (fcs == kError || (fcs != kUnknown && fcs != (unsigned long long)n_unc) ||
+        (fcs == kUnknown && (unsigned long long)n_unc > (1ull << 20) + 32768ull * (unsigned long long)n_cmp)) {
+        err = "zstd decompress failed: declared size does not match the frame";
+        return false;
+    }
+    try {
+        dst.resize(n_unc ? n_unc : 1);
+    } catch (const std::bad_alloc&) {
+        err = "out of memory inflating a block";
+        return false;
+    }
     const size_t r = ZSTD_decompress(dst.data(), n_unc, src, n_cmp);
     if (ZSTD_isError(r) || r != n_unc) {
         err = std::string("zstd decompress failed: ") + (ZSTD_isError(r) ? ZSTD_getErrorName(r) : "size mismatch");
@@ -241,6 +256,7 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     uint64_t n_ent = ix.get<uint64_t>();
     ix.get<uint64_t>();  // m
     ix.get<uint64_t>();  // m_ent
+    if (!ix.ok || n_ent > (uint64_t)(ix.end - ix.p) / 40) { err = "corrupt index (entry count)"; return TWKB_EIO; }
     std::vector<BlockRef> blocks(n_ent);
     uint64_t total = 0;
     for (uint64_t i = 0; i < n_ent; ++i) {  // IndexEntry, lib/index.cpp:8-18
@@ -295,7 +311,7 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     std::atomic<bool> failed{false};
     std::string first_err;
     std::mutex err_mu;
-    auto worker = [&]() {
+    auto worker_body = [&]() {
         std::vector<uint8_t> raw;
         for (;;) {
             const uint64_t b = next.fetch_add(1);
@@ -378,6 +394,14 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
                 }
                 if (cum != H) { fail("run lengths do not cover all samples"); return; }
             }
+        }
+    };
+    auto worker = [&]() {  // an exception must never leave a std::thread (std::terminate would kill the caller's process)
+        try {
+            worker_body();
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> g(err_mu);
+            if (!failed.exchange(true)) first_err = std::string("reader thread: ") + e.what();
         }
     };
     const int nt = std::max(1, std::min<int>(n_threads, (int)n_ent));
@@ -725,6 +749,7 @@ int sort_two(const std::string& in, const std::string& out_path, int c_level, in
     const uint64_t n_ent = ix.get<uint64_t>();
     ix.get<uint64_t>();  // m
     const uint64_t n_contigs = ix.get<uint64_t>();  // m_ent
+    if (!ix.ok || n_ent > (uint64_t)(ix.end - ix.p) / 44 || n_contigs > (1ull << 24)) { err = "corrupt index (entry count)"; return TWKB_EIO; }
     std::vector<TwoIndexEntry> ents(n_ent);
     std::vector<uint64_t> first(n_ent + 1, 0);
     for (uint64_t i = 0; i < n_ent; ++i) {

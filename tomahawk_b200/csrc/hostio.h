@@ -26,6 +26,7 @@ size_t ZSTD_decompress(void* dst, size_t dstCapacity, const void* src, size_t co
 size_t ZSTD_compressBound(size_t srcSize);
 unsigned ZSTD_isError(size_t code);
 const char* ZSTD_getErrorName(size_t code);
+unsigned long long ZSTD_getFrameContentSize(const void* src, size_t srcSize);
 }
 
 // Uninitialised byte buffer (malloc): the pages are first touched by the threads that fill them.

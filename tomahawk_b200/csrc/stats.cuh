@@ -433,8 +433,9 @@ stats_kernel(const Candidate* __restrict__ cands, uint32_t n_cands, const DevVar
         if (cd.mode == 0) {
             unsigned long long c0 = cd.c[0], c1 = cd.c[1], c4 = cd.c[2], c5 = cd.c[3];
             // Q3: the reference's run-length comparator (low allele counts, missing data)
-            // stores the two mixed cells in swapped slots (ld_engine.cpp:1023,1055 vs :683-684).
-            if (prm.emulate_quirks && ((a.flags | b.flags) & VF_GT_MISSING) && (a.ac + b.ac < prm.thresh_miss_phased)) {
+            // stores the two mixed cells in swapped slots (ld_engine.cpp:1023,1055 vs :683-684);
+            // CalculatePhasedBitmap* (-p -m -M) sends every masked pair there (:2393-2397, :2477-2481).
+            if (prm.emulate_quirks && ((a.flags | b.flags) & VF_GT_MISSING) && (prm.bitmap_mode || a.ac + b.ac < prm.thresh_miss_phased)) {
                 unsigned long long tmp = c1; c1 = c4; c4 = tmp;
             }
             pass = phased_stats(c0, c1, c4, c5, prm, lg, a, b, s);
