@@ -72,10 +72,15 @@ def test_window_band_prunes_far_tiles():
     n = 20000
     meta = _meta(n, step=100)
     s_all = tb.default_settings()
-    s_win = tb.default_settings(window=1, l_window=50000)
+    s_win = tb.default_settings(window=1, l_window=50000, force_phased=1)
     all_tiles, _ = tb.plan_tiles(s_all, meta, 128, 128)
     win_tiles, _ = tb.plan_tiles(s_win, meta, 128, 128)
     assert 0 < len(win_tiles) < 0.1 * len(all_tiles)
+    # auto mode (neither -p nor -u): the reference has no per-pair window test, only the balancer's row prune
+    # over 500-variant blocks (ld_balancing.h:189-196) -- a coarser band that contains the -p one
+    auto_tiles, _ = tb.plan_tiles(tb.default_settings(window=1, l_window=50000), meta, 128, 128)
+    assert len(win_tiles) < len(auto_tiles) < 0.2 * len(all_tiles)
+    assert set(map(tuple, win_tiles.tolist())) <= set(map(tuple, auto_tiles.tolist()))
     # every in-window pair's tile is kept
     keep = set(map(tuple, win_tiles.tolist()))
     for i in (0, 777, 10000, 19000):

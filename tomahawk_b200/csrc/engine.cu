@@ -104,7 +104,7 @@ struct Context {
 
     // window-mode block structure
     DevBuf<uint32_t> d_blk_of, d_blk_first, d_blk_last, d_blk_prune;
-    std::vector<uint32_t> h_blk_first, h_blk_last, h_blk_prune;
+    std::vector<uint32_t> h_blk_first, h_blk_last, h_blk_prune, h_blk_of_orig;  // file order
 
     // tile plan of the last run, reused while the sub-problem and the partition are unchanged
     std::vector<uint2> plan_tiles;
@@ -234,11 +234,11 @@ static int ensure_planes(Context* ctx, int mode) {
 // .twk block structure for the window rule (blocks of <= bs variants, one contig
 // per block: lib/importer.cpp:196-236) and the row-prune limit of
 // ld_balancing.h:189-196.
-static int build_blocks(Context* ctx) {
+static void build_blocks_host(Context* ctx, std::vector<uint32_t>& blk_of_orig) {
     const uint32_t M = ctx->n_variants;
     const std::vector<twkb_variant>& mo = ctx->h_meta_orig;  // blocks are defined on the file order
     const uint32_t bs = ctx->st.twk_block_size > 0 ? (uint32_t)ctx->st.twk_block_size : 500u;
-    std::vector<uint32_t> blk_of_orig(M, 0);
+    blk_of_orig.assign(M, 0);
     ctx->h_blk_first.clear();
     ctx->h_blk_last.clear();
     for (uint32_t v = 0; v < M;) {
@@ -262,6 +262,14 @@ static int build_blocks(Context* ctx) {
             }
         }
     }
+    ctx->h_blk_of_orig = blk_of_orig;
+}
+
+static int build_blocks(Context* ctx) {
+    const uint32_t M = ctx->n_variants;
+    std::vector<uint32_t> blk_of_orig;
+    build_blocks_host(ctx, blk_of_orig);
+    const uint32_t nb = (uint32_t)ctx->h_blk_first.size();
     // device copies in resident indices (identical to the file order unless the matrix is
     // ordered [dense | sparse])
     std::vector<uint32_t> inv(M), blk_of(ctx->Mpad, 0), d_first(nb), d_last(nb);
@@ -374,6 +382,9 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
     // tile-level window skip: only the -p / -u rule drops every pair farther apart than the window
     // (the auto-mode and -M rules keep them inside un-pruned block pairs; the kernels decide per pair)
     const bool window = window_kind(ctx->st) == 1u;
+    // auto mode / -M: a tile is dropped when the balancer's row prune (ld_balancing.h:189-196) removes every
+    // block pair it touches (file order == resident order required: not with the rare-variant class)
+    const bool prune_only = window_kind(ctx->st) >= 2u && !ctx->permuted && ctx->h_blk_of_orig.size() == ctx->n_variants;
     const uint32_t w = (uint32_t)ctx->st.l_window;
     const uint32_t M = ctx->n_variants;
     const int parts = std::max(1, ctx->st.part_count), part = ctx->st.part_index;
@@ -401,6 +412,17 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
                         if (a0.rid == a1.rid && a1.rid == b0.rid && b0.rid == b1.rid && b0.pos >= a1.pos &&
                             (uint32_t)(b0.pos - a1.pos) > w)
                             continue;
+                    }
+                }
+                if (prune_only) {
+                    const uint32_t ia = std::max(i0, pb.row_begin), il = std::min(i0 + TI, std::min(M, pb.row_end)) - 1;
+                    const uint32_t jf = std::max(j0, pb.col_begin);
+                    if (ia <= il && jf > il && jf < M) {
+                        const uint32_t bjf = ctx->h_blk_of_orig[jf];
+                        bool all_pruned = true;
+                        for (uint32_t b = ctx->h_blk_of_orig[ia]; b <= ctx->h_blk_of_orig[il] && all_pruned; ++b)
+                            all_pruned = bjf >= ctx->h_blk_prune[b];
+                        if (all_pruned) continue;
                     }
                 }
                 ++n;
@@ -1554,6 +1576,12 @@ static int twkb_plan_tiles_impl(const twkb_settings* s, uint32_t n_variants, con
     Problem pb;
     rc = select_problem(&ctx, pb);
     if (rc) return rc;
+    ctx.h_orig.resize(n_variants);
+    for (uint32_t x = 0; x < n_variants; ++x) ctx.h_orig[x] = x;
+    if (ctx.st.window) {
+        std::vector<uint32_t> blk_of_orig;
+        build_blocks_host(&ctx, blk_of_orig);
+    }
     std::vector<uint2> tiles;
     uint64_t pairs = 0;
     build_tiles(&ctx, pb, tile_i, tile_j, 32, tiles, &pairs);
