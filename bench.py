@@ -398,15 +398,20 @@ def main():
         # fill is loaded, accumulators are not drained; results are discarded). What remains is the
         # tcgen05.mma issue rate under the board's power/clock behaviour.
         mma_only = None
-        if not args.no_mma_ceiling and not args.unphased and args.missing == 0:
+        if not args.no_mma_ceiling and not args.unphased and args.missing == 0 and os.path.exists(tb.PROF_LIB_PATH):
+            # profiling build of the same sources (libtwkb_prof.so); the product library has no such switch
             os.environ["TWKB_DEBUG_FLAGS"] = "3"
             try:
+                peng = tb.Engine(force_phased=1, minR2=args.min_r2, kernel=kernel, device=local_rank, part_index=rank,
+                                 part_count=world, profiling=True)
+                peng.load(n_samples, host_np, host_mask_np, meta)
                 ms = []
                 for _ in range(3):
                     flush.zero_(); torch.cuda.synchronize()
-                    eng.compute_resident()
-                    s3 = eng.stats()
+                    peng.compute_resident()
+                    s3 = peng.stats()
                     ms.append(s3.ms_count_kernel / max(s3.count_launches, 1))
+                peng.close()
                 mma_only = pairs_per_launch * flop_per_pair / (min(ms[1:]) * 1e-3) / 1e12
             finally:
                 del os.environ["TWKB_DEBUG_FLAGS"]

@@ -148,10 +148,12 @@ typedef struct twkb_stats {
 } twkb_stats;
 
 /* Receives `n` packed 106-byte records (forward orientation: A is the variant
- * with the lower index). Called on the calling thread of twkb_compute, between
- * device batches. Return non-zero to abort the run (-> TWKB_ESINK). The reverse
- * copies the reference also writes (lib/ld/ld_engine.cpp:1290-1298) are
- * synthesised by the .two writer (twkb_two_writer_*), not by the device. */
+ * with the lower index). Called from the context's record-drain thread (never
+ * concurrently, and never after twkb_compute has returned) while the device
+ * already computes the next batch. Return non-zero to abort the run
+ * (-> TWKB_ESINK). The reverse copies the reference also writes
+ * (lib/ld/ld_engine.cpp:1290-1298) are synthesised by the .two writer
+ * (twkb_two_writer_*), not by the device. */
 typedef int (*twkb_sink_fn)(void* user, const uint8_t* records, uint64_t n);
 
 void twkb_settings_init(twkb_settings* s); /* reference defaults, lib/core.cpp:297-306 */
@@ -197,7 +199,8 @@ int twkb_compute_resident(void* ctx);
 
 int twkb_get_stats(void* ctx, twkb_stats* out);
 
-/* Test hook: run the count kernel over this context's share of the grid and return
+/* Test hook: run the count kernel the settings select (tensor-core or LOP3+POPC, exactly as
+ * twkb_compute would) over this context's share of the grid and return
  * the raw candidate entries (12 uint32 each: i, j, c[9], mode) instead of records.
  * screen_off != 0 disables the R2 pre-screen so every enumerated pair is returned
  * with its exact contingency counts: mode 0 -> c = {REFREF, slot1 (A alt,B ref),

@@ -147,11 +147,21 @@ def test_unphased_vs_oracle(skw, prm, kernel):
 
 
 # ------------------------------------------------- exact counts for EVERY pair (no screen)
+ALL_KERNELS = [tb.KERNEL_POPC, tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4, tb.KERNEL_AUTO]
+
+
+@pytest.mark.parametrize("kernel", ALL_KERNELS)
 @pytest.mark.parametrize("missing", [0.0, 0.1])
-def test_phased_counts_bit_exact_all_pairs(missing):
+def test_phased_counts_bit_exact_all_pairs(missing, kernel):
+    """Raw 2x2 counts of EVERY pair (screen off) from every count kernel -- the tcgen05 ones included,
+    not only the records that survive their fp32 screen -- against the numpy ground truth."""
+    if missing and kernel == tb.KERNEL_UMMA:
+        pytest.skip("the int8 tensor kernel serves complete data only")
     s = tf.synth_genotypes(512 if missing else 515, 300, seed=61, missing_rate=missing)
-    eng, _, _ = gpu_run(s, dict(force_phased=1, minR2=0.5))
+    eng, _, st0 = gpu_run(s, dict(force_phased=1, minR2=0.5), kernel)
     c = eng.debug_candidates(True)
+    if kernel != tb.KERNEL_POPC:
+        assert eng.stats().kernel_used in (tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4)
     alt, valid, _, _ = exact_tables(s)
     ac = s.ac
     keep = {(i, j) for i in range(s.n_variants) for j in range(i + 1, s.n_variants) if ac[i] + ac[j] > 2}
@@ -165,11 +175,14 @@ def test_phased_counts_bit_exact_all_pairs(missing):
     eng.close()
 
 
+@pytest.mark.parametrize("kernel", [tb.KERNEL_POPC, tb.KERNEL_AUTO])
 @pytest.mark.parametrize("missing", [0.0, 0.15])
-def test_unphased_tables_bit_exact_all_pairs(missing):
+def test_unphased_tables_bit_exact_all_pairs(missing, kernel):
     s = tf.synth_genotypes(333, 220, seed=62, missing_rate=missing)
-    eng, _, _ = gpu_run(s, dict(forced_unphased=1, minR2=0.5))
+    eng, _, _ = gpu_run(s, dict(forced_unphased=1, minR2=0.5), kernel)
     c = eng.debug_candidates(True)
+    if kernel != tb.KERNEL_POPC:
+        assert eng.stats().kernel_used == tb.KERNEL_UMMA_FP4
     _, _, sv, gt = exact_tables(s)
     i, j = c["i"].astype(int), c["j"].astype(int)
     want = np.zeros((len(c), 9), dtype=np.int64)
@@ -503,6 +516,66 @@ def test_properties_at_scale():
     o2 = np.argsort((n - 1 - jb).astype(np.int64) * n + (n - 1 - ja))
     np.testing.assert_allclose(recs["R2"][o1], recs2["R2"][o2], rtol=1e-12)
     eng2.close()
+
+
+# ------------------------------------------- BASELINE.json configs, at size or on a stated sub-sample
+def test_config1_full_size_tensor_records_equal_popc_records():
+    """BASELINE configs[1] AT SIZE (2,504 samples x 200,000 SNVs, R2 >= 0.1, 2.0e10 pairs): the default e2m1
+    tcgen05 kernel (fp32 5-instruction screen -> survivor ring -> exact decision) must hand over the very
+    same records, byte for byte, as the LOP3+POPC kernel (exact integer counts, fp64 screen)."""
+    s = tf.synth_genotypes(2504, 200_000, seed=20)
+    data, mask = tf.pack_bits(s)
+    meta = lc.variant_meta(s)
+    del s
+    out = {}
+    for k in (tb.KERNEL_AUTO, tb.KERNEL_POPC):
+        eng = tb.Engine(kernel=k, force_phased=1, minR2=0.1)
+        eng.load(2504, data, mask, meta)
+        recs = eng.compute()
+        st = eng.stats()
+        assert st.pairs_visited == 200_000 * 199_999 // 2
+        assert st.kernel_used == (tb.KERNEL_UMMA_FP4 if k == tb.KERNEL_AUTO else tb.KERNEL_POPC)
+        out[k] = tf.canonical(recs, forward_only=False).view(np.uint8)   # (ridA, posA, ridB, posB) order: keys are unique
+        eng.close()
+    assert len(out[tb.KERNEL_AUTO]) == len(out[tb.KERNEL_POPC]) > 500_000 * 106
+    assert np.array_equal(out[tb.KERNEL_AUTO], out[tb.KERNEL_POPC])
+
+
+def _live_reference(s, cli, tmpdir, name, threads=None):
+    twk = os.path.join(tmpdir, f"{name}.twk")
+    tf.write_twk(twk, s)
+    info = lc.run_reference_calc(twk, os.path.join(tmpdir, name), cli, threads=threads)
+    return tf.read_two(os.path.join(tmpdir, f"{name}.two")), info
+
+
+@pytest.mark.skipif(not lc.have_reference(), reason="oracle/_ref/tomahawk_calc not built")
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_config0_subsample_vs_reference_binary(kernel, tmpdir_repo):
+    """BASELINE configs[0] shape (2,504 samples, -p, R2 >= 0: EVERY pair is a record and goes through Fisher)
+    on its first 2,000 variants, against the reference's own `tomahawk calc` run on this host."""
+    s = tf.synth_genotypes(2504, 2000, seed=20)
+    ref, info = _live_reference(s, ["-p", "-r", "0"], tmpdir_repo, "c0_sub")
+    eng, got, st = gpu_run(s, dict(force_phased=1, minR2=0.0), kernel)
+    if "pairs" in info:
+        assert st.pairs_visited == info["pairs"]
+    assert len(got) > 1_000_000
+    assert_records_bitexact(got, tf.canonical(ref, forward_only=True), p_rtol=1e-9)
+    eng.close()
+
+
+@pytest.mark.skipif(not lc.have_reference(), reason="oracle/_ref/tomahawk_calc not built")
+def test_config2_subsample_vs_reference_binary(tmpdir_repo):
+    """BASELINE configs[2] shape (10,000 samples, -u, 5 % missing genotypes, Fisher + chi2) on its first 1,500
+    variants, against the reference's own `tomahawk calc`; tolerances of north_star, flips enumerated."""
+    s = tf.synth_genotypes(10_000, 1500, seed=20, missing_rate=0.05)
+    ref, info = _live_reference(s, ["-u", "-r", "0.1"], tmpdir_repo, "c2_sub")
+    prm = dict(forced_unphased=1, minR2=0.1)
+    eng, got, st = gpu_run(s, prm, tb.KERNEL_AUTO)
+    assert st.kernel_used == tb.KERNEL_UMMA_FP4 and st.n_planes == 3
+    if "pairs" in info:
+        assert st.pairs_visited == info["pairs"]
+    check_unphased(s, got, tf.canonical(ref, forward_only=True), prm)
+    eng.close()
 
 
 def test_edge_cases():

@@ -18,6 +18,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtwkb.so")
+# the same sources built with -DTWKB_PROFILING: kernel ablation switches (TWKB_DEBUG_FLAGS) compiled in;
+# measurement aid of bench.py / scripts only, results with a switch on are invalid
+PROF_LIB_PATH = os.path.join(_HERE, "libtwkb_prof.so")
 
 RECORD_BYTES = 106
 KERNEL_AUTO, KERNEL_POPC, KERNEL_UMMA, KERNEL_UMMA_FP4 = 0, 1, 2, 3
@@ -83,6 +86,7 @@ CAND_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("c", "<u4", (9,)), ("mode", 
 SINK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint64)
 
 _lib = None
+_prof_lib = None
 
 EXPORTS = [
     "twkb_settings_init", "twkb_create", "twkb_destroy", "twkb_last_error", "twkb_update_settings",
@@ -95,63 +99,72 @@ EXPORTS = [
 ]
 
 
-def lib():
-    """Load libtwkb.so. Raises if it has not been built (no fallback of any kind)."""
-    global _lib
+def lib(profiling: bool = False):
+    """Load libtwkb.so (or, profiling=True, libtwkb_prof.so). Raises if it has not been built (no fallback of any kind)."""
+    global _lib, _prof_lib
+    if profiling:
+        if _prof_lib is None:
+            if not os.path.exists(PROF_LIB_PATH):
+                raise ImportError(f"{PROF_LIB_PATH} is missing (make -C tomahawk_b200/csrc)")
+            _prof_lib = _bind(ctypes.CDLL(PROF_LIB_PATH))
+        return _prof_lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). tomahawk_b200 has no CPU fallback."
             )
-        L = ctypes.CDLL(LIB_PATH)
-        L.twkb_settings_init.argtypes = [ctypes.POINTER(Settings)]
-        L.twkb_settings_init.restype = None
-        L.twkb_create.argtypes = [ctypes.POINTER(Settings), ctypes.POINTER(ctypes.c_void_p)]
-        L.twkb_destroy.argtypes = [ctypes.c_void_p]
-        L.twkb_destroy.restype = None
-        L.twkb_last_error.argtypes = [ctypes.c_void_p]
-        L.twkb_last_error.restype = ctypes.c_char_p
-        L.twkb_update_settings.argtypes = [ctypes.c_void_p, ctypes.POINTER(Settings)]
-        for name in ("twkb_load_matrix", "twkb_load_matrix_device"):
-            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
-                                         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-        L.twkb_load_runs.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
-                                     ctypes.c_void_p, ctypes.c_void_p]
-        L.twkb_debug_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
-        L.twkb_twk_open_runs.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32,
-                                         ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
-        L.twkb_twk_runs_view.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
-                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
-        L.twkb_two_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int32]
-        L.twkb_two_sort.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
-                                    ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
-        L.twkb_compute.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
-        L.twkb_compute_resident.argtypes = [ctypes.c_void_p]
-        L.twkb_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
-        L.twkb_debug_candidates.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
-                                            ctypes.POINTER(ctypes.c_uint64)]
-        L.twkb_calc_file.argtypes = [ctypes.POINTER(Settings), ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(Stats),
-                                     ctypes.c_char_p, ctypes.c_size_t]
-        L.twkb_twk_open.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
-        L.twkb_calc_file_intervals.argtypes = [ctypes.POINTER(Settings), ctypes.c_char_p, ctypes.c_char_p,
-                                               ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32, ctypes.POINTER(Stats),
-                                               ctypes.c_char_p, ctypes.c_size_t]
-        L.twkb_twk_open_intervals.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32,
-                                              ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
-        L.twkb_twk_dims.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
-                                    ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32)]
-        L.twkb_twk_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-        L.twkb_twk_close.argtypes = [ctypes.c_void_p]
-        L.twkb_twk_close.restype = None
-        L.twkb_two_open.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
-                                    ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
-        L.twkb_two_add.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
-        L.twkb_two_close.argtypes = [ctypes.c_void_p]
-        L.twkb_plan_tiles.argtypes = [ctypes.POINTER(Settings), ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
-                                      ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
-        _lib = L
+        _lib = _bind(ctypes.CDLL(LIB_PATH))
     return _lib
+
+
+def _bind(L):
+    L.twkb_settings_init.argtypes = [ctypes.POINTER(Settings)]
+    L.twkb_settings_init.restype = None
+    L.twkb_create.argtypes = [ctypes.POINTER(Settings), ctypes.POINTER(ctypes.c_void_p)]
+    L.twkb_destroy.argtypes = [ctypes.c_void_p]
+    L.twkb_destroy.restype = None
+    L.twkb_last_error.argtypes = [ctypes.c_void_p]
+    L.twkb_last_error.restype = ctypes.c_char_p
+    L.twkb_update_settings.argtypes = [ctypes.c_void_p, ctypes.POINTER(Settings)]
+    for name in ("twkb_load_matrix", "twkb_load_matrix_device"):
+        getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.twkb_load_runs.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
+                                 ctypes.c_void_p, ctypes.c_void_p]
+    L.twkb_debug_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.twkb_twk_open_runs.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32,
+                                     ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_twk_runs_view.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+                                     ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
+    L.twkb_two_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    L.twkb_two_sort.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
+                                ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_compute.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
+    L.twkb_compute_resident.argtypes = [ctypes.c_void_p]
+    L.twkb_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
+    L.twkb_debug_candidates.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                        ctypes.POINTER(ctypes.c_uint64)]
+    L.twkb_calc_file.argtypes = [ctypes.POINTER(Settings), ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(Stats),
+                                 ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_twk_open.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_calc_file_intervals.argtypes = [ctypes.POINTER(Settings), ctypes.c_char_p, ctypes.c_char_p,
+                                           ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32, ctypes.POINTER(Stats),
+                                           ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_twk_open_intervals.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32,
+                                          ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_twk_dims.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32),
+                                ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32)]
+    L.twkb_twk_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.twkb_twk_close.argtypes = [ctypes.c_void_p]
+    L.twkb_twk_close.restype = None
+    L.twkb_two_open.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
+                                ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_two_add.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+    L.twkb_two_close.argtypes = [ctypes.c_void_p]
+    L.twkb_plan_tiles.argtypes = [ctypes.POINTER(Settings), ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                  ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    return L
 
 
 def _c_strings(strings):
@@ -285,8 +298,8 @@ def default_settings(**kw) -> Settings:
 class Engine:
     """One device context: resident genotype matrix + LD computation."""
 
-    def __init__(self, settings: Settings | None = None, **kw):
-        self._L = lib()
+    def __init__(self, settings: Settings | None = None, profiling: bool = False, **kw):
+        self._L = lib(profiling)
         self.settings = settings if settings is not None else default_settings(**kw)
         self._ctx = ctypes.c_void_p()
         rc = self._L.twkb_create(ctypes.byref(self.settings), ctypes.byref(self._ctx))

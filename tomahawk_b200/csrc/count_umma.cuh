@@ -12,17 +12,9 @@
 // row-major [Mpad][Kbytes], Kbytes = 2N rounded up to 128. int8 products
 // accumulate exactly in int32 for any N < 2^31.
 //
-// CTA = one 128 x 128 tile of variant pairs, 256 threads, 2 CTAs per SM:
-//   warp 0   TMA producer: per 128-byte K block two 2-D tensor-map loads
-//            (A rows i0.., B rows j0.., 128B swizzle) into a 3-stage ring,
-//   warp 1   MMA issuer: one elected lane issues 4 x tcgen05.mma (K = 32) per
-//            K block and commits to the stage's "empty" mbarrier,
-//   warp 2   TMEM allocator (128 columns),
-//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time, fp32 conservative R2
-//            screen inline, exact fp64 screen + warp-aggregated compaction for
-//            the survivors (same candidate format as the POPC kernel).
-// While one CTA of an SM drains its accumulator the other one keeps the tensor
-// pipe busy.
+// One kernel: count_umma3_kernel, a persistent CTA pair (cta_group::2) per TPC -- see the
+// comment above Umma3Cfg. (Two earlier variants, a single-CTA 128 x 128 kernel and a
+// non-persistent CTA-pair kernel, measured 97.6 / 78.7 ms on C2 against 28 ms and were removed.)
 #pragma once
 #include <cuda.h>
 
@@ -33,6 +25,16 @@
 #include "count_popc.cuh"
 
 namespace twkb {
+
+// Profiling switches (CountArgs::debug_flags, env TWKB_DEBUG_FLAGS) switch parts of the kernel off and
+// make its results INVALID. They exist only in the separate profiling build (libtwkb_prof.so,
+// -DTWKB_PROFILING: bench.py's MMA-only ceiling, scripts/ceiling.py); the product library compiles
+// them out.
+#ifdef TWKB_PROFILING
+#define TWKB_DBG(args, bit) (((args).debug_flags & (bit)) != 0u)
+#else
+#define TWKB_DBG(args, bit) false
+#endif
 
 constexpr uint32_t UMMA_TILE_M = 128;
 constexpr uint32_t UMMA_TILE_N = 128;
@@ -145,135 +147,6 @@ __global__ void expand_bits_to_bytes_kernel(const uint64_t* __restrict__ rows, s
     }
 }
 
-__global__ void __launch_bounds__(UMMA_THREADS, 2)
-count_umma_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, DevParams prm, uint32_t num_kblocks) {
-    extern __shared__ uint8_t smem_raw[];
-    // 128B-swizzled operand tiles need 1024-byte alignment
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_base = smem;
-    DevVariant* s_meta = reinterpret_cast<DevVariant*>(smem + (size_t)UMMA_STAGES * UMMA_STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_meta + 128);
-    uint64_t* empty_bar = full_bar + UMMA_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + UMMA_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint2 tile = args.tiles[blockIdx.x];
-    const uint32_t i0 = tile.x, j0 = tile.y;
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < UMMA_STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        mbar_init(tmem_full_bar, 1);
-        mbar_fence_init();
-    }
-    if (warp == 2) tmem_alloc(tmem_slot, UMMA_TMEM_COLS);
-    if (warp >= 4) s_meta[threadIdx.x - 128] = args.meta[j0 + (threadIdx.x - 128)];
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ============================ TMA producer ============================
-        if (lane == 0) {
-            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
-                const int s = kb % UMMA_STAGES;
-                if (kb >= UMMA_STAGES) mbar_wait(&empty_bar[s], ((kb / UMMA_STAGES) - 1) & 1);
-                uint8_t* sA = stage_base + (size_t)s * UMMA_STAGE_BYTES;
-                uint8_t* sB = sA + UMMA_TILE_M * UMMA_BLOCK_K;
-                mbar_arrive_expect_tx(&full_bar[s], UMMA_STAGE_BYTES);
-                tma_load_2d(sA, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)i0);
-                tma_load_2d(sB, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)j0);
-            }
-        }
-    } else if (warp == 1) {
-        // ============================= MMA issuer =============================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_i8(UMMA_TILE_M, UMMA_TILE_N);
-            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
-                const int s = kb % UMMA_STAGES;
-                mbar_wait(&full_bar[s], (kb / UMMA_STAGES) & 1);
-                tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(stage_base + (size_t)s * UMMA_STAGE_BYTES);
-                const uint32_t b_addr = a_addr + UMMA_TILE_M * UMMA_BLOCK_K;
-                const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(b_addr);
-#pragma unroll
-                for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k) {
-                    // advance the start address by 32 bytes inside the 128-byte swizzled row
-                    umma_i8(tmem_base, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
-                            (kb | k) != 0 ? 1u : 0u);
-                }
-                umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
-            }
-            umma_commit(tmem_full_bar);  // accumulator complete
-        }
-    } else if (warp >= 4) {
-        // ============================== epilogue ==============================
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
-        const uint32_t i = i0 + 32 * q + lane;
-        const DevVariant vi = args.meta[i];
-        const uint32_t M = prm.n_variants;
-        const bool i_ok = i >= args.row_begin && i < args.row_end && i < M;
-        const float Tf = (float)(2u * prm.n_samples);
-        const float acA = (float)vi.ac;
-        const float dA = acA * (Tf - acA);
-        const float thr = (float)prm.screenR2 * (1.0f - 1.0e-5f);
-        const bool no_screen = args.screen_off || !(prm.minR2 > 0.0);
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-#pragma unroll 1
-        for (int chunk = 0; chunk < (int)(UMMA_TILE_N / 32); ++chunk) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(chunk * 32), r);
-            // pass bits of this thread's 32 pairs: pure arithmetic, fully unrolled (ILP)
-            uint32_t passmask = 0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int jl = chunk * 32 + c;
-                const uint32_t j = j0 + jl;
-                const DevVariant vj = s_meta[jl];
-                bool pass = i_ok && j >= args.col_begin && j < args.col_end && j < M && (!prm.diag || i < j) && (vi.ac + vj.ac > 2);
-                if (!no_screen) {
-                    // fp32 conservative form of R2 >= minR2: x = n11*T - acA*acB (error bounded by
-                    // `slack`), den = acA(T-acA) acB(T-acB); the exact decision is the fp64 screen
-                    // in emit_pair.
-                    const float n11 = (float)r[c];
-                    const float acB = (float)vj.ac;
-                    const float pab = acA * acB;
-                    const float x = fabsf(fmaf(n11, Tf, -pab));
-                    const float slack = 4.0f + 4.0e-7f * fmaxf(n11 * Tf, pab);
-                    const float lhs = (x + slack) * (x + slack);
-                    const float rhs = thr * (dA * (acB * (Tf - acB)));
-                    pass = pass && (lhs >= rhs);
-                }
-                passmask |= (pass ? 1u : 0u) << c;
-            }
-            // columns in which any lane of the warp has a survivor (warp-uniform)
-            const uint32_t colmask = __reduce_or_sync(0xffffffffu, passmask);
-            if (colmask) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    if ((colmask >> c) & 1u) {
-                        PairAcc<1> pa;
-                        pa.v[0][0] = r[c];
-                        emit_pair<MODE_PHASED_NOMISS>(args, prm, i, j0 + chunk * 32 + c, vi, pa, lane, (passmask >> c) & 1u);
-                    }
-                }
-            }
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tcgen05_fence_after();
-        tmem_dealloc(tmem_base, UMMA_TMEM_COLS);
-    }
-}
-
 // =====================================================================================
 // 2-CTA variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a
 // 256 x 256 tile. Each CTA stages only ITS 128 rows of A and ITS 128 rows of B per K
@@ -331,135 +204,6 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                      smem_u32(bar)),
                  "h"(mask)
                  : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA_THREADS, 2)
-count_umma2_kernel(const __grid_constant__ CUtensorMap tmap, CountArgs args, DevParams prm, uint32_t num_kblocks) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_base = smem;
-    DevVariant* s_meta = reinterpret_cast<DevVariant*>(smem + (size_t)UMMA2_STAGES * UMMA2_STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_meta + UMMA2_TILE);
-    uint64_t* empty_bar = full_bar + UMMA2_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + UMMA2_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const uint2 tile = args.tiles[blockIdx.x >> 1];
-    const uint32_t i0 = tile.x, j0 = tile.y;
-
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < UMMA2_STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        mbar_init(tmem_full_bar, 1);
-        mbar_fence_init();
-    }
-    if (warp == 2) tmem_alloc_2sm(tmem_slot, UMMA2_TMEM_COLS);
-    if (warp >= 4) {
-        const int t = threadIdx.x - 128;
-        s_meta[t] = args.meta[j0 + t];
-        s_meta[t + 128] = args.meta[j0 + t + 128];
-    }
-    tcgen05_fence_before();
-    cluster_sync_all();  // barriers of both CTAs initialised before any remote complete_tx / commit
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ================= TMA producer (both CTAs, own halves of A and B) =================
-        if (lane == 0) {
-            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
-                const int s = kb % UMMA2_STAGES;
-                if (kb >= (uint32_t)UMMA2_STAGES) mbar_wait(&empty_bar[s], ((kb / UMMA2_STAGES) - 1) & 1);
-                uint8_t* sA = stage_base + (size_t)s * UMMA2_STAGE_BYTES;
-                uint8_t* sB = sA + 128 * UMMA_BLOCK_K;
-                if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * UMMA2_STAGE_BYTES);  // both CTAs' bytes
-                tma_load_2d_2sm(sA, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(i0 + 128 * rank));
-                tma_load_2d_2sm(sB, &tmap, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(j0 + 128 * rank));
-            }
-        }
-    } else if (warp == 1) {
-        // ========================= MMA issuer (leader CTA only) =========================
-        if (leader && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_i8(256, 256);
-            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
-                const int s = kb % UMMA2_STAGES;
-                mbar_wait(&full_bar[s], (kb / UMMA2_STAGES) & 1);
-                tcgen05_fence_after();
-                const uint32_t a_addr = smem_u32(stage_base + (size_t)s * UMMA2_STAGE_BYTES);
-                const uint32_t b_addr = a_addr + 128 * UMMA_BLOCK_K;
-                const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(b_addr);
-#pragma unroll
-                for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k)
-                    umma_i8_2sm(tmem_base, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
-                                (kb | k) != 0 ? 1u : 0u);
-                umma_commit_2sm(&empty_bar[s]);
-            }
-            umma_commit_2sm(tmem_full_bar);
-        }
-    } else if (warp >= 4) {
-        // ============== epilogue (both CTAs, own 128 accumulator rows x 256 columns) ==============
-        const int q = warp & 3;
-        const uint32_t i = i0 + 128 * rank + 32 * q + lane;
-        const DevVariant vi = args.meta[i];
-        const uint32_t M = prm.n_variants;
-        const bool i_ok = i >= args.row_begin && i < args.row_end && i < M;
-        const float Tf = (float)(2u * prm.n_samples);
-        const float acA = (float)vi.ac;
-        const float dA = acA * (Tf - acA);
-        const float thr = (float)prm.screenR2 * (1.0f - 1.0e-5f);
-        const bool no_screen = args.screen_off || !(prm.minR2 > 0.0);
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-        // whole-warp shortcut: on diagonal tiles the rows of this warp may lie entirely at or
-        // below every column of a chunk (no i<j pair); the per-pair test covers it as well.
-#pragma unroll 1
-        for (int chunk = 0; chunk < (int)(UMMA2_TILE / 32); ++chunk) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(chunk * 32), r);
-            uint32_t passmask = 0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int jl = chunk * 32 + c;
-                const uint32_t j = j0 + jl;
-                const DevVariant vj = s_meta[jl];
-                bool pass = i_ok && j >= args.col_begin && j < args.col_end && j < M && (!prm.diag || i < j) && (vi.ac + vj.ac > 2);
-                if (!no_screen) {
-                    const float n11 = (float)r[c];
-                    const float acB = (float)vj.ac;
-                    const float pab = acA * acB;
-                    const float x = fabsf(fmaf(n11, Tf, -pab));
-                    const float slack = 4.0f + 4.0e-7f * fmaxf(n11 * Tf, pab);
-                    const float lhs = (x + slack) * (x + slack);
-                    const float rhs = thr * (dA * (acB * (Tf - acB)));
-                    pass = pass && (lhs >= rhs);
-                }
-                passmask |= (pass ? 1u : 0u) << c;
-            }
-            const uint32_t colmask = __reduce_or_sync(0xffffffffu, passmask);
-            if (colmask) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    if ((colmask >> c) & 1u) {
-                        PairAcc<1> pa;
-                        pa.v[0][0] = r[c];
-                        emit_pair<MODE_PHASED_NOMISS>(args, prm, i, j0 + chunk * 32 + c, vi, pa, lane, (passmask >> c) & 1u);
-                    }
-                }
-            }
-        }
-    }
-    tcgen05_fence_before();
-    cluster_sync_all();  // the peer may still be reading this CTA's smem / TMEM pair allocation
-    if (warp == 2) {
-        tcgen05_fence_after();
-        tmem_dealloc_2sm(tmem_base, UMMA2_TMEM_COLS);
-    }
 }
 
 // =====================================================================================
@@ -821,6 +565,7 @@ __device__ __forceinline__ void umma_epilogue_chunk(const CountArgs& args, const
             }
         }
         if (!__any_sync(0xffffffffu, m >= -1.0f)) return;
+        if (TWKB_DBG(args, 16u)) return;  // screen-only ablation: zero registers would flag everything
         // which pairs: the same margins once more, kept as a bit mask (rare path)
         uint32_t mask = 0;
 #pragma unroll
@@ -914,22 +659,33 @@ __device__ __forceinline__ void umma_epilogue_loop(const CountArgs& args, const 
         }
         mbar_wait(&tmem_full_bar[acc], (n >> 1) & 1);
         tcgen05_fence_after();
-        if (!(args.debug_flags & 2u)) {
+        if (!TWKB_DBG(args, 2u)) {
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + acc * TILE_N;
             const uint32_t meta_sa = meta_s0 + acc * 256u * 16u, colf_sa = colf_s0 + acc * 256u * 8u;
             const int c_begin = half * CHUNKS_PER_WARP;
             uint32_t r0[32], r1[32];
+#ifdef TWKB_PROFILING
+            // ablations of the epilogue (results invalid): 8 = TMEM loads only (no screen), 16 = screen only
+            // (no TMEM loads: the registers stay zero, the rare flagged path is cut short)
+            const bool do_ld = !TWKB_DBG(args, 16u), do_math = !TWKB_DBG(args, 8u);
+#pragma unroll
+            for (int z = 0; z < 32; ++z) r0[z] = r1[z] = 0u;
+#else
+            constexpr bool do_ld = true, do_math = true;
+#endif
             // (FP4: the last chunk reads 16 columns past the accumulator; they carry s_j = +inf)
-            tmem_ld_32x32_nowait(taddr + (uint32_t)(c_begin * 32), r0);
-            tmem_ld_wait(r0);
+            if (do_ld) {
+                tmem_ld_32x32_nowait(taddr + (uint32_t)(c_begin * 32), r0);
+                tmem_ld_wait(r0);
+            }
 #pragma unroll 1
             for (int c = c_begin; c < c_begin + CHUNKS_PER_WARP; c += 2) {
-                tmem_ld_32x32_nowait(taddr + (uint32_t)((c + 1) * 32), r1);
-                umma_epilogue_chunk<FP4, SCREEN>(args, prm, r0, row, meta_sa, colf_sa, j0, c, Tf, thr, lane, queue);
-                tmem_ld_wait(r1);
-                if (c + 2 < c_begin + CHUNKS_PER_WARP) tmem_ld_32x32_nowait(taddr + (uint32_t)((c + 2) * 32), r0);
-                umma_epilogue_chunk<FP4, SCREEN>(args, prm, r1, row, meta_sa, colf_sa, j0, c + 1, Tf, thr, lane, queue);
-                tmem_ld_wait(r0);
+                if (do_ld) tmem_ld_32x32_nowait(taddr + (uint32_t)((c + 1) * 32), r1);
+                if (do_math) umma_epilogue_chunk<FP4, SCREEN>(args, prm, r0, row, meta_sa, colf_sa, j0, c, Tf, thr, lane, queue);
+                if (do_ld) tmem_ld_wait(r1);
+                if (do_ld && c + 2 < c_begin + CHUNKS_PER_WARP) tmem_ld_32x32_nowait(taddr + (uint32_t)((c + 2) * 32), r0);
+                if (do_math) umma_epilogue_chunk<FP4, SCREEN>(args, prm, r1, row, meta_sa, colf_sa, j0, c + 1, Tf, thr, lane, queue);
+                if (do_ld) tmem_ld_wait(r0);
             }
         }
         // this warp has read everything it needs from accumulator `acc`
@@ -1248,7 +1004,7 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
                     if (MODE == MODE_UNPHASED_NOMISS) { const uint2 cx = colx[jl]; cxh = (float)cx.x; cxo = (float)cx.y; }
                     flag = active && planes_fast_screen<MODE>(tv, ns_f, row_het_f, row_hom_f, cxh, cxo, thr);
                 }
-                if (!no_screen && !(args.debug_flags & 4u)) {  // (flag 4: A/B aid, exact decision inline)
+                if (!no_screen && !TWKB_DBG(args, 4u)) {  // (flag 4: A/B aid, exact decision inline)
                     // flagged pairs (a fraction of a percent) go to the drain warp
                     planes_queue_push<NP>(q_ring, q_ctrl, flag, i, j0 + jl, tv, lane);
                 } else if (__any_sync(0xffffffffu, flag)) {
@@ -1347,7 +1103,7 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                     if (it >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
                     uint8_t* sA = stage_base + (size_t)s * Cfg::STAGE_BYTES;
                     uint8_t* sB = sA + 128 * UMMA_BLOCK_K;
-                    if (args.debug_flags & 1u) {  // profiling aid: no operand traffic after the first ring fill (results invalid)
+                    if (TWKB_DBG(args, 1u)) {  // profiling aid: no operand traffic after the first ring fill (results invalid)
                         if (it >= (uint32_t)STAGES) {
                             if (leader) mbar_arrive_expect_tx(&full_bar[s], 0);
                             continue;
@@ -1464,20 +1220,9 @@ inline bool umma_supported() {
     return get_tmap_encoder() != nullptr;
 }
 
-// 3 (default) = persistent CTA-pair kernel, 2 = one 256x256 tile per CTA pair,
-// 1 = single-CTA kernel (128x128 tiles). The older variants are kept for A/B profiling.
-inline int umma_cta_group() {
-    if (const char* e = getenv("TWKB_UMMA_CTAS")) {
-        if (e[0] == '1') return 1;
-        if (e[0] == '2') return 2;
-    }
-    return 3;
-}
-// e2m1 operands are served by the persistent kernel only; fp32 accumulation of 0/1 products is
-// exact while every count stays below 2^24.
-inline bool umma_fp4_possible(uint32_t n_samples) { return umma_cta_group() == 3 && 2ull * n_samples < (1ull << 24); }
+// e2m1 operands: fp32 accumulation of 0/1 products is exact while every count stays below 2^24.
+inline bool umma_fp4_possible(uint32_t n_samples) { return 2ull * n_samples < (1ull << 24); }
 inline void umma_tile(bool fp4, uint32_t& TI, uint32_t& TJ) {
-    if (umma_cta_group() < 2) { TI = TJ = UMMA_TILE_M; return; }
     TI = UMMA2_TILE;
     TJ = fp4 ? Umma3Cfg<true>::TILE_N : UMMA2_TILE;
 }
@@ -1649,36 +1394,15 @@ inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const De
 }
 
 inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
-    if (umma_cta_group() == 3)
-    {
-        // the instantiation with the fast screen + survivor queue, or (minR2 = 0 / screen off:
-        // every pair is a candidate) the one that compacts every chunk directly
-        const bool screen = !args.screen_off && prm.minR2 > 0.0;
-        if (op.mode == MODE_PHASED_MISS) return umma3_launch<true, false, MODE_PHASED_MISS>(op, args, prm, n_tiles, stream);
-        if (op.mode == MODE_UNPHASED_NOMISS) return umma3_launch<true, false, MODE_UNPHASED_NOMISS>(op, args, prm, n_tiles, stream);
-        if (op.mode == MODE_UNPHASED_MISS) return umma3_launch<true, false, MODE_UNPHASED_MISS>(op, args, prm, n_tiles, stream);
-        if (op.fp4)
-            return screen ? umma3_launch<true, true, 0>(op, args, prm, n_tiles, stream) : umma3_launch<true, false, 0>(op, args, prm, n_tiles, stream);
-        return screen ? umma3_launch<false, true, 0>(op, args, prm, n_tiles, stream) : umma3_launch<false, false, 0>(op, args, prm, n_tiles, stream);
-    }
-    if (umma_cta_group() == 2) {
-        static bool configured2 = false;
-        if (!configured2) {
-            cudaError_t e = cudaFuncSetAttribute(count_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA2_SMEM_BYTES);
-            if (e != cudaSuccess) return e;
-            configured2 = true;
-        }
-        count_umma2_kernel<<<2 * n_tiles, UMMA_THREADS, UMMA2_SMEM_BYTES, stream>>>(op.tmap, args, prm, op.Kbytes / UMMA_BLOCK_K);
-        return cudaGetLastError();
-    }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(count_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    count_umma_kernel<<<n_tiles, UMMA_THREADS, UMMA_SMEM_BYTES, stream>>>(op.tmap, args, prm, op.Kbytes / UMMA_BLOCK_K);
-    return cudaGetLastError();
+    // the instantiation with the fast screen + survivor queue, or (minR2 = 0 / screen off:
+    // every pair is a candidate) the one that compacts every chunk directly
+    const bool screen = !args.screen_off && prm.minR2 > 0.0;
+    if (op.mode == MODE_PHASED_MISS) return umma3_launch<true, false, MODE_PHASED_MISS>(op, args, prm, n_tiles, stream);
+    if (op.mode == MODE_UNPHASED_NOMISS) return umma3_launch<true, false, MODE_UNPHASED_NOMISS>(op, args, prm, n_tiles, stream);
+    if (op.mode == MODE_UNPHASED_MISS) return umma3_launch<true, false, MODE_UNPHASED_MISS>(op, args, prm, n_tiles, stream);
+    if (op.fp4)
+        return screen ? umma3_launch<true, true, 0>(op, args, prm, n_tiles, stream) : umma3_launch<true, false, 0>(op, args, prm, n_tiles, stream);
+    return screen ? umma3_launch<false, true, 0>(op, args, prm, n_tiles, stream) : umma3_launch<false, false, 0>(op, args, prm, n_tiles, stream);
 }
 
 inline void umma_release(UmmaOperand& op) {

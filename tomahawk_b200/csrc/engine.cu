@@ -9,8 +9,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/twkb.h"
@@ -116,8 +119,11 @@ struct Context {
     // work buffers
     DevBuf<uint2> d_tiles;
     DevBuf<Candidate> d_cands;
-    DevBuf<unsigned long long> d_counters;  // [0] cand count, [1] record count
-    DevBuf<uint8_t> d_records;
+    DevBuf<unsigned long long> d_counters;  // [0] cand count, [1], [2] record counts of the two record buffers
+    DevBuf<uint8_t> d_records[2];           // double-buffered: the statistics kernel fills one while the other drains
+    int rec_cur = 0;                        // buffer the statistics kernel appends to
+    bool stats_timing_pending = false;      // ev2/ev3 of the last statistics launch not read yet
+    struct Flusher* flusher = nullptr;      // record drain thread (D2H + sink), created on first use
     size_t cand_cap = 0, rec_cap = 0;
     uint8_t* h_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
@@ -550,7 +556,8 @@ static int ensure_work_buffers(Context* ctx, uint64_t max_tile_pairs) {
         ctx->cand_cap = want_cand;
     }
     if (ctx->rec_cap < want_rec) {
-        CUDA_TRY(ctx->d_records.alloc(want_rec * TWKB_RECORD_BYTES));
+        CUDA_TRY(ctx->d_records[0].alloc(want_rec * TWKB_RECORD_BYTES));
+        CUDA_TRY(ctx->d_records[1].alloc(want_rec * TWKB_RECORD_BYTES));
         ctx->rec_cap = want_rec;
     }
     CUDA_TRY(ctx->d_counters.alloc(4));
@@ -563,9 +570,33 @@ static int ensure_work_buffers(Context* ctx, uint64_t max_tile_pairs) {
     return TWKB_OK;
 }
 
-// D2H of the record buffer in pinned chunks, overlapped with the sink.
-static int flush_records(Context* ctx, uint64_t n_records, twkb_sink_fn sink, void* user) {
+// ---- record drain ------------------------------------------------------------------------------
+// north_star (4): "compacted results stream to the host writer by async D2H on side streams while
+// the next tiles compute". A context owns one drain thread. The batch loop hands it a FULL record
+// buffer (all statistics kernels that wrote it have completed) and goes on launching count and
+// statistics kernels into the other buffer; the thread copies the records to the host in pinned
+// chunks on copy_stream (two staging buffers: chunk c + 1 is in flight while the sink consumes
+// chunk c) and calls the sink. With R2 >= 0 (configs[0]: 5.2 GB of records) the run is then bound
+// by the PCIe link, not by PCIe + compute.
+struct Flusher {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    struct Job { int buf; uint64_t n; };
+    std::deque<Job> jobs;
+    bool busy[2] = {false, false};
+    bool stop = false;
+    int rc = TWKB_OK;
+    std::string err;
+    twkb_sink_fn sink = nullptr;
+    void* user = nullptr;
+    uint64_t bytes_d2h = 0;
+};
+
+// D2H of one record buffer in pinned chunks, overlapped with the sink (drain thread).
+static int flush_records(Context* ctx, int buf, uint64_t n_records, twkb_sink_fn sink, void* user, std::string& err, uint64_t& bytes) {
     if (n_records == 0) return TWKB_OK;
+    auto fail = [&](cudaError_t e, const char* what) { err = std::string(what) + ": " + cudaGetErrorString(e); return TWKB_ECUDA; };
     const size_t total = (size_t)n_records * TWKB_RECORD_BYTES;
     size_t off = 0;
     int cur = 0;
@@ -575,31 +606,120 @@ static int flush_records(Context* ctx, uint64_t n_records, twkb_sink_fn sink, vo
         size_t nbytes = 0;
         if (off < total) {
             nbytes = std::min(ctx->stage_bytes, total - off);
-            CUDA_TRY(cudaMemcpyAsync(ctx->h_stage[cur], ctx->d_records.p + off, nbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            cudaError_t e = cudaMemcpyAsync(ctx->h_stage[cur], ctx->d_records[buf].p + off, nbytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e != cudaSuccess) return fail(e, "record D2H");
         }
         if (pending >= 0) {
             if (sink && sink(user, ctx->h_stage[pending], pending_bytes / TWKB_RECORD_BYTES) != 0) {
                 cudaStreamSynchronize(ctx->copy_stream);
-                ctx->err = "record sink aborted the run";
+                err = "record sink aborted the run";
                 return TWKB_ESINK;
             }
             pending = -1;
         }
         if (nbytes) {
-            CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+            cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+            if (e != cudaSuccess) return fail(e, "record D2H");
             pending = cur;
             pending_bytes = nbytes;
             off += nbytes;
             cur ^= 1;
-            ctx->stats.bytes_d2h += nbytes;
+            bytes += nbytes;
         }
     }
     return TWKB_OK;
 }
 
+static void flusher_loop(Context* ctx) {
+    Flusher* f = ctx->flusher;
+    cudaSetDevice(ctx->device);
+    std::unique_lock<std::mutex> lk(f->mu);
+    for (;;) {
+        f->cv.wait(lk, [&] { return f->stop || !f->jobs.empty(); });
+        if (f->jobs.empty()) return;  // stop requested and nothing left
+        const Flusher::Job job = f->jobs.front();
+        f->jobs.pop_front();
+        const bool skip = f->rc != TWKB_OK;  // after a failure the remaining buffers are only released
+        twkb_sink_fn sink = f->sink;
+        void* user = f->user;
+        lk.unlock();
+        int rc = TWKB_OK;
+        std::string err;
+        uint64_t bytes = 0;
+        if (!skip) {
+            try {
+                rc = flush_records(ctx, job.buf, job.n, sink, user, err, bytes);
+            } catch (...) {  // a throwing sink must not take the process down from a foreign thread
+                rc = TWKB_ESINK;
+                err = "record sink threw an exception";
+            }
+        }
+        lk.lock();
+        f->bytes_d2h += bytes;
+        if (rc != TWKB_OK && f->rc == TWKB_OK) { f->rc = rc; f->err = err; }
+        f->busy[job.buf] = false;
+        f->cv.notify_all();
+    }
+}
+
+static void flusher_begin(Context* ctx, twkb_sink_fn sink, void* user) {
+    if (!ctx->flusher) {
+        ctx->flusher = new Flusher();
+        ctx->flusher->th = std::thread(flusher_loop, ctx);
+    }
+    std::lock_guard<std::mutex> g(ctx->flusher->mu);
+    ctx->flusher->sink = sink;
+    ctx->flusher->user = user;
+    ctx->flusher->rc = TWKB_OK;
+    ctx->flusher->err.clear();
+    ctx->flusher->bytes_d2h = 0;
+}
+static void flusher_submit(Context* ctx, int buf, uint64_t n) {
+    Flusher* f = ctx->flusher;
+    std::lock_guard<std::mutex> g(f->mu);
+    f->busy[buf] = true;
+    f->jobs.push_back({buf, n});
+    f->cv.notify_all();
+}
+// Blocks until the drain thread has released `buf` (buf < 0: every buffer). Returns the drain's status.
+static int flusher_wait(Context* ctx, int buf) {
+    Flusher* f = ctx->flusher;
+    std::unique_lock<std::mutex> lk(f->mu);
+    f->cv.wait(lk, [&] { return buf >= 0 ? !f->busy[buf] : (!f->busy[0] && !f->busy[1]); });
+    if (f->rc != TWKB_OK) ctx->err = f->err;
+    return f->rc;
+}
+static void flusher_destroy(Context* ctx) {
+    if (!ctx->flusher) return;
+    {
+        std::lock_guard<std::mutex> g(ctx->flusher->mu);
+        ctx->flusher->stop = true;
+        ctx->flusher->cv.notify_all();
+    }
+    if (ctx->flusher->th.joinable()) ctx->flusher->th.join();
+    delete ctx->flusher;
+    ctx->flusher = nullptr;
+}
+
+// The current record buffer cannot take the next batch: hand it to the drain thread (or, for a
+// resident run, just count it) and continue in the other one once that is free.
+static int rotate_records(Context* ctx, uint64_t fill, bool resident) {
+    ctx->stats.records_out += fill;
+    if (!resident && fill) flusher_submit(ctx, ctx->rec_cur, fill);
+    ctx->rec_cur ^= 1;
+    if (!resident) {
+        const int rc = flusher_wait(ctx, ctx->rec_cur);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p + 1 + ctx->rec_cur, 0, sizeof(unsigned long long), ctx->stream));
+    return TWKB_OK;
+}
+
 // Batch loop shared by the dense and the sparse phase of a pass: launches `launch(t, nb)` over
-// the tile list in batches the candidate buffer can hold (retry with fewer tiles on overflow),
-// runs the statistics kernel on the survivors of every batch and drains the record buffer.
+// the tile list in batches the candidate buffer can hold (retry with fewer tiles on overflow) and
+// runs the statistics kernel on the survivors of every batch. ONE host round trip per batch (the
+// candidate count sizes the statistics grid); the statistics kernel of batch b, the record drain
+// and the count kernel of batch b + 1 are never waited for individually.
 struct BatchPlan {
     size_t n_tiles = 0;
     uint64_t tile_pairs = 0;      // pairs per tile (worst-case candidates)
@@ -607,9 +727,17 @@ struct BatchPlan {
     bool sparse = false;
     double* est_cand_per_tile = nullptr;
 };
+static int read_stats_timing(Context* ctx) {
+    if (!ctx->stats_timing_pending) return TWKB_OK;
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
+    ctx->stats.ms_stats_kernel += ms;
+    ctx->stats_timing_pending = false;
+    return TWKB_OK;
+}
 template <typename LaunchFn, typename AccountFn>
 static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, LaunchFn launch, AccountFn account, bool resident,
-                       twkb_sink_fn sink, void* user, std::vector<Candidate>* dump, uint64_t& rec_on_device) {
+                       std::vector<Candidate>* dump) {
     // Batch size: the candidate buffer must hold a whole batch. Start from the
     // worst case when nothing can be screened out, else optimistic and adapt.
     uint64_t batch = bp.no_screen ? std::max<uint64_t>(1, ctx->cand_cap / bp.tile_pairs)
@@ -617,7 +745,6 @@ static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, 
     if (!bp.no_screen && *bp.est_cand_per_tile >= 0.0)  // the previous run over this matrix measured the survivor rate
         batch = std::max<uint64_t>(batch, (uint64_t)(0.25 * ctx->cand_cap / std::max(1.0, *bp.est_cand_per_tile)));
     if (const char* e = getenv("TWKB_BATCH_TILES")) batch = std::max<uint64_t>(1, (uint64_t)atoll(e));
-    int rc = TWKB_OK;
     size_t t = 0;
     while (t < bp.n_tiles) {
         const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, bp.n_tiles - t);
@@ -625,12 +752,16 @@ static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, 
         CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
         CUDA_TRY(launch(t, nb));
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // also completes the statistics kernel of the previous batch
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         if (bp.sparse) { ctx->stats.ms_sparse_kernel += ms; ctx->stats.sparse_launches += 1; }
         else { ctx->stats.ms_count_kernel += ms; ctx->stats.count_launches += 1; }
+        {
+            const int rc = read_stats_timing(ctx);
+            if (rc) return rc;
+        }
         const uint64_t ncand = ctx->h_counters[0];
         if (ncand > ctx->cand_cap) {  // overflow: redo this batch with fewer tiles
             if (nb == 1) { ctx->err = "candidate buffer smaller than one tile"; return TWKB_ENOMEM; }
@@ -647,27 +778,29 @@ static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, 
             continue;
         }
         if (ncand) {
-            if (rec_on_device + ncand > ctx->rec_cap) {
-                if (!resident) {
-                    rc = flush_records(ctx, rec_on_device, sink, user);
-                    if (rc) return rc;
-                }
-                ctx->stats.records_out += rec_on_device;
-                rec_on_device = 0;
-                CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p + 1, 0, sizeof(unsigned long long), ctx->stream));
+            const uint64_t fill = ctx->h_counters[1 + ctx->rec_cur];  // exact: every earlier statistics kernel has completed
+            if (fill + ncand > ctx->rec_cap) {
+                const int rc = rotate_records(ctx, fill, resident);
+                if (rc) return rc;
             }
             CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
-            stats_kernel<<<(unsigned)((ncand + 127) / 128), 128, 0, ctx->stream>>>(
-                ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm, ctx->d_lgamma.p, ctx->d_records.p, ctx->rec_cap,
-                ctx->d_counters.p + 1);
+            const unsigned grid = (unsigned)((ncand + STATS_PER_BLOCK - 1) / STATS_PER_BLOCK);
+            uint8_t* recs = ctx->d_records[ctx->rec_cur].p;
+            unsigned long long* rec_count = ctx->d_counters.p + 1 + ctx->rec_cur;
+            static const int occ3 = [] { const char* e = getenv("TWKB_STATS_OCC"); return e ? atoi(e) : 2; }();
+            if (prm.unphased)
+                stats_kernel<true, 2><<<grid, STATS_THREADS, 0, ctx->stream>>>(ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm,
+                                                                              ctx->d_lgamma.p, recs, ctx->rec_cap, rec_count);
+            else if (occ3 == 3)
+                stats_kernel<false, 3><<<grid, STATS_THREADS, 0, ctx->stream>>>(ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm,
+                                                                               ctx->d_lgamma.p, recs, ctx->rec_cap, rec_count);
+            else
+                stats_kernel<false, 2><<<grid, STATS_THREADS, 0, ctx->stream>>>(ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm,
+                                                                               ctx->d_lgamma.p, recs, ctx->rec_cap, rec_count);
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
-            CUDA_TRY(cudaMemcpyAsync(ctx->h_counters + 1, ctx->d_counters.p + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
-            ctx->stats.ms_stats_kernel += ms;
+            ctx->stats_timing_pending = true;
             ctx->stats.stats_launches += 1;
-            rec_on_device = ctx->h_counters[1];
         }
         // adapt: aim for a half-full candidate buffer
         if (!bp.no_screen && !getenv("TWKB_BATCH_TILES")) {
@@ -700,14 +833,16 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
     // Kernel choice. Tensor pipe (tcgen05) whenever the counts of the mode are a 0/1 contraction
     // whose fp32 accumulation is exact (2N < 2^24): 1 plane -> count_umma3_kernel<.,.,0>, masked
     // phased / unphased tables -> the planes variants (NP operand rows per variant). The LOP3+POPC
-    // kernel serves explicit requests, the candidate dump of the tests, and 2N >= 2^24 with masks.
+    // kernel serves explicit requests and 2N >= 2^24 with masks. The candidate dump of the tests
+    // (twkb_debug_candidates) runs whatever kernel the settings select, so the raw counts of the
+    // tcgen05 paths are checked directly, not only through the records that survive the screen.
     bool use_umma = false, use_fp4 = false;
     const bool planes_mode = mode != MODE_PHASED_NOMISS;
-    if (ctx->st.kernel != TWKB_KERNEL_POPC && !dump && umma_supported()) {
+    if (ctx->st.kernel != TWKB_KERNEL_POPC && umma_supported()) {
         if (!planes_mode) use_umma = true;
         else use_umma = ctx->st.kernel != TWKB_KERNEL_UMMA && umma_fp4_possible(ctx->n_samples) && !getenv("TWKB_PLANES_POPC");
     }
-    if ((ctx->st.kernel == TWKB_KERNEL_UMMA || ctx->st.kernel == TWKB_KERNEL_UMMA_FP4) && !use_umma && !dump) {
+    if ((ctx->st.kernel == TWKB_KERNEL_UMMA || ctx->st.kernel == TWKB_KERNEL_UMMA_FP4) && !use_umma) {
         ctx->err = planes_mode ? "the int8 tensor-core kernel only serves phased data without missing genotypes (use AUTO or UMMA_FP4)"
                                : "tensor-core kernel requested but unavailable";
         return TWKB_EINVAL;
@@ -806,11 +941,15 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
     args.row_begin = pb.row_begin; args.row_end = pb.row_end;
     args.col_begin = pb.col_begin; args.col_end = pb.col_end;
     args.screen_off = screen_off ? 1u : 0u;
+#ifdef TWKB_PROFILING
     if (const char* e = getenv("TWKB_DEBUG_FLAGS")) args.debug_flags = (uint32_t)atoi(e);
+#endif
 
     const bool no_screen = screen_off || !(ctx->st.minR2 > 0.0);
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    uint64_t rec_on_device = 0;
+    ctx->rec_cur = 0;
+    ctx->stats_timing_pending = false;
+    if (!resident && !dump) flusher_begin(ctx, sink, user);
 
     // ---- phase 1: dense x dense tiles
     if (!tiles.empty()) {
@@ -833,7 +972,7 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
             if (use_umma) ctx->stats.mma_macs += (uint64_t)nb * (planes_mode ? 256ull * 240ull : tile_pairs) * ctx->umma.Kelems;
             else ctx->stats.word_ops += (uint64_t)nb * tile_pairs * ctx->K32 * ctx->np * ctx->np;
         };
-        rc = run_batches(ctx, bp, prm, launch, account, resident, sink, user, dump, rec_on_device);
+        rc = run_batches(ctx, bp, prm, launch, account, resident, dump);
         if (rc) return rc;
     }
     // ---- phase 2: every pair with a sparse member (list kernel)
@@ -859,15 +998,23 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
         // word operations actually issued: entries of the tile's rows x columns of the tile
         std::vector<uint64_t>& pre = ctx->sp_tile_words_prefix;
         auto account = [&](size_t t, uint32_t nb) { ctx->stats.sparse_word_ops += pre[t + nb] - pre[t]; };
-        rc = run_batches(ctx, bp, sprm, launch, account, resident, sink, user, dump, rec_on_device);
+        rc = run_batches(ctx, bp, sprm, launch, account, resident, dump);
         if (rc) return rc;
     }
     if (!dump) {
+        // the last statistics kernel: its record count, then the final drain
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        rc = read_stats_timing(ctx);
+        if (rc) return rc;
+        const uint64_t fill = ctx->h_counters[1 + ctx->rec_cur];
+        ctx->stats.records_out += fill;
         if (!resident) {
-            rc = flush_records(ctx, rec_on_device, sink, user);
+            if (fill) flusher_submit(ctx, ctx->rec_cur, fill);
+            rc = flusher_wait(ctx, -1);
+            ctx->stats.bytes_d2h += ctx->flusher->bytes_d2h;
             if (rc) return rc;
         }
-        ctx->stats.records_out += rec_on_device;
     }
     return TWKB_OK;
 }
@@ -907,6 +1054,11 @@ static int compute_impl(Context* ctx, bool resident, twkb_sink_fn sink, void* us
         // bits, so the no-missing phased planes (and the tensor-core kernel) are exact for pass 1.
         rc = run_pass(ctx, pb, MODE_PHASED_NOMISS, 1, resident, screen_off, sink, user, dump);
         if (rc == TWKB_OK) rc = run_pass(ctx, pb, MODE_UNPHASED_MISS, 2, resident, screen_off, sink, user, dump);
+    }
+    if (rc != TWKB_OK && ctx->flusher) {  // an aborted pass: let the drain thread release its buffers before returning
+        const std::string keep = ctx->err;
+        flusher_wait(ctx, -1);
+        ctx->err = keep;
     }
     if (rc == TWKB_OK) {
         CUDA_TRY(cudaEventRecord(ctx->ev_end, ctx->stream));
@@ -1258,7 +1410,8 @@ void twkb_destroy(void* c) {
     ctx->d_raw_data.release(); ctx->d_raw_mask.release(); ctx->d_planes.release(); ctx->d_plane_popc.release();
     ctx->d_meta.release(); ctx->d_lgamma.release(); ctx->d_blk_of.release(); ctx->d_blk_first.release();
     ctx->d_blk_last.release(); ctx->d_blk_prune.release(); ctx->d_tiles.release(); ctx->d_cands.release();
-    ctx->d_counters.release(); ctx->d_records.release();
+    flusher_destroy(ctx);
+    ctx->d_counters.release(); ctx->d_records[0].release(); ctx->d_records[1].release();
     ctx->d_orig.release(); ctx->d_sp_off.release(); ctx->d_sp_ent.release(); ctx->d_sp_tiles.release();
     umma_release(ctx->umma);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);

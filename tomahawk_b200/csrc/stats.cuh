@@ -1,6 +1,7 @@
 // stats.cuh -- the statistics stage of `tomahawk calc` on the device: D, D', R,
 // R2, Fisher's exact P, chi-squared, flags, filters (in the reference's order)
-// and the packed 106-byte record. One thread per surviving pair.
+// and the packed 106-byte record. One thread per surviving pair, pairs re-ordered inside a block so
+// that the lanes of a warp walk Fisher tails of similar length.
 //
 // Reference: twk_ld_engine::PhasedMath lib/ld/ld_engine.cpp:1162-1310,
 // UnphasedMath :1312-1560, ChiSquaredUnphasedTable :1562-1588,
@@ -78,9 +79,10 @@ __device__ __forceinline__ double hyper_move(const LgTable& t, int n11, HyperSta
 // point and every later term is bit-identical to the reference's. Here each tail starts at the
 // multiple of 11 closest to the mode whose probability is still below FISHER_SKIP * q (found by
 // bisection on the closed form; the pmf is monotone on either side of the mode): the skipped terms
-// sum to < 2^13 * 1e-22 * q, far below one ulp of the result (P >= ~q), and the walk shrinks from
-// the support to ~20 standard deviations.
-constexpr double FISHER_SKIP = 1e-22;
+// sum to < 2^20 * 1e-18 * q = 1e-12 * q even at 1 M haplotypes, three orders of magnitude inside the
+// 1e-9 agreement the tests hold P to (P >= ~q), and the walk shrinks from the support to ~18 standard
+// deviations.
+constexpr double FISHER_SKIP = 1e-18;
 constexpr int FISHER_SKIP_MIN_RANGE = 48;  // shorter supports are walked whole
 
 __device__ double fisher_two_sided(const LgTable& t, int n11, int n12, int n21, int n22) {
@@ -415,44 +417,110 @@ __device__ bool unphased_stats(const uint32_t* t, const DevParams& prm, const Lg
 }
 
 // ---------------------------------------------------------------- stats kernel
-// One thread per candidate; passing pairs reserve an output slot with a
-// warp-aggregated atomic and write their packed record.
-__global__ void __launch_bounds__(128)
+// One thread per candidate, but NOT in buffer order. Fisher's walk is 10^1..10^3 recurrence steps
+// (two fp64 divisions each) and its length follows the spread of the hypergeometric distribution of
+// the pair, sigma^2 = n1. n.1 (n - n1.)(n - n.1) / (n^2 (n - 1)): in buffer order the 32 lanes of a
+// warp hold pairs of one row variant with 32 unrelated column variants, so a warp runs for the
+// longest of 32 walks while most lanes idle (C1, R2 >= 0, every pair reaches Fisher: 94 ms for
+// 4.9e7 candidates at ~25 % lane use). Here a block takes STATS_PER_BLOCK consecutive candidates,
+// buckets them by estimated walk length (64 log-spaced bins, shared-memory counting sort) and hands
+// each warp 32 neighbours of that order, so the lanes of a warp finish together. Every candidate
+// is still evaluated by ONE thread with the reference's operation order: results are unchanged.
+constexpr int STATS_THREADS = 256;
+constexpr int STATS_PER_BLOCK = 1024;
+
+// Estimated walk length of kt_fisher_exact for a candidate, as a bin 0..63 (4 bins per octave).
+__device__ __forceinline__ uint32_t fisher_cost_bin(const Candidate& cd) {
+    float n1, m1, n;
+    if (cd.mode == 0) {  // fisher_two_sided(c0, c4, c1, c5): n1. = c0 + c4, n.1 = c0 + c1
+        n1 = (float)cd.c[0] + (float)cd.c[2];
+        m1 = (float)cd.c[0] + (float)cd.c[1];
+        n = n1 + (float)cd.c[1] + (float)cd.c[3];
+    } else {             // 3x3 genotype table: the allele marginals of the estimated 2x2 table
+        const float r0 = (float)(cd.c[0] + cd.c[1] + cd.c[2]), r1 = (float)(cd.c[3] + cd.c[4] + cd.c[5]);
+        const float k0 = (float)(cd.c[0] + cd.c[3] + cd.c[6]), k1 = (float)(cd.c[1] + cd.c[4] + cd.c[7]);
+        const float T = r0 + r1 + (float)(cd.c[6] + cd.c[7] + cd.c[8]);
+        n = 2.0f * T;
+        n1 = 2.0f * r0 + r1;
+        m1 = 2.0f * k0 + k1;
+    }
+    if (!(n > 1.0f)) return 0u;
+    const float range = fminf(fminf(n1, m1), fminf(n - n1, n - m1));  // support size - 1
+    const float var = (n1 / n) * (m1 / n) * (n - n1) * ((n - m1) / (n - 1.0f));
+    const float est = fminf(range, 22.0f * sqrtf(fmaxf(var, 0.0f)) + 24.0f);
+    const int bin = (int)(4.0f * __log2f(1.0f + fmaxf(est, 0.0f)));
+    return (uint32_t)min(max(bin, 0), 63);
+}
+
+// UNPHASED = false: every candidate carries a 2x2 table (mode 0) -- the instantiation of the phased passes,
+// without the cubic solver's registers.
+template <bool UNPHASED, int MIN_BLOCKS>
+__global__ void __launch_bounds__(STATS_THREADS, MIN_BLOCKS)
 stats_kernel(const Candidate* __restrict__ cands, uint32_t n_cands, const DevVariant* __restrict__ meta,
              DevParams prm, const double* __restrict__ lgamma_tab, uint8_t* __restrict__ records,
              unsigned long long rec_capacity, unsigned long long* __restrict__ rec_count) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    bool pass = false;
-    PairStats s;
-    DevVariant a, b;
-    if (idx < n_cands) {
-        Candidate cd = cands[idx];
-        a = meta[cd.i];
-        b = meta[cd.j];
-        LgTable lg{lgamma_tab, prm.lgamma_len};
-        if (cd.mode == 0) {
-            unsigned long long c0 = cd.c[0], c1 = cd.c[1], c4 = cd.c[2], c5 = cd.c[3];
-            // Q3: the reference's run-length comparator (low allele counts, missing data)
-            // stores the two mixed cells in swapped slots (ld_engine.cpp:1023,1055 vs :683-684);
-            // CalculatePhasedBitmap* (-p -m -M) sends every masked pair there (:2393-2397, :2477-2481).
-            if (prm.emulate_quirks && ((a.flags | b.flags) & VF_GT_MISSING) && (prm.bitmap_mode || a.ac + b.ac < prm.thresh_miss_phased)) {
-                unsigned long long tmp = c1; c1 = c4; c4 = tmp;
-            }
-            pass = phased_stats(c0, c1, c4, c5, prm, lg, a, b, s);
-        } else {
-            pass = unphased_stats(cd.c, prm, lg, a, b, s);
-        }
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-    if (ballot == 0) return;
+    __shared__ uint16_t s_perm[STATS_PER_BLOCK];
+    __shared__ uint8_t s_bin[STATS_PER_BLOCK];
+    __shared__ uint32_t s_off[64];
+    const uint32_t base = blockIdx.x * (uint32_t)STATS_PER_BLOCK;
+    const uint32_t cnt = min((uint32_t)STATS_PER_BLOCK, n_cands - base);
     const int lane = threadIdx.x & 31;
-    const int leader = __ffs(ballot) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(rec_count, (unsigned long long)__popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pass) {
-        const unsigned long long slot = base + __popc(ballot & ((1u << lane) - 1));
-        if (slot < rec_capacity) write_record(records + slot * 106ull, s, a, b);
+    if (threadIdx.x < 64) s_off[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < cnt; idx += STATS_THREADS) {
+        const uint32_t b = fisher_cost_bin(cands[base + idx]);
+        s_bin[idx] = (uint8_t)b;
+        atomicAdd(&s_off[b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive prefix sum of the 64 bin counts
+        const uint32_t a = s_off[2 * lane], b = s_off[2 * lane + 1];
+        uint32_t incl = a + b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const uint32_t excl = incl - (a + b);
+        s_off[2 * lane] = excl;
+        s_off[2 * lane + 1] = excl + a;
+    }
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < cnt; idx += STATS_THREADS) s_perm[atomicAdd(&s_off[s_bin[idx]], 1u)] = (uint16_t)idx;
+    __syncthreads();
+    const LgTable lg{lgamma_tab, prm.lgamma_len};
+    for (uint32_t p0 = 0; p0 < cnt; p0 += STATS_THREADS) {  // uniform trip count: every lane takes part in the ballots
+        const uint32_t pos = p0 + threadIdx.x;
+        bool pass = false;
+        PairStats s;
+        DevVariant a, b;
+        if (pos < cnt) {
+            const Candidate cd = cands[base + s_perm[pos]];
+            a = meta[cd.i];
+            b = meta[cd.j];
+            if (!UNPHASED || cd.mode == 0) {
+                unsigned long long c0 = cd.c[0], c1 = cd.c[1], c4 = cd.c[2], c5 = cd.c[3];
+                // Q3: the reference's run-length comparator (low allele counts, missing data)
+                // stores the two mixed cells in swapped slots (ld_engine.cpp:1023,1055 vs :683-684);
+                // CalculatePhasedBitmap* (-p -m -M) sends every masked pair there (:2393-2397, :2477-2481).
+                if (prm.emulate_quirks && ((a.flags | b.flags) & VF_GT_MISSING) && (prm.bitmap_mode || a.ac + b.ac < prm.thresh_miss_phased)) {
+                    unsigned long long tmp = c1; c1 = c4; c4 = tmp;
+                }
+                pass = phased_stats(c0, c1, c4, c5, prm, lg, a, b, s);
+            } else {
+                pass = unphased_stats(cd.c, prm, lg, a, b, s);
+            }
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+        if (ballot == 0) continue;
+        const int leader = __ffs(ballot) - 1;
+        unsigned long long slot0 = 0;
+        if (lane == leader) slot0 = atomicAdd(rec_count, (unsigned long long)__popc(ballot));
+        slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+        if (pass) {
+            const unsigned long long slot = slot0 + __popc(ballot & ((1u << lane) - 1));
+            if (slot < rec_capacity) write_record(records + slot * 106ull, s, a, b);
+        }
     }
 }
 
