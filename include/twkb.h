@@ -186,6 +186,29 @@ int twkb_load_matrix_device(void* ctx, uint32_t n_samples, uint32_t n_variants, 
 int twkb_load_runs(void* ctx, uint32_t n_samples, uint32_t n_variants, const uint8_t* run_bytes, size_t n_run_bytes,
                    const twkb_run_desc* desc, const twkb_variant* meta);
 
+/* ---- multi-GPU data plane: NCCL over NVLink, used once per load ----------------------------------------
+ * Reference analogue: twk_ld::LoadAllBlocks (lib/ld/ld.cpp:370-465) unpacks the file once into host memory
+ * every slave thread shares; twk_ld_balancer (lib/ld/ld_balancing.h:23-80) then deals block pairs. Here one
+ * context per GPU (threads of one process -- include/twkb_ld.hpp, `twkb_calc -g 0,1,..` -- or one process per
+ * GPU -- bench.py under torchrun) forms a communicator; a sliced load sends only rows
+ * [row_begin, row_end) of this rank (twkb_comm_slice) over this GPU's own PCIe link and completes the matrix
+ * on every GPU with NCCL broadcasts over NVLink, chunk by chunk behind the upload. No collective runs during
+ * twkb_compute: tiles are independent (settings.part_index / part_count select this context's tiles).
+ * libnccl.so.2 is loaded on first use; without it these calls fail with TWKB_ENODEVICE. */
+#define TWKB_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+int twkb_comm_unique_id(uint8_t* id /* [TWKB_COMM_ID_BYTES] */);  /* one rank creates it, all ranks pass it to init */
+int twkb_comm_init(void* ctx, const uint8_t* id, int32_t rank, int32_t n_ranks); /* collective (ncclCommInitRank) */
+int twkb_comm_slice(uint32_t n_variants, int32_t rank, int32_t n_ranks, uint32_t* row_begin, uint32_t* row_end);
+/* Collective. slice_*_bits point at row `row_begin` of this rank (the rows of the slice, contiguous, same
+ * layout as twkb_load_matrix); meta holds ALL n_variants entries on every rank. Without a communicator
+ * (or n_ranks == 1) identical to twkb_load_matrix. */
+int twkb_load_matrix_sliced(void* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* slice_data_bits,
+                            const uint64_t* slice_mask_bits, size_t row_stride_words, const twkb_variant* meta);
+/* Collective. Arguments as twkb_load_runs (every rank sees all descriptors, e.g. the threads of one process
+ * sharing the inflated file); a rank uploads and decodes the run words of its own variants only. */
+int twkb_load_runs_sliced(void* ctx, uint32_t n_samples, uint32_t n_variants, const uint8_t* run_bytes, size_t n_run_bytes,
+                          const twkb_run_desc* desc, const twkb_variant* meta);
+
 /* Test hook: copy the resident reference-layout rows (file order unless the rare-variant class
  * re-ordered them) back to the host. mask_bits may be NULL. */
 int twkb_debug_rows(void* ctx, uint64_t* data_bits, uint64_t* mask_bits, size_t row_stride_words);

@@ -23,6 +23,7 @@
 #include <sys/time.h>
 
 #include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <ctime>
 #include <iostream>
@@ -177,17 +178,51 @@ public:
         std::vector<twkb_stats> st(n_dev);
         std::vector<int> rcs(n_dev, 0);
         const auto t0 = std::chrono::steady_clock::now();
-        auto worker = [&](int k) {
+        // Several DISTINCT devices: the contexts form an NCCL communicator and every device uploads (and
+        // decodes) only its slice of the variant rows over its own PCIe link; the slices are exchanged over
+        // NVLink (twkb_load_*_sliced). Contexts are created up front so that a bad device ordinal fails
+        // before anybody waits in a collective.
+        std::vector<void*> ctxs(n_dev, nullptr);
+        for (int k = 0; k < n_dev; ++k) {
             twkb_settings cs;
             settings.ToC(&cs);
             cs.device = settings.devices[k];
             cs.part_index = k;
             cs.part_count = n_dev;
-            void* ctx = nullptr;
-            int r = twkb_create(&cs, &ctx);
-            if (r) { errors[k] = twkb_last_error(nullptr); rcs[k] = r; return; }
-            r = runs ? twkb_load_runs(ctx, n_samples, n_variants, run_bytes, n_run_bytes, run_desc, meta)
-                     : twkb_load_matrix(ctx, n_samples, n_variants, data, mask, stride, meta);
+            const int r = twkb_create(&cs, &ctxs[k]);
+            if (r) {
+                const std::string why = twkb_last_error(nullptr);
+                for (void* c : ctxs) twkb_destroy(c);
+                twkb_two_close(writer);
+                twkb_twk_close(twk);
+                return error("device " + std::to_string(settings.devices[k]) + ": " + why);
+            }
+        }
+        bool distinct = true;
+        for (int a = 0; a < n_dev; ++a)
+            for (int b = a + 1; b < n_dev; ++b) distinct = distinct && settings.devices[a] != settings.devices[b];
+        uint8_t uid[TWKB_COMM_ID_BYTES];
+        const bool use_comm = n_dev > 1 && distinct && !std::getenv("TWKB_NO_NCCL") && twkb_comm_unique_id(uid) == TWKB_OK;
+        if (n_dev > 1)
+            log("THREAD") << (use_comm ? "NCCL communicator over " + std::to_string(n_dev) + " devices: sliced upload + exchange over NVLink"
+                                       : std::string("no communicator (repeated device or NCCL unavailable): every context uploads the whole matrix"))
+                          << std::endl;
+        auto worker = [&](int k) {
+            void* ctx = ctxs[k];
+            int r = TWKB_OK;
+            if (use_comm) r = twkb_comm_init(ctx, uid, k, n_dev);
+            if (r == TWKB_OK) {
+                if (use_comm) {
+                    uint32_t b = 0, e = 0;
+                    twkb_comm_slice(n_variants, k, n_dev, &b, &e);
+                    r = runs ? twkb_load_runs_sliced(ctx, n_samples, n_variants, run_bytes, n_run_bytes, run_desc, meta)
+                             : twkb_load_matrix_sliced(ctx, n_samples, n_variants, data + (size_t)b * stride,
+                                                       mask ? mask + (size_t)b * stride : nullptr, stride, meta);
+                } else {
+                    r = runs ? twkb_load_runs(ctx, n_samples, n_variants, run_bytes, n_run_bytes, run_desc, meta)
+                             : twkb_load_matrix(ctx, n_samples, n_variants, data, mask, stride, meta);
+                }
+            }
             if (r == TWKB_OK) r = twkb_compute(ctx, &twk_ld::sink, &shared);
             if (r) { errors[k] = twkb_last_error(ctx); rcs[k] = r; }
             else twkb_get_stats(ctx, &st[k]);

@@ -96,6 +96,7 @@ EXPORTS = [
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
     "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
     "twkb_two_sort",
+    "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
 ]
 
 
@@ -132,6 +133,14 @@ def _bind(L):
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.twkb_load_runs.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
                                  ctypes.c_void_p, ctypes.c_void_p]
+    L.twkb_load_matrix_sliced.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.twkb_load_runs_sliced.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
+                                        ctypes.c_void_p, ctypes.c_void_p]
+    L.twkb_comm_unique_id.argtypes = [ctypes.c_void_p]
+    L.twkb_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]
+    L.twkb_comm_slice.argtypes = [ctypes.c_uint32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint32),
+                                  ctypes.POINTER(ctypes.c_uint32)]
     L.twkb_debug_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
     L.twkb_twk_open_runs.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32,
                                      ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
@@ -284,6 +293,27 @@ def plan_tiles(settings: Settings, meta: np.ndarray, tile_i: int, tile_j: int):
     return out, int(pairs.value)
 
 
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through libtwkb: create on one rank, ship the bytes to the others (any transport)."""
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    rc = lib().twkb_comm_unique_id(buf)
+    if rc != 0:
+        raise TwkbError(rc, lib().twkb_last_error(None).decode())
+    return buf.raw
+
+
+def comm_slice(n_variants: int, rank: int, n_ranks: int):
+    """Rows [begin, end) a rank uploads in a sliced load."""
+    b, e = ctypes.c_uint32(), ctypes.c_uint32()
+    rc = lib().twkb_comm_slice(n_variants, rank, n_ranks, ctypes.byref(b), ctypes.byref(e))
+    if rc != 0:
+        raise TwkbError(rc, "twkb_comm_slice")
+    return b.value, e.value
+
+
 def default_settings(**kw) -> Settings:
     """Reference defaults (lib/core.cpp:297-306) with keyword overrides."""
     s = Settings()
@@ -338,6 +368,29 @@ class Engine:
         self._check(self._L.twkb_load_matrix(self._ctx, n_samples, data.shape[0], data.ctypes.data,
                                              mask.ctypes.data if mask is not None else None, data.shape[1],
                                              meta.ctypes.data))
+
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        """Join the NCCL communicator of the sliced loads (collective over all ranks' contexts)."""
+        assert len(unique_id) == COMM_ID_BYTES
+        self._check(self._L.twkb_comm_init(self._ctx, unique_id, rank, n_ranks))
+
+    def load_sliced(self, n_samples: int, n_variants: int, slice_data: np.ndarray, slice_mask: np.ndarray | None, meta: np.ndarray):
+        """Collective: this rank's rows (comm_slice) go up over its own PCIe link, NCCL completes the matrix."""
+        slice_data = np.ascontiguousarray(slice_data, dtype=np.uint64)
+        meta = np.ascontiguousarray(meta)
+        assert meta.dtype.itemsize == 32 and len(meta) == n_variants
+        if slice_mask is not None:
+            slice_mask = np.ascontiguousarray(slice_mask, dtype=np.uint64)
+        self._check(self._L.twkb_load_matrix_sliced(self._ctx, n_samples, n_variants, slice_data.ctypes.data,
+                                                    slice_mask.ctypes.data if slice_mask is not None else None,
+                                                    slice_data.shape[1], meta.ctypes.data))
+
+    def load_runs_sliced(self, n_samples: int, run_bytes: np.ndarray, desc: np.ndarray, meta: np.ndarray):
+        run_bytes = np.ascontiguousarray(run_bytes, dtype=np.uint8)
+        desc = np.ascontiguousarray(desc)
+        meta = np.ascontiguousarray(meta)
+        self._check(self._L.twkb_load_runs_sliced(self._ctx, n_samples, len(desc), run_bytes.ctypes.data, run_bytes.size,
+                                                  desc.ctypes.data, meta.ctypes.data))
 
     def load_runs(self, n_samples: int, run_bytes: np.ndarray, desc: np.ndarray, meta: np.ndarray):
         """Run-length records (twk1_igt_t words located by ``desc``) -> resident rows, decoded on the device."""

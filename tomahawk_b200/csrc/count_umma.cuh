@@ -239,6 +239,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t targe
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void epilogue_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// One lane of a converged warp (cute::elect_one_sync).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0u;
+}
 
 // Block-scaled e2m1 MMA (K = 64 per instruction), scale factors read from TMEM.
 __device__ __forceinline__ void umma_mxf4_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
@@ -548,6 +560,38 @@ __device__ __forceinline__ void umma_epilogue_chunk(const CountArgs& args, const
                                                     float thr, int lane, const SurvivorQueue& q) {
     if (SCREEN) {
         float m = __int_as_float(0xff800000);
+#ifdef TWKB_PROFILING
+        if (TWKB_DBG(args, 32u)) {  // ablation: the screen arithmetic without its shared-memory loads (results invalid)
+            const float4 cb = make_float4(row.acA, row.sA, row.dA, row.sA);
+#pragma unroll
+            for (int c2 = 0; c2 < 16; ++c2) {
+                {
+                    const float n11 = FP4 ? __uint_as_float(r[2 * c2]) : (float)r[2 * c2];
+                    const float pab = row.acA * (cb.x + (float)c2);
+                    const float x = fmaf(n11, Tf, -pab);
+                    m = fmaxf(m, fmaf(-row.sA, cb.y, fmaf(pab, 1.0e-6f, fabsf(x))));
+                }
+                {
+                    const float n11 = FP4 ? __uint_as_float(r[2 * c2 + 1]) : (float)r[2 * c2 + 1];
+                    const float pab = row.acA * (cb.z + (float)c2);
+                    const float x = fmaf(n11, Tf, -pab);
+                    m = fmaxf(m, fmaf(-row.sA, cb.w, fmaf(pab, 1.0e-6f, fabsf(x))));
+                }
+            }
+            if (m == 12345.678f) q.ctrl[3] = 1u;  // keeps the arithmetic alive
+            return;
+        }
+        if (TWKB_DBG(args, 64u)) {  // ablation: the shared-memory loads without the arithmetic
+            float acc = 0.0f;
+#pragma unroll
+            for (int c2 = 0; c2 < 16; ++c2) {
+                const float4 cb = lds_f4(colf_saddr + (uint32_t)(chunk * 32 + 2 * c2) * 8u);
+                acc += cb.x;
+            }
+            if (acc == 12345.678f) q.ctrl[3] = 1u;
+            return;
+        }
+#endif
 #pragma unroll
         for (int c2 = 0; c2 < 16; ++c2) {
             const float4 cb = lds_f4(colf_saddr + (uint32_t)(chunk * 32 + 2 * c2) * 8u);  // {ac_j, s_j} of two columns
@@ -1092,62 +1136,70 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         tcgen05_fence_after();
     }
 
+    // The two mainloop warps run CONVERGED (all 32 lanes execute the loops, one elected lane issues the
+    // asynchronous instructions): with a single active lane (`if (lane == 0)`) ptxas cannot keep the
+    // descriptors, barrier addresses and coordinates in uniform registers and wraps every UTCOMMA / UTMALDG /
+    // UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop -- ~110 issue slots per K block on the scheduler the
+    // issuer shares with two epilogue warps, which is what made the kernel 14 % slower with the (cheap) screen
+    // arithmetic running than without it (profiles/round2_epilogue_ablation.log). Stage index and barrier
+    // phase are carried as counters (no division by the ring depth).
     if (warp == 0) {
         // ============================== TMA producer ==============================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters) {
-                const uint2 tile = args.tiles[t];
-                for (uint32_t kb = 0; kb < num_kblocks; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    if (it >= (uint32_t)STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-                    uint8_t* sA = stage_base + (size_t)s * Cfg::STAGE_BYTES;
-                    uint8_t* sB = sA + 128 * UMMA_BLOCK_K;
-                    if (TWKB_DBG(args, 1u)) {  // profiling aid: no operand traffic after the first ring fill (results invalid)
-                        if (it >= (uint32_t)STAGES) {
-                            if (leader) mbar_arrive_expect_tx(&full_bar[s], 0);
-                            continue;
-                        }
+        uint32_t s = 0, wrap = 0;  // ring slot, number of completed passes over the ring
+        for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters) {
+            const uint2 tile = args.tiles[t];
+            // operand rows of this CTA's halves of the tile (planes: the re-ordered copies)
+            const uint32_t a_row = (MODE == MODE_PHASED_NOMISS ? tile.x : (tile.x / PlanesCfg<MODE>::TI) * 256u) + 128u * rank;
+            const uint32_t b_row = (MODE == MODE_PHASED_NOMISS ? tile.y : (tile.y / PlanesCfg<MODE>::TJ) * 240u) + Cfg::B_ROWS * rank;
+            for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
+                if (wrap) mbar_wait(&empty_bar[s], (wrap - 1u) & 1u);
+                uint8_t* sA = stage_base + (size_t)s * Cfg::STAGE_BYTES;
+                uint8_t* sB = sA + 128 * UMMA_BLOCK_K;
+                const bool skip_loads = TWKB_DBG(args, 1u) && wrap;  // profiling aid: no operand traffic after the first ring fill
+                if (elect_one_sync()) {
+                    if (leader) mbar_arrive_expect_tx(&full_bar[s], skip_loads ? 0u : 2u * Cfg::STAGE_BYTES);
+                    if (!skip_loads) {
+                        tma_load_2d_2sm(sA, &tmap_a, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)a_row);
+                        tma_load_2d_2sm(sB, &tmap_b, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)b_row);
                     }
-                    if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
-                    // operand rows of this CTA's halves of the tile (planes: the re-ordered copies)
-                    const uint32_t a_row = MODE == MODE_PHASED_NOMISS ? tile.x : (tile.x / PlanesCfg<MODE>::TI) * 256u;
-                    const uint32_t b_row = MODE == MODE_PHASED_NOMISS ? tile.y : (tile.y / PlanesCfg<MODE>::TJ) * 240u;
-                    tma_load_2d_2sm(sA, &tmap_a, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(a_row + 128 * rank));
-                    tma_load_2d_2sm(sB, &tmap_b, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)(b_row + Cfg::B_ROWS * rank));
                 }
+                __syncwarp();
+                if (++s == (uint32_t)STAGES) { s = 0; ++wrap; }
             }
         }
     } else if (warp == 1) {
         // ========================= MMA issuer (leader only) =========================
-        if (leader && lane == 0) {
+        if (leader) {
             constexpr uint32_t idesc = FP4 ? umma_idesc_mxf4(256, TILE_N) : umma_idesc_i8(256, TILE_N);
-            uint32_t it = 0, n = 0;
+            uint32_t s = 0, phase = 0, n = 0;
             for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters, ++n) {
                 const uint32_t acc = n & 1;
                 if (n >= 2) mbar_wait(&tmem_empty_bar[acc], ((n >> 1) - 1) & 1);  // epilogue drained tile n-2
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * TILE_N;
-                for (uint32_t kb = 0; kb < num_kblocks; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
+                    mbar_wait(&full_bar[s], phase);
                     tcgen05_fence_after();
-                    const uint32_t a_addr = smem_u32(stage_base + (size_t)s * Cfg::STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(stage_base) + s * Cfg::STAGE_BYTES;
                     const uint32_t b_addr = a_addr + 128 * UMMA_BLOCK_K;
                     const uint64_t adesc = umma_smem_desc(a_addr), bdesc = umma_smem_desc(b_addr);
-                    // 32 bytes of K per instruction in both encodings (32 int8 / 64 e2m1)
+                    if (elect_one_sync()) {
+                        // 32 bytes of K per instruction in both encodings (32 int8 / 64 e2m1)
 #pragma unroll
-                    for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k) {
-                        if (FP4)
-                            umma_mxf4_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
-                                          (kb | k) != 0 ? 1u : 0u, tmem_base + Cfg::SF_COL, tmem_base + Cfg::SF_COL + 8);
-                        else
-                            umma_i8_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
-                                        (kb | k) != 0 ? 1u : 0u);
+                        for (uint32_t k = 0; k < UMMA_BLOCK_K / UMMA_K; ++k) {
+                            if (FP4)
+                                umma_mxf4_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
+                                              (kb | k) != 0 ? 1u : 0u, tmem_base + Cfg::SF_COL, tmem_base + Cfg::SF_COL + 8);
+                            else
+                                umma_i8_2sm(d_tmem, adesc + (uint64_t)(k * UMMA_K >> 4), bdesc + (uint64_t)(k * UMMA_K >> 4), idesc,
+                                            (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_2sm(&empty_bar[s]);
+                        if (kb + 1 == num_kblocks) umma_commit_2sm(&tmem_full_bar[acc]);
                     }
-                    umma_commit_2sm(&empty_bar[s]);
+                    __syncwarp();
+                    if (++s == (uint32_t)STAGES) { s = 0; phase ^= 1u; }
                 }
-                umma_commit_2sm(&tmem_full_bar[acc]);
             }
         }
     } else if (warp >= 4) {

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/twkb.h"
+#include "comm.cuh"
 #include "common.cuh"
 #include "count_popc.cuh"
 #include "count_sparse.cuh"
@@ -131,6 +132,11 @@ struct Context {
 
     twkb_stats stats{};
     double ms_decode = 0.0;  // decode_runs_kernel time of the last twkb_load_runs
+
+    // multi-GPU data plane (comm.cuh): set by twkb_comm_init, used by the sliced loads only
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    std::vector<cudaEvent_t> chunk_events;
 
     int fail(const std::string& m) {
         err = m;
@@ -1312,6 +1318,183 @@ static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, cons
     return rc;
 }
 
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        ncclResult_t _r = (expr);                                                                   \
+        if (_r != ncclSuccess) {                                                                    \
+            ctx->err = std::string(#expr) + ": " + nccl_api().GetErrorString(_r);                   \
+            return TWKB_ECUDA;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+// Chunk `chunk` of `n_chunks` of EVERY rank's row slice, exchanged as one group of in-place broadcasts
+// (an all-gather-v: slices may be short or empty). Every rank issues the same sequence of calls.
+static int exchange_slices(Context* ctx, uint64_t* d_rows, size_t stride, uint32_t M, int n_chunks, int chunk) {
+    const NcclApi& nc = nccl_api();
+    NCCL_TRY(nc.GroupStart());
+    for (int k = 0; k < ctx->comm_size; ++k) {
+        uint32_t b, e;
+        comm_slice(M, k, ctx->comm_size, b, e);
+        const uint64_t rows = e - b, per = (rows + n_chunks - 1) / n_chunks;
+        const uint64_t cb = b + std::min<uint64_t>(rows, per * (uint64_t)chunk), ce = b + std::min<uint64_t>(rows, per * (uint64_t)(chunk + 1));
+        if (ce > cb) {
+            uint64_t* ptr = d_rows + cb * stride;
+            NCCL_TRY(nc.Broadcast(ptr, ptr, (size_t)(ce - cb) * stride, ncclUint64, k, ctx->comm, ctx->stream));
+        }
+    }
+    NCCL_TRY(nc.GroupEnd());
+    return TWKB_OK;
+}
+
+static int ensure_chunk_events(Context* ctx, int n) {
+    while ((int)ctx->chunk_events.size() < n) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(ev);
+    }
+    return TWKB_OK;
+}
+
+// twkb_load_matrix_sliced: this rank's rows go up over its own PCIe link in chunks on copy_stream; as soon
+// as chunk c of every rank has landed it is exchanged over NVLink while chunk c + 1 is still uploading.
+static int load_matrix_sliced(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* slice_data, const uint64_t* slice_mask,
+                              size_t stride, const twkb_variant* meta) {
+    if (!ctx->comm || ctx->comm_size <= 1) return load_common(ctx, n_samples, n_variants, slice_data, slice_mask, stride, meta, false);
+    int rc = load_begin(ctx, n_samples, n_variants, stride, meta);
+    if (rc) return rc;
+    ctx->ms_decode = 0.0;
+    uint32_t b, e;
+    comm_slice(n_variants, ctx->comm_rank, ctx->comm_size, b, e);
+    const uint64_t rows = e - b;
+    if (rows && !slice_data) { ctx->err = "null/empty matrix slice"; return TWKB_EINVAL; }
+    if (ctx->any_missing && rows && !slice_mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
+    const size_t words = (size_t)n_variants * stride;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    CUDA_TRY(ctx->d_raw_data.alloc(words));
+    if (ctx->any_missing) CUDA_TRY(ctx->d_raw_mask.alloc(words));
+    // the same chunk count on every rank (derived from the global shape): ~8 MB per chunk, at most 8
+    const uint64_t per_rank = ((uint64_t)n_variants + ctx->comm_size - 1) / ctx->comm_size;
+    const int n_chunks = (int)std::min<uint64_t>(8, std::max<uint64_t>(1, per_rank * stride * 8 / (8u << 20)));
+    rc = ensure_chunk_events(ctx, n_chunks);
+    if (rc) return rc;
+    const uint64_t per = (rows + n_chunks - 1) / n_chunks;
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint64_t cb = std::min<uint64_t>(rows, per * (uint64_t)c), ce = std::min<uint64_t>(rows, per * (uint64_t)(c + 1));
+        if (ce > cb) {
+            CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_data.p + (b + cb) * stride, slice_data + cb * stride, (ce - cb) * stride * 8,
+                                     cudaMemcpyHostToDevice, ctx->copy_stream));
+            if (ctx->any_missing)
+                CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_mask.p + (b + cb) * stride, slice_mask + cb * stride, (ce - cb) * stride * 8,
+                                         cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[c], 0));
+        rc = exchange_slices(ctx, ctx->d_raw_data.p, stride, n_variants, n_chunks, c);
+        if (rc) return rc;
+        if (ctx->any_missing) {
+            rc = exchange_slices(ctx, ctx->d_raw_mask.p, stride, n_variants, n_chunks, c);
+            if (rc) return rc;
+        }
+    }
+    ctx->stats.bytes_h2d = rows * stride * 8 * (ctx->any_missing ? 2 : 1);
+    return load_finish(ctx, meta);
+}
+
+// twkb_load_runs_sliced: this rank uploads the run words of ITS variants only, decodes them on the device
+// into its rows, then the rows are exchanged. The coverage check of the decoder is exchanged too, so that
+// every rank fails (or succeeds) together.
+static int load_runs_sliced(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint8_t* bytes, size_t n_bytes,
+                            const twkb_run_desc* desc, const twkb_variant* meta) {
+    if (!ctx->comm || ctx->comm_size <= 1) return load_runs(ctx, n_samples, n_variants, bytes, n_bytes, desc, meta);
+    if (!bytes || !desc) { ctx->err = "null run buffer"; return TWKB_EINVAL; }
+    const uint64_t H = 2ull * n_samples;
+    const size_t stride = ((H + 63) / 64 + 1) / 2 * 2;
+    int rc = load_begin(ctx, n_samples, n_variants, stride, meta);
+    if (rc) return rc;
+    uint32_t b, e;
+    comm_slice(n_variants, ctx->comm_rank, ctx->comm_size, b, e);
+    const uint32_t rows = e - b;
+    // byte range of the slice's run words (validated like twkb_load_runs; a bad descriptor fails on every rank
+    // because every rank checks ALL descriptors)
+    for (uint32_t v = 0; v < n_variants; ++v) {
+        const twkb_run_desc& d = desc[v];
+        if ((d.width != 1 && d.width != 2 && d.width != 4) || d.miss > 1 || d.offset > n_bytes ||
+            (uint64_t)d.n_runs * d.width > n_bytes - d.offset) {
+            ctx->err = "illegal gt primitive type / truncated runs (variant " + std::to_string(v) + ")";
+            return TWKB_EINVAL;
+        }
+    }
+    uint64_t lo = n_bytes, hi = 0;
+    for (uint32_t v = b; v < e; ++v) {
+        lo = std::min<uint64_t>(lo, desc[v].offset);
+        hi = std::max<uint64_t>(hi, desc[v].offset + (uint64_t)desc[v].n_runs * desc[v].width);
+    }
+    if (hi < lo) lo = hi = 0;
+    std::vector<twkb_run_desc> local(desc + b, desc + e);
+    for (twkb_run_desc& d : local) d.offset -= lo;
+    const size_t words = (size_t)n_variants * stride;
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    DevBuf<uint8_t> d_bytes;
+    DevBuf<twkb_run_desc> d_desc;
+    DevBuf<uint32_t> d_err, d_status;
+    CUDA_TRY(d_bytes.alloc(hi - lo + 16));
+    CUDA_TRY(d_desc.alloc(std::max<uint32_t>(rows, 1)));
+    CUDA_TRY(d_err.alloc(2));
+    CUDA_TRY(d_status.alloc(2 * (size_t)ctx->comm_size));
+    CUDA_TRY(ctx->d_raw_data.alloc(words));
+    if (ctx->any_missing) CUDA_TRY(ctx->d_raw_mask.alloc(words));
+    const uint32_t h_err0[2] = {0u, 0xffffffffu};
+    CUDA_TRY(cudaMemcpyAsync(d_err.p, h_err0, sizeof(h_err0), cudaMemcpyHostToDevice, ctx->stream));
+    if (rows) {
+        CUDA_TRY(cudaMemcpyAsync(d_bytes.p, bytes + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_desc.p, local.data(), (size_t)rows * sizeof(twkb_run_desc), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_raw_data.p + (size_t)b * stride, 0, (size_t)rows * stride * 8, ctx->stream));
+        if (ctx->any_missing) CUDA_TRY(cudaMemsetAsync(ctx->d_raw_mask.p + (size_t)b * stride, 0, (size_t)rows * stride * 8, ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
+        decode_runs_kernel<<<(rows + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, ctx->stream>>>(
+            d_bytes.p, d_desc.p, rows, (uint32_t)H, reinterpret_cast<uint32_t*>(ctx->d_raw_data.p + (size_t)b * stride),
+            ctx->any_missing ? reinterpret_cast<uint32_t*>(ctx->d_raw_mask.p + (size_t)b * stride) : nullptr, stride * 2, d_err.p);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
+        ctx->stats.other_launches += 1;
+    }
+    // status of every rank: {error flag, slice-local variant}
+    CUDA_TRY(cudaMemcpyAsync(d_status.p + 2 * ctx->comm_rank, d_err.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        const NcclApi& nc = nccl_api();
+        NCCL_TRY(nc.GroupStart());
+        for (int k = 0; k < ctx->comm_size; ++k)
+            NCCL_TRY(nc.Broadcast(d_status.p + 2 * k, d_status.p + 2 * k, 2, ncclUint32, k, ctx->comm, ctx->stream));
+        NCCL_TRY(nc.GroupEnd());
+    }
+    rc = exchange_slices(ctx, ctx->d_raw_data.p, stride, n_variants, 1, 0);
+    if (rc) return rc;
+    if (ctx->any_missing) {
+        rc = exchange_slices(ctx, ctx->d_raw_mask.p, stride, n_variants, 1, 0);
+        if (rc) return rc;
+    }
+    std::vector<uint32_t> h_status(2 * (size_t)ctx->comm_size, 0);
+    CUDA_TRY(cudaMemcpyAsync(h_status.data(), d_status.p, h_status.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->ms_decode = 0.0;
+    if (rows) {
+        float ms_dec = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms_dec, ctx->ev2, ctx->ev3));
+        ctx->ms_decode = ms_dec;
+    }
+    ctx->stats.bytes_h2d = (hi - lo) + (size_t)rows * sizeof(twkb_run_desc);
+    for (int k = 0; k < ctx->comm_size; ++k)
+        if (h_status[2 * k]) {
+            uint32_t kb, ke;
+            comm_slice(n_variants, k, ctx->comm_size, kb, ke);
+            ctx->err = "run lengths do not cover all samples (variant " + std::to_string(kb + h_status[2 * k + 1]) + ")";
+            return TWKB_EINVAL;
+        }
+    return load_finish(ctx, meta);
+}
+
 }  // namespace twkb
 
 using namespace twkb;
@@ -1411,6 +1594,8 @@ void twkb_destroy(void* c) {
     ctx->d_meta.release(); ctx->d_lgamma.release(); ctx->d_blk_of.release(); ctx->d_blk_first.release();
     ctx->d_blk_last.release(); ctx->d_blk_prune.release(); ctx->d_tiles.release(); ctx->d_cands.release();
     flusher_destroy(ctx);
+    if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
+    for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
     ctx->d_counters.release(); ctx->d_records[0].release(); ctx->d_records[1].release();
     ctx->d_orig.release(); ctx->d_sp_off.release(); ctx->d_sp_ent.release(); ctx->d_sp_tiles.release();
     umma_release(ctx->umma);
@@ -1457,6 +1642,50 @@ int twkb_load_runs(void* c, uint32_t n_samples, uint32_t n_variants, const uint8
                    const twkb_run_desc* desc, const twkb_variant* meta) {
     if (!c) return TWKB_EINVAL;
     return guarded_ctx(c, [&] { return load_runs(static_cast<Context*>(c), n_samples, n_variants, run_bytes, n_run_bytes, desc, meta); });
+}
+
+int twkb_comm_unique_id(uint8_t* id) {
+    if (!id) return TWKB_EINVAL;
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) { std::lock_guard<std::mutex> lock(g_create_mutex); g_create_error = nc.why; return TWKB_ENODEVICE; }
+    ncclUniqueId uid;
+    if (nc.GetUniqueId(&uid) != ncclSuccess) return TWKB_ECUDA;
+    static_assert(sizeof(uid) == TWKB_COMM_ID_BYTES, "ncclUniqueId size");
+    std::memcpy(id, &uid, sizeof(uid));
+    return TWKB_OK;
+}
+
+int twkb_comm_init(void* c, const uint8_t* id, int32_t rank, int32_t n_ranks) {
+    if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return TWKB_EINVAL;
+    Context* ctx = static_cast<Context*>(c);
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) { ctx->err = nc.why; return TWKB_ENODEVICE; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->comm) { nc.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    NCCL_TRY(nc.CommInitRank(&ctx->comm, n_ranks, uid, rank));
+    ctx->comm_rank = rank;
+    ctx->comm_size = n_ranks;
+    return TWKB_OK;
+}
+
+int twkb_comm_slice(uint32_t n_variants, int32_t rank, int32_t n_ranks, uint32_t* row_begin, uint32_t* row_end) {
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !row_begin || !row_end) return TWKB_EINVAL;
+    comm_slice(n_variants, rank, n_ranks, *row_begin, *row_end);
+    return TWKB_OK;
+}
+
+int twkb_load_matrix_sliced(void* c, uint32_t n_samples, uint32_t n_variants, const uint64_t* slice_data_bits,
+                            const uint64_t* slice_mask_bits, size_t row_stride_words, const twkb_variant* meta) {
+    if (!c) return TWKB_EINVAL;
+    return guarded_ctx(c, [&] { return load_matrix_sliced(static_cast<Context*>(c), n_samples, n_variants, slice_data_bits, slice_mask_bits, row_stride_words, meta); });
+}
+
+int twkb_load_runs_sliced(void* c, uint32_t n_samples, uint32_t n_variants, const uint8_t* run_bytes, size_t n_run_bytes,
+                          const twkb_run_desc* desc, const twkb_variant* meta) {
+    if (!c) return TWKB_EINVAL;
+    return guarded_ctx(c, [&] { return load_runs_sliced(static_cast<Context*>(c), n_samples, n_variants, run_bytes, n_run_bytes, desc, meta); });
 }
 
 int twkb_debug_rows(void* c, uint64_t* data_bits, uint64_t* mask_bits, size_t row_stride_words) {

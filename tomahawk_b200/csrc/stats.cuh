@@ -10,9 +10,11 @@
 // All phased arithmetic uses the round-to-nearest intrinsics (__dmul_rn, ...)
 // so no multiply-add is ever contracted: the reference runs on x86-64 SSE2
 // doubles without FMA, and with the same operation order the device results
-// are bit-identical. Fisher's log-factorials come from a host-built table of
-// glibc lgamma(n+1) (bit-identical to the reference's lgamma calls); only
-// exp() (<= 1 ulp) differs.
+// are bit-identical. Fisher's P is NOT computed in the reference's operation order
+// (see fisher_tail): its log-factorials come from a host-built table of glibc
+// lgamma(n+1) (bit-identical to the reference's lgamma calls), the closed-form
+// points use CUDA's exp() (<= 1 ulp from glibc's) and the recurrence between them is
+// evaluated division-free; P agrees with the reference to ~1e-14 relative (tests: 1e-9).
 #pragma once
 #include "common.cuh"
 
@@ -39,35 +41,107 @@ __device__ __forceinline__ double log_binom(const LgTable& t, int n, int k) {
     return dsub(dsub(t.at(n), t.at(k)), t.at(n - k));
 }
 // :195-198
-__device__ __forceinline__ double hyper_pmf(const LgTable& t, int n11, int n1_, int n_1, int n) {
+__device__ __noinline__ double hyper_pmf(const LgTable& t, int n11, int n1_, int n_1, int n) {
     return exp(dsub(dadd(log_binom(t, n1_, n11), log_binom(t, n - n1_, n_1 - n11)), log_binom(t, n, n_1)));
 }
 
-struct HyperState {
-    int n11, n1_, n_1, n;
-    double p;
-};
-// :206-229 with (n1_, n_1, n) == 0: only n11 moves
-__device__ __forceinline__ double hyper_move(const LgTable& t, int n11, HyperState& st) {
-    if ((n11 % 11) && (n11 + st.n - st.n1_ - st.n_1)) {
-        if (n11 == st.n11 + 1) {
-            double f = ddiv(dmul(ddiv((double)(st.n1_ - st.n11), (double)n11), (double)(st.n_1 - st.n11)),
-                            (double)(n11 + st.n - st.n1_ - st.n_1));
-            st.p = dmul(st.p, f);
-            st.n11 = n11;
-            return st.p;
-        }
-        if (n11 == st.n11 - 1) {
-            double f = ddiv(dmul(ddiv((double)st.n11, (double)(st.n1_ - n11)), (double)(st.n11 + st.n - st.n1_ - st.n_1)),
-                            (double)(st.n_1 - n11));
-            st.p = dmul(st.p, f);
-            st.n11 = n11;
-            return st.p;
-        }
+// One tail of kt_fisher_exact's walk (fisher_math.cpp:240-256), DIR = +1 from the lower end of the support,
+// DIR = -1 from the upper end: starting with p = pmf(cur), add p to `sum` and move one table further while
+// p < qlo and the next table exists; on return p is the first probability that stopped the walk.
+//
+// The reference moves by the recurrence of hypergeo_acc (:211-227)
+//     p(k+1) = p(k) * ((n1. - k) / (k + 1) * (n.1 - k)) / (k + 1 + d),      d = n - n1. - n.1
+// (mirrored downwards) and re-evaluates the closed form at every k that is a multiple of 11 (or where the
+// fourth cell is 0). Between two such points there are at most 10 recurrence steps. Here such a run is done
+// without a single division inside: with n_j, d_j the integer numerator / denominator of step j (products of
+// two counts, exact in a double for n < 2^26),
+//     A_j = n_1 ... n_j,  B_j = d_1 ... d_j,  p_j = p A_j / B_j,  p_0 + ... + p_(j-1) = p W_j / B_(j-1),
+//     W_(j+1) = W_j d_j + A_j   (W_0 = 0, d_0 = 1)
+// so a step costs 2 integer-valued products, 3 multiplications and one FMA; the stop rule p_j < qlo is
+// tested as p A_j < qlo B_j; the run ends with two divisions. Every p_j agrees with the reference's to a few
+// ulp (its own three roundings per step are replaced by ~3 per step of the same size), far inside the 1e-9
+// the tests hold P to, and the 10 steps are straight-line code: the previous one-step-at-a-time loop with its
+// two correctly rounded divisions per step left the kernel stalled on instruction fetch (ncu, C1: "no
+// instruction" 8.3 warps per issue, fp64 pipe 9 % busy; profiles/round2_ncu_stats_c1_before.csv).
+// A run that starts from a DENORMAL probability, in the reference's own operation order (hypergeo_acc,
+// fisher_math.cpp:213-225): there every product is rounded to the denormal grid, and when the ratios are large
+// (far tails of strongly associated pairs) that rounding is carried up into terms that matter at the 1e-9
+// level of a P ~ 1e-288. Rare, so it lives out of line to keep the hot loop small.
+template <int DIR>
+__device__ __noinline__ int fisher_run_denormal(int cur, double& p, int steps, const double qlo, const int n1_, const int n_1, const int n,
+                                               double& sum) {
+    const int d = n - n1_ - n_1;
+    int m = 0;
+    for (; m < steps && p < qlo; ++m) {
+        sum = dadd(sum, p);
+        const int c = cur + DIR * m, x = c + DIR;
+        const double f = DIR > 0 ? ddiv(dmul(ddiv((double)(n1_ - c), (double)x), (double)(n_1 - c)), (double)(x + d))
+                                 : ddiv(dmul(ddiv((double)c, (double)(n1_ - x)), (double)(c + d)), (double)(n_1 - x));
+        p = dmul(p, f);
     }
-    st.n11 = n11;
-    st.p = hyper_pmf(t, st.n11, st.n1_, st.n_1, st.n);
-    return st.p;
+    return m;
+}
+
+template <int DIR>
+__device__ __forceinline__ void fisher_tail(const LgTable& t, int& cur, double& p, const int lim, const double qlo, const int n1_,
+                                            const int n_1, const int n, double& sum) {
+    const int d = n - n1_ - n_1;
+    for (;;) {
+        const int nxt = cur + DIR;
+        if (!(p < qlo) || (DIR > 0 ? nxt > lim : nxt < lim)) return;
+        // recurrence steps before the next closed-form point (a multiple of 11, or the table whose fourth cell is 0)
+        int steps;
+        if (DIR > 0) {
+            const int r = nxt % 11;
+            steps = r ? 11 - r : 0;
+            steps = min(steps, lim - nxt + 1);
+        } else {
+            steps = nxt % 11;
+            const int z = nxt + d;
+            if (z >= 0 && z < steps) steps = z;
+            steps = min(steps, nxt - lim + 1);
+        }
+        if (steps > 0 && p > 0.0 && p < 2.2250738585072014e-308) {
+            const int m = fisher_run_denormal<DIR>(cur, p, steps, qlo, n1_, n_1, n, sum);
+            cur += DIR * m;
+            if (m < steps) return;
+            continue;
+        }
+        if (steps > 0) {
+            double A = 1.0, B = 1.0, Bprev = 1.0, W = 0.0, dlast = 1.0;
+            int m = 0;
+            // factors of the step from table c: up   n = (n1. - c)(n.1 - c),  den = (c + 1)(c + 1 + d)
+            //                                   down n = c (c + d),           den = (n1. - c + 1)(n.1 - c + 1)
+            double fa = DIR > 0 ? (double)(n1_ - cur) : (double)cur;
+            double fb = DIR > 0 ? (double)(n_1 - cur) : (double)(cur + d);
+            double fc = DIR > 0 ? (double)(cur + 1) : (double)(n1_ - cur + 1);
+            double fd = DIR > 0 ? (double)(cur + 1 + d) : (double)(n_1 - cur + 1);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                if (k < steps && p * A < qlo * B) {  // p_k < qlo: p_k joins the sum and the walk moves on
+                    const double nk = fa * fb, dk = fc * fd;
+                    W = fma(W, dlast, A);
+                    A *= nk;
+                    Bprev = B;
+                    B *= dk;
+                    dlast = dk;
+                    fa -= 1.0; fb -= 1.0; fc += 1.0; fd += 1.0;
+                    ++m;
+                }
+            }
+            if (m > 0) {
+                sum += p * (W / Bprev);
+                p = p * (A / B);
+                cur += DIR * m;
+            }
+            if (m < steps) return;  // stopped inside the run: p >= qlo
+            continue;               // re-test the stop rule, then the closed-form point
+        }
+        // closed-form point (fisher_math.cpp:211, :226-228)
+        sum += p;
+        p = hyper_pmf(t, nxt, n1_, n_1, n);
+        cur = nxt;
+    }
 }
 
 // :231-267, two-sided P only.
@@ -76,32 +150,28 @@ __device__ __forceinline__ double hyper_move(const LgTable& t, int n11, HyperSta
 // probability reaches that of the observed table (q): ~min(n1_, n_1) steps, almost all of them
 // over terms that are hundreds of orders of magnitude below q. Its recurrence is re-seeded from
 // the closed form at every n11 that is a multiple of 11 (:211), so a walk may START at any such
-// point and every later term is bit-identical to the reference's. Here each tail starts at the
-// multiple of 11 closest to the mode whose probability is still below FISHER_SKIP * q (found by
-// bisection on the closed form; the pmf is monotone on either side of the mode): the skipped terms
-// sum to < 2^20 * 1e-18 * q = 1e-12 * q even at 1 M haplotypes, three orders of magnitude inside the
-// 1e-9 agreement the tests hold P to (P >= ~q), and the walk shrinks from the support to ~18 standard
-// deviations.
+// point. Here each tail starts at the multiple of 11 closest to the mode whose probability is still
+// below FISHER_SKIP * q (found by bisection on the closed form; the pmf is monotone on either side of
+// the mode): the skipped terms sum to < 2^20 * 1e-18 * q = 1e-12 * q even at 1 M haplotypes, three
+// orders of magnitude inside the 1e-9 agreement the tests hold P to (P >= ~q), and the walk shrinks
+// from the support to ~18 standard deviations.
 constexpr double FISHER_SKIP = 1e-18;
 constexpr int FISHER_SKIP_MIN_RANGE = 48;  // shorter supports are walked whole
 
 __device__ double fisher_two_sided(const LgTable& t, int n11, int n12, int n21, int n22) {
-    int n1_ = n11 + n12, n_1 = n11 + n21, n = n11 + n12 + n21 + n22;
-    int max = (n_1 < n1_) ? n_1 : n1_;
+    const int n1_ = n11 + n12, n_1 = n11 + n21, n = n11 + n12 + n21 + n22;
+    const int max = (n_1 < n1_) ? n_1 : n1_;
     int min = n1_ + n_1 - n;
     if (min < 0) min = 0;
     if (min == max) return 1.0;
-    HyperState st;
-    st.n11 = n11; st.n1_ = n1_; st.n_1 = n_1; st.n = n;
-    st.p = hyper_pmf(t, n11, n1_, n_1, n);
-    const double q = st.p;
+    const double q = hyper_pmf(t, n11, n1_, n_1, n);
     const double qlo = dmul(0.99999999, q), qhi = dmul(1.00000001, q);
     const bool may_skip = max - min > FISHER_SKIP_MIN_RANGE;
     const double cut = FISHER_SKIP * q;
     const int mode = (int)(((long long)(n1_ + 1) * (long long)(n_1 + 1)) / ((long long)n + 2));
-    double p = hyper_move(t, min, st);
-    double left = 0.0;
-    int i = min + 1;
+    // ---- left tail: from min upwards
+    double p = hyper_pmf(t, min, n1_, n_1, n);
+    int cur = min;
     if (may_skip && p < cut) {
         // largest multiple of 11 in (min, mode] whose probability is below the cut
         int lo = min / 11 + 1, hi = mode / 11, best = -1;
@@ -112,21 +182,14 @@ __device__ double fisher_two_sided(const LgTable& t, int n11, int n12, int n21, 
             if (pm < cut) { best = mid; best_p = pm; lo = mid + 1; }
             else hi = mid - 1;
         }
-        if (best >= 0) {
-            st.n11 = 11 * best;
-            st.p = best_p;
-            p = best_p;
-            i = 11 * best + 1;
-        }
+        if (best >= 0) { cur = 11 * best; p = best_p; }
     }
-    for (; p < qlo && i <= max; ++i) {
-        left = dadd(left, p);
-        p = hyper_move(t, i, st);
-    }
-    if (p < qhi) left = dadd(left, p);
-    p = hyper_move(t, max, st);
-    double right = 0.0;
-    int j = max - 1;
+    double left = 0.0;
+    fisher_tail<1>(t, cur, p, max, qlo, n1_, n_1, n, left);
+    if (p < qhi) left += p;
+    // ---- right tail: from max downwards
+    p = hyper_pmf(t, max, n1_, n_1, n);
+    cur = max;
     if (may_skip && p < cut) {
         // smallest multiple of 11 in (mode, max) whose probability is below the cut
         int lo = mode / 11 + 1, hi = (max - 1) / 11, best = -1;
@@ -137,19 +200,12 @@ __device__ double fisher_two_sided(const LgTable& t, int n11, int n12, int n21, 
             if (pm < cut) { best = mid; best_p = pm; hi = mid - 1; }
             else lo = mid + 1;
         }
-        if (best >= 0) {
-            st.n11 = 11 * best;
-            st.p = best_p;
-            p = best_p;
-            j = 11 * best - 1;
-        }
+        if (best >= 0) { cur = 11 * best; p = best_p; }
     }
-    for (; p < qlo && j >= 0; --j) {
-        right = dadd(right, p);
-        p = hyper_move(t, j, st);
-    }
-    if (p < qhi) right = dadd(right, p);
-    double two = dadd(left, right);
+    double right = 0.0;
+    fisher_tail<-1>(t, cur, p, 0, qlo, n1_, n_1, n, right);
+    if (p < qhi) right += p;
+    double two = left + right;
     if (two > 1.0) two = 1.0;
     return two;
 }
