@@ -1,21 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the B200 `tomahawk calc` path (variant-pairs/s).
 
-A "step" is one complete pass of the LD hot path over the synthetic genotype
-matrix: count kernel (+ fused R2 screen/compaction) and statistics kernel for
-every pair of this rank's share of the tile grid.
+A "step" is one complete pass of the LD hot path over the synthetic genotype matrix: count kernel (+ fused R2
+screen / compaction) and statistics kernel for every pair of this rank's share of the tile grid.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--variants M] [--samples S] [--min-r2 R] [--kernel auto|popc|umma]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--variants M] [--samples S]
+                  [--min-r2 R] [--kernel auto|popc|umma|fp4] [--unphased] [--missing F] [--no-extra]
 
-Workload at N=1: BASELINE.json configs[1] -- phased all-pairs, 2,504 samples
-(5,008 haplotypes) x 200,000 SNVs, R2 >= 0.1. For N>1 (weak scaling, launched by
-torchrun, one rank per GPU) the variant count grows as M*sqrt(N) so that every
-GPU keeps the pair count of the N=1 run; rank 0 generates the matrix, it is
-broadcast once over NCCL and each rank computes an interleaved share of the
-tile grid with no further collectives.
+Primary workload. N = 1: BASELINE.json configs[1] -- phased all-pairs, 2,504 samples (5,008 haplotypes) x
+200,000 SNVs, R2 >= 0.1. N > 1 (torchrun, one rank per GPU): weak scaling, M = 200,000 * sqrt(N) variants so
+every GPU keeps the N = 1 pair count. The ranks form an NCCL communicator INSIDE libtwkb (twkb_comm_init);
+every load sends 1/N of the rows over the rank's own PCIe link and completes the matrix with NCCL broadcasts
+over NVLink (twkb_load_matrix_sliced); tiles are then computed with no further collective.
 
-One JSON line is printed by rank 0 (see README / DESIGN.md for every key).
+Secondary workloads in `extra_configs` of the same JSON line (each with its own value / e2e / roofline):
+  N = 1: configs[0] (R2 >= 0: every pair goes through Fisher) and configs[2] (unphased, 5 % missing);
+  N > 1: configs[3] (1,000,000 haplotypes x 100,000 SNVs) strong-scaled over the N GPUs, generated on the device.
+
+One JSON line is printed by rank 0 (README / DESIGN.md section 7 describe every key).
 """
 from __future__ import annotations
 
@@ -39,10 +41,8 @@ METRIC = "variant-pairs/s"
 UNIT = "pairs/s"
 BASE_SAMPLES = 2504
 BASE_VARIANTS = 200_000
-REF_SAMPLE_VARIANTS = 30_000  # bounded CPU sample of the same workload (first M' variants)
-# dram__bytes_read.sum + dram__bytes_write.sum of one count_umma3_kernel<e2m1> launch at the full C2 size
-# (profiles/round1_ncu_c2_fp4_full_v2.csv: 20.256 GB + 0.049 GB; the operand is 0.51 GB, re-read from L2 misses)
-TRAFFIC_C2_FP4 = 20.255835e9 + 48.632064e6
+REF_SAMPLE_VARIANTS = 30_000  # bounded CPU sample of the same workload: its FIRST M' variants
+NOMINAL_TFLOPS = {"fp4": 9000.0, "i8": 4500.0}  # dense tcgen05 rates, B200_PROFILING.md (bf16 2250 x 4 / x 2)
 
 
 def parse_args():
@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--unphased", action="store_true", help="-u: 3x3 genotype tables (BASELINE configs[2] with --missing 0.05)")
     ap.add_argument("--missing", type=float, default=0.0, help="per-genotype missing rate of the synthetic data")
     ap.add_argument("--no-mma-ceiling", action="store_true", help="skip the MMA-only ceiling pass of the roofline block")
+    ap.add_argument("--no-extra", action="store_true", help="primary workload only (no extra_configs, no peak probes)")
+    ap.add_argument("--biobank-variants", type=int, default=100_000, help="SNVs of the configs[3] run at N > 1")
     return ap.parse_args()
 
 
@@ -86,7 +88,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -100,7 +102,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -125,51 +127,97 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# --------------------------------------------------------------------- synthetic workload (numpy, N = 1 and the reference arm)
+def primary_synth(args, n_variants):
+    """The N = 1 workload and, through its first rows, the reference arm's bounded sample: ONE draw."""
+    from tomahawk_b200 import synth
+
+    return synth.synth_genotypes(args.samples, n_variants, seed=args.seed, missing_rate=args.missing)
+
+
+def head_of(s, n):
+    from tomahawk_b200 import synth
+
+    return synth.Synth(alleles=s.alleles[:n], pos=s.pos[:n], rid=s.rid[:n], n_samples=s.n_samples)
+
+
 # --------------------------------------------------------------------- reference arm
-def reference_run(args, n_variants, steps, warmup, as_baseline=False):
-    """Times the reference's own `tomahawk calc` (oracle/_ref/tomahawk_calc, built
-    from /root/reference by oracle/build_ref.sh) on this host's cores, on the first
-    n_variants variants of the same synthetic workload. The only place bench.py
-    executes anything under oracle/."""
+def reference_run(sub, flags, steps, warmup, what, keep_two=False):
+    """Times the reference's own `tomahawk calc` (oracle/_ref/tomahawk_calc, built from /root/reference by
+    oracle/build_ref.sh) on this host's cores on the synthetic genotypes `sub`. One of the two places bench.py
+    executes anything under oracle/ (the other is the parity comparison of the very records this run wrote).
+    Returns (info dict, records or None)."""
     from oracle import ldcore as lc
     from oracle import twk_format as tf
 
     cores = os.cpu_count() or 1
-    s = tf.synth_genotypes(args.samples, n_variants, seed=args.seed, missing_rate=args.missing)
-    mode_flag = "-u" if args.unphased else "-p"
+    n_variants = sub.n_variants
     tmp = tempfile.mkdtemp(prefix="twkb_ref_")
     twk = os.path.join(tmp, "ref.twk")
-    tf.write_twk(twk, s)
+    tf.write_twk(twk, sub)
     pairs = n_variants * (n_variants - 1) // 2
-    sample = f"first {n_variants} of the workload's variants ({pairs} pairs), same N, {mode_flag} -r {args.min_r2} -t {cores}"
+    sample = f"{what} ({pairs} pairs), same N, {' '.join(flags)} -t {cores}"
+    recs = None
     if lc.have_reference():
         kind = "reference"
         rates, times = [], []
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            info = lc.run_reference_calc(twk, os.path.join(tmp, "ref_out"), [mode_flag, "-r", str(args.min_r2)], threads=cores)
+            info = lc.run_reference_calc(twk, os.path.join(tmp, "ref_out"), list(flags), threads=cores)
             dt = time.perf_counter() - t0
             if it >= warmup:
                 rates.append(info.get("pairs_per_s", pairs / dt))
                 times.append(dt)
-            if as_baseline:
-                break
-        if as_baseline and not rates:
-            rates.append(info.get("pairs_per_s", pairs / dt)); times.append(dt)
         value = float(np.mean(rates))
         ms = float(np.mean(times)) * 1e3
+        if keep_two:
+            recs = tf.read_two(os.path.join(tmp, "ref_out.two"))
     else:
         kind = "port"
         cores = 1
-        prm = lc.default_params(minR2=args.min_r2, **({"forced_unphased": 1} if args.unphased else {"force_phased": 1}))
+        prm_kw = {"minR2": float(flags[flags.index("-r") + 1])} if "-r" in flags else {}
+        prm_kw.update({"forced_unphased": 1} if "-u" in flags else {"force_phased": 1})
         t0 = time.perf_counter()
-        lc.calc(s, prm, cap=max(1 << 20, pairs // 4))
+        got, _ = lc.calc(sub, lc.default_params(**prm_kw), cap=max(1 << 20, pairs // 4))
         dt = time.perf_counter() - t0
         value, ms = pairs / dt, dt * 1e3
+        if keep_two:
+            recs = got
     for fn in os.listdir(tmp):
         os.unlink(os.path.join(tmp, fn))
     os.rmdir(tmp)
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "ms": ms, "pairs": pairs}
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "ms": ms, "pairs": pairs}, recs
+
+
+def parity_block(ref_recs, gpu_recs, unphased):
+    """The reference's records against the GPU's on the same variants: identical key sets; counts, flags, D, D', R, R2 and
+    chi-squared bit-equal for phased math; P relative. (tests/ hold the full bars; this is the in-bench statement.)"""
+    from oracle import twk_format as tf
+
+    ref = tf.canonical(ref_recs, forward_only=True)
+    got = tf.canonical(gpu_recs, forward_only=True)
+
+    def keys(r):
+        return set(zip(r["ridA"].tolist(), (r["packA"] >> 2).tolist(), r["ridB"].tolist(), (r["packB"] >> 2).tolist()))
+
+    sa, sb = keys(ref), keys(got)
+    out = {"checked": True, "n_ref": int(len(ref)), "n_gpu": int(len(got)), "only_ref": len(sa - sb), "only_gpu": len(sb - sa)}
+    if out["only_ref"] == 0 and out["only_gpu"] == 0 and len(ref) == len(got):
+        phased = (ref["controller"] & 1) == 1
+        fields = ("controller", "cnt", "D", "Dprime", "R", "R2", "ChiSqFisher")
+        out["bit_equal_fields"] = [f for f in fields if np.array_equal(got[f][phased], ref[f][phased])]
+        out["fields_checked"] = list(fields)
+        out["records_phased_math"] = int(phased.sum())
+        big = ref["P"] > 1e-290
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rel = np.abs(got["P"][big] - ref["P"][big]) / ref["P"][big]
+        out["max_rel_P"] = float(rel.max()) if rel.size else 0.0
+        out["P_underflow_both_tiny"] = bool(np.all(got["P"][~big] <= 1e-289))
+        if unphased and (~phased).any():
+            u = ~phased
+            with np.errstate(divide="ignore", invalid="ignore"):
+                out["max_rel_R2_cubic"] = float(np.max(np.abs(got["R2"][u] - ref["R2"][u]) / np.maximum(ref["R2"][u], 1e-300)))
+    return out
 
 
 _REAL_STDOUT = None
@@ -195,6 +243,120 @@ def emit_json(line):
         os.write(_REAL_STDOUT, data)
 
 
+def flop_per_pair(n_samples, unphased, missing):
+    """GEMM view of SURVEY.md 8d: 2N bit-MACs per phased pair (x4 masked counts with missing data); 4 / 9 plane
+    products over N samples for unphased tables."""
+    if unphased:
+        return 2.0 * (9 if missing else 4) * n_samples
+    return 2.0 * 2 * n_samples * (4 if missing else 1)
+
+
+class Bench:
+    """One workload on one rank: resident steps, end-to-end steps."""
+
+    def __init__(self, torch, tb, dist, rank, world, local_rank, flush):
+        self.torch, self.tb, self.dist = torch, tb, dist
+        self.rank, self.world, self.local_rank, self.flush = rank, world, local_rank, flush
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allreduce(self, vals, op):
+        if self.dist is None:
+            return list(vals)
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(x) for x in t]
+
+    def resident(self, eng, steps, warmup):
+        torch = self.torch
+
+        def one():
+            self.flush.zero_()  # L2 flush between iterations (256 MiB > 126 MB L2)
+            torch.cuda.synchronize()
+            eng.compute_resident()
+            return eng.stats()
+
+        for _ in range(warmup):
+            one()
+        self.barrier()
+        t0 = time.perf_counter()
+        acc = {"dev": [], "cnt": [], "sts": [], "sp": [], "launches": 0, "cnt_launches": 0}
+        st = None
+        for _ in range(steps):
+            st = one()
+            acc["dev"].append(st.ms_device_total); acc["cnt"].append(st.ms_count_kernel); acc["sts"].append(st.ms_stats_kernel)
+            acc["sp"].append(st.ms_sparse_kernel)
+            acc["launches"] += st.count_launches + st.stats_launches + st.other_launches + st.sparse_launches
+            acc["cnt_launches"] += st.count_launches
+        self.barrier()
+        acc["wall"] = time.perf_counter() - t0
+        step_ms = float(np.mean(acc["dev"]))
+        step_ms_max, = self.allreduce([step_ms], "MAX")
+        pairs_total, = self.allreduce([float(st.pairs_visited)], "SUM")
+        acc.update(st=st, step_ms=step_ms_max, pairs_total=pairs_total, pairs_rank=float(st.pairs_visited),
+                   value=pairs_total / (step_ms_max * 1e-3))
+        return acc
+
+    def e2e(self, eng, load_fn, reps):
+        """host buffers -> C-ABI -> records back on the host; copies inside the timed region."""
+        torch = self.torch
+        ms, parts, s2 = [], None, None
+        for it in range(1 + reps):
+            self.flush.zero_()
+            self.barrier()
+            t1 = time.perf_counter()
+            load_fn()                                # H2D from pinned memory (+ NCCL exchange at N > 1) + device layout
+            t_load = time.perf_counter() - t1
+            eng.compute_discard()                    # compute + D2H of every record into pinned staging
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t1
+            s2 = eng.stats()
+            if it > 0:
+                ms.append(dt * 1e3)
+                parts = {"load_wall_ms": t_load * 1e3, "load_device_ms": s2.ms_h2d, "compute_wall_ms": (dt - t_load) * 1e3,
+                         "compute_device_ms": s2.ms_device_total}
+        e2e_ms, = self.allreduce([float(np.mean(ms))], "MAX")
+        h2d, d2h, recs = self.allreduce([float(s2.bytes_h2d), float(s2.bytes_d2h), float(s2.records_out)], "SUM")
+        return {"ms": e2e_ms, "parts": parts, "h2d": int(h2d), "d2h": int(d2h), "records": int(recs),
+                "launches": int(s2.count_launches + s2.stats_launches + s2.other_launches + s2.sparse_launches)}
+
+
+def tensor_roofline(tb, acc, n_samples, unphased, missing, peaks, peak_src, fp4_measured, mma_only=None, traffic=None):
+    st = acc["st"]
+    fp4 = st.kernel_used == tb.KERNEL_UMMA_FP4
+    fpp = flop_per_pair(n_samples, unphased, missing)
+    n_launch = max(acc["cnt_launches"], 1)
+    avg_launch_s = (sum(acc["cnt"]) / n_launch) * 1e-3
+    pairs_per_launch = acc["pairs_rank"] * len(acc["dev"]) / n_launch
+    if st.sparse_variants:
+        # the list kernel served the pairs with a rare member: credit the tensor kernel with the MACs it issued for the
+        # dense x dense triangle (tile padding included -- the only figure available without the dense pair count)
+        achieved = 2.0 * (st.mma_macs / max(1, st.count_launches)) / avg_launch_s / 1e12
+        note_pairs = "dense x dense tiles only (MACs issued, tile padding included); pairs with a rare member run on the list kernel"
+    else:
+        achieved = pairs_per_launch * fpp / avg_launch_s / 1e12
+        note_pairs = f"algorithmic work = pairs x {fpp:g} flop (SURVEY 8d; K padding and tile edges are not counted)"
+    peak = NOMINAL_TFLOPS["fp4" if fp4 else "i8"]
+    ratio = 4.0 if fp4 else 2.0
+    out = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+           "kernel": "count_umma3_kernel<%s,%s>" % ("e2m1" if fp4 else "int8", "planes" if (unphased or missing) else "1 plane"),
+           "peak_source": f"nominal dense {'e2m1 (kind::mxf4)' if fp4 else 'int8 (kind::i8)'} tcgen05 rate; MEASURED_PEAKS.json ({peak_src}) has bf16 only",
+           "frac_of_scaled_measured_bf16": achieved / (ratio * peaks["bf16_tflops_sustained"]),
+           "scaled_measured_bf16_peak": ratio * peaks["bf16_tflops_sustained"],
+           "ms_per_launch": avg_launch_s * 1e3, "note": note_pairs}
+    if fp4 and fp4_measured:
+        out["measured_fp4_gemm_tflops"] = fp4_measured
+        out["frac_of_measured_fp4_gemm_sustained"] = achieved / fp4_measured["sustained"]
+    if mma_only:
+        out["mma_only_ceiling"] = mma_only
+        out["frac_of_mma_only_ceiling"] = achieved / mma_only
+    return out
+
+
 def main():
     args = parse_args()
     claim_stdout()
@@ -203,16 +365,19 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_gpus = max(args.gpus, 1)
 
+    mode_flag = "-u" if args.unphased else "-p"
     mode_name = "-u (unphased 3x3)" if args.unphased else "-p"
     miss_name = f", {100 * args.missing:g}% missing genotypes" if args.missing > 0 else ""
     workload = (f"tomahawk calc {mode_name} all-pairs, synthetic {args.samples} samples ({2 * args.samples} haplotypes) x "
                 f"{args.variants} SNVs{miss_name}, R2>={args.min_r2}")
+    ref_flags = [mode_flag, "-r", str(args.min_r2)]
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         nv = min(args.ref_variants, args.variants)
-        r = reference_run(args, nv, args.steps, args.warmup)
+        s = primary_synth(args, args.variants)
+        r, _ = reference_run(head_of(s, nv), ref_flags, args.steps, args.warmup, f"first {nv} of the workload's {args.variants} variants")
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n_gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
@@ -227,251 +392,370 @@ def main():
 
     import torch
     import tomahawk_b200 as tb
-    from tomahawk_b200 import synth
+    from tomahawk_b200 import synth, tools
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: tomahawk_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dist = None
+    uid = None
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        box = [tb.comm_unique_id() if rank == 0 else None]      # torch.distributed only carries the 128-byte id
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    B = Bench(torch, tb, dist, rank, world, local_rank, flush)
+    peaks, peak_src = measured_peaks()
+    kernel = {"auto": tb.KERNEL_AUTO, "popc": tb.KERNEL_POPC, "umma": tb.KERNEL_UMMA, "i8": tb.KERNEL_UMMA,
+              "fp4": tb.KERNEL_UMMA_FP4}[args.kernel]
 
     # ---- workload: weak scaling keeps pairs per GPU constant => M grows with sqrt(N)
     n_variants = int(round(args.variants * math.sqrt(world)))
     n_samples = args.samples
     stride = synth.words_per_variant(n_samples)
     t_gen0 = time.perf_counter()
-    if rank == 0:
-        s = synth.synth_genotypes(n_samples, n_variants, seed=args.seed, missing_rate=args.missing)
-        data, mask = synth.pack_bits(s)
-        meta = synth.variant_meta(s)
-        del s
+    s_full = None
+    if world == 1:
+        # numpy generator: the very draw whose first rows the reference arm (and the parity block) use
+        s_full = primary_synth(args, n_variants)
+        data, mask = synth.pack_bits(s_full)
+        meta = synth.variant_meta(s_full)
+        host = torch.from_numpy(data.view(np.int64)).pin_memory()
+        host_mask = torch.from_numpy(mask.view(np.int64)).pin_memory() if mask is not None else None
+        del data, mask
+        data_name = "synthetic (numpy generator, seed %d)" % args.seed
     else:
-        data = np.zeros((n_variants, stride), dtype=np.uint64)
-        mask = np.zeros((n_variants, stride), dtype=np.uint64) if args.missing > 0 else None
-        meta = np.zeros(n_variants, dtype=synth.VARIANT_DTYPE)
+        # device generator: the stream is keyed on the global variant index, so every rank produces the same
+        # matrix without a broadcast; a rank keeps ONLY its slice of the rows in (pinned) host memory
+        d_full, m_full, meta = tools.synth_device(n_samples, n_variants, seed=args.seed, missing_rate=args.missing)
+        b_row, e_row = tb.comm_slice(n_variants, rank, world)
+        host = torch.empty((e_row - b_row, stride), dtype=torch.int64).pin_memory()
+        host.copy_(d_full[b_row:e_row])
+        host_mask = None
+        if m_full is not None:
+            host_mask = torch.empty((e_row - b_row, stride), dtype=torch.int64).pin_memory()
+            host_mask.copy_(m_full[b_row:e_row])
+        del d_full, m_full
+        torch.cuda.empty_cache()
+        data_name = "synthetic (device generator libtwkb_tools, seed %d)" % args.seed
     t_gen = time.perf_counter() - t_gen0
+    host_np = host.numpy().view(np.uint64)
+    host_mask_np = host_mask.numpy().view(np.uint64) if host_mask is not None else None
 
-    kernel = {"auto": tb.KERNEL_AUTO, "popc": tb.KERNEL_POPC, "umma": tb.KERNEL_UMMA, "i8": tb.KERNEL_UMMA,
-              "fp4": tb.KERNEL_UMMA_FP4}[args.kernel]
     eng = tb.Engine(force_phased=0 if args.unphased else 1, forced_unphased=1 if args.unphased else 0, minR2=args.min_r2,
                     kernel=kernel, device=local_rank, part_index=rank, part_count=world)
-    # host copy in pinned memory (the e2e leg copies from here every step)
-    host = torch.from_numpy(data.view(np.int64)).pin_memory()
-    host_mask = torch.from_numpy(mask.view(np.int64)).pin_memory() if mask is not None else None
     if world > 1:
-        # ONE broadcast of the packed matrix (+ metadata) over NCCL/NVLink, then no collectives
-        dev = host.cuda(non_blocking=True) if rank == 0 else torch.empty_like(host, device="cuda")
-        dist.broadcast(dev, src=0)
-        meta_t = torch.from_numpy(meta.view(np.uint8).copy()).cuda()
-        dist.broadcast(meta_t, src=0)
-        meta = meta_t.cpu().numpy().view(synth.VARIANT_DTYPE)
-        if rank != 0:
-            host.copy_(dev.cpu())
-        dev_mask = None
-        if host_mask is not None:
-            dev_mask = host_mask.cuda(non_blocking=True) if rank == 0 else torch.empty_like(host_mask, device="cuda")
-            dist.broadcast(dev_mask, src=0)
-            if rank != 0:
-                host_mask.copy_(dev_mask.cpu())
-        torch.cuda.synchronize()
-        eng.load_device(n_samples, n_variants, dev.data_ptr(), dev_mask.data_ptr() if dev_mask is not None else None, stride, meta)
-        del dev, dev_mask
-    else:
-        eng.load(n_samples, host.numpy().view(np.uint64), host_mask.numpy().view(np.uint64) if host_mask is not None else None, meta)
+        eng.comm_init(uid, rank, world)
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    def load_primary():
+        if world > 1:
+            eng.load_sliced(n_samples, n_variants, host_np, host_mask_np, meta)
+        else:
+            eng.load(n_samples, host_np, host_mask_np, meta)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step_resident():
-        flush.zero_()  # L2 flush between iterations (256 MiB > 126 MB L2)
-        torch.cuda.synchronize()
-        eng.compute_resident()
-        return eng.stats()
-
-    for _ in range(args.warmup):
-        step_resident()
-
+    load_primary()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    barrier()
-    dev_ms, cnt_ms, sts_ms, launches = [], [], [], 0
-    cnt_launches = 0
-    t0 = time.perf_counter()
-    st = None
-    for _ in range(args.steps):
-        st = step_resident()
-        dev_ms.append(st.ms_device_total)
-        cnt_ms.append(st.ms_count_kernel)
-        sts_ms.append(st.ms_stats_kernel)
-        launches += st.count_launches + st.stats_launches + st.other_launches
-        cnt_launches += st.count_launches
-    barrier()
-    wall = time.perf_counter() - t0
+    acc = B.resident(eng, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    e2e = B.e2e(eng, load_primary, max(2, min(args.steps, 3)))
+    st = acc["st"]
+    value, step_ms_max, pairs_total = acc["value"], acc["step_ms"], acc["pairs_total"]
+    e2e_value = pairs_total / (e2e["ms"] * 1e-3)
+    tensor = st.kernel_used in (tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4)
+    fp4 = st.kernel_used == tb.KERNEL_UMMA_FP4
+    H = 2 * n_samples
 
-    pairs_rank = st.pairs_visited
-    step_ms = float(np.mean(dev_ms))
-    t = torch.tensor([step_ms, float(pairs_rank)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        step_ms_max, pairs_total = float(tmax[0]), float(tsum[1])
-    else:
-        step_ms_max, pairs_total = step_ms, float(pairs_rank)
-    value = pairs_total / (step_ms_max * 1e-3)
+    # ---- measured denominators (rank 0, N = 1): cuBLASLt block-scaled e2m1 GEMM and the POPC issue rate
+    fp4_measured, popc_measured = None, None
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            b, s_ = tools.fp4_gemm_tflops(8192, 2.0)
+            fp4_measured = {"burst": b, "sustained": s_,
+                            "how": "cuBLASLt NVFP4 (e2m1, 16-element UE4M3 block scales) GEMM 8192^3, best of 10 / 2 s back to back, same run"}
+        except Exception as e:
+            sys.stderr.write(f"[bench] fp4 gemm probe unavailable: {e}\n")
+        try:
+            r_, per, mhz = tools.popc_rate()
+            popc_measured = {"popc_per_s": r_, "popc_per_clk_per_sm_at_nominal_clock": per, "nominal_sm_mhz": mhz}
+        except Exception as e:
+            sys.stderr.write(f"[bench] popc probe unavailable: {e}\n")
 
-    # ---- e2e: host buffers -> C-ABI -> records back on the host, copies inside the timed region.
-    # N > 1: every rank uploads the matrix over its own PCIe link. The alternative (rank 0 uploads, one NCCL broadcast
-    # pipelined in 8 row slices, twkb_load_matrix_device) was measured and is slower on this box: e2e 41.0 vs 39.9 ms
-    # at N = 2 and 46.8 vs 45.1 ms at N = 4 (the broadcast serialises behind rank 0's single PCIe link).
-    e2e_ms = []
-    h2d = d2h = 0
-    host_np = host.numpy().view(np.uint64)
-    host_mask_np = host_mask.numpy().view(np.uint64) if host_mask is not None else None
-    for it in range(1 + max(2, min(args.steps, 3))):
-        flush.zero_()
-        barrier()
-        t1 = time.perf_counter()
-        eng.load(n_samples, host_np, host_mask_np, meta)   # H2D from pinned memory + device transpose
-        t_load = time.perf_counter() - t1
-        eng.compute_discard()                      # compute + D2H of every record into pinned staging
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t1
-        s2 = eng.stats()
-        if it > 0:
-            e2e_ms.append(dt * 1e3)
-            e2e_parts = {"load_wall_ms": t_load * 1e3, "load_device_ms": s2.ms_h2d, "compute_wall_ms": (dt - t_load) * 1e3,
-                         "compute_device_ms": s2.ms_device_total}
-            h2d, d2h = int(s2.bytes_h2d), int(s2.bytes_d2h)
-            launches_e2e = s2.count_launches + s2.stats_launches + s2.other_launches
-    e2e_t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = pairs_total / (float(e2e_t[0]) * 1e-3)
-    records = int(s2.records_out)
+    # ---- roofline of the dominant (count) kernel
+    roofline = None
+    if rank == 0:
+        if tensor:
+            mma_only = None
+            if (world == 1 and not args.no_mma_ceiling and not args.unphased and args.missing == 0 and os.path.exists(tb.PROF_LIB_PATH)):
+                # the same launch with operand traffic and epilogue switched off, in the profiling build of the same sources
+                # (libtwkb_prof.so; the product library has no such switch): what the tcgen05 pipe delivers for this
+                # instruction stream on this board
+                os.environ["TWKB_DEBUG_FLAGS"] = "3"
+                try:
+                    peng = tb.Engine(force_phased=1, minR2=args.min_r2, kernel=kernel, device=local_rank, profiling=True)
+                    peng.load(n_samples, host_np, host_mask_np, meta)
+                    ms = []
+                    for _ in range(3):
+                        flush.zero_(); torch.cuda.synchronize()
+                        peng.compute_resident()
+                        s3 = peng.stats()
+                        ms.append(s3.ms_count_kernel / max(s3.count_launches, 1))
+                    peng.close()
+                    fpp = flop_per_pair(n_samples, args.unphased, args.missing > 0)
+                    mma_only = (acc["pairs_rank"] * len(acc["dev"]) / max(acc["cnt_launches"], 1)) * fpp / (min(ms[1:]) * 1e-3) / 1e12
+                except Exception as e:
+                    sys.stderr.write(f"[bench] MMA-only ceiling skipped: {e}\n")
+                finally:
+                    del os.environ["TWKB_DEBUG_FLAGS"]
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "round2_traffic.json")
+            if os.path.exists(tpath):  # dram bytes per launch from the committed ncu --set full capture of THIS configuration
+                key = f"{n_samples}x{n_variants}:{'u' if args.unphased else 'p'}:{args.missing:g}:{args.min_r2:g}:n{world}"
+                traffic = json.load(open(tpath)).get(key)
+            roofline = tensor_roofline(tb, acc, n_samples, args.unphased, args.missing > 0, peaks, peak_src, fp4_measured, mma_only, traffic)
+        else:
+            w = math.ceil(H / 32)
+            n_launch = max(acc["cnt_launches"], 1)
+            avg_launch_s = (sum(acc["cnt"]) / n_launch) * 1e-3
+            achieved_wops = (acc["pairs_rank"] * len(acc["dev"]) / n_launch) * w / avg_launch_s
+            smax = (clocks or {}).get("sm_max_mhz") or 1965.0
+            peak_wops = popc_measured["popc_per_s"] if popc_measured else 16 * 148 * smax * 1e6
+            roofline = {"bound": "int_pipe_popc", "achieved": achieved_wops / 1e12, "peak": peak_wops / 1e12,
+                        "unit": "Tword-op/s", "frac": achieved_wops / peak_wops, "traffic": None, "kernel": "count_popc_kernel<0>",
+                        "peak_source": "measured POPC issue rate (libtwkb_tools popc_rate_kernel)" if popc_measured else
+                                       "nominal 16 POPC/clk/SM x 148 SM x max SM clock",
+                        "note": f"INT-pipe roofline; {w} AND+POPC word-ops per pair"}
+        if popc_measured:
+            roofline["measured_popc_rate"] = popc_measured
+
+    # ---- parity: the reference's own records on the first M' variants against the GPU's on the same rows
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            nv = min(args.ref_variants, n_variants)
+            r, ref_recs = reference_run(head_of(s_full, nv), ref_flags, 1, 0, f"first {nv} of the workload's {n_variants} variants", keep_two=True)
+            cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            peng = tb.Engine(force_phased=0 if args.unphased else 1, forced_unphased=1 if args.unphased else 0, minR2=args.min_r2,
+                             kernel=kernel, device=local_rank)
+            peng.load(n_samples, host_np[:nv], host_mask_np[:nv] if host_mask_np is not None else None, meta[:nv])
+            got = peng.compute()
+            peng.close()
+            parity = parity_block(ref_recs, got, args.unphased)
+            parity["sample"] = r["sample"]
+            parity["against"] = "the reference binary's .two (oracle/_ref/tomahawk_calc)" if r["kind"] == "reference" else "the oracle port"
+        except Exception as e:  # the baseline is a reported number, never a gate
+            cpu_baseline = cpu_baseline or {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)[:200]}
+            parity = parity or {"checked": False, "why": str(e)[:200]}
+    del s_full
+
+    # ---- secondary workloads
+    extra = []
+    if not args.no_extra and not args.unphased and args.missing == 0 and args.variants == BASE_VARIANTS and args.samples == BASE_SAMPLES:
+        del host, host_np
+        if world == 1:
+            eng.close()
+            torch.cuda.empty_cache()
+            extra.append(extra_config0(args, B, tb, synth, peaks, peak_src, fp4_measured))
+            extra.append(extra_config2(args, B, tb, tools, peaks, peak_src, fp4_measured))
+        else:
+            # same context and communicator (an NCCL unique id serves ONE ncclCommInitRank): only the matrix changes
+            extra.append(extra_config3(args, B, tb, tools, eng, peaks, peak_src))
+        extra = [x for x in extra if x]
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant (count) kernel
-    peaks, peak_src = measured_peaks()
-    H = 2 * n_samples
-    avg_launch_s = (sum(cnt_ms) / max(cnt_launches, 1)) * 1e-3
-    pairs_per_launch = pairs_rank * args.steps / max(cnt_launches, 1)
-    tensor = st.kernel_used in (tb.KERNEL_UMMA, tb.KERNEL_UMMA_FP4)
-    fp4 = st.kernel_used == tb.KERNEL_UMMA_FP4
-    if tensor:
-        # GEMM view: 2N bit-MACs per visited pair = 2*2N flop. The tensor peak of the
-        # operand type is the bf16 figure scaled by the nominal dense ratio (bf16 : int8/fp8 : fp4 =
-        # 1 : 2 : 4; B200_PROFILING.md); the step is longer than a burst, so the sustained figure.
-        if args.unphased:   # 9 (missing) / 4 plane products over N samples
-            flop_per_pair = 2.0 * (9 if args.missing > 0 else 4) * n_samples
-        else:               # 2N bit-MACs, x4 masked counts with missing data
-            flop_per_pair = 2.0 * H * (4 if args.missing > 0 else 1)
-        achieved = pairs_per_launch * flop_per_pair / avg_launch_s / 1e12
-        # MEASURED_PEAKS.json holds bf16 only. The int8 / e2m1 tcgen05 kinds run at 2x / 4x the bf16 MAC
-        # rate (nominal dense 2.25 : 4.5 : 9 PFLOP/s, B200_PROFILING.md). `peak` is that nominal figure of
-        # the operand kind: ncu confirms it is the right denominator (profiles/round1_ncu_c2_fp4_full.csv:
-        # tensor pipe 79.8 % active at 0.79 of nominal). 4x the measured *sustained bf16* number
-        # underestimates the e2m1 pipe (frac would read 1.25: cuBLAS bf16 is power-capped near 1.3 GHz,
-        # this kernel holds 1.84-1.97 GHz at ~760 W); it is reported beside it for reference.
-        ratio = 4.0 if fp4 else 2.0
-        peak = 9000.0 if fp4 else 4500.0
-        c2 = (fp4 and world == 1 and n_variants == BASE_VARIANTS and n_samples == BASE_SAMPLES and not args.unphased
-              and args.missing == 0)
-        traffic = TRAFFIC_C2_FP4 if c2 else None
-        # Measured ceiling of the tensor pipe for THIS kernel's instruction stream on THIS device: the same
-        # launch with operand traffic and epilogue switched off (TWKB_DEBUG_FLAGS=3: only the first ring
-        # fill is loaded, accumulators are not drained; results are discarded). What remains is the
-        # tcgen05.mma issue rate under the board's power/clock behaviour.
-        mma_only = None
-        if not args.no_mma_ceiling and not args.unphased and args.missing == 0 and os.path.exists(tb.PROF_LIB_PATH):
-            # profiling build of the same sources (libtwkb_prof.so); the product library has no such switch
-            os.environ["TWKB_DEBUG_FLAGS"] = "3"
-            try:
-                peng = tb.Engine(force_phased=1, minR2=args.min_r2, kernel=kernel, device=local_rank, part_index=rank,
-                                 part_count=world, profiling=True)
-                peng.load(n_samples, host_np, host_mask_np, meta)
-                ms = []
-                for _ in range(3):
-                    flush.zero_(); torch.cuda.synchronize()
-                    peng.compute_resident()
-                    s3 = peng.stats()
-                    ms.append(s3.ms_count_kernel / max(s3.count_launches, 1))
-                peng.close()
-                mma_only = pairs_per_launch * flop_per_pair / (min(ms[1:]) * 1e-3) / 1e12
-            finally:
-                del os.environ["TWKB_DEBUG_FLAGS"]
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "count_umma3_kernel<%s>" % ("true" if fp4 else "false"),
-                    "peak_source": f"nominal dense {'e2m1 (kind::mxf4)' if fp4 else 'int8 (kind::i8)'} tcgen05 rate; no entry "
-                                   f"for this operand kind in MEASURED_PEAKS.json ({peak_src})",
-                    "frac_of_scaled_measured_bf16": achieved / (ratio * peaks["bf16_tflops_sustained"]),
-                    "scaled_measured_bf16_peak": ratio * peaks["bf16_tflops_sustained"],
-                    "mma_only_ceiling": mma_only, "frac_of_mma_only_ceiling": (achieved / mma_only) if mma_only else None,
-                    "note": f"algorithmic work = pairs x {flop_per_pair:g} flop (SURVEY 8d; K padding to 256 and the 256x240 tile edge "
-                            f"are not counted); traffic = dram read+write bytes of one launch from the committed ncu --set full "
-                            f"capture; mma_only_ceiling = same launch without operand loads and epilogue, measured in this run"}
-    else:
-        # LOP3+POPC kernel: INT-pipe bound. Algorithmic work = ceil(2N/32) AND+POPC word-ops per pair;
-        # peak = 16 POPC lanes/clk/SM x 148 SMs x max SM clock (to be replaced by the measured issue rate).
-        w = math.ceil(H / 32)
-        achieved_wops = pairs_per_launch * w / avg_launch_s
-        smax = (clocks or {}).get("sm_max_mhz") or 1965.0
-        peak_wops = 16 * 148 * smax * 1e6
-        # expressed in GB/s-equivalent of operand bits so the JSON keeps the contract's units
-        roofline = {"bound": "int_pipe_popc", "achieved": achieved_wops / 1e12, "peak": peak_wops / 1e12,
-                    "unit": "Tword-op/s", "frac": achieved_wops / peak_wops, "traffic": None,
-                    "kernel": "count_popc_kernel<0>",
-                    "note": "INT-pipe roofline: 16 POPC/clk/SM x 148 SM x max SM clock; 157 word-ops per pair"}
-
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ("e2m1 x e2m1 -> f32 exact (tcgen05 kind::mxf4) + f64 statistics" if fp4 else
                   "int8 x int8 -> int32 (tcgen05) + f64 statistics" if tensor else "u32 popcount + f64 statistics"),
-        "data": "synthetic",
+        "data": data_name,
         "config": {
             "workload": (f"tomahawk calc {mode_name} all-pairs, synthetic {n_samples} samples ({H} haplotypes) x {n_variants} SNVs"
                          f"{miss_name}, R2>={args.min_r2}" + (f" (weak scaling: {args.variants} x sqrt({world}) variants)" if world > 1 else "")),
-            "baseline_config": "BASELINE.json configs[2]" if args.unphased else "BASELINE.json configs[1]",
-            "pairs_per_step": pairs_total, "haplotype_cmp_per_s": value * H, "records_per_step": records,
+            "baseline_config": baseline_config_name(args),
+            "pairs_per_step": pairs_total, "haplotype_cmp_per_s": value * H, "records_per_step": e2e["records"],
             "kernel": "umma_fp4" if fp4 else "umma_i8" if tensor else "popc",
             "l2": "256 MiB device memset between steps (flush) and operands > L2",
             "seed": args.seed, "gen_seconds": round(t_gen, 2),
-            "ms_count_kernel_per_step": float(np.mean(cnt_ms)), "ms_stats_kernel_per_step": float(np.mean(sts_ms)),
-            "wall_seconds_timed_region": wall,
+            "ms_count_kernel_per_step": float(np.mean(acc["cnt"])), "ms_stats_kernel_per_step": float(np.mean(acc["sts"])),
+            "wall_seconds_timed_region": acc["wall"],
+            "multi_gpu": (f"{world} ranks, NCCL communicator inside libtwkb (twkb_comm_init); each load: own row slice over PCIe + "
+                          f"grouped ncclBroadcast exchange; tiles dealt by part_index/part_count, no collective during compute") if world > 1 else None,
         },
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": float(e2e_t[0]), "gpu_launches_per_step": int(launches_e2e), "parts_last_step": e2e_parts,
-                "path": "every rank: twkb_load_matrix from its pinned host copy -> twkb_compute with a host sink"},
-        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                "ms_per_step": e2e["ms"], "gpu_launches_per_step": e2e["launches"], "parts_last_step": e2e["parts"],
+                "path": ("every rank: twkb_load_matrix_sliced (its 1/N of the rows from pinned host memory, NCCL exchange) -> twkb_compute with a host sink"
+                         if world > 1 else "twkb_load_matrix from pinned host memory -> twkb_compute with a host sink (record drain thread)")},
+        "gpu_launches": int(acc["launches"]),
         "clocks": clocks,
         "roofline": roofline,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            r = reference_run(args, min(args.ref_variants, n_variants), 1, 0, as_baseline=True)
-            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
-        except Exception as e:  # the baseline is a reported number, never a gate
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)[:200]}
+    if cpu_baseline is not None:
+        line["cpu_baseline"] = cpu_baseline
+    if parity is not None:
+        line["parity"] = parity
+    if extra:
+        line["extra_configs"] = extra
     emit_json(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def baseline_config_name(args):
+    if args.unphased:
+        return "BASELINE.json configs[2]" if (args.samples == 10000 and args.variants == 100000) else "configs[2] shape (unphased), other size"
+    if args.samples == BASE_SAMPLES and args.variants == BASE_VARIANTS and args.min_r2 == 0.1:
+        return "BASELINE.json configs[1]"
+    if args.samples == BASE_SAMPLES and args.variants == 10000 and args.min_r2 == 0:
+        return "BASELINE.json configs[0]"
+    return "phased all-pairs, other size"
+
+
+# ------------------------------------------------------------------------------- extra_configs
+def _extra_entry(name, workload, acc, e2e, roofline, H, cpu=None, parity=None, **more):
+    out = {"baseline_config": name, "workload": workload, "value": acc["value"], "unit": UNIT, "ms_per_step": acc["step_ms"],
+           "steps": len(acc["dev"]), "pairs_per_step": acc["pairs_total"], "haplotype_cmp_per_s": acc["value"] * H,
+           "ms_count_kernel_per_step": float(np.mean(acc["cnt"])), "ms_stats_kernel_per_step": float(np.mean(acc["sts"])),
+           "ms_sparse_kernel_per_step": float(np.mean(acc["sp"])), "gpu_launches": int(acc["launches"]), "roofline": roofline}
+    if e2e is not None:
+        out["e2e"] = {"value": acc["pairs_total"] / (e2e["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e2e["ms"], "h2d_bytes_per_step": e2e["h2d"],
+                      "d2h_bytes_per_step": e2e["d2h"], "records_per_step": e2e["records"], "parts_last_step": e2e["parts"]}
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    if parity is not None:
+        out["parity"] = parity
+    out.update(more)
+    return out
+
+
+def extra_config0(args, B, tb, synth, peaks, peak_src, fp4_measured):
+    """BASELINE configs[0]: 2,504 samples x 10,000 SNVs, -p, R2 >= 0 -- every pair is a record and goes through Fisher."""
+    try:
+        torch = B.torch
+        n, m = BASE_SAMPLES, 10_000
+        s = synth.synth_genotypes(n, m, seed=args.seed)
+        data, _ = synth.pack_bits(s)
+        meta = synth.variant_meta(s)
+        host = torch.from_numpy(data.view(np.int64)).pin_memory()
+        hn = host.numpy().view(np.uint64)
+        eng = tb.Engine(force_phased=1, minR2=0.0, device=B.local_rank)
+        eng.load(n, hn, None, meta)
+        acc = B.resident(eng, 5, 3)
+        e2e = B.e2e(eng, lambda: eng.load(n, hn, None, meta), 2)
+        roof = tensor_roofline(tb, acc, n, False, False, peaks, peak_src, fp4_measured)
+        # the step is bound by the statistics kernel (Fisher for every pair) and, end to end, by PCIe
+        st_ms = float(np.mean(acc["sts"]))
+        roof["dominant_kernel"] = {"kernel": "stats_kernel<phased>", "ms_per_step": st_ms, "candidates_per_step": int(acc["st"].pairs_screened),
+                                   "ns_per_fisher_test": st_ms * 1e6 / max(1, int(acc["st"].pairs_screened)),
+                                   "note": "fp64 pipe + instruction issue; profiles/round2_ncu_stats_c1_*.csv"}
+        pcie = e2e["d2h"] / (e2e["ms"] * 1e-3) / 1e9
+        cpu = parity = None
+        if not args.no_cpu_baseline:
+            nv = 2000
+            r, ref_recs = reference_run(head_of(s, nv), ["-p", "-r", "0"], 1, 0, f"first {nv} of the workload's {m} variants", keep_two=True)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            pe = tb.Engine(force_phased=1, minR2=0.0, device=B.local_rank)
+            pe.load(n, hn[:nv], None, meta[:nv])
+            parity = parity_block(ref_recs, pe.compute(), False)
+            parity["sample"] = r["sample"]
+            pe.close()
+        eng.close()
+        return _extra_entry("BASELINE.json configs[0]", f"tomahawk calc -p all-pairs, synthetic {n} samples x {m} SNVs, R2>=0 (every pair a record)",
+                            acc, e2e, roof, 2 * n, cpu, parity, e2e_record_gbps=pcie)
+    except Exception as e:
+        return {"baseline_config": "BASELINE.json configs[0]", "error": str(e)[:300]}
+
+
+def extra_config2(args, B, tb, tools, peaks, peak_src, fp4_measured):
+    """BASELINE configs[2]: 10,000 samples x 100,000 SNVs, -u, 5 % missing genotypes (device generator: numpy needs minutes)."""
+    try:
+        torch = B.torch
+        n, m, miss = 10_000, 100_000, 0.05
+        d, mk, meta = tools.synth_device(n, m, seed=args.seed, missing_rate=miss)
+        host = torch.empty(d.shape, dtype=torch.int64).pin_memory(); host.copy_(d)
+        hostm = torch.empty(mk.shape, dtype=torch.int64).pin_memory(); hostm.copy_(mk)
+        del d, mk
+        torch.cuda.empty_cache()
+        hn, hm = host.numpy().view(np.uint64), hostm.numpy().view(np.uint64)
+        eng = tb.Engine(forced_unphased=1, minR2=0.1, device=B.local_rank)
+        eng.load(n, hn, hm, meta)
+        acc = B.resident(eng, 5, 3)
+        e2e = B.e2e(eng, lambda: eng.load(n, hn, hm, meta), 2)
+        roof = tensor_roofline(tb, acc, n, True, True, peaks, peak_src, fp4_measured)
+        cpu = parity = None
+        if not args.no_cpu_baseline:
+            from oracle import twk_format as tf
+            nv = 1000
+            al = tools.rows_to_alleles(hn[:nv], hm[:nv], n)
+            sub = tf.Synth(alleles=al, pos=meta["pos"][:nv].copy(), rid=meta["rid"][:nv].copy(), n_samples=n)
+            r, ref_recs = reference_run(sub, ["-u", "-r", "0.1"], 1, 0, f"first {nv} of the workload's {m} variants", keep_two=True)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            pe = tb.Engine(forced_unphased=1, minR2=0.1, device=B.local_rank)
+            pe.load(n, hn[:nv], hm[:nv], meta[:nv])
+            parity = parity_block(ref_recs, pe.compute(), True)
+            parity["sample"] = r["sample"]
+            parity["note"] = "unphased pass/fail flips are confined to decision boundaries (enumerated in tests/test_gpu_parity.py)"
+            pe.close()
+        eng.close()
+        return _extra_entry("BASELINE.json configs[2]", f"tomahawk calc -u all-pairs, synthetic {n} samples x {m} SNVs, 5% missing genotypes, R2>=0.1, Fisher + chi2",
+                            acc, e2e, roof, 2 * n, cpu, parity)
+    except Exception as e:
+        return {"baseline_config": "BASELINE.json configs[2]", "error": str(e)[:300]}
+
+
+def extra_config3(args, B, tb, tools, eng, peaks, peak_src):
+    """BASELINE configs[3]: 500,000 samples (1,000,000 haplotypes) x 100,000 SNVs, -p, R2 >= 0.1, STRONG-scaled over the N GPUs
+    (every GPU holds the whole 12.5 GB matrix; the tile grid is dealt to the ranks). Generated on the device."""
+    try:
+        torch = B.torch
+        n, m = 500_000, args.biobank_variants
+        rank, world = B.rank, B.world
+        stride = tools.words_per_variant(n)
+        t0 = time.perf_counter()
+        b, e = tb.comm_slice(m, rank, world)
+        # this rank's slice only: generated on the device, kept in pinned host memory (the e2e "host buffer")
+        d, _, meta_slice = tools.synth_device(n, m, seed=args.seed, first=b, n_rows=e - b)
+        host = torch.empty(d.shape, dtype=torch.int64).pin_memory(); host.copy_(d)
+        del d
+        torch.cuda.empty_cache()
+        # metadata of all variants: every rank computed its slice's allele counts; gathered through torch.distributed
+        parts = [None] * world
+        B.dist.all_gather_object(parts, meta_slice.tobytes())
+        meta = np.concatenate([np.frombuffer(p, dtype=tb.VARIANT_DTYPE) for p in parts])
+        t_gen = time.perf_counter() - t0
+        hn = host.numpy().view(np.uint64)
+        load = lambda: eng.load_sliced(n, m, hn, None, meta)
+        load()
+        acc = B.resident(eng, 2, 1)
+        e2e = B.e2e(eng, load, 1)
+        st = acc["st"]
+        roof = tensor_roofline(tb, acc, n, False, False, peaks, peak_src, None)
+        if st.sparse_variants:
+            sp_ms = float(np.mean(acc["sp"]))
+            roof["list_kernel"] = {"kernel": "count_sparse_kernel", "variants": int(st.sparse_variants), "ms_per_step": sp_ms,
+                                   "word_ops_per_step": int(st.sparse_word_ops), "bound": "hbm",
+                                   "achieved_gbs": st.sparse_word_ops * 4 / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else None,
+                                   "peak_gbs": peaks["hbm_gbs"]}
+        out = _extra_entry("BASELINE.json configs[3]",
+                           f"tomahawk calc -p all-pairs, synthetic {n} samples ({2 * n} haplotypes) x {m} SNVs, R2>=0.1, strong scaling over {world} GPUs",
+                           acc, e2e, roof, 2 * n, scaling="strong", n_gpus=world, gen_seconds=round(t_gen, 2),
+                           matrix_bytes=int(m) * stride * 8)
+        eng.close()
+        return out if rank == 0 else None
+    except Exception as e:
+        return {"baseline_config": "BASELINE.json configs[3]", "error": str(e)[:300]}
 
 
 if __name__ == "__main__":

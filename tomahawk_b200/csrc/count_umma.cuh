@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 
 #include "common.cuh"
@@ -610,7 +611,9 @@ __device__ __forceinline__ void umma_epilogue_chunk(const CountArgs& args, const
         }
         if (!__any_sync(0xffffffffu, m >= -1.0f)) return;
         if (TWKB_DBG(args, 16u)) return;  // screen-only ablation: zero registers would flag everything
-        // which pairs: the same margins once more, kept as a bit mask (rare path)
+        // which pairs: the same margins once more, kept as a bit mask (rare path). Pairs the reference skips for
+        // ac_i + ac_j <= 2 (ld_engine.cpp:1918) are dropped here: two singletons on one haplotype have R2 = 1, and real
+        // cohorts carry many of them -- they would all travel through the ring only to be rejected by the drain warp.
         uint32_t mask = 0;
 #pragma unroll
         for (int c2 = 0; c2 < 16; ++c2) {
@@ -619,13 +622,13 @@ __device__ __forceinline__ void umma_epilogue_chunk(const CountArgs& args, const
                 const float n11 = FP4 ? __uint_as_float(r[2 * c2]) : (float)r[2 * c2];
                 const float pab = row.acA * cb.x;
                 const float x = fmaf(n11, Tf, -pab);
-                mask |= (fmaf(-row.sA, cb.y, fmaf(pab, 1.0e-6f, fabsf(x))) >= -1.0f ? 1u : 0u) << (2 * c2);
+                mask |= (fmaf(-row.sA, cb.y, fmaf(pab, 1.0e-6f, fabsf(x))) >= -1.0f && row.acA + cb.x > 2.5f ? 1u : 0u) << (2 * c2);
             }
             {
                 const float n11 = FP4 ? __uint_as_float(r[2 * c2 + 1]) : (float)r[2 * c2 + 1];
                 const float pab = row.acA * cb.z;
                 const float x = fmaf(n11, Tf, -pab);
-                mask |= (fmaf(-row.sA, cb.w, fmaf(pab, 1.0e-6f, fabsf(x))) >= -1.0f ? 1u : 0u) << (2 * c2 + 1);
+                mask |= (fmaf(-row.sA, cb.w, fmaf(pab, 1.0e-6f, fabsf(x))) >= -1.0f && row.acA + cb.z > 2.5f ? 1u : 0u) << (2 * c2 + 1);
             }
         }
         if (__any_sync(0xffffffffu, mask != 0u)) {  // rare: some lane flagged a pair of this chunk
@@ -1428,17 +1431,23 @@ inline int umma_prepare_planes(UmmaOperand& op, int mode, const uint32_t* d_plan
 
 template <bool FP4, bool SCREEN, int MODE>
 inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
-    static bool configured = false;
-    static int n_sm = 0;
-    if (!configured) {
+    // function attributes and the SM count belong to a device: one process may drive several
+    // (twkb_calc -g 0,1,..., one host thread per device)
+    static std::atomic<uint64_t> configured{0};
+    static std::atomic<int> n_sm_of[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load() & bit)) {
         cudaError_t e = cudaFuncSetAttribute(count_umma3_kernel<FP4, SCREEN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Umma3Cfg<FP4>::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        configured = true;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        n_sm_of[dev & 63].store(n);
+        configured.fetch_or(bit);
     }
+    const int n_sm = n_sm_of[dev & 63].load();
     const uint32_t n_clusters = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, n_sm / 2));
     count_umma3_kernel<FP4, SCREEN, MODE><<<2 * n_clusters, UMMA3_THREADS, Umma3Cfg<FP4>::SMEM_BYTES, stream>>>(
         op.tmap, op.tmap_b, args, prm, op.Kbytes / UMMA_BLOCK_K, n_tiles);

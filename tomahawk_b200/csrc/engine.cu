@@ -4,6 +4,7 @@
 // include/twkb.h. No CPU compute path exists in this file: every count and
 // every statistic is produced by the CUDA kernels included below.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -530,12 +531,14 @@ static void build_sparse_tiles(const Context* ctx, std::vector<uint2>& tiles, ui
 
 template <int MODE>
 static cudaError_t launch_popc(Context* ctx, const CountArgs& args, const DevParams& prm, uint32_t n_tiles) {
-    static bool configured = false;
+    // function attributes belong to a device: one process may drive several (twkb_calc -g 0,1,...)
+    static std::atomic<uint64_t> configured{0};
     const size_t smem = popc_smem_bytes<MODE>();
-    if (!configured) {
+    const uint64_t bit = 1ull << (ctx->device & 63);
+    if (!(configured.load() & bit)) {
         cudaError_t e = cudaFuncSetAttribute(count_popc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.fetch_or(bit);
     }
     count_popc_kernel<MODE><<<n_tiles, POPC_THREADS, smem, ctx->stream>>>(args, prm);
     return cudaGetLastError();
@@ -793,7 +796,7 @@ static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, 
             const unsigned grid = (unsigned)((ncand + STATS_PER_BLOCK - 1) / STATS_PER_BLOCK);
             uint8_t* recs = ctx->d_records[ctx->rec_cur].p;
             unsigned long long* rec_count = ctx->d_counters.p + 1 + ctx->rec_cur;
-            static const int occ3 = [] { const char* e = getenv("TWKB_STATS_OCC"); return e ? atoi(e) : 2; }();
+            static const int occ3 = [] { const char* e = getenv("TWKB_STATS_OCC"); return e ? atoi(e) : 3; }();
             if (prm.unphased)
                 stats_kernel<true, 2><<<grid, STATS_THREADS, 0, ctx->stream>>>(ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm,
                                                                               ctx->d_lgamma.p, recs, ctx->rec_cap, rec_count);

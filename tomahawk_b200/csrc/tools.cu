@@ -114,9 +114,12 @@ __global__ void synth_meta_kernel(SynthPrm p, uint64_t* __restrict__ data, const
         ac = an = 0;
         for (uint32_t i = 0; i < (blockDim.x + 31) / 32; ++i) { ac += s_ac[i]; an += s_an[i]; }
         const uint32_t H = 2u * p.n_samples;
-        if (ac == 0) {  // set the first non-missing haplotype
-            for (uint32_t h = 0; h < H; ++h)
+        if (ac == 0) {  // one carrier at a pseudo-random haplotype (the next non-missing one)
+            const uint32_t h0 = (uint32_t)(key3(p.seed, v, 7) % H);
+            for (uint32_t k = 0; k < H; ++k) {
+                const uint32_t h = (h0 + k) % H;
                 if (!mrow || !((mrow[h >> 6] >> (h & 63)) & 1ull)) { row[h >> 6] |= 1ull << (h & 63); ac = 1; break; }
+            }
         } else if (ac == H - an && ac > 1) {  // clear the first alt haplotype
             for (uint32_t h = 0; h < H; ++h)
                 if ((row[h >> 6] >> (h & 63)) & 1ull) { row[h >> 6] &= ~(1ull << (h & 63)); --ac; break; }
@@ -134,19 +137,24 @@ __global__ void synth_meta_kernel(SynthPrm p, uint64_t* __restrict__ data, const
     }
 }
 
-// ---- POPC issue rate: 8 independent popc + add chains per thread, operands in registers
+// ---- POPC issue rate: 64 DISTINCT popc(a_i & b_j) per iteration per thread (8 x 8 register tile, the shape of
+// count_popc_kernel's inner loop), operands in registers, no memory traffic
 __global__ void popc_rate_kernel(uint32_t iters, uint32_t seed, uint32_t* out) {
-    uint32_t a[8], acc[8];
+    uint32_t a[8], b[8], acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] = seed * (2654435761u + 40503u * i) + threadIdx.x + blockIdx.x * 977u; acc[i] = 0; }
+    for (int i = 0; i < 8; ++i) {
+        a[i] = seed * (2654435761u + 40503u * i) + threadIdx.x + blockIdx.x * 977u;
+        b[i] = seed * (2246822519u + 30011u * i) ^ (threadIdx.x * 31u + blockIdx.x);
+        acc[i] = 0;
+    }
     for (uint32_t it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int j = 0; j < 8; ++j) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] += __popc(a[i] & a[(i + r + 1) & 7]);
+            for (int i = 0; i < 8; ++i) acc[i] += __popc(a[i] & b[j]);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = a[i] + acc[i];  // keeps the compiler from hoisting the popcounts
+        for (int i = 0; i < 8; ++i) { a[i] += acc[i]; b[i] ^= acc[(i + 3) & 7]; }  // keeps the compiler from hoisting the popcounts
     }
     uint32_t x = 0;
 #pragma unroll
