@@ -885,17 +885,23 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
     // partition: build it (and upload it) once and reuse it across runs.
     // (outside window mode the plan is a function of the ranges alone, so it survives a reload of a
     // matrix of the same shape: the end-to-end path does not rebuild and re-upload 3e5 tiles per call)
+    // super-tile edge (in tiles) of the L2-friendly order. Short rows (C2: 2.5 KB of e2m1 per variant): 32 x 32 tiles of
+    // operand rows are a 40 MB working set that stays in L2 (B200 sweep 16/24/32/48: 28.42 / 28.15 / 28.12 / 28.12 ms per C2
+    // launch). Long rows (biobank scale: 500 KB per variant) never fit: what matters then is that the ~74 tiles that are
+    // in flight TOGETHER (one per CTA pair) form a compact block, so that the K blocks they stream in near lock-step are
+    // shared through L2 -- an 8 x 8 super-tile is about one such wave.
+    uint32_t super = 32u;
+    {
+        const size_t row_bytes = ctx->umma.valid ? ctx->umma.Kbytes : (size_t)ctx->K32 * 4;
+        if ((size_t)32 * (TI + TJ) * row_bytes > ((size_t)96 << 20)) super = 8u;  // B200, 1 M haplotypes: 32/16/12/9/8/6 -> 108.7 / 114.6 / 117.5 / 102.4 / 98.8 / 106.2 ms
+    }
+    if (const char* e = getenv("TWKB_SUPER")) super = (uint32_t)std::max(1, atoi(e));
     char keybuf[256];
-    std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u|w%d:%d:%d|p%d/%d",
+    std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u/%u|w%d:%d:%d|p%d/%d",
                   (unsigned long long)(ctx->st.window ? ctx->matrix_epoch : 0ull),
-                  pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, (int)window_kind(ctx->st),
+                  pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, super, (int)window_kind(ctx->st),
                   ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
     if (ctx->plan_key != keybuf) {
-        // super-tile edge (in tiles) of the L2-friendly order: 32 x 32 tiles of e2m1 operand rows are
-        // a 40 MB working set (C2), half the DRAM re-reads of 16 x 16 (B200 sweep 16/24/32/48:
-        // 28.42 / 28.15 / 28.12 / 28.12 ms per C2 launch)
-        uint32_t super = 32u;
-        if (const char* e = getenv("TWKB_SUPER")) super = (uint32_t)std::max(1, atoi(e));
         if (n_dense >= 2) build_tiles(ctx, pb, TI, TJ, super, ctx->plan_tiles, &ctx->plan_pairs);
         else { ctx->plan_tiles.clear(); ctx->plan_pairs = 0; }
         CUDA_TRY(ctx->d_tiles.alloc(std::max<size_t>(ctx->plan_tiles.size(), 1)));
