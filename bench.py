@@ -10,7 +10,7 @@ screen / compaction) and statistics kernel for every pair of this rank's share o
 Primary workload. N = 1: BASELINE.json configs[1] -- phased all-pairs, 2,504 samples (5,008 haplotypes) x
 200,000 SNVs, R2 >= 0.1. N > 1 (torchrun, one rank per GPU): weak scaling, M = 200,000 * sqrt(N) variants so
 every GPU keeps the N = 1 pair count. The ranks form an NCCL communicator INSIDE libtwkb (twkb_comm_init);
-every load sends 1/N of the rows over the rank's own PCIe link and completes the matrix with NCCL broadcasts
+every load sends 1/N of the rows over the rank's own PCIe link and completes the matrix with one ncclAllGather
 over NVLink (twkb_load_matrix_sliced); tiles are then computed with no further collective.
 
 Secondary workloads in `extra_configs` of the same JSON line (each with its own value / e2e / roofline):
@@ -591,7 +591,7 @@ def main():
             "ms_count_kernel_per_step": float(np.mean(acc["cnt"])), "ms_stats_kernel_per_step": float(np.mean(acc["sts"])),
             "wall_seconds_timed_region": acc["wall"],
             "multi_gpu": (f"{world} ranks, NCCL communicator inside libtwkb (twkb_comm_init); each load: own row slice over PCIe + "
-                          f"grouped ncclBroadcast exchange; tiles dealt by part_index/part_count, no collective during compute") if world > 1 else None,
+                          f"one in-place ncclAllGather; tiles dealt by part_index/part_count, no collective during compute") if world > 1 else None,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                 "ms_per_step": e2e["ms"], "gpu_launches_per_step": e2e["launches"], "parts_last_step": e2e["parts"],

@@ -192,8 +192,8 @@ int twkb_load_runs(void* ctx, uint32_t n_samples, uint32_t n_variants, const uin
  * context per GPU (threads of one process -- include/twkb_ld.hpp, `twkb_calc -g 0,1,..` -- or one process per
  * GPU -- bench.py under torchrun) forms a communicator; a sliced load sends only rows
  * [row_begin, row_end) of this rank (twkb_comm_slice) over this GPU's own PCIe link and completes the matrix
- * on every GPU with NCCL broadcasts over NVLink, chunk by chunk behind the upload. No collective runs during
- * twkb_compute: tiles are independent (settings.part_index / part_count select this context's tiles).
+ * on every GPU with one in-place ncclAllGather over NVLink. No collective runs during twkb_compute: tiles are
+ * independent (settings.part_index / part_count select this context's tiles).
  * libnccl.so.2 is loaded on first use; without it these calls fail with TWKB_ENODEVICE. */
 #define TWKB_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
 int twkb_comm_unique_id(uint8_t* id /* [TWKB_COMM_ID_BYTES] */);  /* one rank creates it, all ranks pass it to init */

@@ -5,8 +5,9 @@
 // slave thread of twk_ld::Compute reads it through shared host memory; the balancer
 // (lib/ld/ld_balancing.h:23-80, 176-233) then deals block pairs. On one 8 x B200 box the "shared memory" is
 // eight HBM stacks: every rank uploads (or decodes) 1/N of the variant rows over ITS OWN PCIe link and the
-// ranks exchange their slices with NCCL broadcasts grouped into one all-gather-v. No collective runs after
-// that: tiles are independent (BASELINE.json north_star (4)).
+// ranks complete the matrix with ONE in-place ncclAllGather over NVLink (equal slices of ceil(M / N) rows; the
+// resident buffer is padded to N slices). No collective runs after that: tiles are independent (BASELINE.json
+// north_star (4)).
 //
 // libnccl.so.2 is resolved at run time (dlopen): a single-GPU caller never needs it, and inside a process that
 // already carries PyTorch's NCCL the same library instance is reused.
@@ -26,6 +27,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -50,6 +52,7 @@ inline const NcclApi& nccl_api() {
         api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
         api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
         api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
         api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
         api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
         api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));

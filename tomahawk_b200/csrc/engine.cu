@@ -1336,22 +1336,13 @@ static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, cons
         }                                                                                           \
     } while (0)
 
-// Chunk `chunk` of `n_chunks` of EVERY rank's row slice, exchanged as one group of in-place broadcasts
-// (an all-gather-v: slices may be short or empty). Every rank issues the same sequence of calls.
-static int exchange_slices(Context* ctx, uint64_t* d_rows, size_t stride, uint32_t M, int n_chunks, int chunk) {
+// In-place all-gather of the ranks' row slices: slice k = rows [k S, (k + 1) S), S = ceil(M / N); d_rows holds N S rows
+// (the rows past M are padding). One collective over NVLink / NVSwitch; every rank issues the same call.
+// (A first version exchanged chunks with grouped ncclBroadcast calls behind the upload: 362 MB took 10 ms at 8 ranks.)
+static int exchange_slices(Context* ctx, uint64_t* d_rows, size_t stride, uint32_t M) {
     const NcclApi& nc = nccl_api();
-    NCCL_TRY(nc.GroupStart());
-    for (int k = 0; k < ctx->comm_size; ++k) {
-        uint32_t b, e;
-        comm_slice(M, k, ctx->comm_size, b, e);
-        const uint64_t rows = e - b, per = (rows + n_chunks - 1) / n_chunks;
-        const uint64_t cb = b + std::min<uint64_t>(rows, per * (uint64_t)chunk), ce = b + std::min<uint64_t>(rows, per * (uint64_t)(chunk + 1));
-        if (ce > cb) {
-            uint64_t* ptr = d_rows + cb * stride;
-            NCCL_TRY(nc.Broadcast(ptr, ptr, (size_t)(ce - cb) * stride, ncclUint64, k, ctx->comm, ctx->stream));
-        }
-    }
-    NCCL_TRY(nc.GroupEnd());
+    const uint64_t S = ((uint64_t)M + ctx->comm_size - 1) / ctx->comm_size;
+    NCCL_TRY(nc.AllGather(d_rows + (size_t)ctx->comm_rank * S * stride, d_rows, (size_t)S * stride, ncclUint64, ctx->comm, ctx->stream));
     return TWKB_OK;
 }
 
@@ -1364,8 +1355,8 @@ static int ensure_chunk_events(Context* ctx, int n) {
     return TWKB_OK;
 }
 
-// twkb_load_matrix_sliced: this rank's rows go up over its own PCIe link in chunks on copy_stream; as soon
-// as chunk c of every rank has landed it is exchanged over NVLink while chunk c + 1 is still uploading.
+// twkb_load_matrix_sliced: this rank's rows go up over its own PCIe link (copy_stream), then one in-place
+// all-gather over NVLink completes the matrix on every GPU.
 static int load_matrix_sliced(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* slice_data, const uint64_t* slice_mask,
                               size_t stride, const twkb_variant* meta) {
     if (!ctx->comm || ctx->comm_size <= 1) return load_common(ctx, n_samples, n_variants, slice_data, slice_mask, stride, meta, false);
@@ -1377,35 +1368,33 @@ static int load_matrix_sliced(Context* ctx, uint32_t n_samples, uint32_t n_varia
     const uint64_t rows = e - b;
     if (rows && !slice_data) { ctx->err = "null/empty matrix slice"; return TWKB_EINVAL; }
     if (ctx->any_missing && rows && !slice_mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
-    const size_t words = (size_t)n_variants * stride;
+    const uint64_t S = ((uint64_t)n_variants + ctx->comm_size - 1) / ctx->comm_size;
+    const size_t words = (size_t)S * ctx->comm_size * stride;  // padded to N equal slices
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     CUDA_TRY(ctx->d_raw_data.alloc(words));
     if (ctx->any_missing) CUDA_TRY(ctx->d_raw_mask.alloc(words));
-    // the same chunk count on every rank (derived from the global shape): ~8 MB per chunk, at most 8
-    const uint64_t per_rank = ((uint64_t)n_variants + ctx->comm_size - 1) / ctx->comm_size;
-    const int n_chunks = (int)std::min<uint64_t>(8, std::max<uint64_t>(1, per_rank * stride * 8 / (8u << 20)));
-    rc = ensure_chunk_events(ctx, n_chunks);
+    rc = ensure_chunk_events(ctx, 1);
     if (rc) return rc;
-    const uint64_t per = (rows + n_chunks - 1) / n_chunks;
-    for (int c = 0; c < n_chunks; ++c) {
-        const uint64_t cb = std::min<uint64_t>(rows, per * (uint64_t)c), ce = std::min<uint64_t>(rows, per * (uint64_t)(c + 1));
-        if (ce > cb) {
-            CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_data.p + (b + cb) * stride, slice_data + cb * stride, (ce - cb) * stride * 8,
-                                     cudaMemcpyHostToDevice, ctx->copy_stream));
-            if (ctx->any_missing)
-                CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_mask.p + (b + cb) * stride, slice_mask + cb * stride, (ce - cb) * stride * 8,
-                                         cudaMemcpyHostToDevice, ctx->copy_stream));
-        }
-        CUDA_TRY(cudaEventRecord(ctx->chunk_events[c], ctx->copy_stream));
-    }
-    for (int c = 0; c < n_chunks; ++c) {
-        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[c], 0));
-        rc = exchange_slices(ctx, ctx->d_raw_data.p, stride, n_variants, n_chunks, c);
+    // own slice over this GPU's PCIe link (copy_stream), padding rows of a short slice zeroed, then the collective
+    auto upload = [&](uint64_t* d_rows, const uint64_t* h_rows) -> int {
+        const size_t base = (size_t)S * ctx->comm_rank;  // == b unless the slice is empty
+        if (rows) CUDA_TRY(cudaMemcpyAsync(d_rows + base * stride, h_rows, rows * stride * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (rows < S) CUDA_TRY(cudaMemsetAsync(d_rows + (base + rows) * stride, 0, (S - rows) * stride * 8, ctx->copy_stream));
+        return TWKB_OK;
+    };
+    rc = upload(ctx->d_raw_data.p, slice_data);
+    if (rc) return rc;
+    if (ctx->any_missing) {
+        rc = upload(ctx->d_raw_mask.p, slice_mask);
         if (rc) return rc;
-        if (ctx->any_missing) {
-            rc = exchange_slices(ctx, ctx->d_raw_mask.p, stride, n_variants, n_chunks, c);
-            if (rc) return rc;
-        }
+    }
+    CUDA_TRY(cudaEventRecord(ctx->chunk_events[0], ctx->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[0], 0));
+    rc = exchange_slices(ctx, ctx->d_raw_data.p, stride, n_variants);
+    if (rc) return rc;
+    if (ctx->any_missing) {
+        rc = exchange_slices(ctx, ctx->d_raw_mask.p, stride, n_variants);
+        if (rc) return rc;
     }
     ctx->stats.bytes_h2d = rows * stride * 8 * (ctx->any_missing ? 2 : 1);
     return load_finish(ctx, meta);
@@ -1443,7 +1432,9 @@ static int load_runs_sliced(Context* ctx, uint32_t n_samples, uint32_t n_variant
     if (hi < lo) lo = hi = 0;
     std::vector<twkb_run_desc> local(desc + b, desc + e);
     for (twkb_run_desc& d : local) d.offset -= lo;
-    const size_t words = (size_t)n_variants * stride;
+    const uint64_t S = ((uint64_t)n_variants + ctx->comm_size - 1) / ctx->comm_size;
+    const size_t words = (size_t)S * ctx->comm_size * stride;  // padded to N equal slices
+    const size_t base = (size_t)S * ctx->comm_rank;            // == b unless the slice is empty
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     DevBuf<uint8_t> d_bytes;
     DevBuf<twkb_run_desc> d_desc;
@@ -1459,12 +1450,15 @@ static int load_runs_sliced(Context* ctx, uint32_t n_samples, uint32_t n_variant
     if (rows) {
         CUDA_TRY(cudaMemcpyAsync(d_bytes.p, bytes + lo, hi - lo, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(d_desc.p, local.data(), (size_t)rows * sizeof(twkb_run_desc), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(ctx->d_raw_data.p + (size_t)b * stride, 0, (size_t)rows * stride * 8, ctx->stream));
-        if (ctx->any_missing) CUDA_TRY(cudaMemsetAsync(ctx->d_raw_mask.p + (size_t)b * stride, 0, (size_t)rows * stride * 8, ctx->stream));
+    }
+    // the whole padded slice starts from zero (the decoder ORs runs into the rows)
+    CUDA_TRY(cudaMemsetAsync(ctx->d_raw_data.p + base * stride, 0, (size_t)S * stride * 8, ctx->stream));
+    if (ctx->any_missing) CUDA_TRY(cudaMemsetAsync(ctx->d_raw_mask.p + base * stride, 0, (size_t)S * stride * 8, ctx->stream));
+    if (rows) {
         CUDA_TRY(cudaEventRecord(ctx->ev2, ctx->stream));
         decode_runs_kernel<<<(rows + DEC_WARPS - 1) / DEC_WARPS, DEC_WARPS * 32, 0, ctx->stream>>>(
-            d_bytes.p, d_desc.p, rows, (uint32_t)H, reinterpret_cast<uint32_t*>(ctx->d_raw_data.p + (size_t)b * stride),
-            ctx->any_missing ? reinterpret_cast<uint32_t*>(ctx->d_raw_mask.p + (size_t)b * stride) : nullptr, stride * 2, d_err.p);
+            d_bytes.p, d_desc.p, rows, (uint32_t)H, reinterpret_cast<uint32_t*>(ctx->d_raw_data.p + base * stride),
+            ctx->any_missing ? reinterpret_cast<uint32_t*>(ctx->d_raw_mask.p + base * stride) : nullptr, stride * 2, d_err.p);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ctx->ev3, ctx->stream));
         ctx->stats.other_launches += 1;
@@ -1478,10 +1472,10 @@ static int load_runs_sliced(Context* ctx, uint32_t n_samples, uint32_t n_variant
             NCCL_TRY(nc.Broadcast(d_status.p + 2 * k, d_status.p + 2 * k, 2, ncclUint32, k, ctx->comm, ctx->stream));
         NCCL_TRY(nc.GroupEnd());
     }
-    rc = exchange_slices(ctx, ctx->d_raw_data.p, stride, n_variants, 1, 0);
+    rc = exchange_slices(ctx, ctx->d_raw_data.p, stride, n_variants);
     if (rc) return rc;
     if (ctx->any_missing) {
-        rc = exchange_slices(ctx, ctx->d_raw_mask.p, stride, n_variants, 1, 0);
+        rc = exchange_slices(ctx, ctx->d_raw_mask.p, stride, n_variants);
         if (rc) return rc;
     }
     std::vector<uint32_t> h_status(2 * (size_t)ctx->comm_size, 0);
