@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# Builds the reference's own `calc` (and `view`, as a .two->text dumper, and `sort`) from the
+# Builds the reference's own `calc` and `scalc` (and `view`, as a .two->text dumper, and `sort`) from the
 # sources where they lie under /root/reference into oracle/_ref/ (git-ignored,
 # shipped to the GPU box by gpurun). TEST INFRASTRUCTURE ONLY: the product never
 # links or executes anything built here. Recipe mirrors the reference makefile
@@ -37,7 +37,8 @@ for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 g++ $CXXFLAGS "$HERE/stub_calc_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk_calc" 2>/dev/null
 g++ $CXXFLAGS "$HERE/stub_view_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk_view" 2>/dev/null
 g++ $CXXFLAGS "$HERE/stub_sort_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk_sort" 2>/dev/null
+g++ $CXXFLAGS "$HERE/stub_scalc_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk_scalc" 2>/dev/null
 # The same fisher_math.cpp as a tiny shared object so the C restatement's Fisher
 # can be diffed against the reference's kt_fisher_exact directly (ctypes).
 g++ -O3 -msse4.2 -w -shared -fPIC -I$REF/lib "$REF/lib/fisher_math.cpp" -o "$OUT/libref_fisher.so"
-echo "[oracle] built $OUT/tomahawk_calc $OUT/tomahawk_view $OUT/tomahawk_sort $OUT/libref_fisher.so"
+echo "[oracle] built $OUT/tomahawk_calc $OUT/tomahawk_scalc $OUT/tomahawk_view $OUT/tomahawk_sort $OUT/libref_fisher.so"

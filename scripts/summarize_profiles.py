@@ -19,7 +19,10 @@ KEYS = [
     "launch__cluster_size", "launch__cluster_max_active", "gpc__cycles_elapsed.max", "sm__cycles_active.avg",
     "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_uniform", "smsp__average_warp_latency_issue_stalled", "sm__pipe_alu_cycles_active",
-    "sm__pipe_fp64_cycles_active", "sm__inst_executed_pipe_lsu",
+    "sm__pipe_fp64_cycles_active", "sm__inst_executed_pipe_lsu", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active", "smsp__average_warps_issue_stalled_wait_per_issue_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active", "launch__occupancy_limit_registers", "l1tex__t_sector_hit_rate.pct",
 ]
 
 

@@ -1103,7 +1103,7 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2], the leader's copy is the one used
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    uint32_t* q_ctrl = tmem_slot + 1;              // [3] tail, head, finished producers
+    uint32_t* q_ctrl = tmem_slot + 4;              // [4] tail, head, finished producers (own 16-byte line: tcgen05.alloc writes tmem_slot)
     const SurvivorQueue queue{s_ring, q_ctrl};
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
