@@ -60,7 +60,8 @@ typedef struct twkb_settings {
     uint8_t window;          /* -w given                                          */
     uint8_t low_memory;      /* -m: CPU RAM trick; accepted, no-op                */
     uint8_t bitmaps;         /* -M: EWAH bitmaps; accepted, same kernels          */
-    uint8_t single;          /* scalc mode (not on this path; must be 0)          */
+    uint8_t single;          /* scalc / twk_ld::ComputeSingle: target site(s) against their
+                                neighbourhood (see single_targets)                 */
     uint8_t force_phased;    /* -p                                                */
     uint8_t forced_unphased; /* -u                                                */
     uint8_t emulate_quirks;  /* 1 (default): reproduce count-slot quirk Q3 of the
@@ -90,7 +91,12 @@ typedef struct twkb_settings {
     int32_t host_unpack;     /* twkb_calc_file: 0 (default) = the .twk run-length records are decoded
                                 on the device (twkb_load_runs); 1 = unpack the rows on the host
                                 (twkb_load_matrix), the reference's twk_igt_vec::Build arrangement */
-    int32_t reserved[3];
+    int32_t single_targets;  /* single mode: the FIRST single_targets resident variants are the target site(s); every
+                                pair (target, other variant) and (target, later target) is computed, the target named
+                                first (twk_ld_slave::CalculateSingle, lib/ld/ld_engine.cpp:2226-2332: auto phasing per
+                                pair, no ac_i + ac_j <= 2 skip). twkb_calc_file* fill it from the file; callers of
+                                twkb_load_matrix order their rows [targets | neighbours] and set it themselves */
+    int32_t reserved[2];
 } twkb_settings;
 
 /* Subset of twk1_t (include/core.h:291-295) the LD path reads. */
@@ -248,6 +254,15 @@ int twkb_calc_file(const twkb_settings* s, const char* in_path, const char* out_
 int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const char* out_path,
                              const char* const* intervals, int32_t n_intervals, twkb_stats* stats_out, char* errbuf,
                              size_t errbuf_len);
+
+/* `tomahawk scalc` = twk_ld::ComputeSingle (lib/ld/ld.cpp:673-876): settings->single = 1 and ONE interval string naming
+ * the target site ("chr:pos", 1-based) go through twkb_calc_file_intervals; the variants within settings->l_surrounding
+ * bases on either side are loaded (twk_ld_impl::LoadTargetSingle, lib/ld/ld.cpp:123-255). The reader below does the same
+ * selection for callers that drive the engine themselves. */
+int twkb_twk_open_single(const char* path, int n_threads, const char* interval, int32_t l_surrounding, int32_t emulate_quirks,
+                         int32_t runs_mode, void** handle, uint32_t* n_targets, char* errbuf, size_t errbuf_len);
+/* emulate_quirks: the reference gathers the neighbours in blocks of 100 and drops the last, partial block (lib/ld/ld.cpp:193-195,
+ * :241); with 0 every neighbour takes part. */
 
 /* .twk reader (twk_reader::Open + twk1_blk_iterator::NextBlock + twk_igt_vec::Build):
  * unpacks every block into the row layout twkb_load_matrix takes. */

@@ -104,6 +104,7 @@ struct twk_ld_settings {
         c->minP = minP; c->minR2 = minR2; c->maxR2 = maxR2; c->minDprime = minDprime; c->maxDprime = maxDprime;
         c->kernel = kernel;
         c->host_unpack = host_unpack ? 1 : 0;
+        c->single_targets = 0;
     }
 };
 
@@ -117,12 +118,27 @@ public:
         return Compute();
     }
 
+    // twk_ld::ComputeSingle (include/ld.h:54, lib/ld/ld.cpp:673-876): the target site(s) named by the one interval
+    // string against every variant within l_surrounding bases (`scalc`).
+    bool ComputeSingle(const twk_ld_settings& s) {
+        settings = s;
+        settings.single = true;
+        return Compute();
+    }
+
     // twk_ld::Compute, lib/ld/ld.cpp:477-671: open, select blocks, load, compute, write.
     bool Compute() {
         stats = twkb_stats{};
         if (settings.in.empty()) return error("No file-name provided...");
         if (settings.window && settings.n_chunks != 1) return error("Cannot use chunking in window mode!");
         if (settings.devices.empty()) return error("No device selected...");
+        if (settings.single) {  // ld.cpp:679-697
+            if (settings.n_chunks != 1) return error("Cannot use chunking in single mode!");
+            if (settings.window) return error("Cannot use window in single mode!");
+            if (settings.ival_strings.empty()) return error("An interval has to be provided in single mode!");
+            if (settings.ival_strings.size() != 1) return error("Only a single interval can be provided in single mode!");
+            settings.devices.resize(1);  // one target row: one device
+        }
         // the reference's default "-" streams blocks to stdout; the block writer of this path needs a file
         if (settings.out.empty() || settings.out == "-") return error("Writing to stdout is not supported: give -o <output.two>");
         log("READER") << "Opening " << settings.in << "..." << std::endl;
@@ -132,9 +148,13 @@ public:
         void* twk = nullptr;
         // default: blocks are inflated on the host, the run-length genotypes are decoded on the device
         const bool runs = !settings.host_unpack;
-        int rc = (runs ? twkb_twk_open_runs : twkb_twk_open_intervals)(
-            settings.in.c_str(), settings.n_threads > 0 ? settings.n_threads : 1, iv.empty() ? nullptr : iv.data(),
-            (int32_t)iv.size(), settings.emulate_quirks ? 1 : 0, &twk, errbuf, sizeof(errbuf));
+        uint32_t n_targets = 0;
+        int rc = settings.single
+                     ? twkb_twk_open_single(settings.in.c_str(), settings.n_threads > 0 ? settings.n_threads : 1, iv[0], settings.l_surrounding,
+                                            settings.emulate_quirks ? 1 : 0, runs ? 1 : 0, &twk, &n_targets, errbuf, sizeof(errbuf))
+                     : (runs ? twkb_twk_open_runs : twkb_twk_open_intervals)(
+                           settings.in.c_str(), settings.n_threads > 0 ? settings.n_threads : 1, iv.empty() ? nullptr : iv.data(),
+                           (int32_t)iv.size(), settings.emulate_quirks ? 1 : 0, &twk, errbuf, sizeof(errbuf));
         if (rc) return error(errbuf[0] ? errbuf : "Failed to open file: " + settings.in + "...");
         uint32_t n_samples = 0, n_variants = 0, n_blocks = 0;
         size_t stride = 0;
@@ -189,6 +209,7 @@ public:
             cs.device = settings.devices[k];
             cs.part_index = k;
             cs.part_count = n_dev;
+            cs.single_targets = (int32_t)n_targets;
             const int r = twkb_create(&cs, &ctxs[k]);
             if (r) {
                 const std::string why = twkb_last_error(nullptr);

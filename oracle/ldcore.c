@@ -424,6 +424,35 @@ void ldcore_count_unphased(const uint64_t* A, const uint64_t* mA, const uint64_t
     }
 }
 
+/* One pair through the comparator the reference would pick (twk_ld_slave::{Phased,Unphased,Calculate*}:
+ * -u -> 3x3 table; -p -> 2x2; neither -> unphased iff either variant has missing alleles, :2775) and the math. */
+static int pair_stats(const uint64_t* data, const uint64_t* mask, size_t stride, uint32_t n_samples, uint32_t words,
+                      uint32_t thresh_miss_p, const ld_variant* meta, uint32_t i, uint32_t j, const ld_params* prm, ld_stats* s) {
+    const ld_variant *a = &meta[i], *b = &meta[j];
+    const uint64_t *A = data + (size_t)i * stride, *B = data + (size_t)j * stride;
+    const uint64_t* mA = (mask && a->gt_missing) ? mask + (size_t)i * stride : 0;
+    const uint64_t* mB = (mask && b->gt_missing) ? mask + (size_t)j * stride : 0;
+    int unphased = prm->forced_unphased;
+    if (!prm->force_phased && !prm->forced_unphased) unphased = (a->an || b->an); /* :2775 */
+    if (unphased) {
+        uint64_t t[3][3];
+        ldcore_count_unphased(A, mA, B, mB, n_samples, t);
+        return ldcore_unphased_stats(t, prm, a, b, s);
+    }
+    uint64_t c[4];
+    if (!a->gt_missing && !b->gt_missing) {
+        ldcore_count_phased_nomiss(A, B, words, n_samples, a->ac, b->ac, c);
+    } else if (prm->emulate_quirks && (a->ac + b->ac < thresh_miss_p || (prm->force_phased && prm->bitmaps))) {
+        /* run-length comparator (:1011-1091): same counts, mixed cells in the
+         * opposite slots (Q3) */
+        ldcore_count_phased_masked(A, mA, B, mB, n_samples, 0, c);
+        uint64_t tmp = c[1]; c[1] = c[2]; c[2] = tmp;
+    } else {
+        ldcore_count_phased_masked(A, mA, B, mB, n_samples, prm->emulate_quirks, c);
+    }
+    return ldcore_phased_stats(c[0], c[1], c[2], c[3], prm, a, b, s);
+}
+
 /* ------------------------------------------------------------------ enumeration
  * Pair loop of twk_ld_slave::{Phased,Unphased,Calculate*} over the block-pair
  * grid of twk_ld_dynamic_balancer (lib/ld/ld_engine.cpp:1898-2838,
@@ -474,31 +503,8 @@ int64_t ldcore_calc(const uint64_t* data, const uint64_t* mask, size_t stride, u
                         }
                     }
                     if (a->ac + b->ac <= 2) continue; /* :1918 */
-                    const uint64_t *A = data + (size_t)i * stride, *B = data + (size_t)j * stride;
-                    const uint64_t* mA = (mask && a->gt_missing) ? mask + (size_t)i * stride : 0;
-                    const uint64_t* mB = (mask && b->gt_missing) ? mask + (size_t)j * stride : 0;
                     ld_stats s;
-                    int pass;
-                    int unphased = prm->forced_unphased;
-                    if (!prm->force_phased && !prm->forced_unphased) unphased = (a->an || b->an); /* :2775 */
-                    if (unphased) {
-                        uint64_t t[3][3];
-                        ldcore_count_unphased(A, mA, B, mB, n_samples, t);
-                        pass = ldcore_unphased_stats(t, prm, a, b, &s);
-                    } else {
-                        uint64_t c[4];
-                        if (!a->gt_missing && !b->gt_missing) {
-                            ldcore_count_phased_nomiss(A, B, words, n_samples, a->ac, b->ac, c);
-                        } else if (prm->emulate_quirks && (a->ac + b->ac < thresh_miss_p || (prm->force_phased && prm->bitmaps))) {
-                            /* run-length comparator (:1011-1091): same counts, mixed cells in the
-                             * opposite slots (Q3) */
-                            ldcore_count_phased_masked(A, mA, B, mB, n_samples, 0, c);
-                            uint64_t tmp = c[1]; c[1] = c[2]; c[2] = tmp;
-                        } else {
-                            ldcore_count_phased_masked(A, mA, B, mB, n_samples, prm->emulate_quirks, c);
-                        }
-                        pass = ldcore_phased_stats(c[0], c[1], c[2], c[3], prm, a, b, &s);
-                    }
+                    const int pass = pair_stats(data, mask, stride, n_samples, words, thresh_miss_p, meta, i, j, prm, &s);
                     if (pass) {
                         if (n_out >= out_cap) { overflow = 1; aborted = 1; break; }
                         put_record(out + (size_t)n_out * LD_RECORD_BYTES, &s, a, b);
@@ -515,6 +521,36 @@ int64_t ldcore_calc(const uint64_t* data, const uint64_t* mask, size_t stride, u
     free(bstart);
     if (pairs_visited) *pairs_visited = visited;
     return overflow ? -1 : n_out;
+}
+
+
+/* `scalc` = twk_ld_slave::CalculateSingle (lib/ld/ld_engine.cpp:2226-2332) over the blocks of
+ * twk_ld_impl::LoadTargetSingle (lib/ld/ld.cpp:123-255): the first n_targets variants are the target site(s); every
+ * pair (target, later target) and (target, other) goes through the comparator of AUTO mode whatever -p / -u say
+ * (twk_ld_slave::Start, :1826-1830) and WITHOUT the ac_i + ac_j <= 2 skip (commented out at :2265, :2290). The target
+ * is variant A of every record. */
+int64_t ldcore_calc_single(const uint64_t* data, const uint64_t* mask, size_t stride, uint32_t n_samples, uint32_t n_variants,
+                           const ld_variant* meta, const ld_params* prm_in, uint32_t n_targets, uint8_t* out, int64_t out_cap,
+                           uint64_t* pairs_visited) {
+    ld_params prm = *prm_in;
+    prm.force_phased = prm.forced_unphased = 0;
+    prm.bitmaps = 0;
+    const uint32_t words = (2 * n_samples + 63) / 64;
+    const uint32_t thresh_miss_p = (uint32_t)(0.0047 * n_samples + 5.2913);
+    int64_t n_out = 0;
+    for (uint32_t i = 0; i < n_targets && i < n_variants; ++i)
+        for (uint32_t j = i + 1; j < n_variants; ++j) {
+            ld_stats s;
+            if (!pair_stats(data, mask, stride, n_samples, words, thresh_miss_p, meta, i, j, &prm, &s)) continue;
+            if (n_out >= out_cap) return -1;
+            put_record(out + (size_t)n_out * LD_RECORD_BYTES, &s, &meta[i], &meta[j]);
+            ++n_out;
+        }
+    if (pairs_visited) {
+        const uint64_t t = n_targets, m = n_variants;
+        *pairs_visited = (t * t - t) / 2 + t * (m - t);
+    }
+    return n_out;
 }
 
 int ldcore_record_bytes(void) { return LD_RECORD_BYTES; }

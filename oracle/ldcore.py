@@ -144,6 +144,53 @@ def calc(s: tf.Synth, params: Params, cap: int | None = None):
     return out[:n].copy(), int(visited.value)
 
 
+def scalc_select(s: tf.Synth, contig_rid: int, start: int, stop: int, l_surrounding: int, emulate_quirks: bool = True):
+    """Variant selection of `scalc` (twk_ld_impl::LoadTargetSingle, lib/ld/ld.cpp:123-255): 1-based inclusive matching of
+    pos + 1 against the target interval [start, stop] and the flanks [max(start - L, 0), max(start - 1, 0)], [stop, stop + L].
+    Returns (Synth ordered [targets | neighbours], n_targets). "chr:pos" parses to [pos, pos + 1] (lib/intervals.cpp:113-114)."""
+    p1 = s.pos.astype(np.int64) + 1
+    on = s.rid == contig_rid
+    t = on & (p1 >= start) & (p1 <= stop)
+    left = on & (p1 >= max(start - l_surrounding, 0)) & (p1 <= max(start - 1, 0))
+    right = on & (p1 >= stop) & (p1 <= stop + l_surrounding)
+    others = np.flatnonzero((left | right) & ~t)
+    if emulate_quirks:  # neighbours are gathered in blocks of 100; the last, partial block is dropped (ld.cpp:193-195, :241)
+        others = others[: len(others) // 100 * 100]
+    order = np.concatenate([np.flatnonzero(t), others])
+    sub = tf.Synth(alleles=s.alleles[order], pos=s.pos[order].copy(), rid=s.rid[order].copy(), n_samples=s.n_samples)
+    return sub, int(t.sum())
+
+
+def calc_single(s: tf.Synth, params: Params, n_targets: int):
+    """CPU restatement of `scalc` over a matrix ordered [targets | neighbours] -> (records, pairs_visited)."""
+    L = lib()
+    L.ldcore_calc_single.restype = ctypes.c_int64
+    L.ldcore_calc_single.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p,
+                                     ctypes.POINTER(Params), ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64)]
+    data, mask = tf.pack_bits(s)
+    meta = variant_meta(s)
+    cap = n_targets * s.n_variants + 1
+    out = np.zeros(cap, tf.TWO_DTYPE)
+    visited = ctypes.c_uint64(0)
+    n = L.ldcore_calc_single(data.ctypes.data, mask.ctypes.data if mask is not None else None, data.shape[1], s.n_samples, s.n_variants,
+                             meta.ctypes.data, ctypes.byref(params), n_targets, out.ctypes.data, cap, ctypes.byref(visited))
+    if n < 0:
+        raise RuntimeError("ldcore_calc_single: output capacity too small")
+    return out[:n].copy(), int(visited.value)
+
+
+REF_SCALC = os.path.join(REF_DIR, "tomahawk_scalc")
+
+
+def run_reference_scalc(twk_path: str, out_prefix: str, args: list[str], threads: int = 2, timeout=None):
+    """`tomahawk scalc` of the reference itself (oracle/_ref/tomahawk_scalc)."""
+    cmd = [REF_SCALC, "scalc", "-i", twk_path, "-o", out_prefix, "-t", str(threads)] + list(args)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference scalc failed ({r.returncode}): {r.stderr[-2000:]}")
+    return {"stderr": r.stderr, "cmd": cmd}
+
+
 # ---------------------------------------------------------- compiled reference
 def have_reference() -> bool:
     return os.path.exists(REF_CALC) and os.access(REF_CALC, os.X_OK)

@@ -51,7 +51,7 @@ class Settings(ctypes.Structure):
         ("minDprime", ctypes.c_double), ("maxDprime", ctypes.c_double),
         ("device", ctypes.c_int32), ("part_index", ctypes.c_int32), ("part_count", ctypes.c_int32),
         ("kernel", ctypes.c_int32), ("twk_block_size", ctypes.c_int32), ("sparse_max_words", ctypes.c_int32),
-        ("host_unpack", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
+        ("host_unpack", ctypes.c_int32), ("single_targets", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2),
     ]
 
 
@@ -96,7 +96,7 @@ EXPORTS = [
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
     "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
     "twkb_two_sort",
-    "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
+    "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
 ]
 
 
@@ -144,6 +144,8 @@ def _bind(L):
     L.twkb_debug_rows.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
     L.twkb_twk_open_runs.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_int32,
                                      ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_twk_open_single.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32), ctypes.c_char_p, ctypes.c_size_t]
     L.twkb_twk_runs_view.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]
     L.twkb_two_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int32]
@@ -187,17 +189,27 @@ def _c_strings(strings):
 class TwkFile:
     """A .twk file unpacked by the host reader (twkb_twk_*)."""
 
-    def __init__(self, path: str, n_threads: int = 4, intervals=(), emulate_quirks: bool = True, runs: bool = False):
+    def __init__(self, path: str, n_threads: int = 4, intervals=(), emulate_quirks: bool = True, runs: bool = False,
+                 single_surrounding: int | None = None):
         """``intervals``: the ``-I`` strings of ``calc`` (block-granular selection, lib/ld/ld.cpp:257-365).
-        ``runs``: keep the genotypes run-length encoded for the device decoder (:meth:`runs`)."""
+        ``runs``: keep the genotypes run-length encoded for the device decoder (:meth:`runs`).
+        ``single_surrounding``: scalc selection (lib/ld/ld.cpp:123-255): ``intervals`` holds the ONE target string; the
+        handle then holds [targets | variants within that many bases] and ``n_targets``."""
         L = lib()
         self._L = L
         self._h = ctypes.c_void_p()
         self.runs_mode = runs
+        self.n_targets = 0
         err = ctypes.create_string_buffer(512)
         iv = _c_strings(intervals)
-        opener = L.twkb_twk_open_runs if runs else L.twkb_twk_open_intervals
-        rc = opener(path.encode(), n_threads, iv, len(intervals), int(emulate_quirks), ctypes.byref(self._h), err, 512)
+        if single_surrounding is not None:
+            nt = ctypes.c_uint32(0)
+            rc = L.twkb_twk_open_single(path.encode(), n_threads, intervals[0].encode() if intervals else None, single_surrounding,
+                                        int(emulate_quirks), int(runs), ctypes.byref(self._h), ctypes.byref(nt), err, 512)
+            self.n_targets = nt.value
+        else:
+            opener = L.twkb_twk_open_runs if runs else L.twkb_twk_open_intervals
+            rc = opener(path.encode(), n_threads, iv, len(intervals), int(emulate_quirks), ctypes.byref(self._h), err, 512)
         if rc != 0:
             raise TwkbError(rc, err.value.decode())
         ns, nv, st, am, nb = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t(), ctypes.c_int32(), ctypes.c_uint32()

@@ -3,6 +3,7 @@
 // forwarded to twkb_host::twk_ld::Compute (include/twkb_ld.hpp), i.e. to libtwkb.so.
 //
 //   twkb_calc [calc] [options] -i <in.twk> -o <output.two>
+//   twkb_calc scalc  [options] -i <in.twk> -I <contig:pos> -o <output.two>      (reference lib/scalc.h)
 //
 // Additions: -g/--devices LIST (CUDA ordinals, comma separated; one context per entry) and
 // -K/--kernel auto|popc|umma|fp4.
@@ -61,7 +62,97 @@ static bool parse_window(const char* s, int32_t* out) {
     return true;
 }
 
+// `scalc` (reference lib/scalc.h:28-194): one target site against its neighbourhood. Same option letters, range checks and
+// messages; -w is the neighbourhood in bases (l_surrounding), -r keeps its twk_ld_settings default.
+static void scalc_usage() {
+    std::cerr << "About:  Calculate linkage disequilibrium for a single variant versus its neighbourhood (B200 engine).\n\n"
+                 "Usage:  twkb_calc scalc [options] -i <in.twk> -I <SNP position> -o <output.two>\n\n"
+                 "Options:\n"
+                 "  -i FILE   input Tomahawk (required)\n"
+                 "  -o FILE   output file or file prefix (required)\n"
+                 "  -I STRING filter interval <contig>:pos-pos (see manual; required)\n"
+                 "  -w INT    number of bases to include around the target snp (default: 500kbp)\n"
+                 "  -t INT    number of host threads (default: maximum available)\n"
+                 "  -m, -M, -b  accepted for compatibility\n"
+                 "  -P FLOAT  Fisher's exact test / Chi-squared cutoff P-value (default: 1)\n"
+                 "  -r FLOAT  Pearson's R-squared minimum cut-off value\n"
+                 "  -k INT    compression level to use (default: 1, max = 22).\n"
+                 "  -g INT    CUDA device (default: 0)\n"
+              << std::endl;
+}
+
+static int scalc_main(int argc, char** argv) {
+    if (argc < 3) {
+        scalc_usage();
+        return 1;
+    }
+    static struct option long_options[] = {{"input", required_argument, 0, 'i'},   {"output", required_argument, 0, 'o'},
+                                           {"interval", required_argument, 0, 'I'}, {"window", optional_argument, 0, 'w'},
+                                           {"threads", optional_argument, 0, 't'}, {"low-memory", optional_argument, 0, 'm'},
+                                           {"block-size", optional_argument, 0, 'b'}, {"bitmaps", optional_argument, 0, 'M'},
+                                           {"compression-level", optional_argument, 0, 'k'}, {"minP", optional_argument, 0, 'P'},
+                                           {"minR2", optional_argument, 0, 'r'},   {"silent", no_argument, 0, 's'},
+                                           {"devices", required_argument, 0, 'g'}, {0, 0, 0, 0}};
+    twkb_host::twk_ld_settings settings;
+    std::string literal;
+    for (int i = 0; i < argc; ++i) literal += (i ? " " : "") + std::string(argv[i]);
+    auto err = [](const char* m) {
+        std::cerr << timestamp("ERROR") << m << std::endl;
+        return 1;
+    };
+    int c, option_index = 0;
+    while ((c = getopt_long(argc, argv, "i:o:t:P:a:A:r:I:smMb:k:w:g:?", long_options, &option_index)) != -1) {
+        switch (c) {
+            case 'i': settings.in = optarg; break;
+            case 'o': settings.out = optarg; break;
+            case 'I': settings.ival_strings.push_back(optarg); break;
+            case 'm': settings.low_memory = true; break;
+            case 'M': settings.force_phased = true; settings.low_memory = true; settings.bitmaps = true; break;
+            case 't':
+                settings.n_threads = std::atoi(optarg);
+                if (settings.n_threads <= 0) return err("Cannot have a non-positive number of worker threads");
+                break;
+            case 'b':
+                settings.bl_size = std::atoi(optarg);
+                if (settings.bl_size <= 0) return err("Cannot have a non-positive number of entries in a block!");
+                break;
+            case 'r':
+                settings.minR2 = std::atof(optarg);
+                if (settings.minR2 < 0) return err("Cannot have a negative minimum R-squared value");
+                if (settings.minR2 > 1) return err("Cannot have minimum R-squared value > 1");
+                break;
+            case 'P':
+                settings.minP = std::atof(optarg);
+                if (settings.minP < 0) return err("Cannot have a negative cutoff P-value");
+                if (settings.minP > 1) return err("Cannot have a cutoff P-value > 1");
+                break;
+            case 'k': settings.c_level = std::atoi(optarg); break;
+            case 'w':
+                settings.l_surrounding = std::atoi(optarg);
+                if (settings.l_surrounding < 1) return err("Cannot have neighbourhood (-w) <= 1");
+                break;
+            case 's': settings.silent = true; break;
+            case 'a': case 'A': break;
+            case 'g':
+                if (!all_digits(optarg)) return err("Illegal device list");
+                settings.devices.assign(1, std::atoi(optarg));
+                break;
+            default:
+                std::cerr << timestamp("ERROR") << "Unrecognized option: " << (char)c << std::endl;
+                return 1;
+        }
+    }
+    if (settings.in.empty()) return err("No input value specified...");
+    if (settings.out.empty()) return err("No output value specified...");
+    if (!settings.silent) std::cerr << timestamp("LOG") << "Calling scalc..." << std::endl;
+    settings.minR2 = 0;  // the reference's scalc overrides -r after parsing it (lib/scalc.h:188): every neighbour is reported
+    twkb_host::twk_ld ld;
+    ld.command_line = literal;
+    return ld.ComputeSingle(settings) ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::strcmp(argv[1], "scalc") == 0) return scalc_main(argc - 1, argv + 1);
     if (argc >= 2 && std::strcmp(argv[1], "calc") == 0) { --argc; ++argv; }
     if (argc < 3) {
         calc_usage();

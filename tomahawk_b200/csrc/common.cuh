@@ -46,6 +46,7 @@ struct DevParams {
     uint32_t diag;                // 1: row range == col range, only i<j
     uint32_t lgamma_len;
     uint32_t bitmap_mode;         // -p -m -M with emulate_quirks: every masked pair takes the run-length slots (Q3)
+    uint32_t single;              // scalc: no ac_i + ac_j <= 2 skip (ld_engine.cpp:2265, 2290: commented out there)
     uint32_t pair_filter;         // auto mode passes: 0 all pairs, 1 only pairs without a variant
                                   // with missing alleles, 2 only pairs with one (ld_engine.cpp:2775)
 };

@@ -124,7 +124,7 @@ __device__ __forceinline__ bool pair_decide(const CountArgs& args, const DevPara
                                             const DevVariant& vj, const PairAcc<PopcCfg<MODE>::NP>& pa, uint32_t (&c)[9],
                                             uint32_t& mode) {
     constexpr int NP = PopcCfg<MODE>::NP;
-    bool ok = (vi.ac + vj.ac > 2);  // ld_engine.cpp:1918
+    bool ok = prm.single || (vi.ac + vj.ac > 2);  // ld_engine.cpp:1918 (not in CalculateSingle)
     if (prm.pair_filter) {
         const bool miss = ((vi.flags | vj.flags) & VF_HAS_MISSING) != 0;
         ok = ok && (prm.pair_filter == 1u ? !miss : miss);

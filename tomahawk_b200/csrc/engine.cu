@@ -171,7 +171,12 @@ static void settings_defaults(twkb_settings* s) {
 }
 
 static int validate_settings(const twkb_settings* s, std::string& why) {
-    if (s->single) { why = "single-site mode (scalc) is not part of this path"; return TWKB_EINVAL; }
+    if (s->single) {  // twk_ld::ComputeSingle, lib/ld/ld.cpp:679-687
+        if (s->n_chunks != 1) { why = "Cannot use chunking in single mode!"; return TWKB_EINVAL; }
+        if (s->window) { why = "Cannot use window in single mode!"; return TWKB_EINVAL; }
+        if (s->single_targets < 0) { why = "illegal single_targets"; return TWKB_EINVAL; }
+        if (s->part_count > 1) { why = "single mode runs on one device"; return TWKB_EINVAL; }
+    }
     if (s->force_phased && s->forced_unphased) { why = "cannot force both phased and unphased"; return TWKB_EINVAL; }
     if (s->window && s->n_chunks != 1) { why = "Cannot use chunking in window mode!"; return TWKB_EINVAL; }  // ld.cpp:485
     if (s->n_chunks < 1 || s->c_chunk < 0 || s->c_chunk >= s->n_chunks) { why = "illegal chunk selection"; return TWKB_EINVAL; }
@@ -201,7 +206,8 @@ static DevParams make_params(const Context* ctx, const Problem& pb) {
     p.n_samples = ctx->n_samples;
     p.n_variants = ctx->n_variants;
     p.window = window_kind(s);
-    p.bitmap_mode = (s.emulate_quirks && s.force_phased && s.low_memory && s.bitmaps) ? 1u : 0u;
+    p.bitmap_mode = (s.emulate_quirks && s.force_phased && s.low_memory && s.bitmaps && !s.single) ? 1u : 0u;
+    p.single = s.single ? 1u : 0u;
     p.l_window = (uint32_t)s.l_window;
     p.emulate_quirks = s.emulate_quirks ? 1u : 0u;
     p.thresh_miss_phased = (uint32_t)(0.0047 * ctx->n_samples + 5.2913);
@@ -847,11 +853,12 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
     // tcgen05 paths are checked directly, not only through the records that survive the screen.
     bool use_umma = false, use_fp4 = false;
     const bool planes_mode = mode != MODE_PHASED_NOMISS;
-    if (ctx->st.kernel != TWKB_KERNEL_POPC && umma_supported()) {
+    // single mode (scalc): a handful of target rows against a neighbourhood -- the 128-row LOP3+POPC tiles, not 256 x 240 MMA tiles
+    if (ctx->st.kernel != TWKB_KERNEL_POPC && !ctx->st.single && umma_supported()) {
         if (!planes_mode) use_umma = true;
         else use_umma = ctx->st.kernel != TWKB_KERNEL_UMMA && umma_fp4_possible(ctx->n_samples) && !getenv("TWKB_PLANES_POPC");
     }
-    if ((ctx->st.kernel == TWKB_KERNEL_UMMA || ctx->st.kernel == TWKB_KERNEL_UMMA_FP4) && !use_umma) {
+    if ((ctx->st.kernel == TWKB_KERNEL_UMMA || ctx->st.kernel == TWKB_KERNEL_UMMA_FP4) && !use_umma && !ctx->st.single) {
         ctx->err = planes_mode ? "the int8 tensor-core kernel only serves phased data without missing genotypes (use AUTO or UMMA_FP4)"
                                : "tensor-core kernel requested but unavailable";
         return TWKB_EINVAL;
@@ -1049,19 +1056,32 @@ static int compute_impl(Context* ctx, bool resident, twkb_sink_fn sink, void* us
     Problem pb;
     int rc = select_problem(ctx, pb);
     if (rc) return rc;
+    if (ctx->st.single) {
+        // twk_ld_balancer::BuildSingleSite + CalculateSingle: block 0 (the targets) against itself (i < j) and against
+        // every other block -- rows = targets, columns = everything, each pair once with the target first
+        const uint32_t nT = (uint32_t)ctx->st.single_targets;
+        if (nT == 0 || nT > ctx->n_variants) { ctx->err = "no data found for reference"; return TWKB_EINVAL; }
+        if (nT == ctx->n_variants && nT < 2) { ctx->err = "no surrounding variants"; return TWKB_EINVAL; }
+        pb = Problem{0, nT, 0, ctx->n_variants, true};
+    }
     if (ctx->st.window) {
         rc = build_blocks(ctx);
         if (rc) return rc;
     }
     ctx->stats.pairs_visited = visited_pairs(ctx, pb);
+    if (ctx->st.single) {
+        const uint64_t nT = pb.row_end, M = ctx->n_variants;
+        ctx->stats.pairs_visited = (nT * nT - nT) / 2 + nT * (M - nT);
+    }
     if (ctx->st.part_count > 1) {
         // every part reports its share of the visited pairs (tiles are dealt round-robin)
         const uint64_t v = ctx->stats.pairs_visited, n = ctx->st.part_count, r = ctx->st.part_index;
         ctx->stats.pairs_visited = v / n + (r < v % n ? 1 : 0);
     }
-    if (ctx->st.force_phased || ctx->st.forced_unphased || !ctx->any_missing) {
+    // (single mode always picks the comparator per pair, whatever -p / -u say: twk_ld_slave::Start, ld_engine.cpp:1826-1830)
+    if (((ctx->st.force_phased || ctx->st.forced_unphased) && !ctx->st.single) || !ctx->any_missing) {
         // -p, -u, or auto mode on complete data (auto => phased for every pair, ld_engine.cpp:2775-2790)
-        rc = run_pass(ctx, pb, wanted_mode(ctx, ctx->st.forced_unphased), 0, resident, screen_off, sink, user, dump);
+        rc = run_pass(ctx, pb, wanted_mode(ctx, ctx->st.forced_unphased && !ctx->st.single), 0, resident, screen_off, sink, user, dump);
     } else {
         // Auto mode (ld_engine.cpp:2737-2838): a pair takes the unphased path iff either variant
         // has missing alleles (an != 0), else the phased path; gt_phase is never consulted (Q4).
@@ -1111,7 +1131,7 @@ static int classify_sparse(Context* ctx) {
     if (st.sparse_max_words >= 0) {
         if (const char* e = getenv("TWKB_SPARSE_T")) T = atoll(e);
     }
-    if (T <= 0 || ctx->any_missing || st.forced_unphased || st.n_chunks != 1 || M < 2) return TWKB_OK;
+    if (T <= 0 || ctx->any_missing || st.forced_unphased || st.n_chunks != 1 || M < 2 || st.single) return TWKB_OK;
     DevBuf<uint32_t> d_nnz;
     CUDA_TRY(d_nnz.alloc(M));
     row_nnz32_kernel<<<(M + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_raw_data.p, ctx->raw_stride, M, n_bits, d_nnz.p);
@@ -1770,8 +1790,18 @@ static int twkb_calc_file_intervals_impl(const twkb_settings* s, const char* in_
     const bool runs = s->host_unpack == 0;  // default: the device decodes the run-length records
     const auto t_open = std::chrono::steady_clock::now();
     auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); };
-    int rc = read_twk(in_path, std::max(1, s->n_threads), twk, err, ivals.empty() ? nullptr : &ivals, s->emulate_quirks != 0, runs);
+    twkb_settings settings = *s;
+    if (s->single) {  // scalc: twk_ld::ComputeSingle, lib/ld/ld.cpp:673-697
+        if (s->n_chunks != 1) return fail(TWKB_EINVAL, "Cannot use chunking in single mode!");
+        if (s->window) return fail(TWKB_EINVAL, "Cannot use window in single mode!");
+        if (ivals.empty()) return fail(TWKB_EINVAL, "An interval has to be provided in single mode!");
+        if (ivals.size() != 1) return fail(TWKB_EINVAL, "Only a single interval can be provided in single mode!");
+    }
+    int rc = read_twk(in_path, std::max(1, s->n_threads), twk, err, ivals.empty() ? nullptr : &ivals, s->emulate_quirks != 0, runs,
+                      s->single ? std::max(0, s->l_surrounding) : -1);
     if (rc) return fail(rc, err);
+    if (s->single) settings.single_targets = (int32_t)twk.n_targets;
+    s = &settings;
     const double sec_read = since(t_open);
     void* c = nullptr;
     rc = twkb_create(s, &c);
@@ -1855,6 +1885,21 @@ static int twkb_twk_open_runs_impl(const char* path, int n_threads, const char* 
     if (rc) { delete f; return copy_err(errbuf, errbuf_len, err, rc); }
     *handle = f;
     return TWKB_OK;
+}
+
+int twkb_twk_open_single(const char* path, int n_threads, const char* interval, int32_t l_surrounding, int32_t emulate_quirks,
+                         int32_t runs_mode, void** handle, uint32_t* n_targets, char* errbuf, size_t errbuf_len) {
+    return guarded_buf(errbuf, errbuf_len, [&]() -> int {
+        if (!path || !handle || !interval) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
+        std::vector<std::string> ivals{std::string(interval)};
+        TwkFile* f = new TwkFile();
+        std::string err;
+        const int rc = read_twk(path, std::max(1, n_threads), *f, err, &ivals, emulate_quirks != 0, runs_mode != 0, std::max(0, l_surrounding));
+        if (rc) { delete f; return copy_err(errbuf, errbuf_len, err, rc); }
+        if (n_targets) *n_targets = f->n_targets;
+        *handle = f;
+        return TWKB_OK;
+    });
 }
 
 int twkb_twk_runs_view(void* handle, const uint8_t** run_bytes, size_t* n_run_bytes, const twkb_run_desc** desc,

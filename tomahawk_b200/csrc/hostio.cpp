@@ -87,7 +87,7 @@ inline void or_range(uint64_t* row, uint64_t start, uint64_t end, uint64_t patte
 
 struct BlockRef { uint64_t foff; uint32_t n, first_variant; int32_t rid; uint32_t minpos, maxpos; };
 
-struct Contig { std::string name; int64_t n_bases; };
+struct Contig { std::string name; int64_t n_bases; uint32_t idx; };  // idx: VcfContig::idx, the key blocks' rid refers to (include/header.h:115-148)
 struct Ival { uint32_t start, stop; };
 
 // Grammar of the reference's interval strings (include/tomahawk.h:57-59): a number is
@@ -119,40 +119,57 @@ bool is_number(const std::string& s) {
 // loading rule of twk_ld_impl::LoadTargetBlocks (lib/ld/ld.cpp:279-365): `calc -I` works at
 // .twk BLOCK granularity -- every variant of every block that overlaps an interval takes part.
 // Returns the index-entry numbers to load, in load order.
+// One interval string -> (position of the contig in `contigs`, start, stop); grammar and value rules of
+// twk_intervals::ParseIntervalString (lib/intervals.cpp:91-136).
+int parse_interval_string(const std::string& s, const std::vector<Contig>& contigs, int& c, uint32_t& start, uint32_t& stop, std::string& err) {
+    auto contig_of = [&](const std::string& name) -> int {
+        for (size_t k = 0; k < contigs.size(); ++k)
+            if (contigs[k].name == name) return (int)k;
+        return -1;
+    };
+    const size_t colon = s.find(':');
+    const std::string name = s.substr(0, colon);
+    if (colon != std::string::npos && s.find(':', colon + 1) != std::string::npos) { err = "Illegal format: " + s; return TWKB_EINVAL; }
+    if (!is_name(name)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
+    c = contig_of(name);
+    if (colon == std::string::npos) {  // contig only: [0, n_bases]
+        if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
+        start = 0u;
+        stop = (uint32_t)contigs[c].n_bases;
+        return TWKB_OK;
+    }
+    const std::string rest = s.substr(colon + 1);
+    // a '-' can only separate the two numbers (names were cut at the colon)
+    const size_t dash = rest.find('-');
+    if (dash == std::string::npos) {  // contig:pos -> [pos, pos + 1]
+        if (!is_number(rest)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
+        if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
+        start = (uint32_t)std::atof(rest.c_str());
+        stop = start + 1;
+    } else {
+        const std::string a = rest.substr(0, dash), b = rest.substr(dash + 1);
+        if (!is_number(a) || !is_number(b)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
+        if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
+        start = (uint32_t)std::atof(a.c_str());
+        stop = (uint32_t)std::atof(b.c_str());
+    }
+    return TWKB_OK;
+}
+
 int select_interval_blocks(const std::vector<std::string>& strings, const std::vector<Contig>& contigs,
                            const std::vector<BlockRef>& blocks, bool emulate_quirks, std::vector<uint32_t>& sel,
                            std::string& err) {
-    std::vector<std::vector<Ival>> ivecs(contigs.size());
-    auto contig_of = [&](const std::string& name) -> int {
-        for (size_t c = 0; c < contigs.size(); ++c)
-            if (contigs[c].name == name) return (int)c;
-        return -1;
-    };
+    // the reference keys its interval vectors by VcfContig::idx (lib/intervals.cpp:109) and walks them in idx order
+    uint32_t max_idx = 0;
+    for (const Contig& ct : contigs) max_idx = std::max(max_idx, ct.idx);
+    if (max_idx > (1u << 24)) { err = "corrupt contig index"; return TWKB_EIO; }
+    std::vector<std::vector<Ival>> ivecs((size_t)max_idx + 1);
     for (const std::string& s : strings) {
-        const size_t colon = s.find(':');
-        const std::string name = s.substr(0, colon);
-        if (colon != std::string::npos && s.find(':', colon + 1) != std::string::npos) { err = "Illegal format: " + s; return TWKB_EINVAL; }
-        if (!is_name(name)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
-        const int c = contig_of(name);
-        if (colon == std::string::npos) {  // contig only: [0, n_bases]
-            if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
-            ivecs[c].push_back({0u, (uint32_t)contigs[c].n_bases});
-            continue;
-        }
-        const std::string rest = s.substr(colon + 1);
-        // a '-' can only separate the two numbers (names were cut at the colon)
-        const size_t dash = rest.find('-');
-        if (dash == std::string::npos) {  // contig:pos -> [pos, pos + 1]
-            if (!is_number(rest)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
-            if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
-            const uint32_t p = (uint32_t)std::atof(rest.c_str());
-            ivecs[c].push_back({p, p + 1});
-        } else {
-            const std::string a = rest.substr(0, dash), b = rest.substr(dash + 1);
-            if (!is_number(a) || !is_number(b)) { err = "Illegal interval: " + s; return TWKB_EINVAL; }
-            if (c < 0) { err = "Contig does not exist in string " + s; return TWKB_EINVAL; }
-            ivecs[c].push_back({(uint32_t)std::atof(a.c_str()), (uint32_t)std::atof(b.c_str())});
-        }
+        int c = -1;
+        uint32_t a = 0, b = 0;
+        const int rc = parse_interval_string(s, contigs, c, a, b, err);
+        if (rc) return rc;
+        ivecs[contigs[c].idx].push_back({a, b});
     }
     std::vector<uint32_t> overlap;
     for (size_t c = 0; c < ivecs.size(); ++c) {
@@ -192,7 +209,7 @@ int select_interval_blocks(const std::vector<std::string>& strings, const std::v
 // lib/twk_reader.cpp:49-125 (Open), :8-44 (NextBlock), lib/core.cpp:75-101 (twk1_t),
 // include/core.h:195-215 (run words), lib/core.cpp:365-383 (bitvector + mask).
 int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err, const std::vector<std::string>* intervals,
-             bool emulate_quirks, bool keep_runs) {
+             bool emulate_quirks, bool keep_runs, int32_t single_surrounding) {
     // the file is mapped, not copied: the worker threads fault its pages in as they inflate blocks
     struct Mapped {
         const uint8_t* p = nullptr;
@@ -230,8 +247,8 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
         if (!h.ok) { err = "corrupt VcfHeader"; return TWKB_EIO; }
         out.header_tail.assign(reinterpret_cast<const char*>(tail), hdr.data() + hdr.size() - tail);
         for (uint32_t i = 0; i < out.n_contigs && h.ok; ++i) {  // VcfContig, include/header.h:115-128
-            h.get<uint32_t>();                                    // idx
             Contig ct;
+            ct.idx = h.get<uint32_t>();
             ct.name = h.str();
             h.str();                                              // description
             ct.n_bases = h.get<int64_t>();
@@ -270,7 +287,34 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
         total += n;
     }
     if (!ix.ok || total == 0 || total > 0xffffffffull) { err = "No valid data available..."; return TWKB_EIO; }
-    if (intervals && !intervals->empty()) {  // calc -I: keep the overlapping blocks only
+    // scalc (twk_ld_impl::LoadTargetSingle, lib/ld/ld.cpp:123-255): ONE interval names the target site(s); the variants
+    // within l_surrounding bases on either side are its neighbourhood. Matching is per VARIANT, 1-based, inclusive.
+    const bool single = single_surrounding >= 0;
+    int single_c = -1;
+    uint32_t s_start = 0, s_stop = 0, s_left0 = 0, s_left1 = 0, s_right1 = 0;
+    if (single) {
+        if (!intervals || intervals->empty()) { err = "An interval has to be provided in single mode!"; return TWKB_EINVAL; }  // ld.cpp:689
+        if (intervals->size() != 1) { err = "Only a single interval can be provided in single mode!"; return TWKB_EINVAL; }   // ld.cpp:694
+        const int rc = parse_interval_string((*intervals)[0], contigs, single_c, s_start, s_stop, err);
+        if (rc) return rc;
+        // flanks (ld.cpp:147-156): [max(start - L, 0), max(start - 1, 0)] and [stop, stop + L]
+        s_left0 = (uint32_t)std::max<int32_t>((int32_t)s_start - single_surrounding, 0);
+        s_left1 = (uint32_t)std::max<int32_t>((int32_t)s_start - 1, 0);
+        s_right1 = (uint32_t)((int32_t)s_stop + single_surrounding);
+        const Ival iv[3] = {{s_left0, s_left1}, {s_start, s_stop}, {s_stop, s_right1}};
+        std::vector<BlockRef> kept;
+        total = 0;
+        for (const BlockRef& b : blocks) {  // Index::FindOverlap, lib/index.cpp:125-134, distinct blocks in file order
+            bool hit = false;
+            for (const Ival& v : iv) hit = hit || (b.rid == (int32_t)contigs[single_c].idx && b.minpos <= v.stop && b.maxpos >= v.start);
+            if (!hit) continue;
+            kept.push_back(b);
+            kept.back().first_variant = (uint32_t)total;
+            total += b.n;
+        }
+        if (kept.empty()) { err = "Found no blocks overlapping the provided range(s)..."; return TWKB_EINVAL; }
+        blocks.swap(kept);
+    } else if (intervals && !intervals->empty()) {  // calc -I: keep the overlapping blocks only
         std::vector<uint32_t> sel;
         const int rc = select_interval_blocks(*intervals, contigs, blocks, emulate_quirks, sel, err);
         if (rc) return rc;
@@ -412,6 +456,68 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     if (failed.load()) { err = first_err; return TWKB_EIO; }
     out.any_missing = any_miss_flag.load();
     for (auto& m : block_masks) if (!m.empty()) out.any_missing = true;
+    if (single) {
+        // per-variant classification (ld.cpp:185-222): pos + 1 against the three inclusive intervals; a variant that
+        // matches the target interval is a target whatever else it matches. Resident order = [targets | neighbours],
+        // both in file order: the reference's records name the target first (block 0 of CalculateSingle).
+        std::vector<uint32_t> targets, others;
+        for (uint32_t v = 0; v < (uint32_t)total; ++v) {
+            const twkb_variant& mv = out.meta[v];
+            if (mv.rid != contigs[single_c].idx) continue;
+            const uint32_t p1 = mv.pos + 1;
+            const bool t = p1 >= s_start && p1 <= s_stop;
+            const bool l = p1 >= s_left0 && p1 <= s_left1, r = p1 >= s_stop && p1 <= s_right1;
+            if (t) targets.push_back(v);
+            else if (l && r) { err = "Corrupted intervals! (Too many matches)"; return TWKB_EINVAL; }
+            else if (l || r) others.push_back(v);
+        }
+        if (targets.empty()) { err = "no data found for reference"; return TWKB_EINVAL; }   // ld.cpp:232
+        // The reference collects the neighbours in blocks of 100 and only counts a block once it is FULL (ld.cpp:193-195,
+        // n_blks = ldd2_n at :241): the last (n mod 100) neighbours in file order never take part, and fewer than 100
+        // neighbours are "no surrounding variants". Reproduced with emulate_quirks, like the other quirks of the path.
+        if (emulate_quirks) others.resize(others.size() / 100 * 100);
+        if (others.empty()) { err = "no surrounding variants"; return TWKB_EINVAL; }        // ld.cpp:237
+        std::vector<uint32_t> order(targets);
+        order.insert(order.end(), others.begin(), others.end());
+        const size_t n2 = order.size();
+        std::vector<twkb_variant> meta2(n2);
+        for (size_t k = 0; k < n2; ++k) meta2[k] = out.meta[order[k]];
+        if (keep_runs) {
+            std::vector<twkb_run_desc> rd2(n2);
+            for (size_t k = 0; k < n2; ++k) rd2[k] = out.run_desc[order[k]];
+            out.run_desc.swap(rd2);
+        } else {
+            std::vector<uint64_t> d2(n2 * out.stride);
+            for (size_t k = 0; k < n2; ++k) std::memcpy(d2.data() + k * out.stride, out.data.data() + (size_t)order[k] * out.stride, out.stride * 8);
+            out.data.swap(d2);
+        }
+        // masks of the host-unpack path are gathered below from the per-block buffers
+        out.meta.swap(meta2);
+        out.n_targets = (uint32_t)targets.size();
+        out.n_variants = (uint32_t)n2;
+        out.any_missing = false;
+        if (!keep_runs) {
+            bool any = false;
+            for (const auto& m : block_masks) any = any || !m.empty();
+            if (any) {
+                std::vector<uint64_t> m2(n2 * out.stride, 0);
+                for (size_t k = 0; k < n2; ++k) {
+                    // block of the source variant
+                    size_t b = 0;
+                    while (b + 1 < blocks.size() && blocks[b + 1].first_variant <= order[k]) ++b;
+                    if (!block_masks[b].empty())
+                        std::memcpy(m2.data() + k * out.stride, block_masks[b].data() + (size_t)(order[k] - blocks[b].first_variant) * out.stride, out.stride * 8);
+                }
+                out.mask.swap(m2);
+                out.any_missing = true;
+            }
+        }
+        for (auto& mv : out.meta) if (mv.an || mv.gt_missing) out.any_missing = true;
+        if (keep_runs)
+            for (const auto& rd : out.run_desc) if (rd.miss) out.any_missing = true;
+        if (out.any_missing && !keep_runs && out.mask.empty()) out.mask.assign(n2 * out.stride, 0);
+        return TWKB_OK;
+    }
     for (auto& mv : out.meta) if (mv.an || mv.gt_missing) out.any_missing = true;
     if (out.any_missing && !keep_runs) {
         out.mask.assign((size_t)total * out.stride, 0);

@@ -57,6 +57,7 @@ struct ByteBuf {
 struct TwkFile {
     uint32_t n_samples = 0;
     uint32_t n_variants = 0;
+    uint32_t n_targets = 0;  // single mode (scalc): the first n_targets variants are the target site(s)
     size_t stride = 0;  // u64 words per row (128-bit aligned)
     bool any_missing = false;
     std::vector<uint64_t> data, mask;
@@ -78,8 +79,11 @@ struct TwkFile {
 // `intervals` (nullable): the -I strings of `calc` ("chr", "chr:pos", "chr:from-to"); only the
 // .twk blocks that overlap them are loaded (reference lib/ld/ld.cpp:257-365, lib/intervals.cpp).
 // keep_runs: leave the genotypes run-length encoded for the device decoder (see TwkFile::raw).
+// single_surrounding >= 0: scalc selection (lib/ld/ld.cpp:123-255) -- `intervals` holds ONE string naming the target site(s);
+// the result holds [targets | variants within single_surrounding bases], see TwkFile::n_targets.
 int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& err,
-             const std::vector<std::string>* intervals = nullptr, bool emulate_quirks = true, bool keep_runs = false);
+             const std::vector<std::string>* intervals = nullptr, bool emulate_quirks = true, bool keep_runs = false,
+             int32_t single_surrounding = -1);
 
 // Streaming .two writer: takes forward records, writes forward and reverse
 // blocks of <= b_size records, the index and the EOF marker. Finished blocks queue up and are
