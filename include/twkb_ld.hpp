@@ -139,8 +139,7 @@ public:
             if (settings.ival_strings.size() != 1) return error("Only a single interval can be provided in single mode!");
             settings.devices.resize(1);  // one target row: one device
         }
-        // the reference's default "-" streams blocks to stdout; the block writer of this path needs a file
-        if (settings.out.empty() || settings.out == "-") return error("Writing to stdout is not supported: give -o <output.two>");
+        const bool to_stdout = settings.out.empty() || settings.out == "-";  // the reference's default: stream the .two to stdout (ld.cpp:585-588)
         log("READER") << "Opening " << settings.in << "..." << std::endl;
         char errbuf[1024] = {0};
         std::vector<const char*> iv;
@@ -181,7 +180,8 @@ public:
             for (char& ch : ext) ch = (char)std::tolower((unsigned char)ch);
             if (ext != "two") out = (has_ext ? out.substr(0, dot) : out) + ".two";
         }
-        log("WRITER") << "Opening " << out << "..." << std::endl;
+        if (to_stdout) out = "-";
+        log("WRITER") << (to_stdout ? std::string("Writing to stdout...") : "Opening " + out + "...") << std::endl;
         void* writer = nullptr;
         rc = twkb_two_open(out.c_str(), twk, command_line.c_str(), settings.c_level, settings.b_size, &writer, errbuf, sizeof(errbuf));
         if (rc) {

@@ -37,7 +37,7 @@ def test_cli_is_built_and_prints_usage():
     (["-i", "a.twk", "-o", "b", "-w", "12x"], "not an integer"),
     (["-i", "a.twk", "-o", "b", "-w", "0"], "Cannot have a non-positive window size"),
     (["-o", "b", "-p", "-u"], "No input value specified..."),
-    (["-i", "a.twk", "-p", "-u"], "Writing to stdout is not supported"),
+    (["-i", "does_not_exist.twk", "-p"], "Failed to open"),   # default -o is "-" (stdout) like the reference: only the input is wrong
     (["-i", "a.twk", "-o", "", "-p"], "No output value specified..."),
     (["-i", "a.twk", "-o", "b", "-g", "0,x"], "Illegal device list"),
     (["-i", "a.twk", "-o", "b", "-K", "avx"], "Unknown kernel"),
@@ -101,6 +101,22 @@ def test_cli_window_and_interval_modes(tmpdir_repo):
     r = run("calc", "-i", twk, "-o", out, *cli.split())
     assert r.returncode == 0, r.stderr
     assert_records_bitexact(tf.canonical(tf.read_two(out + ".two"), forward_only=True), ref, p_rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_cli_streams_to_stdout_by_default(tmpdir_repo):
+    """No -o (the reference's default out = "-", include/core.h:909-924): the complete .two goes to stdout, byte-compatible
+    with the file the same run writes with -o (offsets in the index come from a byte counter, not ftell)."""
+    s, ref, prm, pairs, cli = load_golden("phased_r01")
+    twk = os.path.join(tmpdir_repo, "cli_so.twk")
+    tf.write_twk(twk, s)
+    r = subprocess.run([CLI, "calc", "-i", twk, "-s", *cli.split()], capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    piped = os.path.join(tmpdir_repo, "cli_so_piped.two")
+    open(piped, "wb").write(r.stdout)
+    assert_records_bitexact(tf.canonical(tf.read_two(piped), forward_only=True), ref, p_rtol=1e-9)
+    state, ents, meta = tf.read_two_index(piped)
+    assert sum(e[1] for e in ents) == 2 * len(ref)          # the index covers every record of the stream
 
 
 # ---- twkb_sort: the reference's `sort` command line (lib/sort.h) over twkb_two_sort ----

@@ -1825,6 +1825,7 @@ static int twkb_calc_file_intervals_impl(const twkb_settings* s, const char* in_
         std::string ext = has_ext ? out.substr(dot + 1) : "";
         for (auto& ch : ext) ch = (char)std::tolower(ch);
         if (ext != "two") out = (has_ext ? out.substr(0, dot) : out) + ".two";
+        if (std::strcmp(out_path, "-") == 0) out = "-";  // stream to stdout (the reference's default, ld.cpp:585-588)
     }
     TwoWriter writer;
     std::string cmd = std::string("tomahawk_b200 calc -i ") + in_path + " -o " + out_path;

@@ -532,7 +532,15 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
 // ------------------------------------------------------------------ .two writer
 TwoWriter::~TwoWriter() {
     stop_writer();
-    if (fp_) std::fclose(fp_);
+    if (fp_ && !to_stdout_) std::fclose(fp_);
+}
+
+// Every byte goes through here: the file offsets of the index come from this counter, not from ftell(), so the
+// writer also works on a pipe ("-o -": the reference's default streams the .two to stdout, lib/ld/ld.cpp:585-588).
+bool TwoWriter::emit(const void* p, size_t n) {
+    if (n && std::fwrite(p, 1, n, fp_) != n) return false;
+    pos_ += n;
+    return true;
 }
 
 void TwoWriter::set_threads(int n) {
@@ -597,8 +605,10 @@ static void put_str(std::vector<uint8_t>& b, const std::string& s) {
 // include/writer.h:225-242 + lib/ld/ld.cpp:609-612
 int TwoWriter::open(const std::string& path, const TwkFile& src, const std::string& command_line, int c_level, int b_size,
                     std::string& err) {
-    fp_ = std::fopen(path.c_str(), "wb");
+    to_stdout_ = path.empty() || path == "-";
+    fp_ = to_stdout_ ? stdout : std::fopen(path.c_str(), "wb");
     if (!fp_) { err = "Failed to open file: " + path + "..."; return TWKB_EIO; }
+    pos_ = 0;
     c_level_ = c_level;
     b_size_ = (uint32_t)std::max(2, b_size);
     n_contigs_ = src.n_contigs;
@@ -615,10 +625,7 @@ int TwoWriter::open(const std::string& path, const TwkFile& src, const std::stri
     const size_t zn = ZSTD_compress(z.data(), z.size(), hdr.data(), hdr.size(), c_level_);
     if (ZSTD_isError(zn)) { err = "failed to compress"; return TWKB_EIO; }
     const uint64_t unc = hdr.size(), cmp = zn;
-    std::fwrite(kTwoMagic, 1, 4, fp_);
-    std::fwrite(&unc, 8, 1, fp_);
-    std::fwrite(&cmp, 8, 1, fp_);
-    std::fwrite(z.data(), 1, zn, fp_);
+    if (!emit(kTwoMagic, 4) || !emit(&unc, 8) || !emit(&cmp, 8) || !emit(z.data(), zn)) { err = "Failed to write header!"; return TWKB_EIO; }
     fwd_.ent = IndexEntry{-1, -1, 0, 0, 0, 0, 0, 0, 0};
     rev_.ent = fwd_.ent;
     return TWKB_OK;
@@ -653,13 +660,12 @@ int TwoWriter::drain() {
     for (Pending& pb : pending_) {
         const uint8_t marker = 1;
         const uint32_t unc = (uint32_t)pb.raw.size(), cmp = (uint32_t)pb.zn;
-        pb.ent.foff = (uint64_t)std::ftell(fp_);
-        if (std::fwrite(&marker, 1, 1, fp_) != 1 || std::fwrite(&unc, 4, 1, fp_) != 1 || std::fwrite(&cmp, 4, 1, fp_) != 1 ||
-            std::fwrite(pb.z.data(), 1, pb.zn, fp_) != pb.zn) {
+        pb.ent.foff = pos_;
+        if (!emit(&marker, 1) || !emit(&unc, 4) || !emit(&cmp, 4) || !emit(pb.z.data(), pb.zn)) {
             err_ = "write failed";
             return TWKB_EIO;
         }
-        pb.ent.fend = (uint64_t)std::ftell(fp_);
+        pb.ent.fend = pos_;
         pb.ent.b_cmp = cmp;
         index_.push_back(pb.ent);
     }
@@ -782,16 +788,11 @@ int TwoWriter::finish() {
     std::vector<uint8_t> z(ZSTD_compressBound(idx.size()));
     const size_t zn = ZSTD_compress(z.data(), z.size(), idx.data(), idx.size(), c_level_);
     if (ZSTD_isError(zn)) { err_ = "failed compression"; return TWKB_EIO; }
-    const uint64_t off = (uint64_t)std::ftell(fp_), unc = idx.size(), cmp = zn;
+    const uint64_t off = pos_, unc = idx.size(), cmp = zn;
     const uint8_t marker = 0;
-    std::fwrite(&marker, 1, 1, fp_);
-    std::fwrite(&unc, 8, 1, fp_);
-    std::fwrite(&cmp, 8, 1, fp_);
-    std::fwrite(z.data(), 1, zn, fp_);
-    std::fwrite(&off, 8, 1, fp_);
-    std::fwrite(kEof, 1, 32, fp_);
-    const bool ok = std::fflush(fp_) == 0;
-    std::fclose(fp_);
+    bool ok = emit(&marker, 1) && emit(&unc, 8) && emit(&cmp, 8) && emit(z.data(), zn) && emit(&off, 8) && emit(kEof, 32);
+    ok = ok && std::fflush(fp_) == 0 && !std::ferror(fp_);
+    if (!to_stdout_) ok = (std::fclose(fp_) == 0) && ok;
     fp_ = nullptr;
     if (!ok) { err_ = "Failed to write final block!"; return TWKB_EIO; }
     return TWKB_OK;

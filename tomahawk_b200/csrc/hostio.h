@@ -125,7 +125,11 @@ private:
     void writer_loop();
     int stop_writer();
 
+    bool emit(const void* p, size_t n);
+
     FILE* fp_ = nullptr;
+    bool to_stdout_ = false;  // path "-": stream the file to stdout (the reference's default out)
+    uint64_t pos_ = 0;        // bytes written so far (index offsets; a pipe has no ftell)
     int c_level_ = 1;
     uint32_t b_size_ = 10000;
     uint32_t n_contigs_ = 0;
