@@ -293,13 +293,18 @@ int twkb_two_set_threads(void* writer, int32_t n_threads); /* zstd block compres
 int twkb_two_add(void* writer, const uint8_t* records, uint64_t n);
 int twkb_two_close(void* writer); /* finishes the file and frees the writer */
 
-/* `tomahawk sort` for .two files that fit in host memory (two_reader::Sort, lib/two_reader.cpp:162-420):
+/* `tomahawk sort` (two_reader::Sort, lib/two_reader.cpp:162-420):
  * orders the records by (ridA, ridB, posA, posB) -- twk1_two_t::operator<, lib/core.cpp:458-468 -- and
  * writes blocks cut at every change of ridA with the sorted-state index (per-block rid / ridB / minpos /
  * maxpos and the per-contig entries) that lets the reference's `view -I` seek. Host only; zstd blocks are
  * inflated and compressed by up to n_threads threads. n_records may be NULL. */
 int twkb_two_sort(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t* n_records,
                   char* errbuf, size_t errbuf_len);
+/* The same with a memory budget in bytes (the reference's `sort -m`; 0 = unbounded): a file whose records + sort keys exceed it
+ * is sorted in runs spilled to temporary files "<out>_<pid>_<k>.tmp" and merged k-way (two_reader::Sort's external merge,
+ * lib/two_reader.cpp:262-420). The output is identical whatever the budget. A failed run removes its partial output. */
+int twkb_two_sort_mem(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t memory_limit_bytes,
+                      uint64_t* n_records, char* errbuf, size_t errbuf_len);
 
 /* Tile scheduler, host only (the B200 counterpart of twk_ld_balancer /
  * twk_ld_dynamic_balancer, lib/ld/ld_balancing.h): the (i0, j0) variant offsets of the

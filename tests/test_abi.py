@@ -47,7 +47,8 @@ def test_struct_layouts():
 def test_invalid_settings_are_rejected():
     L = tb.lib()
     ctx = ctypes.c_void_p()
-    for kw in (dict(single=1), dict(force_phased=1, forced_unphased=1), dict(window=1, n_chunks=3), dict(n_chunks=3, c_chunk=5),
+    for kw in (dict(single=1, n_chunks=3), dict(single=1, window=1), dict(single=1, part_count=2, part_index=1),
+               dict(force_phased=1, forced_unphased=1), dict(window=1, n_chunks=3), dict(n_chunks=3, c_chunk=5),
                dict(minR2=1.5), dict(part_count=2, part_index=2)):
         s = tb.default_settings(**kw)
         assert L.twkb_create(ctypes.byref(s), ctypes.byref(ctx)) == -1, kw

@@ -96,7 +96,7 @@ EXPORTS = [
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
     "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
     "twkb_two_sort",
-    "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
+    "twkb_two_sort_mem", "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
 ]
 
 
@@ -151,6 +151,8 @@ def _bind(L):
     L.twkb_two_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     L.twkb_two_sort.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                 ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_two_sort_mem.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
+                                    ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
     L.twkb_compute.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
     L.twkb_compute_resident.argtypes = [ctypes.c_void_p]
     L.twkb_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
@@ -279,11 +281,12 @@ class TwoWriter:
                 raise TwkbError(rc, "twkb_two_close failed")
 
 
-def sort_two(in_path: str, out_path: str, c_level: int = 1, n_threads: int = 4) -> int:
-    """`tomahawk sort` (two_reader::Sort): writes the sorted, indexed .two file; returns the record count."""
+def sort_two(in_path: str, out_path: str, c_level: int = 1, n_threads: int = 4, memory_limit: int = 0) -> int:
+    """`tomahawk sort` (two_reader::Sort): writes the sorted, indexed .two file; returns the record count.
+    ``memory_limit`` bytes (0 = unbounded): larger inputs go through spilled runs and a k-way merge."""
     n = ctypes.c_uint64(0)
     err = ctypes.create_string_buffer(512)
-    rc = lib().twkb_two_sort(in_path.encode(), out_path.encode(), c_level, n_threads, ctypes.byref(n), err, 512)
+    rc = lib().twkb_two_sort_mem(in_path.encode(), out_path.encode(), c_level, n_threads, memory_limit, ctypes.byref(n), err, 512)
     if rc != 0:
         raise TwkbError(rc, err.value.decode())
     return int(n.value)

@@ -1984,12 +1984,19 @@ static int twkb_two_close_impl(void* writer) {
 
 static int twkb_two_sort_impl(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t* n_records,
                   char* errbuf, size_t errbuf_len) {
-    if (!in_path || !out_path) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
-    if (std::strlen(in_path) == 0) return copy_err(errbuf, errbuf_len, "No input value specified...", TWKB_EINVAL);  // two_reader.cpp:169
-    std::string err;
-    const int rc = sort_two(in_path, out_path, c_level, n_threads, err, n_records);
-    if (rc) return copy_err(errbuf, errbuf_len, err, rc);
-    return TWKB_OK;
+    return twkb_two_sort_mem(in_path, out_path, c_level, n_threads, 0, n_records, errbuf, errbuf_len);
+}
+
+int twkb_two_sort_mem(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t memory_limit_bytes,
+                      uint64_t* n_records, char* errbuf, size_t errbuf_len) {
+    return guarded_buf(errbuf, errbuf_len, [&]() -> int {
+        if (!in_path || !out_path) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
+        if (std::strlen(in_path) == 0) return copy_err(errbuf, errbuf_len, "No input value specified...", TWKB_EINVAL);  // two_reader.cpp:169
+        std::string err;
+        const int rc = sort_two(in_path, out_path, c_level, n_threads, err, n_records, memory_limit_bytes);
+        if (rc) return copy_err(errbuf, errbuf_len, err, rc);
+        return TWKB_OK;
+    });
 }
 
 static int twkb_plan_tiles_impl(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i, uint32_t tile_j,

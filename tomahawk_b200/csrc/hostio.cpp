@@ -822,9 +822,162 @@ inline void get_rec_key(const uint8_t* rec, int32_t& ridA, int32_t& ridB, uint32
 
 }  // namespace
 
-int sort_two(const std::string& in, const std::string& out_path, int c_level, int n_threads, std::string& err, uint64_t* n_records) {
+namespace {
+
+struct SortKey { uint64_t hi, lo; uint64_t idx; };  // (ridA, ridB | posA, posB | original record number)
+inline bool key_less(const SortKey& a, const SortKey& b) { return a.hi != b.hi ? a.hi < b.hi : (a.lo != b.lo ? a.lo < b.lo : a.idx < b.idx); }
+inline SortKey key_of(const uint8_t* rec, uint64_t idx) {
+    int32_t ridA, ridB; uint32_t pA, pB;
+    get_rec_key(rec, ridA, ridB, pA, pB);
+    // the reference compares rid as int32 (twk1_two_t::operator<, lib/core.cpp:458-468): bias to keep the order under unsigned comparison
+    return SortKey{((uint64_t)((uint32_t)ridA ^ 0x80000000u) << 32) | ((uint32_t)ridB ^ 0x80000000u), ((uint64_t)pA << 32) | pB, idx};
+}
+
+// A sorted run: either resident (records + sorted keys in memory) or spilled to a temporary file as zstd chunks of
+// <= kRunChunk records ([u32 n][u32 n_cmp][frame]) that are read back one chunk at a time by the merge.
+constexpr uint32_t kRunChunk = 16384;
+struct SortedRun {
+    // resident
+    const uint8_t* recs = nullptr;
+    const SortKey* keys = nullptr;
+    uint64_t n = 0, next = 0, base_idx = 0;
+    // spilled
+    FILE* fp = nullptr;
+    std::string path;
+    std::vector<uint8_t> buf, zbuf;
+    uint32_t buf_n = 0, buf_next = 0;
+    uint64_t emitted = 0;
+
+    bool fill(std::string& err) {  // spilled: load the next chunk
+        uint32_t hdr[2];
+        if (std::fread(hdr, 4, 2, fp) != 2) { err = "failed to read a temporary run"; return false; }
+        zbuf.resize(hdr[1]);
+        buf.resize((size_t)hdr[0] * TWKB_RECORD_BYTES);
+        if (hdr[0] == 0 || hdr[0] > kRunChunk || std::fread(zbuf.data(), 1, hdr[1], fp) != hdr[1]) { err = "failed to read a temporary run"; return false; }
+        const size_t r = ZSTD_decompress(buf.data(), buf.size(), zbuf.data(), zbuf.size());
+        if (ZSTD_isError(r) || r != buf.size()) { err = "corrupt temporary run"; return false; }
+        buf_n = hdr[0];
+        buf_next = 0;
+        return true;
+    }
+    bool empty() const { return fp ? emitted == n : next == n; }
+    const uint8_t* head() const { return fp ? buf.data() + (size_t)buf_next * TWKB_RECORD_BYTES : recs + (size_t)(keys[next].idx - base_idx) * TWKB_RECORD_BYTES; }
+    bool pop(std::string& err) {
+        if (fp) {
+            ++emitted;
+            if (++buf_next == buf_n && emitted < n) return fill(err);
+            return true;
+        }
+        ++next;
+        return true;
+    }
+};
+
+// Sorted output: blocks of <= 10,000 records (twk_two_writer_t::n_blk_lim, include/writer.h:164), cut at every change of
+// ridA, compressed in parallel batches, sorted-state index with per-contig entries.
+struct SortedWriter {
+    FILE* fp = nullptr;
+    uint64_t pos = 0;
+    int c_level = 1, n_threads = 1;
+    uint64_t n_contigs = 0;
+    struct Blk { std::vector<uint8_t> raw, z; size_t zn = 0; TwoIndexEntry ent{}; bool uniform = true; int32_t ridB0 = 0; uint32_t pA_first = 0, pA_last = 0; };
+    std::vector<Blk> batch;
+    std::vector<TwoIndexEntry> index;
+    std::vector<TwoMetaEntry> meta;
+    Blk cur;
+    uint32_t cur_n = 0;
+    int32_t cur_rid = 0;
+    std::string err;
+    static constexpr uint32_t blk_lim = 10000;
+
+    bool emit(const void* p, size_t n) {
+        if (n && std::fwrite(p, 1, n, fp) != n) { err = "write failed (disk full?)"; return false; }
+        pos += n;
+        return true;
+    }
+    void close_block() {
+        if (!cur_n) return;
+        const uint32_t m = blk_lim;
+        std::memcpy(cur.raw.data(), &cur_n, 4);
+        std::memcpy(cur.raw.data() + 4, &m, 4);
+        cur.ent.rid = cur_rid;
+        cur.ent.ridB = cur.uniform ? cur.ridB0 : -1;
+        cur.ent.n = cur_n;
+        // include/writer.h:363-374: minpos / maxpos are Apos (the position, flag bits dropped) of the first / last record
+        cur.ent.minpos = cur.pA_first >> 2;
+        cur.ent.maxpos = cur.pA_last >> 2;
+        batch.push_back(std::move(cur));
+        cur = Blk{};
+        cur_n = 0;
+    }
+    bool add(const uint8_t* rec) {
+        int32_t ra, rb; uint32_t pa, pb;
+        get_rec_key(rec, ra, rb, pa, pb);
+        if (cur_n && (ra != cur_rid || cur_n == blk_lim)) {
+            close_block();
+            if (batch.size() >= (size_t)std::max(8, 4 * n_threads) && !flush()) return false;
+        }
+        if (!cur_n) {
+            cur.raw.resize(8);
+            cur.raw.reserve(8 + (size_t)blk_lim * TWKB_RECORD_BYTES);
+            cur_rid = ra; cur.ridB0 = rb; cur.pA_first = pa; cur.uniform = true;
+        } else if (rb != cur.ridB0) cur.uniform = false;
+        cur.pA_last = pa;
+        cur.raw.insert(cur.raw.end(), rec, rec + TWKB_RECORD_BYTES);
+        ++cur_n;
+        return true;
+    }
+    bool flush() {  // compress the closed blocks in parallel, then write them in order
+        if (batch.empty()) return true;
+        std::atomic<size_t> next{0};
+        std::atomic<bool> bad{false};
+        auto work = [&]() {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= batch.size()) return;
+                Blk& b = batch[k];
+                b.z.resize(ZSTD_compressBound(b.raw.size()));
+                b.zn = ZSTD_compress(b.z.data(), b.z.size(), b.raw.data(), b.raw.size(), c_level);
+                if (ZSTD_isError(b.zn)) { bad.store(true); return; }
+            }
+        };
+        std::vector<std::thread> pool;
+        const int nt = (int)std::min<size_t>((size_t)n_threads, batch.size());
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        if (bad.load()) { err = "failed compression"; return false; }
+        for (Blk& b : batch) {
+            const uint8_t mk = 1;
+            b.ent.b_unc = (uint32_t)b.raw.size();
+            b.ent.b_cmp = (uint32_t)b.zn;
+            b.ent.foff = pos;
+            if (!emit(&mk, 1) || !emit(&b.ent.b_unc, 4) || !emit(&b.ent.b_cmp, 4) || !emit(b.z.data(), b.zn)) return false;
+            b.ent.fend = pos;
+            if (b.ent.rid < 0 || (uint64_t)b.ent.rid >= n_contigs) { err = "record with a contig id outside the header"; return false; }
+            TwoMetaEntry& me = meta[b.ent.rid];  // IndexEntryEntry::operator+=, lib/index.cpp:70-88
+            if (me.n == 0) { me.minpos = b.ent.minpos; me.foff = b.ent.foff; me.rid = b.ent.rid; }
+            me.n += b.ent.n;
+            me.maxpos = b.ent.maxpos;
+            me.fend = b.ent.fend;
+            ++me.nn;
+            index.push_back(b.ent);
+        }
+        batch.clear();
+        return true;
+    }
+};
+
+}  // namespace
+
+// `tomahawk sort` (two_reader::Sort, lib/two_reader.cpp:162-420). Bounded memory like the reference's: the input blocks are
+// taken in runs that fit `memory_limit` bytes (records + keys); a run is inflated and sorted in parallel; if everything is
+// one run it is merged straight from memory, otherwise every run is spilled to "<out>_<pid>_<k>.tmp" (zstd chunks) and the
+// runs are merged k-way with a heap. Ties (identical ridA, ridB, posA, posB) keep the input order in both arrangements,
+// so the output does not depend on the limit.
+int sort_two(const std::string& in, const std::string& out_path, int c_level, int n_threads, std::string& err, uint64_t* n_records,
+             uint64_t memory_limit) {
     n_threads = std::max(1, n_threads);
-    // ---- map the input and locate header, index and blocks (two_reader::Open, lib/two_reader.cpp:100-160)
     const int fd = ::open(in.c_str(), O_RDONLY);
     if (fd < 0) { err = "Failed to open \"" + in + "\"..."; return TWKB_EIO; }
     struct stat sb;
@@ -871,123 +1024,22 @@ int sort_two(const std::string& in, const std::string& out_path, int c_level, in
     if (total == 0) { err = "Cannot sort empty file..."; return TWKB_EINVAL; }  // two_reader.cpp:191-194
     if (n_records) *n_records = total;
 
-    // ---- inflate every block into one record array (parallel over blocks)
-    ByteBuf recs;
-    if (!recs.alloc((size_t)total * TWKB_RECORD_BYTES)) { err = "out of memory"; return TWKB_ENOMEM; }
+    // ---- runs of input blocks that fit the memory budget (records + keys)
+    const uint64_t per_rec = TWKB_RECORD_BYTES + sizeof(SortKey);
+    if (memory_limit == 0) memory_limit = ~0ull;
+    std::vector<std::pair<uint64_t, uint64_t>> run_blocks;  // [first block, last block)
     {
-        std::atomic<uint64_t> next{0};
-        std::atomic<bool> failed{false};
-        auto worker = [&]() {
-            std::vector<uint8_t> raw;
-            std::string e;
-            for (;;) {
-                const uint64_t b = next.fetch_add(1);
-                if (b >= n_ent || failed.load()) return;
-                const TwoIndexEntry& en = ents[b];
-                if (en.foff + 9 > fsz) { failed.store(true); return; }
-                Cursor bc{file + en.foff, file + fsz};
-                if (bc.get<uint8_t>() != 1) { failed.store(true); return; }
-                const uint32_t unc = bc.get<uint32_t>(), cmp = bc.get<uint32_t>();
-                if ((uint64_t)(bc.end - bc.p) < cmp || !zstd_inflate(bc.p, cmp, unc, raw, e)) { failed.store(true); return; }
-                uint32_t n = 0;
-                if (raw.size() >= 8) std::memcpy(&n, raw.data(), 4);
-                if (n != en.n || raw.size() < 8 + (size_t)n * TWKB_RECORD_BYTES) { failed.store(true); return; }
-                std::memcpy(recs.data() + first[b] * TWKB_RECORD_BYTES, raw.data() + 8, (size_t)n * TWKB_RECORD_BYTES);
-            }
-        };
-        std::vector<std::thread> pool;
-        const int nt = (int)std::min<uint64_t>((uint64_t)n_threads, n_ent);
-        for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
-        worker();
-        for (auto& th : pool) th.join();
-        if (failed.load()) { err = "Failed to load a block of \"" + in + "\""; return TWKB_EIO; }
-    }
-
-    // ---- order: twk1_two_t::operator< (lib/core.cpp:458-468): ridA, ridB, Apos, Bpos (packed positions)
-    struct Key { uint64_t hi, lo; uint32_t idx; };
-    std::vector<Key> keys((size_t)total);
-    for (uint64_t r = 0; r < total; ++r) {
-        int32_t ridA, ridB; uint32_t pA, pB;
-        get_rec_key(recs.data() + r * TWKB_RECORD_BYTES, ridA, ridB, pA, pB);
-        // the reference compares rid as int32: bias to keep the order under unsigned comparison
-        keys[r].hi = ((uint64_t)((uint32_t)ridA ^ 0x80000000u) << 32) | ((uint32_t)ridB ^ 0x80000000u);
-        keys[r].lo = ((uint64_t)pA << 32) | pB;
-        keys[r].idx = (uint32_t)r;
-    }
-    if (total > 0xffffffffull) { err = "too many records for the in-memory sorter"; return TWKB_ENOMEM; }
-    auto less = [](const Key& a, const Key& b) { return a.hi != b.hi ? a.hi < b.hi : (a.lo != b.lo ? a.lo < b.lo : a.idx < b.idx); };
-    {   // sorted runs per thread, then pairwise merges
-        const int nt = (int)std::min<uint64_t>((uint64_t)n_threads, std::max<uint64_t>(1, total / 65536));
-        std::vector<size_t> cut(nt + 1);
-        for (int t = 0; t <= nt; ++t) cut[t] = (size_t)(total * (uint64_t)t / nt);
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back([&, t]() { std::sort(keys.begin() + cut[t], keys.begin() + cut[t + 1], less); });
-        std::sort(keys.begin() + cut[0], keys.begin() + cut[1], less);
-        for (auto& th : pool) th.join();
-        for (int width = 1; width < nt; width *= 2)
-            for (int t = 0; t + width < nt; t += 2 * width)
-                std::inplace_merge(keys.begin() + cut[t], keys.begin() + cut[t + width], keys.begin() + cut[std::min(t + 2 * width, nt)], less);
-    }
-
-    // ---- output blocks: <= 10,000 records (twk_two_writer_t::n_blk_lim, include/writer.h:164), cut at every change of ridA
-    const uint32_t blk_lim = 10000;
-    struct OutBlock { uint64_t begin, end; std::vector<uint8_t> z; size_t zn = 0; TwoIndexEntry ent{}; };
-    std::vector<OutBlock> blocks;
-    {
-        uint64_t b0 = 0;
-        int32_t cur = (int32_t)((uint32_t)(keys[0].hi >> 32) ^ 0x80000000u);
-        for (uint64_t r = 1; r <= total; ++r) {
-            const int32_t ra = r < total ? (int32_t)((uint32_t)(keys[r].hi >> 32) ^ 0x80000000u) : 0;
-            if (r == total || ra != cur || r - b0 == blk_lim) {
-                blocks.push_back(OutBlock{b0, r, {}, 0, {}});
-                b0 = r;
-                cur = ra;
-            }
+        uint64_t b0 = 0, acc = 0;
+        for (uint64_t b = 0; b < n_ent; ++b) {
+            const uint64_t need = (uint64_t)ents[b].n * per_rec;
+            if (acc && acc + need > memory_limit) { run_blocks.push_back({b0, b}); b0 = b; acc = 0; }
+            acc += need;
         }
+        run_blocks.push_back({b0, n_ent});
     }
-    {
-        std::atomic<size_t> next{0};
-        std::atomic<bool> bad{false};
-        auto work = [&]() {
-            std::vector<uint8_t> raw;
-            for (;;) {
-                const size_t k = next.fetch_add(1);
-                if (k >= blocks.size()) return;
-                OutBlock& ob = blocks[k];
-                const uint32_t n = (uint32_t)(ob.end - ob.begin), m = blk_lim;
-                raw.resize(8 + (size_t)n * TWKB_RECORD_BYTES);
-                std::memcpy(raw.data(), &n, 4);
-                std::memcpy(raw.data() + 4, &m, 4);
-                bool uniform = true;
-                int32_t ridA0 = 0, ridB0 = 0;
-                uint32_t pA_first = 0, pA_last = 0;
-                for (uint32_t i = 0; i < n; ++i) {
-                    const uint8_t* src = recs.data() + (size_t)keys[ob.begin + i].idx * TWKB_RECORD_BYTES;
-                    std::memcpy(raw.data() + 8 + (size_t)i * TWKB_RECORD_BYTES, src, TWKB_RECORD_BYTES);
-                    int32_t ra, rb; uint32_t pa, pb;
-                    get_rec_key(src, ra, rb, pa, pb);
-                    if (i == 0) { ridA0 = ra; ridB0 = rb; pA_first = pa; }
-                    else if (rb != ridB0) uniform = false;
-                    pA_last = pa;
-                }
-                ob.z.resize(ZSTD_compressBound(raw.size()));
-                ob.zn = ZSTD_compress(ob.z.data(), ob.z.size(), raw.data(), raw.size(), c_level);
-                if (ZSTD_isError(ob.zn)) { bad.store(true); return; }
-                // include/writer.h:363-374: minpos / maxpos are Apos (the position, flag bits dropped) of the first / last record
-                ob.ent.rid = ridA0; ob.ent.ridB = uniform ? ridB0 : -1;
-                ob.ent.n = n; ob.ent.minpos = pA_first >> 2; ob.ent.maxpos = pA_last >> 2;
-                ob.ent.b_unc = (uint32_t)raw.size(); ob.ent.b_cmp = (uint32_t)ob.zn;
-            }
-        };
-        std::vector<std::thread> pool;
-        const int nt = (int)std::min<size_t>((size_t)n_threads, blocks.size());
-        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-        work();
-        for (auto& th : pool) th.join();
-        if (bad.load()) { err = "failed compression"; return TWKB_EIO; }
-    }
+    const bool external = run_blocks.size() > 1;
 
-    // ---- write: header (+ sort provenance lines, two_reader.cpp:346-349), blocks, sorted index, EOF
+    // ---- output file: header (+ sort provenance lines, two_reader.cpp:346-349)
     std::string out = out_path;
     {
         const size_t slash = out.find_last_of('/'), dot = out.find_last_of('.');
@@ -996,13 +1048,24 @@ int sort_two(const std::string& in, const std::string& out_path, int c_level, in
         for (auto& ch : ext) ch = (char)std::tolower((unsigned char)ch);
         if (ext != "two") out += ".two";  // two_reader.cpp:330-333
     }
-    FILE* fp = std::fopen(out.c_str(), "wb");
-    if (!fp) { err = "Failed top open \"" + out + "\"..."; return TWKB_EIO; }
+    SortedWriter w;
+    w.c_level = c_level;
+    w.n_threads = n_threads;
+    w.n_contigs = n_contigs;
+    w.meta.resize((size_t)n_contigs);
+    std::vector<std::string> temp_files;
+    auto cleanup = [&](bool remove_out) {
+        if (w.fp) { std::fclose(w.fp); w.fp = nullptr; }
+        for (const std::string& t : temp_files) ::unlink(t.c_str());
+        if (remove_out) ::unlink(out.c_str());  // never leave a truncated .two behind
+    };
+    w.fp = std::fopen(out.c_str(), "wb");
+    if (!w.fp) { err = "Failed top open \"" + out + "\"..."; return TWKB_EIO; }
     {
         Cursor h{hdr.data(), hdr.data() + hdr.size()};
         const std::string fileformat = h.str();
         std::string literals = h.str();
-        if (!h.ok) { std::fclose(fp); err = "corrupt VcfHeader"; return TWKB_EIO; }
+        if (!h.ok) { cleanup(true); err = "corrupt VcfHeader"; return TWKB_EIO; }
         char date[64];
         std::time_t now = std::time(nullptr);
         std::strftime(date, sizeof(date), "%Y-%m-%d %H:%M:%S", std::localtime(&now));
@@ -1013,57 +1076,160 @@ int sort_two(const std::string& in, const std::string& out_path, int c_level, in
         nh.insert(nh.end(), h.p, h.end);
         std::vector<uint8_t> z(ZSTD_compressBound(nh.size()));
         const size_t zn = ZSTD_compress(z.data(), z.size(), nh.data(), nh.size(), c_level);
-        if (ZSTD_isError(zn)) { std::fclose(fp); err = "failed to compress"; return TWKB_EIO; }
+        if (ZSTD_isError(zn)) { cleanup(true); err = "failed to compress"; return TWKB_EIO; }
         const uint64_t unc = nh.size(), cmp = zn;
-        std::fwrite(kTwoMagic, 1, 4, fp);
-        std::fwrite(&unc, 8, 1, fp);
-        std::fwrite(&cmp, 8, 1, fp);
-        std::fwrite(z.data(), 1, zn, fp);
+        if (!w.emit(kTwoMagic, 4) || !w.emit(&unc, 8) || !w.emit(&cmp, 8) || !w.emit(z.data(), zn)) { cleanup(true); err = w.err; return TWKB_EIO; }
     }
-    std::vector<TwoMetaEntry> meta((size_t)n_contigs);
-    for (OutBlock& ob : blocks) {
-        const uint8_t mk = 1;
-        ob.ent.foff = (uint64_t)std::ftell(fp);
-        std::fwrite(&mk, 1, 1, fp);
-        std::fwrite(&ob.ent.b_unc, 4, 1, fp);
-        std::fwrite(&ob.ent.b_cmp, 4, 1, fp);
-        if (std::fwrite(ob.z.data(), 1, ob.zn, fp) != ob.zn) { std::fclose(fp); err = "write failed"; return TWKB_EIO; }
-        ob.ent.fend = (uint64_t)std::ftell(fp);
-        if (ob.ent.rid < 0 || (uint64_t)ob.ent.rid >= n_contigs) { std::fclose(fp); err = "record with a contig id outside the header"; return TWKB_EINVAL; }
-        TwoMetaEntry& me = meta[ob.ent.rid];  // IndexEntryEntry::operator+=, lib/index.cpp:70-88
-        if (me.n == 0) { me.minpos = ob.ent.minpos; me.foff = ob.ent.foff; me.rid = ob.ent.rid; }
-        me.n += ob.ent.n;
-        me.maxpos = ob.ent.maxpos;
-        me.fend = ob.ent.fend;
-        ++me.nn;
+
+    // ---- build the runs
+    ByteBuf recs;
+    std::vector<SortKey> keys;
+    std::vector<SortedRun> runs(run_blocks.size());
+    for (size_t k = 0; k < run_blocks.size(); ++k) {
+        const uint64_t b_lo = run_blocks[k].first, b_hi = run_blocks[k].second;
+        const uint64_t r_lo = first[b_lo], n_run = first[b_hi] - r_lo;
+        if (!recs.alloc((size_t)n_run * TWKB_RECORD_BYTES)) { cleanup(true); err = "out of memory"; return TWKB_ENOMEM; }
+        try {
+            keys.resize((size_t)n_run);
+        } catch (const std::bad_alloc&) { cleanup(true); err = "out of memory"; return TWKB_ENOMEM; }
+        {   // inflate the run's blocks (parallel over blocks)
+            std::atomic<uint64_t> next{b_lo};
+            std::atomic<bool> failed{false};
+            auto worker = [&]() {
+                std::vector<uint8_t> raw;
+                std::string e;
+                try {
+                    for (;;) {
+                        const uint64_t b = next.fetch_add(1);
+                        if (b >= b_hi || failed.load()) return;
+                        const TwoIndexEntry& en = ents[b];
+                        if (en.foff + 9 > fsz) { failed.store(true); return; }
+                        Cursor bc{file + en.foff, file + fsz};
+                        if (bc.get<uint8_t>() != 1) { failed.store(true); return; }
+                        const uint32_t unc = bc.get<uint32_t>(), cmp = bc.get<uint32_t>();
+                        if ((uint64_t)(bc.end - bc.p) < cmp || !zstd_inflate(bc.p, cmp, unc, raw, e)) { failed.store(true); return; }
+                        uint32_t n = 0;
+                        if (raw.size() >= 8) std::memcpy(&n, raw.data(), 4);
+                        if (n != en.n || raw.size() < 8 + (size_t)n * TWKB_RECORD_BYTES) { failed.store(true); return; }
+                        uint8_t* dst = recs.data() + (first[b] - r_lo) * TWKB_RECORD_BYTES;
+                        std::memcpy(dst, raw.data() + 8, (size_t)n * TWKB_RECORD_BYTES);
+                        for (uint32_t r = 0; r < n; ++r) keys[first[b] - r_lo + r] = key_of(dst + (size_t)r * TWKB_RECORD_BYTES, first[b] + r);
+                    }
+                } catch (...) { failed.store(true); }
+            };
+            std::vector<std::thread> pool;
+            const int nt = (int)std::min<uint64_t>((uint64_t)n_threads, b_hi - b_lo);
+            for (int t = 1; t < nt; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto& th : pool) th.join();
+            if (failed.load()) { cleanup(true); err = "Failed to load a block of \"" + in + "\""; return TWKB_EIO; }
+        }
+        {   // sorted sub-ranges per thread, then pairwise merges
+            const int nt = (int)std::min<uint64_t>((uint64_t)n_threads, std::max<uint64_t>(1, n_run / 65536));
+            std::vector<size_t> cut(nt + 1);
+            for (int t = 0; t <= nt; ++t) cut[t] = (size_t)(n_run * (uint64_t)t / nt);
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nt; ++t) pool.emplace_back([&, t]() { std::sort(keys.begin() + cut[t], keys.begin() + cut[t + 1], key_less); });
+            std::sort(keys.begin() + cut[0], keys.begin() + cut[1], key_less);
+            for (auto& th : pool) th.join();
+            for (int width = 1; width < nt; width *= 2)
+                for (int t = 0; t + width < nt; t += 2 * width)
+                    std::inplace_merge(keys.begin() + cut[t], keys.begin() + cut[t + width], keys.begin() + cut[std::min(t + 2 * width, nt)], key_less);
+        }
+        SortedRun& run = runs[k];
+        run.n = n_run;
+        run.base_idx = r_lo;
+        if (!external) {
+            run.recs = recs.data();
+            run.keys = keys.data();
+            break;
+        }
+        // spill: zstd chunks in sorted order
+        run.path = out + "_" + std::to_string((long)getpid()) + "_" + std::to_string(k) + ".tmp";
+        FILE* tf = std::fopen(run.path.c_str(), "wb");
+        if (!tf) { cleanup(true); err = "Failed to open temporary file \"" + run.path + "\""; return TWKB_EIO; }
+        temp_files.push_back(run.path);
+        std::vector<uint8_t> chunk, z;
+        bool ok = true;
+        for (uint64_t r = 0; r < n_run && ok; r += kRunChunk) {
+            const uint32_t n = (uint32_t)std::min<uint64_t>(kRunChunk, n_run - r);
+            chunk.resize((size_t)n * TWKB_RECORD_BYTES);
+            for (uint32_t q = 0; q < n; ++q)
+                std::memcpy(chunk.data() + (size_t)q * TWKB_RECORD_BYTES, recs.data() + (size_t)(keys[r + q].idx - r_lo) * TWKB_RECORD_BYTES, TWKB_RECORD_BYTES);
+            z.resize(ZSTD_compressBound(chunk.size()));
+            const size_t zn = ZSTD_compress(z.data(), z.size(), chunk.data(), chunk.size(), 1);
+            const uint32_t hdr2[2] = {n, (uint32_t)zn};
+            ok = !ZSTD_isError(zn) && std::fwrite(hdr2, 4, 2, tf) == 2 && std::fwrite(z.data(), 1, zn, tf) == zn;
+        }
+        ok = (std::fclose(tf) == 0) && ok;
+        if (!ok) { cleanup(true); err = "Failed to write temporary file \"" + run.path + "\" (disk full?)"; return TWKB_EIO; }
     }
+    if (external) {
+        recs.release();
+        std::vector<SortKey>().swap(keys);
+        for (SortedRun& run : runs) {
+            run.fp = std::fopen(run.path.c_str(), "rb");
+            if (!run.fp || !run.fill(err)) { for (SortedRun& r2 : runs) if (r2.fp) std::fclose(r2.fp); cleanup(true); if (err.empty()) err = "Failed to reopen a temporary run"; return TWKB_EIO; }
+        }
+    }
+
+    // ---- k-way merge (one run: a plain walk). Heap of run ids ordered by the head record's key; equal keys by run id = input order.
+    int rc = TWKB_OK;
+    {
+        struct Head { SortKey k; uint32_t run; };
+        auto worse = [](const Head& a, const Head& b) { return key_less(b.k, a.k) || (!key_less(a.k, b.k) && a.run > b.run); };  // min-heap
+        std::vector<Head> heap;
+        auto head_of = [&](uint32_t r) {
+            SortKey k = key_of(runs[r].head(), 0);
+            k.idx = 0;  // ties: run order (runs are consecutive input ranges and stable inside)
+            return Head{k, r};
+        };
+        for (uint32_t r = 0; r < runs.size(); ++r)
+            if (!runs[r].empty()) heap.push_back(head_of(r));
+        std::make_heap(heap.begin(), heap.end(), worse);
+        while (!heap.empty() && rc == TWKB_OK) {
+            std::pop_heap(heap.begin(), heap.end(), worse);
+            const uint32_t r = heap.back().run;
+            heap.pop_back();
+            if (!w.add(runs[r].head())) { rc = TWKB_EIO; err = w.err; break; }
+            if (!runs[r].pop(err)) { rc = TWKB_EIO; break; }
+            if (!runs[r].empty()) {
+                heap.push_back(head_of(r));
+                std::push_heap(heap.begin(), heap.end(), worse);
+            }
+        }
+    }
+    for (SortedRun& run : runs) if (run.fp) { std::fclose(run.fp); run.fp = nullptr; }
+    if (rc == TWKB_OK) {
+        w.close_block();
+        if (!w.flush()) { rc = TWKB_EIO; err = w.err; }
+    }
+    if (rc != TWKB_OK) { cleanup(true); return rc; }
+
+    // ---- sorted index + EOF
     std::vector<uint8_t> ob_idx;
     auto put = [&](const void* p, size_t n) { ob_idx.insert(ob_idx.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
     const uint8_t state = 2;  // TWK_IDX_SORTED, include/index.h:105
-    uint64_t n_out = blocks.size(), m_out = 500;
+    uint64_t n_out = w.index.size(), m_out = 500;
     while (m_out < n_out) m_out *= 2;
     put(&kIndexMarker, 8); put(&state, 1); put(&n_out, 8); put(&m_out, 8); put(&n_contigs, 8);
-    for (const OutBlock& b : blocks) {
-        const TwoIndexEntry& e = b.ent;
+    for (const TwoIndexEntry& e : w.index) {
         put(&e.rid, 4); put(&e.n, 4); put(&e.minpos, 4); put(&e.maxpos, 4); put(&e.b_unc, 4); put(&e.b_cmp, 4);
         put(&e.foff, 8); put(&e.fend, 8); put(&e.ridB, 4);
     }
-    for (const TwoMetaEntry& me : meta) {
+    for (const TwoMetaEntry& me : w.meta) {
         put(&me.rid, 4); put(&me.n, 4); put(&me.minpos, 4); put(&me.maxpos, 4); put(&me.foff, 8); put(&me.fend, 8); put(&me.nn, 8);
     }
     std::vector<uint8_t> z(ZSTD_compressBound(ob_idx.size()));
     const size_t zn = ZSTD_compress(z.data(), z.size(), ob_idx.data(), ob_idx.size(), c_level);
-    if (ZSTD_isError(zn)) { std::fclose(fp); err = "failed compression"; return TWKB_EIO; }
-    const uint64_t off = (uint64_t)std::ftell(fp), unc = ob_idx.size(), cmp = zn;
+    if (ZSTD_isError(zn)) { cleanup(true); err = "failed compression"; return TWKB_EIO; }
+    const uint64_t off = w.pos, unc = ob_idx.size(), cmp = zn;
     const uint8_t mk0 = 0;
-    std::fwrite(&mk0, 1, 1, fp);
-    std::fwrite(&unc, 8, 1, fp);
-    std::fwrite(&cmp, 8, 1, fp);
-    std::fwrite(z.data(), 1, zn, fp);
-    std::fwrite(&off, 8, 1, fp);
-    std::fwrite(kEof, 1, 32, fp);
-    const bool ok = std::fflush(fp) == 0;
-    std::fclose(fp);
+    bool ok = w.emit(&mk0, 1) && w.emit(&unc, 8) && w.emit(&cmp, 8) && w.emit(z.data(), zn) && w.emit(&off, 8) && w.emit(kEof, 32);
+    ok = ok && std::fflush(w.fp) == 0 && !std::ferror(w.fp);
+    ok = (std::fclose(w.fp) == 0) && ok;
+    w.fp = nullptr;
+    cleanup(!ok);
     if (!ok) { err = "Failed to write final block!"; return TWKB_EIO; }
     return TWKB_OK;
 }

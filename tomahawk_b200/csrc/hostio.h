@@ -156,7 +156,9 @@ private:
 // <= 10,000 records cut at every change of ridA, index state TWK_IDX_SORTED with per-block
 // (rid, ridB, minpos, maxpos) and the per-contig summary entries that make `view -I` seek
 // (include/writer.h:344-390, lib/index.cpp:70-88).
+// memory_limit (bytes, 0 = unbounded): inputs whose records + keys exceed it are sorted in runs that are spilled to
+// temporary files next to `out` and merged k-way, like the reference's external merge (lib/two_reader.cpp:262-420).
 int sort_two(const std::string& in, const std::string& out, int c_level, int n_threads, std::string& err,
-             uint64_t* n_records = nullptr);
+             uint64_t* n_records = nullptr, uint64_t memory_limit = 0);
 
 }  // namespace twkb

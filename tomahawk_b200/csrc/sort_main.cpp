@@ -1,7 +1,6 @@
 // sort_main.cpp -- the `sort` command line of the reference (lib/sort.h:28-120) in front of
-// twkb_two_sort (libtwkb.so): same options, range checks, messages and exit codes. The sorter
-// works in host memory, so -m (memory per thread of the reference's external merge) is checked
-// but otherwise unused.
+// twkb_two_sort_mem (libtwkb.so): same options, range checks, messages and exit codes. -m is the memory budget per
+// thread of the reference's external merge: inputs beyond it are sorted in spilled runs and merged k-way.
 //
 //   twkb_sort [sort] [options] -i <in.two> -o <out.two>
 #include <getopt.h>
@@ -22,7 +21,7 @@ static void sort_usage() {
                  "Options:\n"
                  "  -i FILE   input TWO file (required)\n"
                  "  -o FILE   output file (required)\n"
-                 "  -m FLOAT  accepted for compatibility (memory per thread of the reference's external merge)\n"
+                 "  -m FLOAT  memory budget in GB per thread (default 0.5): larger inputs are sorted in runs spilled to temporary files and merged\n"
                  "  -c INT    compression level 1-20 (default: 1)\n"
                  "  -t INT    number of threads (default: maximum available)\n\n";
 }
@@ -55,7 +54,9 @@ int main(int argc, char** argv) {
     std::cerr << timestamp("LOG") << "Calling sort..." << std::endl;
     char err[1024] = {0};
     uint64_t n = 0;
-    const int rc = twkb_two_sort(in.c_str(), out.c_str(), c_level, n_threads, &n, err, sizeof(err));
+    // -m: GB per thread in the reference (two_sorter_settings::memory_limit, lib/sort.h); here the budget of the whole sort
+    const uint64_t budget = (uint64_t)((double)memory_limit * 1e9 * (double)n_threads);
+    const int rc = twkb_two_sort_mem(in.c_str(), out.c_str(), c_level, n_threads, budget, &n, err, sizeof(err));
     if (rc != TWKB_OK) { std::cerr << timestamp("ERROR") << err << std::endl; return 1; }
     std::cerr << timestamp("LOG") << "Sorted " << twkb_host::pretty(n) << " records..." << std::endl;
     std::cerr << timestamp("LOG") << "Finished!" << std::endl;
