@@ -215,6 +215,14 @@ int twkb_load_matrix_sliced(void* ctx, uint32_t n_samples, uint32_t n_variants, 
 int twkb_load_runs_sliced(void* ctx, uint32_t n_samples, uint32_t n_variants, const uint8_t* run_bytes, size_t n_run_bytes,
                           const twkb_run_desc* desc, const twkb_variant* meta);
 
+/* The .twk block structure of the loaded variants: block_first[b] = index (file order) of the first variant of block b,
+ * n_blocks entries, strictly increasing from 0. The reference's -w rules (balancer row prune, block-pair abort) and its -c / -C
+ * chunks are defined on .twk blocks, whose length `import -b` makes configurable; call this after a load (twkb_calc_file* and
+ * the C++ mirror pass the file's index). Without it blocks of settings.twk_block_size variants per contig are assumed. */
+int twkb_set_blocks(void* ctx, const uint32_t* block_first, uint32_t n_blocks);
+/* Borrow the block structure of an open .twk handle (n_blocks + 1 entries, the last one = n_variants). */
+int twkb_twk_blocks(void* handle, const uint32_t** block_first, uint32_t* n_blocks);
+
 /* Test hook: copy the resident reference-layout rows (file order unless the rare-variant class
  * re-ordered them) back to the host. mask_bits may be NULL. */
 int twkb_debug_rows(void* ctx, uint64_t* data_bits, uint64_t* mask_bits, size_t row_stride_words);

@@ -167,6 +167,9 @@ public:
         const twkb_run_desc* run_desc = nullptr;
         if (runs) twkb_twk_runs_view(twk, &run_bytes, &n_run_bytes, &run_desc, &meta);
         else twkb_twk_view(twk, &data, &mask, &meta);
+        const uint32_t* file_blocks = nullptr;  // the file's block structure: window rules and -c chunks are defined on it
+        uint32_t n_file_blocks = 0;
+        twkb_twk_blocks(twk, &file_blocks, &n_file_blocks);
         log() << "Samples: " << pretty(n_samples) << "..." << std::endl;
         log() << pretty(n_variants) << " variants from " << pretty(n_blocks) << " blocks..." << std::endl;
         log("PARAMS") << settings.GetString() << std::endl;
@@ -244,6 +247,7 @@ public:
                              : twkb_load_matrix(ctx, n_samples, n_variants, data, mask, stride, meta);
                 }
             }
+            if (r == TWKB_OK && file_blocks && n_file_blocks) r = twkb_set_blocks(ctx, file_blocks, n_file_blocks);
             if (r == TWKB_OK) r = twkb_compute(ctx, &twk_ld::sink, &shared);
             if (r) { errors[k] = twkb_last_error(ctx); rcs[k] = r; }
             else twkb_get_stats(ctx, &st[k]);

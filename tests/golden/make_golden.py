@@ -46,6 +46,9 @@ CASES = {
     "bitmap_window": (dict(n_samples=200, n_variants=1700, seed=123, missing_rate=0.01, two_contigs=1100),
                       ["-p", "-m", "-M", "-r", "0.05", "-w", "60000"],
                       dict(force_phased=1, bitmaps=1, minR2=0.05, window=1, l_window=60000)),
+    # a .twk imported with -b 300: the window rules (row prune, block-pair abort) follow the FILE's blocks
+    "window_blocks300": (dict(n_samples=300, n_variants=1900, seed=131, twk_block=300), ["-p", "-r", "0.1", "-w", "45000"],
+                         dict(force_phased=1, minR2=0.1, window=1, l_window=45000, block_size=300)),
     "minp_filter": (dict(n_samples=600, n_variants=250, seed=109), ["-p", "-r", "0.05", "-P", "1e-3"],
                     dict(force_phased=1, minR2=0.05, minP=1e-3)),
 }
@@ -59,6 +62,7 @@ def main():
             continue
         skw = dict(skw)
         split = skw.pop("two_contigs", None)
+        twk_block = skw.pop("twk_block", 500)
         s = tf.synth_genotypes(**skw)
         contigs = None
         if split:  # second contig restarts its positions
@@ -66,7 +70,7 @@ def main():
             s.pos[split:] = (np.arange(s.n_variants - split) * 100).astype(np.uint32)
             contigs = [("1", 10**6), ("2", 10**6)]
         twk = os.path.join(TMP, f"g_{name}.twk")
-        tf.write_twk(twk, s, contigs=contigs)
+        tf.write_twk(twk, s, contigs=contigs, block_size=twk_block)
         info = lc.run_reference_calc(twk, os.path.join(TMP, f"g_{name}"), cli, threads=4)
         recs = tf.canonical(tf.read_two(os.path.join(TMP, f"g_{name}.two")), forward_only=True)
         # pairs visited: the reference's own figure when its (racy) stderr summary parses,

@@ -11,6 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["phased_r01", "phased_r0", "phased_odd_n", "unphased_miss", "unphased_nomiss_r0",
                 "phased_miss_aligned", "phased_miss_quirks", "window", "minp_filter", "auto_mixed", "auto_window",
                 "bitmap_window"]
+BLOCK_CASES = ["window_blocks300"]   # block structure comes from the FILE: run through twkb_calc_file (block_size is an oracle parameter)
 INTERVAL_CASES = ["interval_one", "interval_two"]   # need the file reader: run through twkb_calc_file_intervals
 
 # Tolerances of BASELINE.json's north_star

@@ -578,6 +578,31 @@ def test_config2_subsample_vs_reference_binary(tmpdir_repo):
     eng.close()
 
 
+def test_calc_file_follows_the_files_block_structure(tmpdir_repo):
+    """`import -b 300`: the reference's window rules (balancer row prune over blocks, abort of a block pair at its first
+    out-of-window pair) are defined on the file's own blocks, which twkb_calc_file takes from the index (twkb_set_blocks);
+    assuming 500-variant blocks gives a different record set."""
+    s, ref, prm, pairs, cli = load_golden("window_blocks300")
+    twk = os.path.join(tmpdir_repo, "blk300.twk")
+    assert tf.write_twk(twk, s, block_size=300) == 7
+    assert list(tb.TwkFile(twk).blocks()) == [0, 300, 600, 900, 1200, 1500, 1800]
+    st = tb.default_settings(force_phased=1, minR2=0.1, window=1, l_window=45000)
+    ld = tb.twk_ld()
+    out = os.path.join(tmpdir_repo, "blk300.two")
+    assert ld.Compute(st, twk, out)
+    assert ld.last_stats.pairs_visited == pairs
+    assert_records_bitexact(tf.canonical(tf.read_two(out), forward_only=True), ref, p_rtol=1e-9)
+    # the same matrix without the file's blocks: 500-variant blocks are assumed, and the result differs
+    data, mask = tf.pack_bits(s)
+    eng = tb.Engine(force_phased=1, minR2=0.1, window=1, l_window=45000)
+    eng.load(s.n_samples, data, mask, lc.variant_meta(s))
+    other = eng.compute()
+    assert len(keyset(other) ^ keyset(ref)) > 0
+    eng.set_blocks(np.arange(0, 1900, 300))
+    assert_records_bitexact(eng.compute(), ref, p_rtol=1e-9)
+    eng.close()
+
+
 def test_edge_cases():
     # a single pair
     s = tf.synth_genotypes(50, 2, seed=95)

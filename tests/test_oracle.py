@@ -6,7 +6,7 @@ import pytest
 
 from oracle import ldcore as lc
 from oracle import twk_format as tf
-from tests.helpers import GOLDEN_CASES, assert_records_bitexact, load_golden
+from tests.helpers import BLOCK_CASES, GOLDEN_CASES, assert_records_bitexact, load_golden
 
 # docs/tutorial.md:608-612 of the reference: counts -> D, D', R, R2, P, T*R2
 TUTORIAL_ROWS = [
@@ -49,7 +49,7 @@ def test_fisher_edge_cases():
     assert 0.0 <= big < 1e-300
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + BLOCK_CASES)
 def test_oracle_matches_reference_golden(name):
     s, ref, prm, pairs, _ = load_golden(name)
     got, visited = lc.calc(s, lc.default_params(**prm))

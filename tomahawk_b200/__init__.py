@@ -96,7 +96,7 @@ EXPORTS = [
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
     "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
     "twkb_two_sort",
-    "twkb_two_sort_mem", "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
+    "twkb_set_blocks", "twkb_twk_blocks", "twkb_two_sort_mem", "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
 ]
 
 
@@ -151,6 +151,8 @@ def _bind(L):
     L.twkb_two_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     L.twkb_two_sort.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                 ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_set_blocks.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+    L.twkb_twk_blocks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32)]
     L.twkb_two_sort_mem.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
                                     ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
     L.twkb_compute.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
@@ -230,6 +232,14 @@ class TwkFile:
         desc = np.frombuffer((ctypes.c_uint8 * (16 * self.n_variants)).from_address(d.value), dtype=RUN_DESC_DTYPE)
         meta = np.frombuffer((ctypes.c_uint8 * (32 * self.n_variants)).from_address(m.value), dtype=VARIANT_DTYPE)
         return raw, desc, meta
+
+    def blocks(self) -> np.ndarray:
+        """First variant of every loaded .twk block (file order)."""
+        p, n = ctypes.c_void_p(), ctypes.c_uint32()
+        self._L.twkb_twk_blocks(self._h, ctypes.byref(p), ctypes.byref(n))
+        if not n.value:
+            return np.zeros(0, np.uint32)
+        return np.frombuffer((ctypes.c_uint8 * (4 * n.value)).from_address(p.value), dtype=np.uint32).copy()
 
     def matrix(self):
         if self.runs_mode:
@@ -406,6 +416,11 @@ class Engine:
         meta = np.ascontiguousarray(meta)
         self._check(self._L.twkb_load_runs_sliced(self._ctx, n_samples, len(desc), run_bytes.ctypes.data, run_bytes.size,
                                                   desc.ctypes.data, meta.ctypes.data))
+
+    def set_blocks(self, block_first):
+        """The .twk block structure (first variant of every block) the window rules / -c chunks are defined on."""
+        bf = np.ascontiguousarray(block_first, dtype=np.uint32)
+        self._check(self._L.twkb_set_blocks(self._ctx, bf.ctypes.data, len(bf)))
 
     def load_runs(self, n_samples: int, run_bytes: np.ndarray, desc: np.ndarray, meta: np.ndarray):
         """Run-length records (twk1_igt_t words located by ``desc``) -> resident rows, decoded on the device."""

@@ -110,6 +110,7 @@ struct Context {
     // window-mode block structure
     DevBuf<uint32_t> d_blk_of, d_blk_first, d_blk_last, d_blk_prune;
     std::vector<uint32_t> h_blk_first, h_blk_last, h_blk_prune, h_blk_of_orig;  // file order
+    std::vector<uint32_t> file_blocks;  // twkb_set_blocks: first variant of every .twk block (empty: assume twk_block_size)
 
     // tile plan of the last run, reused while the sub-problem and the partition are unchanged
     std::vector<uint2> plan_tiles;
@@ -253,21 +254,38 @@ static int ensure_planes(Context* ctx, int mode) {
 // .twk block structure for the window rule (blocks of <= bs variants, one contig
 // per block: lib/importer.cpp:196-236) and the row-prune limit of
 // ld_balancing.h:189-196.
-static void build_blocks_host(Context* ctx, std::vector<uint32_t>& blk_of_orig) {
+// First variant of every .twk block in file order (+ M at the end): from the file's index when the caller supplied it
+// (twkb_set_blocks), else blocks of twk_block_size variants that never span two contigs (lib/importer.cpp:196-236).
+static std::vector<uint32_t> block_starts(const Context* ctx, const std::vector<twkb_variant>& mo) {
     const uint32_t M = ctx->n_variants;
-    const std::vector<twkb_variant>& mo = ctx->h_meta_orig;  // blocks are defined on the file order
+    std::vector<uint32_t> first;
+    if (!ctx->file_blocks.empty() && ctx->file_blocks.back() < M) {
+        first = ctx->file_blocks;
+        first.push_back(M);
+        return first;
+    }
     const uint32_t bs = ctx->st.twk_block_size > 0 ? (uint32_t)ctx->st.twk_block_size : 500u;
-    blk_of_orig.assign(M, 0);
-    ctx->h_blk_first.clear();
-    ctx->h_blk_last.clear();
     for (uint32_t v = 0; v < M;) {
         uint32_t e = v + 1;
         while (e < M && e - v < bs && mo[e].rid == mo[v].rid) ++e;
-        const uint32_t b = (uint32_t)ctx->h_blk_first.size();
-        for (uint32_t x = v; x < e; ++x) blk_of_orig[x] = b;
-        ctx->h_blk_first.push_back(v);
-        ctx->h_blk_last.push_back(e - 1);
+        first.push_back(v);
         v = e;
+    }
+    first.push_back(M);
+    return first;
+}
+
+static void build_blocks_host(Context* ctx, std::vector<uint32_t>& blk_of_orig) {
+    const uint32_t M = ctx->n_variants;
+    const std::vector<twkb_variant>& mo = ctx->h_meta_orig;  // blocks are defined on the file order
+    blk_of_orig.assign(M, 0);
+    ctx->h_blk_first.clear();
+    ctx->h_blk_last.clear();
+    const std::vector<uint32_t> first = block_starts(ctx, mo);
+    for (size_t b = 0; b + 1 < first.size(); ++b) {
+        for (uint32_t x = first[b]; x < first[b + 1]; ++x) blk_of_orig[x] = (uint32_t)b;
+        ctx->h_blk_first.push_back(first[b]);
+        ctx->h_blk_last.push_back(first[b + 1] - 1);
     }
     const uint32_t nb = (uint32_t)ctx->h_blk_first.size();
     const uint32_t w = (uint32_t)ctx->st.l_window;
@@ -340,16 +358,7 @@ static int select_problem(Context* ctx, Problem& pb) {
     pb = {0, M, 0, M, true};
     const int parts = ctx->st.n_chunks;
     if (parts <= 1) return TWKB_OK;
-    // blocks of twk_block_size variants / contig breaks
-    std::vector<uint32_t> first;
-    const uint32_t bs = ctx->st.twk_block_size > 0 ? (uint32_t)ctx->st.twk_block_size : 500u;
-    for (uint32_t v = 0; v < M;) {
-        uint32_t e = v + 1;
-        while (e < M && e - v < bs && ctx->h_meta[e].rid == ctx->h_meta[v].rid) ++e;
-        first.push_back(v);
-        v = e;
-    }
-    first.push_back(M);
+    const std::vector<uint32_t> first = block_starts(ctx, ctx->h_meta_orig.size() == M ? ctx->h_meta_orig : ctx->h_meta);
     const uint32_t nb = (uint32_t)first.size() - 1;
     if ((uint32_t)parts > nb) { ctx->err = "more sub-problems than blocks"; return TWKB_EINVAL; }
     uint32_t factor = 0;
@@ -1201,6 +1210,7 @@ static int load_begin(Context* ctx, uint32_t n_samples, uint32_t n_variants, siz
     ctx->Mpad = (n_variants + 255) / 256 * 256;
     ctx->raw_stride = stride;
     ctx->h_meta_orig.assign(meta, meta + n_variants);
+    ctx->file_blocks.clear();
     ctx->any_missing = false;
     for (uint32_t v = 0; v < n_variants; ++v)
         if (meta[v].gt_missing || meta[v].an) ctx->any_missing = true;
@@ -1667,6 +1677,29 @@ int twkb_load_runs(void* c, uint32_t n_samples, uint32_t n_variants, const uint8
     return guarded_ctx(c, [&] { return load_runs(static_cast<Context*>(c), n_samples, n_variants, run_bytes, n_run_bytes, desc, meta); });
 }
 
+int twkb_set_blocks(void* c, const uint32_t* block_first, uint32_t n_blocks) {
+    if (!c || (!block_first && n_blocks)) return TWKB_EINVAL;
+    Context* ctx = static_cast<Context*>(c);
+    if (!ctx->loaded) { ctx->err = "twkb_set_blocks before a load"; return TWKB_ESTATE; }
+    for (uint32_t b = 0; b < n_blocks; ++b)
+        if ((b == 0 && block_first[0] != 0) || (b && block_first[b] <= block_first[b - 1]) || block_first[b] >= ctx->n_variants) {
+            ctx->err = "block_first must start at 0 and increase strictly below n_variants";
+            return TWKB_EINVAL;
+        }
+    ctx->file_blocks.assign(block_first, block_first + n_blocks);
+    ctx->plan_key.clear();
+    ctx->sp_plan_key.clear();
+    return TWKB_OK;
+}
+
+int twkb_twk_blocks(void* handle, const uint32_t** block_first, uint32_t* n_blocks) {
+    if (!handle) return TWKB_EINVAL;
+    const TwkFile* f = static_cast<TwkFile*>(handle);
+    if (block_first) *block_first = f->block_first.empty() ? nullptr : f->block_first.data();
+    if (n_blocks) *n_blocks = f->block_first.empty() ? 0u : (uint32_t)f->block_first.size() - 1u;
+    return TWKB_OK;
+}
+
 int twkb_comm_unique_id(uint8_t* id) {
     if (!id) return TWKB_EINVAL;
     const NcclApi& nc = nccl_api();
@@ -1813,6 +1846,8 @@ static int twkb_calc_file_intervals_impl(const twkb_settings* s, const char* in_
     else
         rc = twkb_load_matrix(c, twk.n_samples, twk.n_variants, twk.data.data(), twk.any_missing ? twk.mask.data() : nullptr,
                               twk.stride, twk.meta.data());
+    if (rc == TWKB_OK && twk.block_first.size() > 1)  // the file's own block structure (window rules, -c chunks)
+        rc = twkb_set_blocks(c, twk.block_first.data(), (uint32_t)twk.block_first.size() - 1);
     if (rc == TWKB_OK && runs) twk.raw.release();  // the runs now live on the device
     const double sec_load = since(t_load);
     if (rc) { err = ctx->err; twkb_destroy(c); return fail(rc, err); }

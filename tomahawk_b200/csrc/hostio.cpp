@@ -329,6 +329,9 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
     }
     n_ent = blocks.size();
     out.n_blocks = (uint32_t)blocks.size();
+    out.block_first.clear();
+    for (const BlockRef& b : blocks) out.block_first.push_back(b.first_variant);
+    out.block_first.push_back((uint32_t)total);
     out.n_variants = (uint32_t)total;
     const uint64_t H = 2ull * out.n_samples;
     out.stride = ((H + 63) / 64 + 1) / 2 * 2;
@@ -495,6 +498,7 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
         out.meta.swap(meta2);
         out.n_targets = (uint32_t)targets.size();
         out.n_variants = (uint32_t)n2;
+        out.block_first.clear();  // the rows were re-ordered [targets | neighbours]: no block structure
         out.any_missing = false;
         if (!keep_runs) {
             bool any = false;

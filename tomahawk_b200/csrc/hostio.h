@@ -67,6 +67,8 @@ struct TwkFile {
     std::string header_tail;  // serialized samples + contigs, copied through verbatim
     uint32_t n_contigs = 0;
     uint32_t n_blocks = 0;
+    std::vector<uint32_t> block_first;  // first variant of every loaded .twk block (+ n_variants at the end): the block structure the
+                                        // reference's window rule and -c chunks are defined on (`import -b` makes the length configurable)
     // Runs mode (keep_runs): the rows are NOT unpacked on the host. `raw` holds the inflated .twk
     // blocks back to back and run_desc[v] locates the run-length words of variant v inside it
     // (twk1_igt_t, include/core.h:188-256); the device decodes them (decode.cuh, twkb_load_runs).
