@@ -234,6 +234,14 @@ int twkb_compute(void* ctx, twkb_sink_fn sink, void* user);
  * them (used to time the device-resident path; no D2H of records). */
 int twkb_compute_resident(void* ctx);
 
+/* Downstream consumer fed from the device-resident records: LD decay over distance, the reference's
+ * two_reader::Decay (lib/two_reader.cpp:424-475), without writing and re-reading a .two file. Runs the LD computation like
+ * twkb_compute_resident and reduces every record with ridA == ridB and posA < posB into
+ *     bin = min((posB - posA) / (window_bp / n_bins), n_bins - 1):  sum_r2[bin] += R2, count[bin] += 1
+ * on the device; the reference prints From = bin * width, To = (bin + 1) * width, Mean = sum / max(count, 1), Frequency = count.
+ * Only 16 bytes per bin leave the GPU. sum_r2 / count: host arrays of n_bins entries. */
+int twkb_compute_decay(void* ctx, int64_t window_bp, int32_t n_bins, double* sum_r2, uint64_t* count);
+
 int twkb_get_stats(void* ctx, twkb_stats* out);
 
 /* Test hook: run the count kernel the settings select (tensor-core or LOP3+POPC, exactly as

@@ -96,7 +96,7 @@ EXPORTS = [
     "twkb_two_open", "twkb_two_add", "twkb_two_close", "twkb_plan_tiles",
     "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
     "twkb_two_sort",
-    "twkb_set_blocks", "twkb_twk_blocks", "twkb_two_sort_mem", "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
+    "twkb_compute_decay", "twkb_set_blocks", "twkb_twk_blocks", "twkb_two_sort_mem", "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
 ]
 
 
@@ -151,6 +151,7 @@ def _bind(L):
     L.twkb_two_set_threads.argtypes = [ctypes.c_void_p, ctypes.c_int32]
     L.twkb_two_sort.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                 ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_compute_decay.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
     L.twkb_set_blocks.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
     L.twkb_twk_blocks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32)]
     L.twkb_two_sort_mem.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
@@ -472,6 +473,15 @@ class Engine:
 
     def compute_resident(self):
         self._check(self._L.twkb_compute_resident(self._ctx))
+
+    def compute_decay(self, window_bp: int, n_bins: int):
+        """LD decay over distance (two_reader::Decay) reduced on the device from the resident records:
+        returns (sum_r2[n_bins], count[n_bins])."""
+        n = max(int(n_bins), 1)
+        sums = np.zeros(n, dtype=np.float64)
+        cnt = np.zeros(n, dtype=np.uint64)
+        self._check(self._L.twkb_compute_decay(self._ctx, window_bp, n_bins, sums.ctypes.data, cnt.ctypes.data))
+        return sums, cnt
 
     def stats(self) -> Stats:
         s = Stats()

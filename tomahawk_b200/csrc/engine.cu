@@ -135,6 +135,11 @@ struct Context {
     twkb_stats stats{};
     double ms_decode = 0.0;  // decode_runs_kernel time of the last twkb_load_runs
 
+    // downstream consumer fed from the device-resident records (twkb_compute_decay): active while decay_bins != 0
+    uint32_t decay_bins = 0, decay_width = 0;
+    DevBuf<double> d_decay_sum;
+    DevBuf<unsigned long long> d_decay_cnt;
+
     // multi-GPU data plane (comm.cuh): set by twkb_comm_init, used by the sliced loads only
     ncclComm_t comm = nullptr;
     int comm_rank = 0, comm_size = 1;
@@ -727,8 +732,23 @@ static void flusher_destroy(Context* ctx) {
 
 // The current record buffer cannot take the next batch: hand it to the drain thread (or, for a
 // resident run, just count it) and continue in the other one once that is free.
+// Device-side consumers of a record buffer whose statistics kernels have completed (stream order).
+static int consume_records(Context* ctx, int buf, uint64_t n) {
+    if (!ctx->decay_bins || n == 0) return TWKB_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
+    decay_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_records[buf].p, n, ctx->decay_width, ctx->decay_bins, ctx->d_decay_sum.p,
+                                               ctx->d_decay_cnt.p);
+    CUDA_TRY(cudaGetLastError());
+    ctx->stats.other_launches += 1;
+    return TWKB_OK;
+}
+
 static int rotate_records(Context* ctx, uint64_t fill, bool resident) {
     ctx->stats.records_out += fill;
+    if (resident) {
+        const int rc = consume_records(ctx, ctx->rec_cur, fill);
+        if (rc) return rc;
+    }
     if (!resident && fill) flusher_submit(ctx, ctx->rec_cur, fill);
     ctx->rec_cur ^= 1;
     if (!resident) {
@@ -1040,6 +1060,10 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
         if (rc) return rc;
         const uint64_t fill = ctx->h_counters[1 + ctx->rec_cur];
         ctx->stats.records_out += fill;
+        if (resident) {
+            rc = consume_records(ctx, ctx->rec_cur, fill);
+            if (rc) return rc;
+        }
         if (!resident) {
             if (fill) flusher_submit(ctx, ctx->rec_cur, fill);
             rc = flusher_wait(ctx, -1);
@@ -1630,6 +1654,7 @@ void twkb_destroy(void* c) {
     if (ctx->comm && nccl_api().ok) nccl_api().CommDestroy(ctx->comm);
     for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
     ctx->d_counters.release(); ctx->d_records[0].release(); ctx->d_records[1].release();
+    ctx->d_decay_sum.release(); ctx->d_decay_cnt.release();
     ctx->d_orig.release(); ctx->d_sp_off.release(); ctx->d_sp_ent.release(); ctx->d_sp_tiles.release();
     umma_release(ctx->umma);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
@@ -1769,6 +1794,31 @@ int twkb_compute(void* c, twkb_sink_fn sink, void* user) {
 int twkb_compute_resident(void* c) {
     if (!c) return TWKB_EINVAL;
     return guarded_ctx(c, [&] { return compute_impl(static_cast<Context*>(c), true, nullptr, nullptr, false, nullptr); });
+}
+
+int twkb_compute_decay(void* c, int64_t window_bp, int32_t n_bins, double* sum_r2, uint64_t* count) {
+    if (!c || !sum_r2 || !count) return TWKB_EINVAL;
+    Context* ctx = static_cast<Context*>(c);
+    // two_reader::Decay, lib/two_reader.cpp:425-433
+    if (window_bp <= 0) { ctx->err = "Window size cannot be <= 0 (provided " + std::to_string(window_bp) + ")..."; return TWKB_EINVAL; }
+    if (n_bins <= 0) { ctx->err = "Number of bins cannot be <= 0 (provided " + std::to_string(n_bins) + ")..."; return TWKB_EINVAL; }
+    if (window_bp / n_bins <= 0 || window_bp / n_bins > 0xffffffffll) { ctx->err = "window / bins must be a positive 32-bit bin width"; return TWKB_EINVAL; }
+    return guarded_ctx(c, [&]() -> int {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        CUDA_TRY(ctx->d_decay_sum.alloc((size_t)n_bins));
+        CUDA_TRY(ctx->d_decay_cnt.alloc((size_t)n_bins));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_decay_sum.p, 0, (size_t)n_bins * 8, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_decay_cnt.p, 0, (size_t)n_bins * 8, ctx->stream));
+        ctx->decay_bins = (uint32_t)n_bins;
+        ctx->decay_width = (uint32_t)(window_bp / n_bins);
+        int rc = compute_impl(ctx, true, nullptr, nullptr, false, nullptr);
+        ctx->decay_bins = 0;
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(sum_r2, ctx->d_decay_sum.p, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(count, ctx->d_decay_cnt.p, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return TWKB_OK;
+    });
 }
 
 int twkb_get_stats(void* c, twkb_stats* out) {

@@ -580,4 +580,38 @@ stats_kernel(const Candidate* __restrict__ cands, uint32_t n_cands, const DevVar
     }
 }
 
+// ---------------------------------------------------------------- decay consumer
+// LD decay over distance straight from the device-resident records (reference two_reader::Decay,
+// lib/two_reader.cpp:424-475, which reads them back from the .two file): a record with ridA == ridB and posA < posB
+// adds its R2 and 1 to bin min((posB - posA) / bin_width, n_bins - 1). Per-block partial sums in shared memory
+// (DECAY_SMEM_BINS bins at most; larger tables go straight to global atomics), one global atomic per touched bin.
+constexpr int DECAY_SMEM_BINS = 1024;
+__global__ void __launch_bounds__(256)
+decay_kernel(const uint8_t* __restrict__ records, unsigned long long n_records, uint32_t bin_width, uint32_t n_bins,
+             double* __restrict__ sum_r2, unsigned long long* __restrict__ count) {
+    __shared__ double s_sum[DECAY_SMEM_BINS];
+    __shared__ unsigned int s_cnt[DECAY_SMEM_BINS];
+    const bool use_smem = n_bins <= (uint32_t)DECAY_SMEM_BINS;
+    if (use_smem)
+        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x) { s_sum[b] = 0.0; s_cnt[b] = 0u; }
+    __syncthreads();
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_records;
+         r += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint16_t* h = reinterpret_cast<const uint16_t*>(records + r * 106ull);  // records are 2-byte aligned
+        const uint32_t ridA = h[1] | ((uint32_t)h[2] << 16), ridB = h[3] | ((uint32_t)h[4] << 16);
+        const uint32_t posA = (h[5] | ((uint32_t)h[6] << 16)) >> 2, posB = (h[7] | ((uint32_t)h[8] << 16)) >> 2;
+        if (ridA != ridB || !(posA < posB)) continue;
+        const unsigned long long bits = (unsigned long long)h[37] | ((unsigned long long)h[38] << 16) | ((unsigned long long)h[39] << 32) |
+                                        ((unsigned long long)h[40] << 48);  // R2 at byte 74
+        const double r2 = __longlong_as_double((long long)bits);
+        const uint32_t bin = min((posB - posA) / bin_width, n_bins - 1u);
+        if (use_smem) { atomicAdd(&s_sum[bin], r2); atomicAdd(&s_cnt[bin], 1u); }
+        else { atomicAdd(&sum_r2[bin], r2); atomicAdd(&count[bin], 1ull); }
+    }
+    __syncthreads();
+    if (use_smem)
+        for (uint32_t b = threadIdx.x; b < n_bins; b += blockDim.x)
+            if (s_cnt[b]) { atomicAdd(&sum_r2[b], s_sum[b]); atomicAdd(&count[b], (unsigned long long)s_cnt[b]); }
+}
+
 }  // namespace twkb
