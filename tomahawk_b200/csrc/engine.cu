@@ -95,7 +95,10 @@ struct Context {
     bool permuted = false;
     uint32_t nD = 0, nS = 0, sparse_T = 0;
     std::vector<uint32_t> h_orig;            // resident -> original index (identity when !permuted)
-    std::vector<twkb_variant> h_meta_orig;   // metadata in file order (block structure, visited pairs)
+    std::vector<twkb_variant> h_meta_orig;   // metadata in file order -- filled only when the rows were re-ordered (meta_orig())
+    DevVariant* h_dm = nullptr;              // pinned staging of the device metadata
+    size_t h_dm_cap = 0;
+    uint32_t lgamma_ready = 0;               // length of the log-factorial table resident in d_lgamma
     DevBuf<uint32_t> d_orig, d_sp_off;
     DevBuf<uint2> d_sp_ent;
     uint64_t sp_entries = 0;
@@ -150,6 +153,9 @@ struct Context {
         return TWKB_ECUDA;
     }
 };
+
+// Metadata in FILE order (block structure, visited pairs): h_meta itself unless the rare-variant class re-ordered the rows.
+static const std::vector<twkb_variant>& meta_orig(const Context* ctx) { return ctx->permuted ? ctx->h_meta_orig : ctx->h_meta; }
 
 static void settings_defaults(twkb_settings* s) {
     // reference lib/core.cpp:297-306
@@ -282,7 +288,7 @@ static std::vector<uint32_t> block_starts(const Context* ctx, const std::vector<
 
 static void build_blocks_host(Context* ctx, std::vector<uint32_t>& blk_of_orig) {
     const uint32_t M = ctx->n_variants;
-    const std::vector<twkb_variant>& mo = ctx->h_meta_orig;  // blocks are defined on the file order
+    const std::vector<twkb_variant>& mo = meta_orig(ctx);  // blocks are defined on the file order
     blk_of_orig.assign(M, 0);
     ctx->h_blk_first.clear();
     ctx->h_blk_last.clear();
@@ -342,10 +348,10 @@ static uint64_t visited_pairs(const Context* ctx, const Problem& pb) {
     const uint32_t kind = window_kind(ctx->st);
     for (uint32_t bi = 0; bi < nb; ++bi) {
         const uint64_t ni = ctx->h_blk_last[bi] - ctx->h_blk_first[bi] + 1;
-        const twkb_variant& vf = ctx->h_meta_orig[ctx->h_blk_first[bi]];
+        const twkb_variant& vf = meta_orig(ctx)[ctx->h_blk_first[bi]];
         for (uint32_t bj = bi; bj < ctx->h_blk_prune[bi] || bj == bi; ++bj) {
             if (bj >= nb) break;
-            const twkb_variant& vl = ctx->h_meta_orig[ctx->h_blk_last[bj]];
+            const twkb_variant& vl = meta_orig(ctx)[ctx->h_blk_last[bj]];
             const bool aborted = kind == 1u && vf.rid == vl.rid && (uint32_t)(vl.pos - vf.pos) > w;
             if (!aborted) {
                 const uint64_t nj = ctx->h_blk_last[bj] - ctx->h_blk_first[bj] + 1;
@@ -363,7 +369,7 @@ static int select_problem(Context* ctx, Problem& pb) {
     pb = {0, M, 0, M, true};
     const int parts = ctx->st.n_chunks;
     if (parts <= 1) return TWKB_OK;
-    const std::vector<uint32_t> first = block_starts(ctx, ctx->h_meta_orig.size() == M ? ctx->h_meta_orig : ctx->h_meta);
+    const std::vector<uint32_t> first = block_starts(ctx, meta_orig(ctx));
     const uint32_t nb = (uint32_t)first.size() - 1;
     if ((uint32_t)parts > nb) { ctx->err = "more sub-problems than blocks"; return TWKB_EINVAL; }
     uint32_t factor = 0;
@@ -1233,7 +1239,9 @@ static int load_begin(Context* ctx, uint32_t n_samples, uint32_t n_variants, siz
     ctx->n_variants = n_variants;
     ctx->Mpad = (n_variants + 255) / 256 * 256;
     ctx->raw_stride = stride;
-    ctx->h_meta_orig.assign(meta, meta + n_variants);
+    ctx->h_meta.assign(meta, meta + n_variants);  // file order; load_finish re-orders it if the rare-variant class does
+    ctx->h_meta_orig.clear();
+    ctx->permuted = false;
     ctx->file_blocks.clear();
     ctx->any_missing = false;
     for (uint32_t v = 0; v < n_variants; ++v)
@@ -1250,12 +1258,20 @@ static int load_finish(Context* ctx, const twkb_variant* meta) {
         const int rc_sp = classify_sparse(ctx);
         if (rc_sp) return rc_sp;
     }
-    ctx->h_meta.resize(n_variants);
-    for (uint32_t x = 0; x < n_variants; ++x) ctx->h_meta[x] = meta[ctx->h_orig[x]];
+    if (ctx->permuted) {  // resident order != file order: keep both
+        ctx->h_meta_orig = ctx->h_meta;
+        for (uint32_t x = 0; x < n_variants; ++x) ctx->h_meta[x] = ctx->h_meta_orig[ctx->h_orig[x]];
+    }
     meta = ctx->h_meta.data();  // resident order from here on
-    // device metadata
-    std::vector<DevVariant> dm(ctx->Mpad);
-    std::memset(dm.data(), 0, dm.size() * sizeof(DevVariant));
+    // device metadata, staged in pinned memory so that the copy is asynchronous
+    if (ctx->h_dm_cap < ctx->Mpad) {
+        if (ctx->h_dm) cudaFreeHost(ctx->h_dm);
+        ctx->h_dm = nullptr;
+        ctx->h_dm_cap = 0;
+        CUDA_TRY(cudaMallocHost((void**)&ctx->h_dm, (size_t)ctx->Mpad * sizeof(DevVariant)));
+        ctx->h_dm_cap = ctx->Mpad;
+    }
+    DevVariant* dm = ctx->h_dm;
     for (uint32_t v = 0; v < n_variants; ++v) {
         dm[v].pos = meta[v].pos;
         dm[v].ac = meta[v].ac;
@@ -1263,16 +1279,24 @@ static int load_finish(Context* ctx, const twkb_variant* meta) {
         dm[v].flags = (meta[v].an ? VF_HAS_MISSING : 0u) | (meta[v].hwe < 1e-4 ? VF_BAD_HWE : 0u) |
                       (meta[v].gt_missing ? VF_GT_MISSING : 0u);
     }
+    std::memset(dm + n_variants, 0, (size_t)(ctx->Mpad - n_variants) * sizeof(DevVariant));
     CUDA_TRY(ctx->d_meta.alloc(ctx->Mpad));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_meta.p, dm.data(), dm.size() * sizeof(DevVariant), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_meta.p, dm, (size_t)ctx->Mpad * sizeof(DevVariant), cudaMemcpyHostToDevice, ctx->stream));
     // log-factorial table from the host libm: lg[n] = lgamma(n+1), the exact values the
-    // reference's lbinom() (lib/fisher_math.cpp:183-187) obtains from glibc.
+    // reference's lbinom() (lib/fisher_math.cpp:183-187) obtains from glibc. It depends on the sample count only:
+    // kept across loads (1 M haplotypes = 1 M lgamma calls, ~50 ms of host time).
     ctx->lgamma_len = 2 * n_samples + 64;
-    std::vector<double> lg(ctx->lgamma_len);
-    for (uint32_t n = 0; n < ctx->lgamma_len; ++n) lg[n] = lgamma((double)n + 1.0);
-    CUDA_TRY(ctx->d_lgamma.alloc(ctx->lgamma_len));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_lgamma.p, lg.data(), lg.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.bytes_h2d += dm.size() * sizeof(DevVariant) + lg.size() * 8;
+    size_t lg_bytes = 0;
+    if (ctx->lgamma_ready != ctx->lgamma_len) {
+        std::vector<double> lg(ctx->lgamma_len);
+        for (uint32_t n = 0; n < ctx->lgamma_len; ++n) lg[n] = lgamma((double)n + 1.0);
+        CUDA_TRY(ctx->d_lgamma.alloc(ctx->lgamma_len));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_lgamma.p, lg.data(), lg.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // lg is a local
+        ctx->lgamma_ready = ctx->lgamma_len;
+        lg_bytes = lg.size() * 8;
+    }
+    ctx->stats.bytes_h2d += (size_t)ctx->Mpad * sizeof(DevVariant) + lg_bytes;
     ctx->loaded = true;
     // build the planes the configured mode needs right away so that the upload cost
     // (H2D + transpose) is accounted to the load, not to the first compute
@@ -1660,6 +1684,7 @@ void twkb_destroy(void* c) {
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
     if (ctx->h_stage[1]) cudaFreeHost(ctx->h_stage[1]);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    if (ctx->h_dm) cudaFreeHost(ctx->h_dm);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -2095,7 +2120,6 @@ static int twkb_plan_tiles_impl(const twkb_settings* s, uint32_t n_variants, con
     if (ctx.st.part_count <= 0) { ctx.st.part_count = 1; ctx.st.part_index = 0; }
     ctx.n_variants = n_variants;
     ctx.h_meta.assign(meta, meta + n_variants);
-    ctx.h_meta_orig = ctx.h_meta;
     Problem pb;
     rc = select_problem(&ctx, pb);
     if (rc) return rc;
