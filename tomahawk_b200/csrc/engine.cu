@@ -1225,7 +1225,7 @@ static int classify_sparse(Context* ctx) {
 }
 
 // First half of every load: shape, file-order metadata, missing-data flag.
-static int load_begin(Context* ctx, uint32_t n_samples, uint32_t n_variants, size_t stride, const twkb_variant* meta) {
+static int load_begin_shapes(Context* ctx, uint32_t n_samples, uint32_t n_variants, size_t stride, const twkb_variant* meta) {
     if (!meta || n_samples == 0 || n_variants == 0) { ctx->err = "null/empty matrix"; return TWKB_EINVAL; }
     if (stride * 64 < 2 * (size_t)n_samples) { ctx->err = "row_stride_words too small for n_samples"; return TWKB_EINVAL; }
     if (2 * (uint64_t)n_samples >= (1ull << 31)) { ctx->err = "n_samples too large"; return TWKB_EINVAL; }
@@ -1239,19 +1239,57 @@ static int load_begin(Context* ctx, uint32_t n_samples, uint32_t n_variants, siz
     ctx->n_variants = n_variants;
     ctx->Mpad = (n_variants + 255) / 256 * 256;
     ctx->raw_stride = stride;
-    ctx->h_meta.assign(meta, meta + n_variants);  // file order; load_finish re-orders it if the rare-variant class does
     ctx->h_meta_orig.clear();
     ctx->permuted = false;
     ctx->file_blocks.clear();
+    return TWKB_OK;
+}
+// Host side of a load, per variant: (a) the copy of the caller's metadata (file order; the scheduler consults it for window
+// rules, chunks and the rare-variant class) and (b) the 16-byte device records, staged in pinned memory. At 566,000
+// variants (8-GPU weak scaling) that is 18 MB read twice and 27 MB written -- 8 ms when done serially in front of the
+// upload, with 8 ranks competing for the host's memory bandwidth. The matrix loads therefore enqueue the row upload (and
+// the all-gather) FIRST, then run (a) on a helper thread and (b) on the calling thread, both hidden behind the transfer.
+static void copy_meta(Context* ctx, const twkb_variant* meta) { ctx->h_meta.assign(meta, meta + ctx->n_variants); }
+static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing) {
+    const uint32_t n_variants = ctx->n_variants;
+    if (ctx->h_dm_cap < ctx->Mpad) {
+        if (ctx->h_dm) cudaFreeHost(ctx->h_dm);
+        ctx->h_dm = nullptr;
+        ctx->h_dm_cap = 0;
+        CUDA_TRY(cudaMallocHost((void**)&ctx->h_dm, (size_t)ctx->Mpad * sizeof(DevVariant)));
+        ctx->h_dm_cap = ctx->Mpad;
+    }
+    DevVariant* dm = ctx->h_dm;
+    bool miss = false;
+    for (uint32_t v = 0; v < n_variants; ++v) {
+        dm[v].pos = meta[v].pos;
+        dm[v].ac = meta[v].ac;
+        dm[v].rid = meta[v].rid;
+        dm[v].flags = (meta[v].an ? VF_HAS_MISSING : 0u) | (meta[v].hwe < 1e-4 ? VF_BAD_HWE : 0u) |
+                      (meta[v].gt_missing ? VF_GT_MISSING : 0u);
+        miss = miss || meta[v].gt_missing || meta[v].an;
+    }
+    std::memset(dm + n_variants, 0, (size_t)(ctx->Mpad - n_variants) * sizeof(DevVariant));
+    if (any_missing) *any_missing = miss;
+    return TWKB_OK;
+}
+static void load_meta(Context* ctx, const twkb_variant* meta) {
+    const uint32_t n_variants = ctx->n_variants;
+    copy_meta(ctx, meta);
     ctx->any_missing = false;
     for (uint32_t v = 0; v < n_variants; ++v)
-        if (meta[v].gt_missing || meta[v].an) ctx->any_missing = true;
+        if (meta[v].gt_missing || meta[v].an) { ctx->any_missing = true; break; }
+}
+static int load_begin(Context* ctx, uint32_t n_samples, uint32_t n_variants, size_t stride, const twkb_variant* meta) {
+    const int rc = load_begin_shapes(ctx, n_samples, n_variants, stride, meta);
+    if (rc) return rc;
+    load_meta(ctx, meta);
     return TWKB_OK;
 }
 
 // Second half: d_raw_data (+ d_raw_mask) hold the reference-layout rows, however they got there
 // (ev0 was recorded before the upload started).
-static int load_finish(Context* ctx, const twkb_variant* meta) {
+static int load_finish(Context* ctx, const twkb_variant* meta, bool dm_ready = false) {
     const uint32_t n_samples = ctx->n_samples, n_variants = ctx->n_variants;
     // rare-variant class: may re-order the resident rows [dense | sparse]
     {
@@ -1263,23 +1301,13 @@ static int load_finish(Context* ctx, const twkb_variant* meta) {
         for (uint32_t x = 0; x < n_variants; ++x) ctx->h_meta[x] = ctx->h_meta_orig[ctx->h_orig[x]];
     }
     meta = ctx->h_meta.data();  // resident order from here on
-    // device metadata, staged in pinned memory so that the copy is asynchronous
-    if (ctx->h_dm_cap < ctx->Mpad) {
-        if (ctx->h_dm) cudaFreeHost(ctx->h_dm);
-        ctx->h_dm = nullptr;
-        ctx->h_dm_cap = 0;
-        CUDA_TRY(cudaMallocHost((void**)&ctx->h_dm, (size_t)ctx->Mpad * sizeof(DevVariant)));
-        ctx->h_dm_cap = ctx->Mpad;
+    // device metadata, staged in pinned memory so that the copy is asynchronous (already filled by the matrix loads
+    // while the rows were in flight, unless the rare-variant class re-ordered the variants)
+    if (!dm_ready || ctx->permuted) {
+        const int rc_dm = fill_dm(ctx, meta, nullptr);
+        if (rc_dm) return rc_dm;
     }
     DevVariant* dm = ctx->h_dm;
-    for (uint32_t v = 0; v < n_variants; ++v) {
-        dm[v].pos = meta[v].pos;
-        dm[v].ac = meta[v].ac;
-        dm[v].rid = meta[v].rid;
-        dm[v].flags = (meta[v].an ? VF_HAS_MISSING : 0u) | (meta[v].hwe < 1e-4 ? VF_BAD_HWE : 0u) |
-                      (meta[v].gt_missing ? VF_GT_MISSING : 0u);
-    }
-    std::memset(dm + n_variants, 0, (size_t)(ctx->Mpad - n_variants) * sizeof(DevVariant));
     CUDA_TRY(ctx->d_meta.alloc(ctx->Mpad));
     CUDA_TRY(cudaMemcpyAsync(ctx->d_meta.p, dm, (size_t)ctx->Mpad * sizeof(DevVariant), cudaMemcpyHostToDevice, ctx->stream));
     // log-factorial table from the host libm: lg[n] = lgamma(n+1), the exact values the
@@ -1315,22 +1343,29 @@ static int load_finish(Context* ctx, const twkb_variant* meta) {
 static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* data, const uint64_t* mask,
                        size_t stride, const twkb_variant* meta, bool device_src) {
     if (!data) { ctx->err = "null/empty matrix"; return TWKB_EINVAL; }
-    int rc = load_begin(ctx, n_samples, n_variants, stride, meta);
+    int rc = load_begin_shapes(ctx, n_samples, n_variants, stride, meta);
     if (rc) return rc;
     ctx->ms_decode = 0.0;
-    if (ctx->any_missing && !mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
     const size_t words = (size_t)n_variants * stride;
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     CUDA_TRY(ctx->d_raw_data.alloc(words));
     const cudaMemcpyKind kind = device_src ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_data.p, data, words * 8, kind, ctx->stream));
     ctx->stats.bytes_h2d = device_src ? 0 : words * 8;
-    if (ctx->any_missing) {
+    // host metadata work behind the transfer: copy on a helper thread, device records (+ the missing-data flag) here
+    std::thread helper(copy_meta, ctx, meta);
+    bool miss = false;
+    rc = fill_dm(ctx, meta, &miss);
+    helper.join();
+    if (rc) return rc;
+    ctx->any_missing = miss;
+    if (miss && !mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
+    if (miss) {
         CUDA_TRY(ctx->d_raw_mask.alloc(words));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_mask.p, mask, words * 8, kind, ctx->stream));
         if (!device_src) ctx->stats.bytes_h2d += words * 8;
     }
-    return load_finish(ctx, meta);
+    return load_finish(ctx, meta, true);
 }
 
 // twkb_load_runs: run-length records -> resident rows, decoded by decode_runs_kernel.
@@ -1438,20 +1473,18 @@ static int ensure_chunk_events(Context* ctx, int n) {
 static int load_matrix_sliced(Context* ctx, uint32_t n_samples, uint32_t n_variants, const uint64_t* slice_data, const uint64_t* slice_mask,
                               size_t stride, const twkb_variant* meta) {
     if (!ctx->comm || ctx->comm_size <= 1) return load_common(ctx, n_samples, n_variants, slice_data, slice_mask, stride, meta, false);
-    int rc = load_begin(ctx, n_samples, n_variants, stride, meta);
+    int rc = load_begin_shapes(ctx, n_samples, n_variants, stride, meta);
     if (rc) return rc;
     ctx->ms_decode = 0.0;
     uint32_t b, e;
     comm_slice(n_variants, ctx->comm_rank, ctx->comm_size, b, e);
     const uint64_t rows = e - b;
     if (rows && !slice_data) { ctx->err = "null/empty matrix slice"; return TWKB_EINVAL; }
-    if (ctx->any_missing && rows && !slice_mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
     const uint64_t S = ((uint64_t)n_variants + ctx->comm_size - 1) / ctx->comm_size;
     const size_t words = (size_t)S * ctx->comm_size * stride;  // padded to N equal slices
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     CUDA_TRY(ctx->d_raw_data.alloc(words));
-    if (ctx->any_missing) CUDA_TRY(ctx->d_raw_mask.alloc(words));
-    rc = ensure_chunk_events(ctx, 1);
+    rc = ensure_chunk_events(ctx, 2);
     if (rc) return rc;
     // own slice over this GPU's PCIe link (copy_stream), padding rows of a short slice zeroed, then the collective
     auto upload = [&](uint64_t* d_rows, const uint64_t* h_rows) -> int {
@@ -1460,22 +1493,45 @@ static int load_matrix_sliced(Context* ctx, uint32_t n_samples, uint32_t n_varia
         if (rows < S) CUDA_TRY(cudaMemsetAsync(d_rows + (base + rows) * stride, 0, (S - rows) * stride * 8, ctx->copy_stream));
         return TWKB_OK;
     };
+    const bool trace = getenv("TWKB_TRACE") != nullptr;  // development aid: synchronous phase times on stderr
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        std::fprintf(stderr, "[twkb trace] rank %d load_sliced %-12s %8.3f ms\n", ctx->comm_rank, what,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count());
+    };
     rc = upload(ctx->d_raw_data.p, slice_data);
     if (rc) return rc;
-    if (ctx->any_missing) {
-        rc = upload(ctx->d_raw_mask.p, slice_mask);
-        if (rc) return rc;
-    }
     CUDA_TRY(cudaEventRecord(ctx->chunk_events[0], ctx->copy_stream));
     CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[0], 0));
     rc = exchange_slices(ctx, ctx->d_raw_data.p, stride, n_variants);
     if (rc) return rc;
-    if (ctx->any_missing) {
+    // host metadata work behind the transfer + collective: copy on a helper thread, device records here. The
+    // missing-data flag comes out of the same pass; it is identical on every rank (same metadata), so all ranks
+    // agree on whether a mask exchange follows.
+    std::thread helper(copy_meta, ctx, meta);
+    bool miss = false;
+    rc = fill_dm(ctx, meta, &miss);
+    helper.join();
+    if (rc) return rc;
+    ctx->any_missing = miss;
+    if (miss && rows && !slice_mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
+    mark("data + meta");
+    if (miss) {
+        CUDA_TRY(ctx->d_raw_mask.alloc(words));
+        rc = upload(ctx->d_raw_mask.p, slice_mask);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->chunk_events[1], ctx->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->chunk_events[1], 0));
         rc = exchange_slices(ctx, ctx->d_raw_mask.p, stride, n_variants);
         if (rc) return rc;
     }
     ctx->stats.bytes_h2d = rows * stride * 8 * (ctx->any_missing ? 2 : 1);
-    return load_finish(ctx, meta);
+    rc = load_finish(ctx, meta, true);
+    mark("finish");
+    return rc;
 }
 
 // twkb_load_runs_sliced: this rank uploads the run words of ITS variants only, decodes them on the device
