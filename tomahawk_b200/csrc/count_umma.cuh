@@ -60,6 +60,8 @@ struct UmmaOperand {
     int mode = 0;                // CountMode the operand was built for (planes kernels: 1..3)
     uint8_t* d_bytes_b = nullptr;  // planes kernels: the plane-major B copy [RB][Kbytes]
     size_t capacity_b = 0;
+    uint32_t* d_pace = nullptr;    // K-sweep pacing counters of the persistent kernel (long rows only), [waves][chunks per tile]
+    size_t pace_capacity = 0;      // in counters
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -301,6 +303,7 @@ __device__ __forceinline__ void tmem_fill_32x32(uint32_t taddr, uint32_t v) {
 // while chunk c is screened, and the release of the accumulator is a CTA-scope arrive.
 constexpr int UMMA3_EPI_WARPS = 8;
 constexpr int UMMA3_THREADS = 128 + 32 * UMMA3_EPI_WARPS;
+constexpr uint32_t UMMA3_PACE_MIN_KBLOCKS = 128;  // operand rows of >= 16 KB sweep K in paced chunks (count_umma3_kernel)
 
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -1088,7 +1091,7 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
 template <bool FP4, bool SCREEN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA3_THREADS, 1)
 count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, CountArgs args,
-                   DevParams prm, uint32_t num_kblocks, uint32_t n_tiles) {
+                   DevParams prm, uint32_t num_kblocks, uint32_t n_tiles, uint32_t* pace, uint32_t pace_kb, uint32_t pace_depth) {
     using Cfg = Umma3Cfg<FP4>;
     constexpr uint32_t TILE_N = Cfg::TILE_N;
     constexpr int STAGES = Cfg::STAGES;
@@ -1149,12 +1152,39 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (warp == 0) {
         // ============================== TMA producer ==============================
         uint32_t s = 0, wrap = 0;  // ring slot, number of completed passes over the ring
-        for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters) {
+        // K-sweep pacing (long operand rows, pace != nullptr). The ~74 tiles in flight together (one per CTA pair, a
+        // compact block of the super-tile order) read the same operand rows; whether a row's K block is fetched from
+        // DRAM once or once per tile depends on the CTA pairs sweeping K in near lock-step, and at 1 M haplotypes
+        // (500 KB per row, ~1 ms per tile) they drift apart by far more than L2 holds -- ncu: L2 hit 50 %, DRAM
+        // 5.9 TB/s, tensor pipe half idle. So the leader's producer announces every chunk of pace_kb K blocks it
+        // starts in a global counter (one per wave and chunk) and does not start chunk c before ALL pairs of the
+        // wave have started chunk c - pace_depth: the spread of the wave's K positions -- and with it the L2
+        // working set, rows of the wave x (pace_depth + 1) chunks -- is bounded. Pure pacing: no data depends on
+        // it, the slowest pair never waits, all pairs are co-resident (grid <= SMs), so it cannot deadlock.
+        const uint32_t pace_cpt = pace ? (num_kblocks + pace_kb - 1u) / pace_kb : 0u;  // chunks per tile
+        uint32_t wave = 0;
+        for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters, ++wave) {
             const uint2 tile = args.tiles[t];
             // operand rows of this CTA's halves of the tile (planes: the re-ordered copies)
             const uint32_t a_row = (MODE == MODE_PHASED_NOMISS ? tile.x : (tile.x / PlanesCfg<MODE>::TI) * 256u) + 128u * rank;
             const uint32_t b_row = (MODE == MODE_PHASED_NOMISS ? tile.y : (tile.y / PlanesCfg<MODE>::TJ) * 240u) + Cfg::B_ROWS * rank;
+            uint32_t pace_next = 0, pace_chunk = 0;
             for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
+                if (pace != nullptr && leader && kb == pace_next) {
+                    if (elect_one_sync()) {
+                        const uint32_t seq = wave * pace_cpt + pace_chunk;
+                        atomicAdd(&pace[seq], 1u);
+                        if (seq >= pace_depth) {
+                            const uint32_t w_back = pace_chunk >= pace_depth ? wave : wave - 1u;  // pace_depth <= pace_cpt
+                            const uint32_t expect = min(n_clusters, n_tiles - w_back * n_clusters);
+                            const volatile uint32_t* c = pace + (seq - pace_depth);
+                            while (*c < expect) __nanosleep(64);
+                        }
+                    }
+                    __syncwarp();
+                    pace_next += pace_kb;
+                    ++pace_chunk;
+                }
                 if (wrap) mbar_wait(&empty_bar[s], (wrap - 1u) & 1u);
                 uint8_t* sA = stage_base + (size_t)s * Cfg::STAGE_BYTES;
                 uint8_t* sB = sA + 128 * UMMA_BLOCK_K;
@@ -1449,8 +1479,33 @@ inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const De
     }
     const int n_sm = n_sm_of[dev & 63].load();
     const uint32_t n_clusters = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, n_sm / 2));
+    const uint32_t num_kblocks = op.Kbytes / UMMA_BLOCK_K;
+    // K-sweep pacing (see the producer warp): rows of >= 16 KB, more than one CTA pair. Chunk = 16 K blocks (2 KB per
+    // row), look-ahead 2 chunks: wave rows (<= ~8,000) x ~3 chunks in flight = <= ~50 MB of L2.
+    uint32_t pace_kb = 16, pace_depth = 2;
+    uint32_t* pace = nullptr;
+#ifdef TWKB_PROFILING
+    if (const char* e = getenv("TWKB_PACE_KB")) pace_kb = (uint32_t)std::max(1, atoi(e));
+    if (const char* e = getenv("TWKB_PACE_DEPTH")) pace_depth = (uint32_t)std::max(0, atoi(e));
+#endif
+    if (num_kblocks >= UMMA3_PACE_MIN_KBLOCKS && n_clusters > 1 && pace_depth > 0) {
+        const uint32_t cpt = (num_kblocks + pace_kb - 1) / pace_kb;
+        pace_depth = std::min(pace_depth, cpt);
+        const size_t need = (size_t)((n_tiles + n_clusters - 1) / n_clusters) * cpt;
+        if (op.pace_capacity < need) {
+            if (op.d_pace) cudaFree(op.d_pace);
+            op.d_pace = nullptr;
+            op.pace_capacity = 0;
+            cudaError_t e = cudaMalloc((void**)&op.d_pace, need * sizeof(uint32_t));
+            if (e != cudaSuccess) return e;
+            op.pace_capacity = need;
+        }
+        cudaError_t e = cudaMemsetAsync(op.d_pace, 0, need * sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+        pace = op.d_pace;
+    }
     count_umma3_kernel<FP4, SCREEN, MODE><<<2 * n_clusters, UMMA3_THREADS, Umma3Cfg<FP4>::SMEM_BYTES, stream>>>(
-        op.tmap, op.tmap_b, args, prm, op.Kbytes / UMMA_BLOCK_K, n_tiles);
+        op.tmap, op.tmap_b, args, prm, num_kblocks, n_tiles, pace, pace_kb, pace_depth);
     return cudaGetLastError();
 }
 
@@ -1469,8 +1524,10 @@ inline cudaError_t umma_launch(UmmaOperand& op, const CountArgs& args, const Dev
 inline void umma_release(UmmaOperand& op) {
     if (op.d_bytes) cudaFree(op.d_bytes);
     if (op.d_bytes_b) cudaFree(op.d_bytes_b);
+    if (op.d_pace) cudaFree(op.d_pace);
     op.d_bytes = op.d_bytes_b = nullptr;
-    op.capacity = op.capacity_b = 0;
+    op.d_pace = nullptr;
+    op.capacity = op.capacity_b = op.pace_capacity = 0;
     op.valid = false;
 }
 
