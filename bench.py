@@ -15,7 +15,8 @@ over NVLink (twkb_load_matrix_sliced); tiles are then computed with no further c
 
 Secondary workloads in `extra_configs` of the same JSON line (each with its own value / e2e / roofline):
   N = 1: configs[0] (R2 >= 0: every pair goes through Fisher) and configs[2] (unphased, 5 % missing);
-  N > 1: configs[3] (1,000,000 haplotypes x 100,000 SNVs) strong-scaled over the N GPUs, generated on the device.
+  N > 1: configs[3] (1,000,000 haplotypes x 100,000 SNVs) strong-scaled over the N GPUs, generated on the device;
+         a window-banded slice of configs[4] (1,000,000 haplotypes, -w 500kb, 80 % rare), position-sharded with halo.
 
 One JSON line is printed by rank 0 (README / DESIGN.md section 7 describe every key).
 """
@@ -63,6 +64,8 @@ def parse_args():
     ap.add_argument("--no-mma-ceiling", action="store_true", help="skip the MMA-only ceiling pass of the roofline block")
     ap.add_argument("--no-extra", action="store_true", help="primary workload only (no extra_configs, no peak probes)")
     ap.add_argument("--biobank-variants", type=int, default=100_000, help="SNVs of the configs[3] run at N > 1")
+    ap.add_argument("--c5-variants-per-gpu", type=int, default=50_000, help="own SNVs per GPU of the configs[4] window slice (N > 1)")
+    ap.add_argument("--c5", action="store_true", help="N = 1: run the configs[4] window slice (one shard) instead of configs[0] / configs[2]")
     return ap.parse_args()
 
 
@@ -562,11 +565,14 @@ def main():
         if world == 1:
             eng.close()
             torch.cuda.empty_cache()
-            extra.append(extra_config0(args, B, tb, synth, peaks, peak_src, fp4_measured))
-            extra.append(extra_config2(args, B, tb, tools, peaks, peak_src, fp4_measured))
+            if not args.c5:
+                extra.append(extra_config0(args, B, tb, synth, peaks, peak_src, fp4_measured))
+                extra.append(extra_config2(args, B, tb, tools, peaks, peak_src, fp4_measured))
         else:
             # same context and communicator (an NCCL unique id serves ONE ncclCommInitRank): only the matrix changes
             extra.append(extra_config3(args, B, tb, tools, eng, peaks, peak_src))
+        if world > 1 or args.c5:
+            extra.append(extra_config4(args, B, tb, tools, peaks, peak_src))
         extra = [x for x in extra if x]
 
     if rank != 0:
@@ -756,6 +762,82 @@ def extra_config3(args, B, tb, tools, eng, peaks, peak_src):
         return out if rank == 0 else None
     except Exception as e:
         return {"baseline_config": "BASELINE.json configs[3]", "error": str(e)[:300]}
+
+
+def spot_check_counts(recs, rows, meta, n_samples, pos_step, first_variant, k=48):
+    """Counts of k records against the bits of this rank's host rows: ALTALT = popcount(rowA & rowB), margins = the allele
+    counts, cells sum to 2N. Records whose rows this rank does not hold on the host are skipped."""
+    if len(recs) == 0:
+        return {"records": 0, "checked": 0, "counts_equal_bits": None}
+    ia = (recs["packA"] >> 2).astype(np.int64) // pos_step - first_variant
+    ib = (recs["packB"] >> 2).astype(np.int64) // pos_step - first_variant
+    ok = np.flatnonzero((ia >= 0) & (ia < len(rows)) & (ib >= 0) & (ib < len(rows)))
+    pick = ok[np.linspace(0, len(ok) - 1, min(k, len(ok))).astype(np.int64)] if len(ok) else ok
+    good = True
+    for r in pick:
+        a, b = int(ia[r]), int(ib[r])
+        n11 = int(np.unpackbits((rows[a] & rows[b]).view(np.uint8)).sum())
+        c = recs["cnt"][r]
+        good = good and c[3] == n11 and c[1] + c[3] == meta["ac"][a] and c[2] + c[3] == meta["ac"][b] and c.sum() == 2 * n_samples
+    return {"records": int(len(recs)), "checked": int(len(pick)), "counts_equal_bits": bool(good)}
+
+
+def extra_config4(args, B, tb, tools, peaks, peak_src):
+    """A window-banded slice of BASELINE configs[4] (1,000,000 haplotypes x 2,000,000 SNVs, -w 500kb, 80 % of the variants with
+    MAF < 1 %): c5_variants_per_gpu x N SNVs at the configuration's density (500 kb = 10,000 variants), POSITION-SHARDED
+    (SURVEY 8e): every rank generates, uploads and holds only its own .twk blocks + the halo the window reaches
+    (twkb_plan_shards), nothing is exchanged. Weak scaling: the slice grows with N; the full configuration is 2,000,000 / N
+    own variants per GPU of the same band."""
+    name = "BASELINE.json configs[4] (window-banded slice)"
+    try:
+        torch = B.torch
+        rank, world = B.rank, B.world
+        n, per_gpu, pos_step, w, bs = 500_000, args.c5_variants_per_gpu, 50, 500_000, 500
+        m = per_gpu * world
+        stride = tools.words_per_variant(n)
+        t0 = time.perf_counter()
+        first = np.arange(0, m + bs, bs, dtype=np.uint32); first[-1] = m      # .twk blocks of 500 variants (lib/importer.h:36)
+        pos_meta = np.zeros(m, dtype=tb.VARIANT_DTYPE); pos_meta["pos"] = np.arange(m, dtype=np.uint64) * pos_step
+        own, halo = tb.plan_shards(first, pos_meta, w, world)
+        v0, v_own, v1 = int(first[own[rank]]), int(first[own[rank + 1]]), int(first[halo[rank]])
+        d, _, meta = tools.synth_device(n, m, seed=args.seed + 4, rare_fraction=0.8, pos_step=pos_step, first=v0, n_rows=v1 - v0)
+        host = torch.empty(d.shape, dtype=torch.int64).pin_memory(); host.copy_(d)
+        del d
+        torch.cuda.empty_cache()
+        t_gen = time.perf_counter() - t0
+        hn = host.numpy().view(np.uint64)
+        eng = tb.Engine(force_phased=1, minR2=0.1, window=1, l_window=w, shard_blocks=int(own[rank + 1] - own[rank]), device=B.local_rank)
+        blocks = first[own[rank]:halo[rank]] - v0
+
+        def load():
+            eng.load(n, hn, None, meta)
+            eng.set_blocks(blocks)
+        load()
+        acc = B.resident(eng, 2, 1)
+        e2e = B.e2e(eng, load, 1)
+        st = acc["st"]
+        spot = spot_check_counts(eng.compute(), hn, meta, n, pos_step, v0)
+        roof = tensor_roofline(tb, acc, n, False, False, peaks, peak_src, None)
+        sp_ms = float(np.mean(acc["sp"]))
+        roof["list_kernel"] = {"kernel": "count_sparse_kernel", "variants": int(st.sparse_variants), "ms_per_step": sp_ms,
+                               "word_ops_per_step": int(st.sparse_word_ops), "bound": "hbm",
+                               "achieved_gbs": st.sparse_word_ops * 4 / (sp_ms * 1e-3) / 1e9 if sp_ms > 0 else None,
+                               "peak_gbs": peaks["hbm_gbs"]}
+        loaded, = B.allreduce([float(v1 - v0)], "SUM")
+        spot_ok, = B.allreduce([1.0 if spot["counts_equal_bits"] in (True, None) else 0.0], "MIN")
+        spot["all_ranks_ok"] = bool(spot_ok)
+        out = _extra_entry(name,
+                           f"tomahawk calc -p -w {w}, synthetic {n} samples ({2 * n} haplotypes) x {m} SNVs ({per_gpu} per GPU, {pos_step} bp apart), "
+                           f"80% of the variants MAF<1%, R2>=0.1, position-sharded over {world} GPU(s)",
+                           acc, e2e, roof, 2 * n, scaling="weak", n_gpus=world, gen_seconds=round(t_gen, 2),
+                           shard={"own_variants_rank0": v_own - v0, "halo_variants_rank0": v1 - v_own, "variants_loaded_all_ranks": int(loaded),
+                                  "matrix_bytes_whole": int(m) * stride * 8, "matrix_bytes_rank0": int(v1 - v0) * stride * 8,
+                                  "collectives": "none (own blocks + halo loaded by every rank)"},
+                           parity_spot=spot)
+        eng.close()
+        return out if rank == 0 else None
+    except Exception as e:
+        return {"baseline_config": name, "error": str(e)[:300]}
 
 
 if __name__ == "__main__":

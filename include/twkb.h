@@ -96,7 +96,12 @@ typedef struct twkb_settings {
                                 first (twk_ld_slave::CalculateSingle, lib/ld/ld_engine.cpp:2226-2332: auto phasing per
                                 pair, no ac_i + ac_j <= 2 skip). twkb_calc_file* fill it from the file; callers of
                                 twkb_load_matrix order their rows [targets | neighbours] and set it themselves */
-    int32_t reserved[2];
+    int32_t shard_blocks;    /* position-sharded window runs (matrix larger than one GPU): this context holds ONE
+                                shard of the variants -- its own .twk blocks followed by the halo blocks a -w window can reach
+                                (twkb_plan_shards) -- and computes only the pairs whose earlier member lies in its first
+                                shard_blocks blocks; the union over the shards is the whole-matrix -w result. 0 = off;
+                                needs window = 1. The block structure is the one twkb_set_blocks gave (or twk_block_size) */
+    int32_t reserved[1];
 } twkb_settings;
 
 /* Subset of twk1_t (include/core.h:291-295) the LD path reads. */
@@ -328,6 +333,17 @@ int twkb_two_sort_mem(const char* in_path, const char* out_path, int32_t c_level
  * (-c/-C chunk, -w window band and diagonal rules applied). out may be NULL to count. */
 int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i,
                     uint32_t tile_j, uint32_t* out_ij, uint64_t capacity, uint64_t* n_tiles, uint64_t* n_pairs);
+
+/* Position shards of a -w run, host only ("position-sharding with +-window halo"). The variants are cut
+ * at .twk block boundaries into n_shards consecutive ranges of about equal pair work; shard k owns blocks
+ * [own_begin[k], own_begin[k+1]) and must also hold the halo blocks up to halo_end[k] (exclusive): every block the
+ * reference's row prune (ld_balancing.h:189-196, positions only) leaves reachable from one of its own blocks. A context
+ * that loads variants block_first[own_begin[k]] .. block_first[halo_end[k]] - 1 with settings.shard_blocks =
+ * own_begin[k+1] - own_begin[k] (and the same blocks, re-based, through twkb_set_blocks) computes exactly the pairs of
+ * the whole-matrix run whose earlier member it owns. block_first: n_blocks + 1 entries (last = n_variants);
+ * own_begin: n_shards + 1 entries out; halo_end: n_shards entries out. */
+int twkb_plan_shards(const uint32_t* block_first, uint32_t n_blocks, const twkb_variant* meta, uint32_t n_variants,
+                     int32_t l_window, int32_t n_shards, uint32_t* own_begin, uint32_t* halo_end);
 
 int twkb_version(void);
 

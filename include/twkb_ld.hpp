@@ -22,7 +22,9 @@
 
 #include <sys/time.h>
 
+#include <algorithm>
 #include <chrono>
+#include <cstdint>
 #include <cstdlib>
 #include <cstdio>
 #include <ctime>
@@ -76,6 +78,9 @@ struct twk_ld_settings {
     bool emulate_quirks = true;
     bool host_unpack = false;  // true: unpack the .twk rows on the host instead of decoding the runs on the device
     bool silent = false;  // suppress the LOG lines (errors are always printed)
+    bool position_shards = true;  // -w on several devices: every device loads only its own .twk blocks + the halo blocks the
+                                  // window reaches (twkb_plan_shards) instead of the whole matrix; false = deal tiles of
+                                  // the whole matrix like the all-pairs modes
 
     std::string GetString() const {
         auto tf = [](bool b) { return std::string(b ? "TRUE" : "FALSE"); };
@@ -205,13 +210,22 @@ public:
         // decodes) only its slice of the variant rows over its own PCIe link; the slices are exchanged over
         // NVLink (twkb_load_*_sliced). Contexts are created up front so that a bad device ordinal fails
         // before anybody waits in a collective.
+        // -w on several devices: position shards. The dependency range of a window run is bounded, so
+        // device k holds only its own blocks and their halo -- the matrix as a whole never has to fit one GPU and
+        // nothing is exchanged between the devices.
+        std::vector<uint32_t> own_begin(n_dev + 1, 0), halo_end(n_dev, 0);
+        const bool shard = settings.position_shards && settings.window && !settings.single && n_dev > 1 && file_blocks &&
+                           n_file_blocks >= (uint32_t)n_dev &&
+                           twkb_plan_shards(file_blocks, n_file_blocks, meta, n_variants, settings.l_window, n_dev, own_begin.data(),
+                                            halo_end.data()) == TWKB_OK;
         std::vector<void*> ctxs(n_dev, nullptr);
         for (int k = 0; k < n_dev; ++k) {
             twkb_settings cs;
             settings.ToC(&cs);
             cs.device = settings.devices[k];
-            cs.part_index = k;
-            cs.part_count = n_dev;
+            cs.part_index = shard ? 0 : k;
+            cs.part_count = shard ? 1 : n_dev;
+            cs.shard_blocks = shard ? (int32_t)(own_begin[k + 1] - own_begin[k]) : 0;
             cs.single_targets = (int32_t)n_targets;
             const int r = twkb_create(&cs, &ctxs[k]);
             if (r) {
@@ -222,16 +236,47 @@ public:
                 return error("device " + std::to_string(settings.devices[k]) + ": " + why);
             }
         }
+        if (shard)
+            log("THREAD") << "Window mode on " << n_dev << " devices: position shards (own blocks + halo within " << settings.l_window
+                          << " bases), no matrix exchange" << std::endl;
         bool distinct = true;
         for (int a = 0; a < n_dev; ++a)
             for (int b = a + 1; b < n_dev; ++b) distinct = distinct && settings.devices[a] != settings.devices[b];
         uint8_t uid[TWKB_COMM_ID_BYTES];
-        const bool use_comm = n_dev > 1 && distinct && !std::getenv("TWKB_NO_NCCL") && twkb_comm_unique_id(uid) == TWKB_OK;
-        if (n_dev > 1)
+        const bool use_comm = !shard && n_dev > 1 && distinct && !std::getenv("TWKB_NO_NCCL") && twkb_comm_unique_id(uid) == TWKB_OK;
+        if (n_dev > 1 && !shard)
             log("THREAD") << (use_comm ? "NCCL communicator over " + std::to_string(n_dev) + " devices: sliced upload + exchange over NVLink"
                                        : std::string("no communicator (repeated device or NCCL unavailable): every context uploads the whole matrix"))
                           << std::endl;
+        auto shard_worker = [&](int k) {
+            void* ctx = ctxs[k];
+            const uint32_t v0 = file_blocks[own_begin[k]], v1 = file_blocks[halo_end[k]], nv = v1 - v0;
+            int r = TWKB_OK;
+            if (nv && own_begin[k + 1] > own_begin[k]) {
+                if (runs) {  // the shard's run words: one contiguous byte range of the inflated blocks, descriptors re-based
+                    std::vector<twkb_run_desc> d(run_desc + v0, run_desc + v1);
+                    uint64_t lo = UINT64_MAX, hi = 0;
+                    for (const twkb_run_desc& x : d) {
+                        lo = std::min<uint64_t>(lo, x.offset);
+                        hi = std::max<uint64_t>(hi, x.offset + (uint64_t)x.n_runs * x.width);
+                    }
+                    for (twkb_run_desc& x : d) x.offset -= lo;
+                    r = twkb_load_runs(ctx, n_samples, nv, run_bytes + lo, (size_t)(hi - lo), d.data(), meta + v0);
+                } else {
+                    r = twkb_load_matrix(ctx, n_samples, nv, data + (size_t)v0 * stride, mask ? mask + (size_t)v0 * stride : nullptr, stride,
+                                         meta + v0);
+                }
+                std::vector<uint32_t> lb;
+                for (uint32_t b = own_begin[k]; b < halo_end[k]; ++b) lb.push_back(file_blocks[b] - v0);
+                if (r == TWKB_OK) r = twkb_set_blocks(ctx, lb.data(), (uint32_t)lb.size());
+                if (r == TWKB_OK) r = twkb_compute(ctx, &twk_ld::sink, &shared);
+            }
+            if (r) { errors[k] = twkb_last_error(ctx); rcs[k] = r; }
+            else twkb_get_stats(ctx, &st[k]);
+            twkb_destroy(ctx);
+        };
         auto worker = [&](int k) {
+            if (shard) return shard_worker(k);
             void* ctx = ctxs[k];
             int r = TWKB_OK;
             if (use_comm) r = twkb_comm_init(ctx, uid, k, n_dev);

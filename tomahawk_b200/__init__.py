@@ -51,7 +51,8 @@ class Settings(ctypes.Structure):
         ("minDprime", ctypes.c_double), ("maxDprime", ctypes.c_double),
         ("device", ctypes.c_int32), ("part_index", ctypes.c_int32), ("part_count", ctypes.c_int32),
         ("kernel", ctypes.c_int32), ("twk_block_size", ctypes.c_int32), ("sparse_max_words", ctypes.c_int32),
-        ("host_unpack", ctypes.c_int32), ("single_targets", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2),
+        ("host_unpack", ctypes.c_int32), ("single_targets", ctypes.c_int32), ("shard_blocks", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 1),
     ]
 
 
@@ -97,6 +98,7 @@ EXPORTS = [
     "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
     "twkb_two_sort",
     "twkb_compute_decay", "twkb_set_blocks", "twkb_twk_blocks", "twkb_two_sort_mem", "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
+    "twkb_plan_shards",
 ]
 
 
@@ -320,6 +322,21 @@ def plan_tiles(settings: Settings, meta: np.ndarray, tile_i: int, tile_j: int):
 
 
 COMM_ID_BYTES = 128
+
+
+def plan_shards(block_first, meta: np.ndarray, l_window: int, n_shards: int):
+    """twkb_plan_shards: position shards of a -w run. block_first: first variant of every .twk block (+ n_variants at the
+    end). Returns (own_begin [n_shards + 1], halo_end [n_shards]) in blocks."""
+    bf = np.ascontiguousarray(block_first, dtype=np.uint32)
+    meta = np.ascontiguousarray(meta)
+    own = np.zeros(n_shards + 1, dtype=np.uint32)
+    halo = np.zeros(n_shards, dtype=np.uint32)
+    rc = lib().twkb_plan_shards(bf.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(bf) - 1), meta.ctypes.data_as(ctypes.c_void_p),
+                                ctypes.c_uint32(len(meta)), ctypes.c_int32(l_window), ctypes.c_int32(n_shards),
+                                own.ctypes.data_as(ctypes.c_void_p), halo.ctypes.data_as(ctypes.c_void_p))
+    if rc != 0:
+        raise TwkbError(rc, "twkb_plan_shards")
+    return own, halo
 
 
 def comm_unique_id() -> bytes:

@@ -6,7 +6,7 @@
 //   twkb_calc scalc  [options] -i <in.twk> -I <contig:pos> -o <output.two>      (reference lib/scalc.h)
 //
 // Additions: -g/--devices LIST (CUDA ordinals, comma separated; one context per entry) and
-// -K/--kernel auto|popc|umma|fp4.
+// -K/--kernel auto|popc|umma|fp4, --host-unpack, --no-shards.
 #include <getopt.h>
 
 #include <cstdlib>
@@ -41,6 +41,8 @@ static void calc_usage() {
                  "  -k INT    compression level to use (default: 1, max = 22).\n"
                  "  -g LIST   CUDA devices, e.g. 0,1,2,3 (default: 0)\n"
                  "  -K NAME   count kernel: auto | popc | umma | fp4 (default: auto)\n"
+                 "  --host-unpack  unpack the .twk genotypes on the host instead of decoding the runs on the device\n"
+                 "  --no-shards    -w on several devices: deal tiles of the whole matrix instead of position shards\n"
               << std::endl;
 }
 
@@ -180,6 +182,8 @@ int main(int argc, char** argv) {
                                            {"windowBases", optional_argument, 0, 'w'},
                                            {"devices", required_argument, 0, 'g'},
                                            {"kernel", required_argument, 0, 'K'},
+                                           {"host-unpack", no_argument, 0, 1001},
+                                           {"no-shards", no_argument, 0, 1002},
                                            {0, 0, 0, 0}};
     twkb_host::twk_ld_settings settings;
     std::string literal;
@@ -249,6 +253,8 @@ int main(int argc, char** argv) {
                 }
                 break;
             }
+            case 1001: settings.host_unpack = true; break;
+            case 1002: settings.position_shards = false; break;
             case 'K': {
                 const std::string k = optarg;
                 if (k == "auto") settings.kernel = TWKB_KERNEL_AUTO;

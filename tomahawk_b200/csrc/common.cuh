@@ -49,6 +49,8 @@ struct DevParams {
     uint32_t single;              // scalc: no ac_i + ac_j <= 2 skip (ld_engine.cpp:2265, 2290: commented out there)
     uint32_t pair_filter;         // auto mode passes: 0 all pairs, 1 only pairs without a variant
                                   // with missing alleles, 2 only pairs with one (ld_engine.cpp:2775)
+    uint32_t shard_blocks;        // position-sharded window runs: > 0 = only pairs whose earlier member lies in the first
+                                  // shard_blocks .twk blocks of the loaded variants (the later blocks are the halo)
 };
 
 // Window-mode block structure (reference .twk blocks):

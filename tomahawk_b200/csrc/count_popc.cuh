@@ -130,6 +130,8 @@ __device__ __forceinline__ bool pair_decide(const CountArgs& args, const DevPara
         ok = ok && (prm.pair_filter == 1u ? !miss : miss);
     }
     if (ok && prm.window) ok = window_pair_allowed(prm.window, i, j, vi, vj, args.meta, args.blocks, prm.l_window);
+    // position shard: pairs among the halo blocks belong to the shard that owns their earlier member
+    if (ok && prm.shard_blocks) ok = min(args.blocks.blk_of[i], args.blocks.blk_of[j]) < prm.shard_blocks;
     if (!ok) return false;
     if (MODE == MODE_PHASED_NOMISS) {
         // ld_engine.cpp:244-246 / :682-685

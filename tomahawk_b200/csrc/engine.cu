@@ -197,6 +197,7 @@ static int validate_settings(const twkb_settings* s, std::string& why) {
         return TWKB_EINVAL;
     }
     if (s->minR2 < 0 || s->minR2 > 1) { why = "minR2 out of range"; return TWKB_EINVAL; }  // calc.h range checks
+    if (s->shard_blocks < 0 || (s->shard_blocks > 0 && !s->window)) { why = "shard_blocks needs window mode"; return TWKB_EINVAL; }
     return TWKB_OK;
 }
 
@@ -226,6 +227,7 @@ static DevParams make_params(const Context* ctx, const Problem& pb) {
     p.unphased = (ctx->mode >= 2) ? 1u : 0u;
     p.diag = pb.diag ? 1u : 0u;
     p.lgamma_len = ctx->lgamma_len;
+    p.shard_blocks = s.window ? (uint32_t)s.shard_blocks : 0u;
     return p;
 }
 
@@ -346,7 +348,8 @@ static uint64_t visited_pairs(const Context* ctx, const Problem& pb) {
     const uint32_t nb = (uint32_t)ctx->h_blk_first.size();
     const uint32_t w = (uint32_t)ctx->st.l_window;
     const uint32_t kind = window_kind(ctx->st);
-    for (uint32_t bi = 0; bi < nb; ++bi) {
+    const uint32_t own = ctx->st.shard_blocks > 0 ? std::min(nb, (uint32_t)ctx->st.shard_blocks) : nb;  // a position shard counts its own block rows
+    for (uint32_t bi = 0; bi < own; ++bi) {
         const uint64_t ni = ctx->h_blk_last[bi] - ctx->h_blk_first[bi] + 1;
         const twkb_variant& vf = meta_orig(ctx)[ctx->h_blk_first[bi]];
         for (uint32_t bj = bi; bj < ctx->h_blk_prune[bi] || bj == bi; ++bj) {
@@ -427,6 +430,9 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
     const uint32_t w = (uint32_t)ctx->st.l_window;
     const uint32_t M = ctx->n_variants;
     const int parts = std::max(1, ctx->st.part_count), part = ctx->st.part_index;
+    const uint32_t shard_blocks = (ctx->st.window && ctx->st.shard_blocks > 0 && ctx->h_blk_of_orig.size() == M && ctx->h_orig.size() == M)
+                                      ? (uint32_t)ctx->st.shard_blocks : 0u;
+    auto blk_res = [&](uint32_t x) { return ctx->h_blk_of_orig[ctx->h_orig[x]]; };  // .twk block of a resident index
     // A part's share. Many super-tiles (>= 16 per part): whole super-tiles are dealt, each to the part
     // with the fewest tiles so far (every part computes the same assignment), so that a part's
     // operand working set is the rows of ITS super-tiles -- dealing single tiles round-robin makes
@@ -452,6 +458,12 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
                             (uint32_t)(b0.pos - a1.pos) > w)
                             continue;
                     }
+                }
+                if (shard_blocks) {
+                    // position shard: both members of every pair of the tile lie in halo blocks (file order is monotone
+                    // within the range a tile plan covers, so the first row / column has the lowest block)
+                    const uint32_t ia = std::max(i0, pb.row_begin), ja = std::max(j0, pb.col_begin);
+                    if (ia < M && ja < M && blk_res(ia) >= shard_blocks && blk_res(ja) >= shard_blocks) continue;
                 }
                 if (prune_only) {
                     const uint32_t ia = std::max(i0, pb.row_begin), il = std::min(i0 + TI, std::min(M, pb.row_end)) - 1;
@@ -520,6 +532,9 @@ static void build_sparse_tiles(const Context* ctx, std::vector<uint2>& tiles, ui
     const bool window = window_kind(ctx->st) == 1u;
     const uint32_t w = (uint32_t)ctx->st.l_window;
     const int parts = std::max(1, ctx->st.part_count), part = ctx->st.part_index;
+    const uint32_t shard_blocks = (ctx->st.window && ctx->st.shard_blocks > 0 && ctx->h_blk_of_orig.size() == M && ctx->h_orig.size() == M)
+                                      ? (uint32_t)ctx->st.shard_blocks : 0u;
+    auto blk_res = [&](uint32_t x) { return ctx->h_blk_of_orig[ctx->h_orig[x]]; };
     uint64_t group = 0, pairs = 0;
     for (uint32_t r0 = nD; r0 < M; r0 += SP_ROWS) {
         const uint32_t r1 = std::min<uint32_t>(r0 + SP_ROWS, M);
@@ -530,6 +545,9 @@ static void build_sparse_tiles(const Context* ctx, std::vector<uint2>& tiles, ui
             const uint32_t sa = std::max(j0, r0 + 1), sb = j1;   // sparse columns later than the first row
             const bool has_d = da < db, has_s = sa < sb;
             if (!has_d && !has_s) continue;
+            if (shard_blocks && blk_res(r0) >= shard_blocks && (!has_d || blk_res(da) >= shard_blocks) &&
+                (!has_s || blk_res(sa) >= shard_blocks))
+                continue;  // position shard: halo rows x halo columns
             if (window) {
                 auto far = [&](uint32_t ca, uint32_t cb) {
                     const twkb_variant &b0 = ctx->h_meta[ca], &b1 = ctx->h_meta[cb - 1];
@@ -939,10 +957,10 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
     }
     if (const char* e = getenv("TWKB_SUPER")) super = (uint32_t)std::max(1, atoi(e));
     char keybuf[256];
-    std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u/%u|w%d:%d:%d|p%d/%d",
+    std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u/%u|w%d:%d:%d|p%d/%d|s%d",
                   (unsigned long long)(ctx->st.window ? ctx->matrix_epoch : 0ull),
                   pb.row_begin, pb.row_end, pb.col_begin, pb.col_end, (int)pb.diag, TI, TJ, super, (int)window_kind(ctx->st),
-                  ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
+                  ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count, ctx->st.shard_blocks);
     if (ctx->plan_key != keybuf) {
         if (n_dense >= 2) build_tiles(ctx, pb, TI, TJ, super, ctx->plan_tiles, &ctx->plan_pairs);
         else { ctx->plan_tiles.clear(); ctx->plan_pairs = 0; }
@@ -954,8 +972,8 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
         ctx->plan_key = keybuf;
     }
     if (sparse_phase) {
-        std::snprintf(keybuf, sizeof(keybuf), "%llu|w%d:%d:%d|p%d/%d", (unsigned long long)ctx->matrix_epoch, (int)window_kind(ctx->st),
-                      ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count);
+        std::snprintf(keybuf, sizeof(keybuf), "%llu|w%d:%d:%d|p%d/%d|s%d", (unsigned long long)ctx->matrix_epoch, (int)window_kind(ctx->st),
+                      ctx->st.l_window, ctx->st.twk_block_size, ctx->st.part_index, ctx->st.part_count, ctx->st.shard_blocks);
         if (ctx->sp_plan_key != keybuf) {
             build_sparse_tiles(ctx, ctx->sp_plan_tiles, &ctx->sp_plan_pairs);
             ctx->sp_tile_words_prefix.assign(ctx->sp_plan_tiles.size() + 1, 0);
@@ -2197,6 +2215,46 @@ static int twkb_plan_tiles_impl(const twkb_settings* s, uint32_t n_variants, con
     return TWKB_OK;
 }
 
+// Position shards of a -w run (twkb.h). The reach of a block row is the balancer's row prune (ld_balancing.h:189-196,
+// the same loop as build_blocks_host): block bj is reachable from bi until the first bj whose first position is more
+// than the window past bi's last position -- positions only, uint32 wrap-around included, no contig test.
+static int twkb_plan_shards_impl(const uint32_t* block_first, uint32_t n_blocks, const twkb_variant* meta, uint32_t n_variants,
+                                 int32_t l_window, int32_t n_shards, uint32_t* own_begin, uint32_t* halo_end) {
+    if (!block_first || !meta || !own_begin || !halo_end || n_blocks == 0 || n_shards < 1 || l_window < 0) return TWKB_EINVAL;
+    if (block_first[0] != 0 || block_first[n_blocks] != n_variants) return TWKB_EINVAL;
+    for (uint32_t b = 0; b < n_blocks; ++b)
+        if (block_first[b + 1] <= block_first[b]) return TWKB_EINVAL;
+    const uint32_t w = (uint32_t)l_window;
+    std::vector<uint32_t> prune(n_blocks, n_blocks);
+    std::vector<double> work(n_blocks + 1, 0.0);  // prefix sums of the pairs a block row visits
+    for (uint32_t bi = 0; bi < n_blocks; ++bi) {
+        const uint32_t last_pos = meta[block_first[bi + 1] - 1].pos;
+        for (uint32_t bj = bi + 1; bj < n_blocks; ++bj)
+            if ((uint32_t)(meta[block_first[bj]].pos - last_pos) > w) { prune[bi] = bj; break; }
+        const double ni = (double)(block_first[bi + 1] - block_first[bi]);
+        const double reach = (double)(block_first[prune[bi]] - block_first[bi + 1]);
+        work[bi + 1] = work[bi] + ni * (ni - 1.0) / 2.0 + ni * reach;
+    }
+    const uint32_t shards = std::min<uint32_t>((uint32_t)n_shards, n_blocks);
+    own_begin[0] = 0;
+    uint32_t b = 0;
+    for (uint32_t k = 1; k < (uint32_t)n_shards; ++k) {
+        if (k >= shards) { own_begin[k] = n_blocks; continue; }  // more shards than blocks: the extra ones are empty
+        const double target = work[n_blocks] * (double)k / (double)shards;
+        while (b < n_blocks && work[b] < target) ++b;
+        b = std::max(b, own_begin[k - 1] + 1);                    // every shard owns at least one block ...
+        b = std::min(b, n_blocks - (shards - k));                 // ... and leaves one for each later shard
+        own_begin[k] = b;
+    }
+    own_begin[n_shards] = n_blocks;
+    for (uint32_t k = 0; k < (uint32_t)n_shards; ++k) {
+        uint32_t e = own_begin[k + 1];
+        for (uint32_t bi = own_begin[k]; bi < own_begin[k + 1]; ++bi) e = std::max(e, prune[bi]);
+        halo_end[k] = e;
+    }
+    return TWKB_OK;
+}
+
 // ---- exception-safe entry points (see guarded_buf / guarded_ctx)
 int twkb_calc_file_intervals(const twkb_settings* s, const char* in_path, const char* out_path, const char* const* intervals,
                              int32_t n_intervals, twkb_stats* stats_out, char* errbuf, size_t errbuf_len) {
@@ -2234,6 +2292,11 @@ int twkb_two_close(void* writer) {
 int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i, uint32_t tile_j,
                     uint32_t* out_ij, uint64_t capacity, uint64_t* n_tiles, uint64_t* n_pairs) {
     return guarded_buf(nullptr, 0, [&] { return twkb_plan_tiles_impl(s, n_variants, meta, tile_i, tile_j, out_ij, capacity, n_tiles, n_pairs); });
+}
+
+int twkb_plan_shards(const uint32_t* block_first, uint32_t n_blocks, const twkb_variant* meta, uint32_t n_variants, int32_t l_window,
+                     int32_t n_shards, uint32_t* own_begin, uint32_t* halo_end) {
+    return guarded_buf(nullptr, 0, [&] { return twkb_plan_shards_impl(block_first, n_blocks, meta, n_variants, l_window, n_shards, own_begin, halo_end); });
 }
 
 int twkb_create(const twkb_settings* s, void** out) {
