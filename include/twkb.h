@@ -247,6 +247,43 @@ int twkb_compute_resident(void* ctx);
  * Only 16 bytes per bin leave the GPU. sum_r2 / count: host arrays of n_bins entries. */
 int twkb_compute_decay(void* ctx, int64_t window_bp, int32_t n_bins, double* sum_r2, uint64_t* count);
 
+/* Downstream consumer fed from the device-resident records: `tomahawk aggregate`, the reference's
+ * two_reader::Aggregate (lib/two_reader.cpp:543-853, lib/aggregation.h:127-175) -- a xbins x ybins raster of the LD landscape --
+ * without writing and re-reading a .two file. Every record lands in bin [coord(ridA, posA) / bpx][coord(ridB, posB) / bpy] and, as
+ * the reverse copy the reference writes, in [coord(ridB, posB) / bpx][coord(ridA, posA) / bpy]; a bin keeps the reference's
+ * twk_sstats (include/core.h:929-990: n, total, total_squared, min and max -- both of which start at 0 there) of the chosen field.
+ * Two passes like the reference: the first finds the position range of every contig that occurs in a record, the second
+ * rasterises; the LD computation runs once per pass and only the raster leaves the GPU (40 bytes per bin).
+ * Coordinates (two_reader.cpp:743-797, aggregation.h:157): one contig with records (any contig but the first -- the
+ * reference counts contig 0 twice, :737-740; kept with settings.emulate_quirks) spans [min, max] of the positions seen,
+ * otherwise every contig with records spans its whole length contig_n_bases[rid]; bpx = ceil((float)range / xbins).
+ * Not reproduced: the reference skips .two blocks with fewer than 5 records (aggregation.h:131,152; depends on how its
+ * writer threads happened to cut the file) and indexes one bin past the raster for the very last coordinate (clamped here). */
+#define TWKB_AGG_R2 0
+#define TWKB_AGG_R 1
+#define TWKB_AGG_D 2
+#define TWKB_AGG_DPRIME 3
+#define TWKB_AGG_P 4
+#define TWKB_AGG_HETS 5 /* (cnt[1] + cnt[2]) / sum(cnt), twk_sstats::AddHets */
+#define TWKB_AGG_ALTS 6 /* cnt[3] / sum(cnt),            twk_sstats::AddAlts */
+typedef struct twkb_agg_bin { /* twk_sstats */
+    uint64_t n;
+    double total, total_squared, min, max;
+} twkb_agg_bin;
+typedef struct twkb_agg_layout { /* twk1_aggregate_t header fields, include/core.h:1014-1017 */
+    uint64_t range;      /* bases covered by the raster                */
+    uint32_t bpx, bpy;   /* bases per bin                              */
+    uint32_t n_contigs_set;
+    uint64_t n_records;  /* records rasterised, reverse copies included */
+} twkb_agg_layout;
+/* bins: xbins * ybins entries, row-major [x][y]. contig_offset / contig_min / contig_max (nullable, n_contigs entries each):
+ * the reference's rid_offsets (cumulative range, min, max). */
+int twkb_compute_aggregate(void* ctx, int32_t field, int32_t xbins, int32_t ybins, const int64_t* contig_n_bases, uint32_t n_contigs,
+                           twkb_agg_bin* bins, twkb_agg_layout* layout, uint64_t* contig_offset, uint32_t* contig_min,
+                           uint32_t* contig_max);
+/* Contig lengths of an open .twk handle in header order (what twkb_compute_aggregate takes). n_bases may be NULL to count. */
+int twkb_twk_contigs(void* handle, int64_t* n_bases, uint32_t capacity, uint32_t* n_contigs);
+
 int twkb_get_stats(void* ctx, twkb_stats* out);
 
 /* Test hook: run the count kernel the settings select (tensor-core or LOP3+POPC, exactly as

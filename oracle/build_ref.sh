@@ -39,7 +39,8 @@ g++ $CXXFLAGS "$HERE/stub_view_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk
 g++ $CXXFLAGS "$HERE/stub_sort_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk_sort" 2>/dev/null
 g++ $CXXFLAGS "$HERE/stub_scalc_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk_scalc" 2>/dev/null
 g++ $CXXFLAGS "$HERE/stub_decay_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk_decay" 2>/dev/null
+g++ $CXXFLAGS "$HERE/stub_aggregate_main.cpp" $OBJS -l:libzstd.so.1 -o "$OUT/tomahawk_aggregate" 2>/dev/null
 # The same fisher_math.cpp as a tiny shared object so the C restatement's Fisher
 # can be diffed against the reference's kt_fisher_exact directly (ctypes).
 g++ -O3 -msse4.2 -w -shared -fPIC -I$REF/lib "$REF/lib/fisher_math.cpp" -o "$OUT/libref_fisher.so"
-echo "[oracle] built $OUT/tomahawk_calc $OUT/tomahawk_scalc $OUT/tomahawk_decay $OUT/tomahawk_view $OUT/tomahawk_sort $OUT/libref_fisher.so"
+echo "[oracle] built $OUT/tomahawk_calc $OUT/tomahawk_scalc $OUT/tomahawk_decay $OUT/tomahawk_aggregate $OUT/tomahawk_view $OUT/tomahawk_sort $OUT/libref_fisher.so"

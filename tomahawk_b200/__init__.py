@@ -83,6 +83,9 @@ TWO_DTYPE = np.dtype(
      ("ChiSqFisher", "<f8"), ("ChiSqModel", "<f8")]
 )
 RUN_DESC_DTYPE = np.dtype([("offset", "<u8"), ("n_runs", "<u4"), ("width", "u1"), ("miss", "u1"), ("pad", "u1", (2,))])
+AGG_BIN_DTYPE = np.dtype([("n", "<u8"), ("total", "<f8"), ("total_squared", "<f8"), ("min", "<f8"), ("max", "<f8")])  # twk_sstats
+AGG_LAYOUT_DTYPE = np.dtype([("range", "<u8"), ("bpx", "<u4"), ("bpy", "<u4"), ("n_contigs_set", "<u4"), ("pad", "<u4"), ("n_records", "<u8")])
+AGG_FIELDS = {"r2": 0, "r": 1, "d": 2, "dprime": 3, "dp": 3, "p": 4, "hets": 5, "het": 5, "alts": 6, "alt": 6}  # two_reader.cpp:574-588
 CAND_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("c", "<u4", (9,)), ("mode", "<u4")])
 SINK_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_uint64)
 
@@ -98,7 +101,7 @@ EXPORTS = [
     "twkb_load_runs", "twkb_debug_rows", "twkb_twk_open_runs", "twkb_twk_runs_view", "twkb_two_set_threads",
     "twkb_two_sort",
     "twkb_compute_decay", "twkb_set_blocks", "twkb_twk_blocks", "twkb_two_sort_mem", "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
-    "twkb_plan_shards",
+    "twkb_plan_shards", "twkb_compute_aggregate", "twkb_twk_contigs",
 ]
 
 
@@ -154,6 +157,9 @@ def _bind(L):
     L.twkb_two_sort.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                 ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
     L.twkb_compute_decay.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    L.twkb_compute_aggregate.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_uint32,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.twkb_twk_contigs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32)]
     L.twkb_set_blocks.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
     L.twkb_twk_blocks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32)]
     L.twkb_two_sort_mem.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
@@ -235,6 +241,16 @@ class TwkFile:
         desc = np.frombuffer((ctypes.c_uint8 * (16 * self.n_variants)).from_address(d.value), dtype=RUN_DESC_DTYPE)
         meta = np.frombuffer((ctypes.c_uint8 * (32 * self.n_variants)).from_address(m.value), dtype=VARIANT_DTYPE)
         return raw, desc, meta
+
+    def contigs(self) -> np.ndarray:
+        """Contig lengths in header order (int64)."""
+        n = ctypes.c_uint32(0)
+        self._L.twkb_twk_contigs(self._h, None, 0, ctypes.byref(n))
+        out = np.zeros(n.value, dtype=np.int64)
+        rc = self._L.twkb_twk_contigs(self._h, out.ctypes.data, n.value, ctypes.byref(n))
+        if rc != 0:
+            raise TwkbError(rc, "twkb_twk_contigs")
+        return out
 
     def blocks(self) -> np.ndarray:
         """First variant of every loaded .twk block (file order)."""
@@ -322,6 +338,29 @@ def plan_tiles(settings: Settings, meta: np.ndarray, tile_i: int, tile_j: int):
 
 
 COMM_ID_BYTES = 128
+
+
+def aggregate_reduce(bins: np.ndarray, reduce: str = "mean", min_cutoff: int = 5) -> np.ndarray:
+    """The reduce functions of `tomahawk aggregate -r` over a raster of twk_sstats (include/core.h:957-976), including their
+    cutoff rules: mean = 0 when n < cutoff or cutoff == 0; count = 0 when n < cutoff; sd = 0 when n < cutoff; total = 0 when
+    total < cutoff; min / max ignore the cutoff."""
+    n, tot, sq = bins["n"].astype(np.float64), bins["total"], bins["total_squared"]
+    r = reduce.lower()
+    safe = np.maximum(n, 1.0)
+    if r == "mean":
+        return np.where((n < min_cutoff) | (min_cutoff == 0), 0.0, tot / safe)
+    if r in ("count", "n"):
+        return np.where(n < min_cutoff, 0.0, n)
+    if r == "total":
+        return np.where(tot < min_cutoff, 0.0, tot)
+    if r == "sd":
+        with np.errstate(invalid="ignore"):   # like the reference: NaN where rounding makes the variance negative
+            return np.where(n < min_cutoff, 0.0, np.sqrt(sq / safe - (tot / safe) * (tot / safe)))
+    if r == "min":
+        return bins["min"].copy()
+    if r == "max":
+        return bins["max"].copy()
+    raise TwkbError(-1, f'Unknown reduce function "{reduce}"...')
 
 
 def plan_shards(block_first, meta: np.ndarray, l_window: int, n_shards: int):
@@ -499,6 +538,20 @@ class Engine:
         cnt = np.zeros(n, dtype=np.uint64)
         self._check(self._L.twkb_compute_decay(self._ctx, window_bp, n_bins, sums.ctypes.data, cnt.ctypes.data))
         return sums, cnt
+
+    def compute_aggregate(self, field: str, xbins: int, ybins: int, contig_n_bases):
+        """`tomahawk aggregate` from the device-resident records (two_reader::Aggregate): returns (bins [xbins, ybins] of
+        AGG_BIN_DTYPE, layout dict, rid_offsets dict). Reduce with aggregate_reduce()."""
+        if field.lower() not in AGG_FIELDS:
+            raise TwkbError(-1, f'Unknown aggregation function "{field}"...')
+        nb = np.ascontiguousarray(contig_n_bases, dtype=np.int64)
+        bins = np.zeros((xbins, ybins), dtype=AGG_BIN_DTYPE)
+        layout = np.zeros(1, dtype=AGG_LAYOUT_DTYPE)
+        off, cmin, cmax = np.zeros(len(nb), np.uint64), np.zeros(len(nb), np.uint32), np.zeros(len(nb), np.uint32)
+        self._check(self._L.twkb_compute_aggregate(self._ctx, AGG_FIELDS[field.lower()], xbins, ybins, nb.ctypes.data, len(nb), bins.ctypes.data,
+                                                   layout.ctypes.data, off.ctypes.data, cmin.ctypes.data, cmax.ctypes.data))
+        lay = {k: int(layout[0][k]) for k in ("range", "bpx", "bpy", "n_contigs_set", "n_records")}
+        return bins, lay, {"range": off, "min": cmin, "max": cmax}
 
     def stats(self) -> Stats:
         s = Stats()

@@ -142,6 +142,12 @@ struct Context {
     uint32_t decay_bins = 0, decay_width = 0;
     DevBuf<double> d_decay_sum;
     DevBuf<unsigned long long> d_decay_cnt;
+    // twkb_compute_aggregate: 0 off, 1 = pass 1 (contig position ranges), 2 = pass 2 (raster)
+    int agg_pass = 0;
+    AggLayout agg_layout{};
+    DevBuf<uint32_t> d_agg_min, d_agg_max;
+    DevBuf<unsigned long long> d_agg_base;  // [n_contigs] coordinate bases + 1 counter of records with an unknown contig
+    DevBuf<AggBin> d_agg_bins;
 
     // multi-GPU data plane (comm.cuh): set by twkb_comm_init, used by the sliced loads only
     ncclComm_t comm = nullptr;
@@ -758,6 +764,17 @@ static void flusher_destroy(Context* ctx) {
 // resident run, just count it) and continue in the other one once that is free.
 // Device-side consumers of a record buffer whose statistics kernels have completed (stream order).
 static int consume_records(Context* ctx, int buf, uint64_t n) {
+    if (ctx->agg_pass && n) {
+        const unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
+        if (ctx->agg_pass == 1)
+            agg_range_kernel<<<g, 256, 0, ctx->stream>>>(ctx->d_records[buf].p, n, ctx->agg_layout.n_contigs, ctx->d_agg_min.p, ctx->d_agg_max.p,
+                                                        ctx->d_agg_base.p + ctx->agg_layout.n_contigs);
+        else
+            agg_bin_kernel<<<g, 256, 0, ctx->stream>>>(ctx->d_records[buf].p, n, ctx->agg_layout, ctx->d_agg_bins.p);
+        CUDA_TRY(cudaGetLastError());
+        ctx->stats.other_launches += 1;
+        return TWKB_OK;
+    }
     if (!ctx->decay_bins || n == 0) return TWKB_OK;
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
     decay_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_records[buf].p, n, ctx->decay_width, ctx->decay_bins, ctx->d_decay_sum.p,
@@ -1753,6 +1770,7 @@ void twkb_destroy(void* c) {
     for (cudaEvent_t ev : ctx->chunk_events) cudaEventDestroy(ev);
     ctx->d_counters.release(); ctx->d_records[0].release(); ctx->d_records[1].release();
     ctx->d_decay_sum.release(); ctx->d_decay_cnt.release();
+    ctx->d_agg_min.release(); ctx->d_agg_max.release(); ctx->d_agg_base.release(); ctx->d_agg_bins.release();
     ctx->d_orig.release(); ctx->d_sp_off.release(); ctx->d_sp_ent.release(); ctx->d_sp_tiles.release();
     umma_release(ctx->umma);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
@@ -1918,6 +1936,95 @@ int twkb_compute_decay(void* c, int64_t window_bp, int32_t n_bins, double* sum_r
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return TWKB_OK;
     });
+}
+
+int twkb_compute_aggregate(void* c, int32_t field, int32_t xbins, int32_t ybins, const int64_t* contig_n_bases, uint32_t n_contigs,
+                           twkb_agg_bin* bins, twkb_agg_layout* layout, uint64_t* contig_offset, uint32_t* contig_min, uint32_t* contig_max) {
+    if (!c || !bins || !contig_n_bases || n_contigs == 0 || n_contigs > (1u << 24)) return TWKB_EINVAL;
+    Context* ctx = static_cast<Context*>(c);
+    static_assert(sizeof(twkb_agg_bin) == sizeof(AggBin), "twk_sstats layout");
+    // two_reader::Aggregate, lib/two_reader.cpp:620-628
+    if (field < TWKB_AGG_R2 || field > TWKB_AGG_ALTS) { ctx->err = "Unknown aggregation function..."; return TWKB_EINVAL; }
+    if (xbins < 5) { ctx->err = "Number of x-bins cannot be < 5!"; return TWKB_EINVAL; }
+    if (ybins < 5) { ctx->err = "Number of y-bins cannot be < 5!"; return TWKB_EINVAL; }
+    if ((uint64_t)xbins * (uint64_t)ybins > (1ull << 28)) { ctx->err = "raster too large"; return TWKB_EINVAL; }
+    return guarded_ctx(c, [&]() -> int {
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        const size_t nb = (size_t)xbins * ybins;
+        // ---- pass 1: which contigs occur, and their position ranges (FindRangesUnsorted, aggregation.h:127-148)
+        CUDA_TRY(ctx->d_agg_min.alloc(n_contigs));
+        CUDA_TRY(ctx->d_agg_max.alloc(n_contigs));
+        CUDA_TRY(ctx->d_agg_base.alloc((size_t)n_contigs + 1));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_agg_min.p, 0xff, (size_t)n_contigs * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_agg_max.p, 0, (size_t)n_contigs * 4, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_agg_base.p, 0, ((size_t)n_contigs + 1) * 8, ctx->stream));
+        ctx->agg_layout = AggLayout{};
+        ctx->agg_layout.n_contigs = n_contigs;
+        ctx->agg_pass = 1;
+        int rc = compute_impl(ctx, true, nullptr, nullptr, false, nullptr);
+        ctx->agg_pass = 0;
+        if (rc) return rc;
+        std::vector<uint32_t> cmin(n_contigs), cmax(n_contigs);
+        unsigned long long bad = 0;
+        CUDA_TRY(cudaMemcpyAsync(cmin.data(), ctx->d_agg_min.p, (size_t)n_contigs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(cmax.data(), ctx->d_agg_max.p, (size_t)n_contigs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&bad, ctx->d_agg_base.p + n_contigs, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (bad) { ctx->err = "a record names a contig beyond n_contigs"; return TWKB_EINVAL; }
+        const uint64_t n_fwd = ctx->stats.records_out;
+        // ---- coordinate system (two_reader.cpp:734-797)
+        std::vector<uint8_t> set(n_contigs);
+        uint32_t n_set = 0, n_set_ref = 0;
+        for (uint32_t i = 0; i < n_contigs; ++i) { set[i] = cmin[i] != 0xffffffffu; n_set += set[i]; }
+        n_set_ref = n_set + (ctx->st.emulate_quirks && set[0] ? 1u : 0u);  // :737-740 starts the sum AT contig_avail[0].set and adds it again
+        std::vector<uint64_t> cum(n_contigs, 0);
+        std::vector<uint32_t> omin(n_contigs), omax(n_contigs);
+        uint64_t range = 0;
+        for (uint32_t i = 0; i < n_contigs; ++i) {
+            uint64_t span;
+            if (n_set_ref == 1) { omin[i] = cmin[i]; omax[i] = cmax[i]; span = set[i] ? (uint64_t)(cmax[i] - cmin[i]) + 1 : 0; }
+            else { omin[i] = 0; omax[i] = (uint32_t)contig_n_bases[i]; span = set[i] ? (uint64_t)contig_n_bases[i] : 0; }
+            range += span;
+            cum[i] = range;
+        }
+        std::memset(bins, 0, nb * sizeof(twkb_agg_bin));
+        if (layout) *layout = twkb_agg_layout{range, 0, 0, n_set, 2 * n_fwd};
+        for (uint32_t i = 0; i < n_contigs; ++i) {
+            if (contig_offset) contig_offset[i] = cum[i];
+            if (contig_min) contig_min[i] = omin[i];
+            if (contig_max) contig_max[i] = omax[i];
+        }
+        if (n_fwd == 0 || range == 0) return TWKB_OK;  // "Cannot aggregate empty file...": an all-zero raster
+        const uint32_t xrange = (uint32_t)std::ceil((float)range / xbins), yrange = (uint32_t)std::ceil((float)range / ybins);  // :801-802
+        if (layout) { layout->bpx = xrange; layout->bpy = yrange; }
+        // ---- pass 2: the raster (BuildMatrix, aggregation.h:150-172)
+        std::vector<unsigned long long> base(n_contigs);
+        for (uint32_t i = 0; i < n_contigs; ++i) base[i] = cum[i] - (uint64_t)(uint32_t)(omax[i] - omin[i]);
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_agg_base.p, base.data(), (size_t)n_contigs * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_agg_min.p, omin.data(), (size_t)n_contigs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx->d_agg_bins.alloc(nb));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_agg_bins.p, 0, nb * sizeof(AggBin), ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // base / omin are stack vectors
+        ctx->agg_layout = AggLayout{ctx->d_agg_base.p, ctx->d_agg_min.p, n_contigs, xrange, yrange, (uint32_t)xbins, (uint32_t)ybins, field};
+        ctx->agg_pass = 2;
+        rc = compute_impl(ctx, true, nullptr, nullptr, false, nullptr);
+        ctx->agg_pass = 0;
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(bins, ctx->d_agg_bins.p, nb * sizeof(AggBin), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return TWKB_OK;
+    });
+}
+
+int twkb_twk_contigs(void* handle, int64_t* n_bases, uint32_t capacity, uint32_t* n_contigs) {
+    if (!handle) return TWKB_EINVAL;
+    const TwkFile* f = static_cast<TwkFile*>(handle);
+    if (n_contigs) *n_contigs = (uint32_t)f->contig_n_bases.size();
+    if (n_bases) {
+        if (capacity < f->contig_n_bases.size()) return TWKB_ENOMEM;
+        std::copy(f->contig_n_bases.begin(), f->contig_n_bases.end(), n_bases);
+    }
+    return TWKB_OK;
 }
 
 int twkb_get_stats(void* c, twkb_stats* out) {

@@ -257,6 +257,8 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
             contigs.push_back(ct);
         }
         if (!h.ok) contigs.clear();  // names are only needed for -I
+        out.contig_n_bases.clear();
+        for (const Contig& ct : contigs) out.contig_n_bases.push_back(ct.n_bases);
     }
     // footer: ... u64 offset_of_index, 32-byte EOF
     uint64_t idx_off = 0;

@@ -66,6 +66,7 @@ struct TwkFile {
     std::string fileformat, literals;
     std::string header_tail;  // serialized samples + contigs, copied through verbatim
     uint32_t n_contigs = 0;
+    std::vector<int64_t> contig_n_bases;  // VcfContig::n_bases in header order (the aggregate consumer's coordinate system)
     uint32_t n_blocks = 0;
     std::vector<uint32_t> block_first;  // first variant of every loaded .twk block (+ n_variants at the end): the block structure the
                                         // reference's window rule and -c chunks are defined on (`import -b` makes the length configurable)

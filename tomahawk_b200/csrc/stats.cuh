@@ -614,4 +614,99 @@ decay_kernel(const uint8_t* __restrict__ records, unsigned long long n_records, 
             if (s_cnt[b]) { atomicAdd(&sum_r2[b], s_sum[b]); atomicAdd(&count[b], (unsigned long long)s_cnt[b]); }
 }
 
+// ---------------------------------------------------------------- aggregate consumer
+// `tomahawk aggregate` straight from the device-resident records (reference two_reader::Aggregate, lib/two_reader.cpp:543-853,
+// twk_agg_slave::FindRangesUnsorted / BuildMatrix, lib/aggregation.h:127-175). Pass 1: position range per contig; pass 2: raster
+// of twk_sstats (include/core.h:929-990) over forward + reverse orientation of every record.
+struct AggBin { unsigned long long n; double total, total_squared, min, max; };
+struct AggLayout {
+    const unsigned long long* base;  // [n_contigs] coordinate of position cmin[rid]: rid_offsets.range - (max - min)
+    const uint32_t* cmin;            // [n_contigs]
+    uint32_t n_contigs, xrange, yrange, xbins, ybins;
+    int field;
+};
+
+__device__ __forceinline__ uint32_t rec_u32(const uint16_t* h, int byte) { return h[byte >> 1] | ((uint32_t)h[(byte >> 1) + 1] << 16); }
+__device__ __forceinline__ double rec_f64(const uint16_t* h, int byte) {
+    const int k = byte >> 1;
+    const unsigned long long bits = (unsigned long long)h[k] | ((unsigned long long)h[k + 1] << 16) | ((unsigned long long)h[k + 2] << 32) |
+                                    ((unsigned long long)h[k + 3] << 48);
+    return __longlong_as_double((long long)bits);
+}
+
+__global__ void __launch_bounds__(256)
+agg_range_kernel(const uint8_t* __restrict__ records, unsigned long long n_records, uint32_t n_contigs, uint32_t* __restrict__ cmin,
+                 uint32_t* __restrict__ cmax, unsigned long long* __restrict__ bad) {
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_records;
+         r += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint16_t* h = reinterpret_cast<const uint16_t*>(records + r * 106ull);
+        const uint32_t rid[2] = {rec_u32(h, 2), rec_u32(h, 6)};
+        const uint32_t pos[2] = {rec_u32(h, 10) >> 2, rec_u32(h, 14) >> 2};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (rid[k] >= n_contigs) { atomicAdd(bad, 1ull); continue; }
+            // most records improve nothing: look before paying for the atomic
+            if (pos[k] < cmin[rid[k]]) atomicMin(&cmin[rid[k]], pos[k]);
+            if (pos[k] > cmax[rid[k]]) atomicMax(&cmax[rid[k]], pos[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+    unsigned long long old = *reinterpret_cast<unsigned long long*>(addr);
+    while (v < __longlong_as_double((long long)old)) {
+        const unsigned long long seen = atomicCAS(reinterpret_cast<unsigned long long*>(addr), old, (unsigned long long)__double_as_longlong(v));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
+    unsigned long long old = *reinterpret_cast<unsigned long long*>(addr);
+    while (v > __longlong_as_double((long long)old)) {
+        const unsigned long long seen = atomicCAS(reinterpret_cast<unsigned long long*>(addr), old, (unsigned long long)__double_as_longlong(v));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+agg_bin_kernel(const uint8_t* __restrict__ records, unsigned long long n_records, AggLayout L, AggBin* __restrict__ bins) {
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_records;
+         r += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint16_t* h = reinterpret_cast<const uint16_t*>(records + r * 106ull);
+        const uint32_t ridA = rec_u32(h, 2), ridB = rec_u32(h, 6);
+        if (ridA >= L.n_contigs || ridB >= L.n_contigs) continue;
+        const uint32_t posA = rec_u32(h, 10) >> 2, posB = rec_u32(h, 14) >> 2;
+        double v;
+        switch (L.field) {
+            case 1: v = rec_f64(h, 66); break;   // R
+            case 2: v = rec_f64(h, 50); break;   // D
+            case 3: v = rec_f64(h, 58); break;   // Dprime
+            case 4: v = rec_f64(h, 82); break;   // P
+            case 5: case 6: {
+                const double c0 = rec_f64(h, 18), c1 = rec_f64(h, 26), c2 = rec_f64(h, 34), c3 = rec_f64(h, 42);
+                const double tot = __dadd_rn(__dadd_rn(__dadd_rn(c0, c1), c2), c3);
+                v = L.field == 5 ? __ddiv_rn(__dadd_rn(c1, c2), tot) : __ddiv_rn(c3, tot);
+                break;
+            }
+            default: v = rec_f64(h, 74); break;  // R2
+        }
+        // aggregation.h:157: (range - (max - min)) + (pos - min)
+        const unsigned long long ca = L.base[ridA] + (unsigned long long)(uint32_t)(posA - L.cmin[ridA]);
+        const unsigned long long cb = L.base[ridB] + (unsigned long long)(uint32_t)(posB - L.cmin[ridB]);
+        const uint32_t x[2] = {(uint32_t)min(ca / L.xrange, (unsigned long long)(L.xbins - 1u)), (uint32_t)min(cb / L.xrange, (unsigned long long)(L.xbins - 1u))};
+        const uint32_t y[2] = {(uint32_t)min(cb / L.yrange, (unsigned long long)(L.ybins - 1u)), (uint32_t)min(ca / L.yrange, (unsigned long long)(L.ybins - 1u))};
+        const double vv = __dmul_rn(v, v);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {  // forward, reverse
+            AggBin* b = bins + (size_t)x[k] * L.ybins + y[k];
+            atomicAdd(&b->n, 1ull);
+            atomicAdd(&b->total, v);
+            atomicAdd(&b->total_squared, vv);
+            atomic_min_f64(&b->min, v);
+            atomic_max_f64(&b->max, v);
+        }
+    }
+}
+
 }  // namespace twkb
