@@ -155,7 +155,7 @@ def test_cli_window_on_several_devices_runs_position_shards(tmpdir_repo):
     outs = {}
     for name, extra in (("one", ["-g", "0"]), ("shards", ["-g", "0,0,0"]), ("shards_host", ["-g", "0,0", "--host-unpack"])):
         out = os.path.join(tmpdir_repo, f"shard_cli_{name}.two")
-        r = subprocess.run([exe, "calc", "-p", "-r", "0.05", "-w", "25000", "-i", twk, "-o", out, "-t", "4", *extra],
+        r = subprocess.run([exe, "calc", "-p", "-r", "0.05", "-w", "50000", "-i", twk, "-o", out, "-t", "4", *extra],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         assert ("position shards" in r.stderr) == (name != "one")
