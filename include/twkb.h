@@ -101,7 +101,8 @@ typedef struct twkb_settings {
                                 (twkb_plan_shards) -- and computes only the pairs whose earlier member lies in its first
                                 shard_blocks blocks; the union over the shards is the whole-matrix -w result. 0 = off;
                                 needs window = 1. The block structure is the one twkb_set_blocks gave (or twk_block_size) */
-    int32_t reserved[1];
+    int32_t sorted_output;   /* twkb_calc_file*: 1 = order the records on the device (twkb_compute_sorted) and write a SORTED .two
+                                (the reference needs calc, then sort); one device, output to a file */
 } twkb_settings;
 
 /* Subset of twk1_t (include/core.h:291-295) the LD path reads. */
@@ -239,6 +240,14 @@ int twkb_compute(void* ctx, twkb_sink_fn sink, void* user);
  * them (used to time the device-resident path; no D2H of records). */
 int twkb_compute_resident(void* ctx);
 
+/* Like twkb_compute, with the output already in the order of `tomahawk sort` (two_reader::Sort, lib/two_reader.cpp:162-420;
+ * twk1_two_t::operator<, lib/core.cpp:458-468: ridA, ridB, posA, posB): the forward records stay in device memory until the
+ * computation ends, both orientations (the reverse copies the reference's calc also writes) are ordered by a radix sort ON
+ * THE DEVICE, and the sink receives forward AND reverse records in file order -- write them with twkb_two_open_sorted /
+ * twkb_two_add_sorted and the reference's `view -I` can seek in the file without a `sort` run. One device (part_count <= 1);
+ * device memory: 106 B per forward record + 40 B per sorted item. */
+int twkb_compute_sorted(void* ctx, twkb_sink_fn sink, void* user);
+
 /* Downstream consumer fed from the device-resident records: LD decay over distance, the reference's
  * two_reader::Decay (lib/two_reader.cpp:424-475), without writing and re-reading a .two file. Runs the LD computation like
  * twkb_compute_resident and reduces every record with ridA == ridB and posA < posB into
@@ -350,6 +359,14 @@ int twkb_two_open(const char* path, void* twk_handle, const char* command_line, 
 int twkb_two_set_threads(void* writer, int32_t n_threads); /* zstd block compression threads (default 1) */
 int twkb_two_add(void* writer, const uint8_t* records, uint64_t n);
 int twkb_two_close(void* writer); /* finishes the file and frees the writer */
+
+/* Writer of a SORTED .two (what `tomahawk sort` produces): takes records that are already in order (twkb_compute_sorted:
+ * forward and reverse copies), cuts blocks of <= 10,000 records at every change of ridA and writes the sorted-state index
+ * with the per-contig entries (lib/two_reader.cpp:350-420, include/writer.h:363-374). A failed close removes the file. */
+int twkb_two_open_sorted(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t n_threads,
+                         void** writer, char* errbuf, size_t errbuf_len);
+int twkb_two_add_sorted(void* writer, const uint8_t* records, uint64_t n);
+int twkb_two_close_sorted(void* writer);
 
 /* `tomahawk sort` (two_reader::Sort, lib/two_reader.cpp:162-420):
  * orders the records by (ridA, ridB, posA, posB) -- twk1_two_t::operator<, lib/core.cpp:458-468 -- and

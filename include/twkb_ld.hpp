@@ -78,6 +78,8 @@ struct twk_ld_settings {
     bool emulate_quirks = true;
     bool host_unpack = false;  // true: unpack the .twk rows on the host instead of decoding the runs on the device
     bool silent = false;  // suppress the LOG lines (errors are always printed)
+    bool sorted_output = false;  // order the records on the device and write a SORTED .two (calc + sort of the reference in one run);
+                                 // one device, output to a file
     bool position_shards = true;  // -w on several devices: every device loads only its own .twk blocks + the halo blocks the
                                   // window reaches (twkb_plan_shards) instead of the whole matrix; false = deal tiles of
                                   // the whole matrix like the all-pairs modes
@@ -145,6 +147,10 @@ public:
             settings.devices.resize(1);  // one target row: one device
         }
         const bool to_stdout = settings.out.empty() || settings.out == "-";  // the reference's default: stream the .two to stdout (ld.cpp:585-588)
+        if (settings.sorted_output) {
+            if (to_stdout) return error("Sorted output needs an output file (-o)...");
+            if (settings.devices.size() != 1) return error("Sorted output runs on one device...");
+        }
         log("READER") << "Opening " << settings.in << "..." << std::endl;
         char errbuf[1024] = {0};
         std::vector<const char*> iv;
@@ -191,12 +197,16 @@ public:
         if (to_stdout) out = "-";
         log("WRITER") << (to_stdout ? std::string("Writing to stdout...") : "Opening " + out + "...") << std::endl;
         void* writer = nullptr;
-        rc = twkb_two_open(out.c_str(), twk, command_line.c_str(), settings.c_level, settings.b_size, &writer, errbuf, sizeof(errbuf));
+        rc = settings.sorted_output
+                 ? twkb_two_open_sorted(out.c_str(), twk, command_line.c_str(), settings.c_level, settings.n_threads > 0 ? settings.n_threads : 1,
+                                        &writer, errbuf, sizeof(errbuf))
+                 : twkb_two_open(out.c_str(), twk, command_line.c_str(), settings.c_level, settings.b_size, &writer, errbuf, sizeof(errbuf));
         if (rc) {
             twkb_twk_close(twk);
             return error(errbuf[0] ? errbuf : "Failed to open file: " + out + "...");
         }
-        twkb_two_set_threads(writer, settings.n_threads > 0 ? settings.n_threads : 1);
+        if (!settings.sorted_output) twkb_two_set_threads(writer, settings.n_threads > 0 ? settings.n_threads : 1);
+        auto close_writer = [&]() { return settings.sorted_output ? twkb_two_close_sorted(writer) : twkb_two_close(writer); };
 
         const int n_dev = (int)settings.devices.size();
         log("THREAD") << "Spawning " << n_dev << " device context(s)..." << std::endl;
@@ -231,7 +241,7 @@ public:
             if (r) {
                 const std::string why = twkb_last_error(nullptr);
                 for (void* c : ctxs) twkb_destroy(c);
-                twkb_two_close(writer);
+                close_writer();
                 twkb_twk_close(twk);
                 return error("device " + std::to_string(settings.devices[k]) + ": " + why);
             }
@@ -293,7 +303,7 @@ public:
                 }
             }
             if (r == TWKB_OK && file_blocks && n_file_blocks) r = twkb_set_blocks(ctx, file_blocks, n_file_blocks);
-            if (r == TWKB_OK) r = twkb_compute(ctx, &twk_ld::sink, &shared);
+            if (r == TWKB_OK) r = settings.sorted_output ? twkb_compute_sorted(ctx, &twk_ld::sorted_sink, &shared) : twkb_compute(ctx, &twk_ld::sink, &shared);
             if (r) { errors[k] = twkb_last_error(ctx); rcs[k] = r; }
             else twkb_get_stats(ctx, &st[k]);
             twkb_destroy(ctx);
@@ -306,7 +316,7 @@ public:
         bool ok = true;
         for (int k = 0; k < n_dev; ++k)
             if (rcs[k]) { error("device " + std::to_string(settings.devices[k]) + ": " + errors[k]); ok = false; }
-        rc = twkb_two_close(writer);
+        rc = close_writer();
         twkb_twk_close(twk);
         if (!ok) return false;
         if (rc) return error("Failed to write final block!");
@@ -339,6 +349,9 @@ private:
         Shared* s = static_cast<Shared*>(user);
         std::lock_guard<std::mutex> g(s->mu);
         return twkb_two_add(s->writer, recs, n);
+    }
+    static int sorted_sink(void* user, const uint8_t* recs, uint64_t n) {
+        return twkb_two_add_sorted(static_cast<Shared*>(user)->writer, recs, n);
     }
     bool error(const std::string& m) const {
         std::cerr << timestamp("ERROR") << m << std::endl;

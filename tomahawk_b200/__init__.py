@@ -52,7 +52,7 @@ class Settings(ctypes.Structure):
         ("device", ctypes.c_int32), ("part_index", ctypes.c_int32), ("part_count", ctypes.c_int32),
         ("kernel", ctypes.c_int32), ("twk_block_size", ctypes.c_int32), ("sparse_max_words", ctypes.c_int32),
         ("host_unpack", ctypes.c_int32), ("single_targets", ctypes.c_int32), ("shard_blocks", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 1),
+        ("sorted_output", ctypes.c_int32),
     ]
 
 
@@ -102,6 +102,7 @@ EXPORTS = [
     "twkb_two_sort",
     "twkb_compute_decay", "twkb_set_blocks", "twkb_twk_blocks", "twkb_two_sort_mem", "twkb_twk_open_single", "twkb_comm_unique_id", "twkb_comm_init", "twkb_comm_slice", "twkb_load_matrix_sliced", "twkb_load_runs_sliced",
     "twkb_plan_shards", "twkb_compute_aggregate", "twkb_twk_contigs",
+    "twkb_compute_sorted", "twkb_two_open_sorted", "twkb_two_add_sorted", "twkb_two_close_sorted",
 ]
 
 
@@ -165,6 +166,11 @@ def _bind(L):
     L.twkb_two_sort_mem.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64,
                                     ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
     L.twkb_compute.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
+    L.twkb_compute_sorted.argtypes = [ctypes.c_void_p, SINK_FN, ctypes.c_void_p]
+    L.twkb_two_open_sorted.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_size_t]
+    L.twkb_two_add_sorted.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+    L.twkb_two_close_sorted.argtypes = [ctypes.c_void_p]
     L.twkb_compute_resident.argtypes = [ctypes.c_void_p]
     L.twkb_get_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(Stats)]
     L.twkb_debug_candidates.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
@@ -308,6 +314,33 @@ class TwoWriter:
             self._w = ctypes.c_void_p()
             if rc != 0:
                 raise TwkbError(rc, "twkb_two_close failed")
+
+
+class SortedTwoWriter:
+    """Writer of a SORTED .two (twkb_two_*_sorted): takes the record stream of Engine.compute_sorted()."""
+
+    def __init__(self, path: str, twk: TwkFile, command_line: str = "", c_level: int = 1, n_threads: int = 1):
+        L = lib()
+        self._L = L
+        self._w = ctypes.c_void_p()
+        err = ctypes.create_string_buffer(512)
+        rc = L.twkb_two_open_sorted(path.encode(), twk._h, command_line.encode(), c_level, n_threads, ctypes.byref(self._w), err, 512)
+        if rc != 0:
+            raise TwkbError(rc, err.value.decode())
+
+    def add(self, records: np.ndarray):
+        records = np.ascontiguousarray(records)
+        assert records.dtype.itemsize == RECORD_BYTES
+        rc = self._L.twkb_two_add_sorted(self._w, records.ctypes.data, len(records))
+        if rc != 0:
+            raise TwkbError(rc, "twkb_two_add_sorted failed (records out of order?)")
+
+    def close(self):
+        if self._w:
+            rc = self._L.twkb_two_close_sorted(self._w)
+            self._w = ctypes.c_void_p()
+            if rc != 0:
+                raise TwkbError(rc, "twkb_two_close_sorted failed")
 
 
 def sort_two(in_path: str, out_path: str, c_level: int = 1, n_threads: int = 4, memory_limit: int = 0) -> int:
@@ -514,6 +547,18 @@ class Engine:
         if not chunks:
             return np.zeros(0, dtype=TWO_DTYPE)
         return np.concatenate(chunks)
+
+    def compute_sorted(self) -> np.ndarray:
+        """Run and collect forward AND reverse records in `tomahawk sort` order (sorted on the device)."""
+        chunks = []
+
+        def _sink(user, ptr, n):
+            chunks.append(np.frombuffer(ctypes.string_at(ptr, int(n) * RECORD_BYTES), dtype=TWO_DTYPE))
+            return 0
+
+        cb = SINK_FN(_sink)
+        self._check(self._L.twkb_compute_sorted(self._ctx, cb, None))
+        return np.concatenate(chunks) if chunks else np.zeros(0, dtype=TWO_DTYPE)
 
     def compute_discard(self) -> int:
         """Run with a sink that only counts (end-to-end timing: D2H included)."""

@@ -6,7 +6,7 @@
 //   twkb_calc scalc  [options] -i <in.twk> -I <contig:pos> -o <output.two>      (reference lib/scalc.h)
 //
 // Additions: -g/--devices LIST (CUDA ordinals, comma separated; one context per entry) and
-// -K/--kernel auto|popc|umma|fp4, --host-unpack, --no-shards.
+// -K/--kernel auto|popc|umma|fp4, --host-unpack, --no-shards, --sorted.
 #include <getopt.h>
 
 #include <cstdlib>
@@ -43,6 +43,7 @@ static void calc_usage() {
                  "  -K NAME   count kernel: auto | popc | umma | fp4 (default: auto)\n"
                  "  --host-unpack  unpack the .twk genotypes on the host instead of decoding the runs on the device\n"
                  "  --no-shards    -w on several devices: deal tiles of the whole matrix instead of position shards\n"
+                 "  --sorted       sort the records on the device and write a sorted, indexed .two (calc + sort in one run)\n"
               << std::endl;
 }
 
@@ -184,6 +185,7 @@ int main(int argc, char** argv) {
                                            {"kernel", required_argument, 0, 'K'},
                                            {"host-unpack", no_argument, 0, 1001},
                                            {"no-shards", no_argument, 0, 1002},
+                                           {"sorted", no_argument, 0, 1003},
                                            {0, 0, 0, 0}};
     twkb_host::twk_ld_settings settings;
     std::string literal;
@@ -255,6 +257,7 @@ int main(int argc, char** argv) {
             }
             case 1001: settings.host_unpack = true; break;
             case 1002: settings.position_shards = false; break;
+            case 1003: settings.sorted_output = true; break;
             case 'K': {
                 const std::string k = optarg;
                 if (k == "auto") settings.kernel = TWKB_KERNEL_AUTO;

@@ -26,6 +26,7 @@
 #include "decode.cuh"
 #include "hostio.h"
 #include "pack.cuh"
+#include "sort.cuh"
 #include "stats.cuh"
 
 namespace twkb {
@@ -142,6 +143,10 @@ struct Context {
     uint32_t decay_bins = 0, decay_width = 0;
     DevBuf<double> d_decay_sum;
     DevBuf<unsigned long long> d_decay_cnt;
+    // twkb_compute_sorted: the forward records of the run are collected in d_collect instead of leaving the device
+    bool collect = false;
+    DevBuf<uint8_t> d_collect;
+    uint64_t n_collected = 0;
     // twkb_compute_aggregate: 0 off, 1 = pass 1 (contig position ranges), 2 = pass 2 (raster)
     int agg_pass = 0;
     AggLayout agg_layout{};
@@ -764,6 +769,24 @@ static void flusher_destroy(Context* ctx) {
 // resident run, just count it) and continue in the other one once that is free.
 // Device-side consumers of a record buffer whose statistics kernels have completed (stream order).
 static int consume_records(Context* ctx, int buf, uint64_t n) {
+    if (ctx->collect) {
+        if (n == 0) return TWKB_OK;
+        const size_t need = (size_t)(ctx->n_collected + n) * TWKB_RECORD_BYTES;
+        if (need > ctx->d_collect.n) {  // grow: at least double, keep what is there
+            DevBuf<uint8_t> bigger;
+            CUDA_TRY(bigger.alloc(std::max(need, 2 * ctx->d_collect.n)));
+            if (ctx->n_collected)
+                CUDA_TRY(cudaMemcpyAsync(bigger.p, ctx->d_collect.p, (size_t)ctx->n_collected * TWKB_RECORD_BYTES, cudaMemcpyDeviceToDevice, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            std::swap(bigger.p, ctx->d_collect.p);
+            std::swap(bigger.n, ctx->d_collect.n);
+            bigger.release();
+        }
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_collect.p + (size_t)ctx->n_collected * TWKB_RECORD_BYTES, ctx->d_records[buf].p, (size_t)n * TWKB_RECORD_BYTES,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->n_collected += n;
+        return TWKB_OK;
+    }
     if (ctx->agg_pass && n) {
         const unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 8);
         if (ctx->agg_pass == 1)
@@ -1771,6 +1794,7 @@ void twkb_destroy(void* c) {
     ctx->d_counters.release(); ctx->d_records[0].release(); ctx->d_records[1].release();
     ctx->d_decay_sum.release(); ctx->d_decay_cnt.release();
     ctx->d_agg_min.release(); ctx->d_agg_max.release(); ctx->d_agg_base.release(); ctx->d_agg_bins.release();
+    ctx->d_collect.release();
     ctx->d_orig.release(); ctx->d_sp_off.release(); ctx->d_sp_ent.release(); ctx->d_sp_tiles.release();
     umma_release(ctx->umma);
     if (ctx->h_stage[0]) cudaFreeHost(ctx->h_stage[0]);
@@ -1936,6 +1960,105 @@ int twkb_compute_decay(void* c, int64_t window_bp, int32_t n_bins, double* sum_r
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return TWKB_OK;
     });
+}
+
+// twkb_compute_sorted: LD computation with the records kept on the device, device radix sort of both orientations
+// (sort.cuh), sorted records streamed to the sink through two pinned staging buffers.
+static int compute_sorted_impl(Context* ctx, twkb_sink_fn sink, void* user) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ctx->collect = true;
+    ctx->n_collected = 0;
+    int rc = compute_impl(ctx, true, nullptr, nullptr, false, nullptr);
+    ctx->collect = false;
+    if (rc) return rc;
+    const uint64_t n_fwd = ctx->n_collected, n_items = 2 * n_fwd;
+    if (n_items == 0) return TWKB_OK;
+    if (n_items > 0xffffffffull) { ctx->err = "too many records for the device sorter (2^31 forward records)"; return TWKB_ENOMEM; }
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaStream_t st = ctx->stream;
+    const uint32_t n_tiles = (uint32_t)((n_items + SORT_TILE - 1) / SORT_TILE);
+    DevBuf<unsigned long long> k_hi[2], k_lo[2], or_and;
+    DevBuf<uint32_t> ref[2], counts;
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(k_hi[b].alloc(n_items));
+        CUDA_TRY(k_lo[b].alloc(n_items));
+        CUDA_TRY(ref[b].alloc(n_items));
+    }
+    CUDA_TRY(counts.alloc((size_t)256 * n_tiles));
+    CUDA_TRY(or_and.alloc(4));
+    const unsigned long long init[4] = {0ull, 0ull, ~0ull, ~0ull};
+    CUDA_TRY(cudaMemcpyAsync(or_and.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const unsigned g_keys = (unsigned)std::min<uint64_t>((n_items + SORT_THREADS - 1) / SORT_THREADS, 148ull * 16);
+    sort_keys_kernel<<<g_keys, SORT_THREADS, 0, st>>>(ctx->d_collect.p, n_items, k_hi[0].p, k_lo[0].p, ref[0].p, or_and.p);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long oa[4];
+    CUDA_TRY(cudaMemcpyAsync(oa, or_and.p, sizeof(oa), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const unsigned long long diff_lo = oa[1] ^ oa[3], diff_hi = oa[0] ^ oa[2];  // bits that differ between some two keys
+    const unsigned g_tiles = (n_tiles + SORT_WARPS - 1) / SORT_WARPS;
+    int cur = 0, passes = 0;
+    for (int pass = 0; pass < 16; ++pass) {
+        const unsigned long long diff = pass < 8 ? diff_lo : diff_hi;
+        if (((diff >> ((pass & 7) * 8)) & 0xffull) == 0) continue;  // every key has the same digit here
+        radix_hist_kernel<<<g_tiles, SORT_THREADS, 0, st>>>(k_hi[cur].p, k_lo[cur].p, n_items, pass, n_tiles, counts.p);
+        exclusive_scan_kernel<<<1, 1024, 0, st>>>(counts.p, (unsigned long long)256 * n_tiles);
+        radix_scatter_kernel<<<g_tiles, SORT_THREADS, 0, st>>>(k_hi[cur].p, k_lo[cur].p, ref[cur].p, n_items, pass, n_tiles, counts.p,
+                                                              k_hi[cur ^ 1].p, k_lo[cur ^ 1].p, ref[cur ^ 1].p);
+        CUDA_TRY(cudaGetLastError());
+        cur ^= 1;
+        ++passes;
+    }
+    ctx->stats.other_launches += 1 + 3 * (uint64_t)passes;
+    // ---- gather in file order and stream out: chunk c is gathered + copied while the sink consumes chunk c - 1
+    const uint64_t chunk = 1u << 17;  // records per chunk (13.9 MB)
+    DevBuf<uint8_t> d_out[2];
+    uint8_t* h_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; ++b) {
+            if (h_out[b]) cudaFreeHost(h_out[b]);
+            if (ev[b]) cudaEventDestroy(ev[b]);
+        }
+    };
+    for (int b = 0; b < 2; ++b) {
+        cudaError_t e = d_out[b].alloc((size_t)chunk * TWKB_RECORD_BYTES);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&h_out[b], (size_t)chunk * TWKB_RECORD_BYTES, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+        if (e != cudaSuccess) { cleanup(); ctx->err = std::string("device sorter staging: ") + cudaGetErrorString(e); return TWKB_ENOMEM; }
+    }
+    const uint64_t n_chunks = (n_items + chunk - 1) / chunk;
+    for (uint64_t c = 0; c <= n_chunks && rc == TWKB_OK; ++c) {
+        if (c < n_chunks) {
+            const int b = (int)(c & 1);
+            const uint64_t first = c * chunk, n = std::min(chunk, n_items - first);
+            const unsigned long long words = n * 53ull;
+            sort_gather_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(ctx->d_collect.p, ref[cur].p, first, n, d_out[b].p);
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_out[b], d_out[b].p, (size_t)n * TWKB_RECORD_BYTES, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[b], st);
+            if (e != cudaSuccess) { cleanup(); return ctx->fail(std::string("device sorter: ") + cudaGetErrorString(e)); }
+            ctx->stats.other_launches += 1;
+            ctx->stats.bytes_d2h += n * TWKB_RECORD_BYTES;
+        }
+        if (c > 0) {
+            const int b = (int)((c - 1) & 1);
+            const uint64_t first = (c - 1) * chunk, n = std::min(chunk, n_items - first);
+            cudaError_t e = cudaEventSynchronize(ev[b]);
+            if (e != cudaSuccess) { cleanup(); return ctx->fail(std::string("device sorter: ") + cudaGetErrorString(e)); }
+            if (sink && sink(user, h_out[b], n) != 0) { rc = TWKB_ESINK; ctx->err = "the record sink returned non-zero"; }
+        }
+    }
+    cudaStreamSynchronize(st);
+    cleanup();
+    ctx->stats.seconds_total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+int twkb_compute_sorted(void* c, twkb_sink_fn sink, void* user) {
+    if (!c || !sink) return TWKB_EINVAL;
+    Context* ctx = static_cast<Context*>(c);
+    if (ctx->st.part_count > 1) { ctx->err = "sorted output needs every record on one device (part_count = 1)"; return TWKB_EINVAL; }
+    return guarded_ctx(c, [&] { return compute_sorted_impl(ctx, sink, user); });
 }
 
 int twkb_compute_aggregate(void* c, int32_t field, int32_t xbins, int32_t ybins, const int64_t* contig_n_bases, uint32_t n_contigs,
@@ -2118,8 +2241,27 @@ static int twkb_calc_file_intervals_impl(const twkb_settings* s, const char* in_
         if (ext != "two") out = (has_ext ? out.substr(0, dot) : out) + ".two";
         if (std::strcmp(out_path, "-") == 0) out = "-";  // stream to stdout (the reference's default, ld.cpp:585-588)
     }
-    TwoWriter writer;
     std::string cmd = std::string("tomahawk_b200 calc -i ") + in_path + " -o " + out_path;
+    if (s->sorted_output) {  // records ordered on the device, written as a sorted .two (what calc + sort produce in the reference)
+        if (out == "-") { twkb_destroy(c); return fail(TWKB_EINVAL, "sorted output needs a file (-o), not stdout"); }
+        SortedTwoWriter sw;
+        rc = sw.open(out, twk, cmd, s->c_level, std::max(1, s->n_threads), err);
+        if (rc) { twkb_destroy(c); return fail(rc, err); }
+        auto ssink = [](void* user, const uint8_t* recs, uint64_t n) -> int { return static_cast<SortedTwoWriter*>(user)->add(recs, n); };
+        rc = twkb_compute_sorted(c, ssink, &sw);
+        if (rc) { err = ctx->err.empty() || rc == TWKB_ESINK ? sw.error() : ctx->err; twkb_destroy(c); return fail(rc, err); }
+        rc = sw.finish();
+        if (rc) { err = sw.error(); twkb_destroy(c); return fail(rc, err); }
+        if (stats_out) {
+            *stats_out = ctx->stats;
+            stats_out->seconds_file_read = sec_read;
+            stats_out->seconds_file_load = sec_load;
+            stats_out->seconds_file_total = since(t_open);
+        }
+        twkb_destroy(c);
+        return TWKB_OK;
+    }
+    TwoWriter writer;
     rc = writer.open(out, twk, cmd, s->c_level, s->b_size, err);
     if (rc) { twkb_destroy(c); return fail(rc, err); }
     writer.set_threads(std::max(1, s->n_threads));
@@ -2273,6 +2415,17 @@ static int twkb_two_close_impl(void* writer) {
     return rc;
 }
 
+static int twkb_two_open_sorted_impl(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t n_threads,
+                                     void** writer, char* errbuf, size_t errbuf_len) {
+    if (!path || !twk_handle || !writer) return copy_err(errbuf, errbuf_len, "null argument", TWKB_EINVAL);
+    SortedTwoWriter* w = new SortedTwoWriter();
+    std::string err;
+    const int rc = w->open(path, *static_cast<TwkFile*>(twk_handle), command_line ? command_line : "", c_level, n_threads, err);
+    if (rc) { delete w; return copy_err(errbuf, errbuf_len, err, rc); }
+    *writer = w;
+    return TWKB_OK;
+}
+
 static int twkb_two_sort_impl(const char* in_path, const char* out_path, int32_t c_level, int32_t n_threads, uint64_t* n_records,
                   char* errbuf, size_t errbuf_len) {
     return twkb_two_sort_mem(in_path, out_path, c_level, n_threads, 0, n_records, errbuf, errbuf_len);
@@ -2394,6 +2547,26 @@ int twkb_two_add(void* writer, const uint8_t* records, uint64_t n) {
 
 int twkb_two_close(void* writer) {
     return guarded_buf(nullptr, 0, [&] { return twkb_two_close_impl(writer); });
+}
+
+int twkb_two_open_sorted(const char* path, void* twk_handle, const char* command_line, int32_t c_level, int32_t n_threads, void** writer,
+                         char* errbuf, size_t errbuf_len) {
+    return guarded_buf(errbuf, errbuf_len, [&] { return twkb_two_open_sorted_impl(path, twk_handle, command_line, c_level, n_threads, writer, errbuf, errbuf_len); });
+}
+
+int twkb_two_add_sorted(void* writer, const uint8_t* records, uint64_t n) {
+    if (!writer || (!records && n)) return TWKB_EINVAL;
+    return guarded_buf(nullptr, 0, [&] { return static_cast<SortedTwoWriter*>(writer)->add(records, n); });
+}
+
+int twkb_two_close_sorted(void* writer) {
+    if (!writer) return TWKB_EINVAL;
+    return guarded_buf(nullptr, 0, [&] {
+        SortedTwoWriter* w = static_cast<SortedTwoWriter*>(writer);
+        const int rc = w->finish();
+        delete w;
+        return rc;
+    });
 }
 
 int twkb_plan_tiles(const twkb_settings* s, uint32_t n_variants, const twkb_variant* meta, uint32_t tile_i, uint32_t tile_j,

@@ -974,6 +974,33 @@ struct SortedWriter {
     }
 };
 
+// Sorted-state index (TWK_IDX_SORTED, include/index.h:105; block entries + per-contig entries) and the EOF marker; closes the file.
+static bool write_sorted_tail(SortedWriter& w, uint64_t n_contigs, int c_level) {
+    std::vector<uint8_t> ob_idx;
+    auto put = [&](const void* p, size_t n) { ob_idx.insert(ob_idx.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+    const uint8_t state = 2;
+    uint64_t n_out = w.index.size(), m_out = 500;
+    while (m_out < n_out) m_out *= 2;
+    put(&kIndexMarker, 8); put(&state, 1); put(&n_out, 8); put(&m_out, 8); put(&n_contigs, 8);
+    for (const TwoIndexEntry& e : w.index) {
+        put(&e.rid, 4); put(&e.n, 4); put(&e.minpos, 4); put(&e.maxpos, 4); put(&e.b_unc, 4); put(&e.b_cmp, 4);
+        put(&e.foff, 8); put(&e.fend, 8); put(&e.ridB, 4);
+    }
+    for (const TwoMetaEntry& me : w.meta) {
+        put(&me.rid, 4); put(&me.n, 4); put(&me.minpos, 4); put(&me.maxpos, 4); put(&me.foff, 8); put(&me.fend, 8); put(&me.nn, 8);
+    }
+    std::vector<uint8_t> z(ZSTD_compressBound(ob_idx.size()));
+    const size_t zn = ZSTD_compress(z.data(), z.size(), ob_idx.data(), ob_idx.size(), c_level);
+    bool ok = !ZSTD_isError(zn);
+    const uint64_t off = w.pos, unc = ob_idx.size(), cmp = zn;
+    const uint8_t mk0 = 0;
+    ok = ok && w.emit(&mk0, 1) && w.emit(&unc, 8) && w.emit(&cmp, 8) && w.emit(z.data(), zn) && w.emit(&off, 8) && w.emit(kEof, 32);
+    ok = ok && std::fflush(w.fp) == 0 && !std::ferror(w.fp);
+    ok = (std::fclose(w.fp) == 0) && ok;
+    w.fp = nullptr;
+    return ok;
+}
+
 }  // namespace
 
 // `tomahawk sort` (two_reader::Sort, lib/two_reader.cpp:162-420). Bounded memory like the reference's: the input blocks are
@@ -1213,30 +1240,86 @@ int sort_two(const std::string& in, const std::string& out_path, int c_level, in
     if (rc != TWKB_OK) { cleanup(true); return rc; }
 
     // ---- sorted index + EOF
-    std::vector<uint8_t> ob_idx;
-    auto put = [&](const void* p, size_t n) { ob_idx.insert(ob_idx.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
-    const uint8_t state = 2;  // TWK_IDX_SORTED, include/index.h:105
-    uint64_t n_out = w.index.size(), m_out = 500;
-    while (m_out < n_out) m_out *= 2;
-    put(&kIndexMarker, 8); put(&state, 1); put(&n_out, 8); put(&m_out, 8); put(&n_contigs, 8);
-    for (const TwoIndexEntry& e : w.index) {
-        put(&e.rid, 4); put(&e.n, 4); put(&e.minpos, 4); put(&e.maxpos, 4); put(&e.b_unc, 4); put(&e.b_cmp, 4);
-        put(&e.foff, 8); put(&e.fend, 8); put(&e.ridB, 4);
-    }
-    for (const TwoMetaEntry& me : w.meta) {
-        put(&me.rid, 4); put(&me.n, 4); put(&me.minpos, 4); put(&me.maxpos, 4); put(&me.foff, 8); put(&me.fend, 8); put(&me.nn, 8);
-    }
-    std::vector<uint8_t> z(ZSTD_compressBound(ob_idx.size()));
-    const size_t zn = ZSTD_compress(z.data(), z.size(), ob_idx.data(), ob_idx.size(), c_level);
-    if (ZSTD_isError(zn)) { cleanup(true); err = "failed compression"; return TWKB_EIO; }
-    const uint64_t off = w.pos, unc = ob_idx.size(), cmp = zn;
-    const uint8_t mk0 = 0;
-    bool ok = w.emit(&mk0, 1) && w.emit(&unc, 8) && w.emit(&cmp, 8) && w.emit(z.data(), zn) && w.emit(&off, 8) && w.emit(kEof, 32);
-    ok = ok && std::fflush(w.fp) == 0 && !std::ferror(w.fp);
-    ok = (std::fclose(w.fp) == 0) && ok;
-    w.fp = nullptr;
+    const bool ok = write_sorted_tail(w, n_contigs, c_level);
     cleanup(!ok);
     if (!ok) { err = "Failed to write final block!"; return TWKB_EIO; }
+    return TWKB_OK;
+}
+
+// ------------------------------------------------------------------ writer of an already sorted record stream
+struct SortedTwoWriter::Impl {
+    SortedWriter w;
+    std::string path;
+    uint64_t n_contigs = 0;
+    int c_level = 1;
+    bool have_prev = false;
+    SortKey prev{};
+};
+
+SortedTwoWriter::~SortedTwoWriter() {
+    if (p_) {
+        if (p_->w.fp) { std::fclose(p_->w.fp); ::unlink(p_->path.c_str()); }  // never finished: no truncated file left behind
+        delete p_;
+    }
+}
+
+int SortedTwoWriter::open(const std::string& path, const TwkFile& src, const std::string& command_line, int c_level, int n_threads,
+                          std::string& err) {
+    p_ = new Impl;
+    p_->path = path;
+    p_->c_level = c_level;
+    p_->n_contigs = src.n_contigs;
+    SortedWriter& w = p_->w;
+    w.c_level = c_level;
+    w.n_threads = std::max(1, n_threads);
+    w.n_contigs = src.n_contigs;
+    w.meta.resize(src.n_contigs);
+    w.fp = std::fopen(path.c_str(), "wb");
+    if (!w.fp) { err = "Failed to open file: " + path + "..."; return TWKB_EIO; }
+    char date[64];
+    std::time_t now = std::time(nullptr);
+    std::strftime(date, sizeof(date), "%Y-%m-%d %H:%M:%S", std::localtime(&now));
+    // the provenance of both steps the reference would have run: calc (ld.cpp:609-612), then sort (two_reader.cpp:346-349)
+    const std::string literals = src.literals + "\n##tomahawk_calcVersion=b200-0.1.0\n##tomahawk_calcCommand=" + command_line + "; Date=" + date +
+                                 "\n##tomahawk_sortVersion=b200-0.1.0\n##tomahawk_sortCommand=device radix sort of the resident records; Date=" + date + "\n";
+    std::vector<uint8_t> hdr;
+    put_str(hdr, src.fileformat);
+    put_str(hdr, literals);
+    hdr.insert(hdr.end(), src.header_tail.begin(), src.header_tail.end());
+    std::vector<uint8_t> z(ZSTD_compressBound(hdr.size()));
+    const size_t zn = ZSTD_compress(z.data(), z.size(), hdr.data(), hdr.size(), c_level);
+    if (ZSTD_isError(zn)) { err = "failed to compress"; return TWKB_EIO; }
+    const uint64_t unc = hdr.size(), cmp = zn;
+    if (!w.emit(kTwoMagic, 4) || !w.emit(&unc, 8) || !w.emit(&cmp, 8) || !w.emit(z.data(), zn)) { err = "Failed to write header!"; return TWKB_EIO; }
+    return TWKB_OK;
+}
+
+int SortedTwoWriter::add(const uint8_t* records, uint64_t n) {
+    if (!p_ || !p_->w.fp) return TWKB_ESTATE;
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint8_t* rec = records + r * TWKB_RECORD_BYTES;
+        SortKey k = key_of(rec, 0);
+        if (p_->have_prev && key_less(k, p_->prev)) { err_ = "records are not in sorted order"; return TWKB_EINVAL; }
+        p_->prev = k;
+        p_->have_prev = true;
+        if (!p_->w.add(rec)) { err_ = p_->w.err; return TWKB_EIO; }
+    }
+    return TWKB_OK;
+}
+
+int SortedTwoWriter::finish() {
+    if (!p_ || !p_->w.fp) return TWKB_ESTATE;
+    SortedWriter& w = p_->w;
+    w.close_block();
+    bool ok = w.flush();
+    if (!ok) err_ = w.err;
+    ok = ok && write_sorted_tail(w, p_->n_contigs, p_->c_level);
+    if (w.fp) { std::fclose(w.fp); w.fp = nullptr; }
+    if (!ok) {
+        ::unlink(p_->path.c_str());
+        if (err_.empty()) err_ = "Failed to write final block!";
+        return TWKB_EIO;
+    }
     return TWKB_OK;
 }
 

@@ -161,6 +161,26 @@ private:
 // (include/writer.h:344-390, lib/index.cpp:70-88).
 // memory_limit (bytes, 0 = unbounded): inputs whose records + keys exceed it are sorted in runs that are spilled to
 // temporary files next to `out` and merged k-way, like the reference's external merge (lib/two_reader.cpp:262-420).
+// Writer of a SORTED .two from a record stream that is already in twk1_two_t::operator< order (both orientations): blocks cut
+// at every change of ridA, sorted-state index with per-contig entries -- the file `tomahawk sort` would have produced
+// (two_reader::Sort, lib/two_reader.cpp:350-420). add() rejects a record that sorts before its predecessor.
+class SortedTwoWriter {
+public:
+    SortedTwoWriter() = default;
+    ~SortedTwoWriter();
+    SortedTwoWriter(const SortedTwoWriter&) = delete;
+    SortedTwoWriter& operator=(const SortedTwoWriter&) = delete;
+    int open(const std::string& path, const TwkFile& src, const std::string& command_line, int c_level, int n_threads, std::string& err);
+    int add(const uint8_t* records, uint64_t n);
+    int finish();
+    const std::string& error() const { return err_; }
+
+private:
+    struct Impl;
+    Impl* p_ = nullptr;
+    std::string err_;
+};
+
 int sort_two(const std::string& in, const std::string& out, int c_level, int n_threads, std::string& err,
              uint64_t* n_records = nullptr, uint64_t memory_limit = 0);
 
