@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reference", type=int, default=0)
     ap.add_argument("--seed", type=int, default=20)
     ap.add_argument("--rare-fraction", type=float, default=0.0)
+    ap.add_argument("--sorted", action="store_true", help="also time the sorted-output arrangements (device sort vs calc + host sorter)")
     a = ap.parse_args()
     tmp = tempfile.mkdtemp(prefix="twkb_file_")
     t0 = time.perf_counter()
@@ -56,6 +57,30 @@ def main():
     names = list(outs)
     same = all(np.array_equal(outs[names[0]].view(np.uint8), outs[n].view(np.uint8)) for n in names[1:])
     print(json.dumps({"outputs_identical": bool(same), "records_fwd_plus_rev": int(len(outs[names[0]]))}), flush=True)
+    if a.sorted:
+        # queryable (sorted, indexed) output: records ordered on the device vs calc followed by the host sorter (and the reference's sort)
+        import subprocess
+        from oracle import ldcore as lc
+        best = None
+        for rep in range(3):
+            ld = tb.twk_ld()
+            st = tb.default_settings(force_phased=1, minR2=a.min_r2, n_threads=a.threads, sorted_output=1)
+            t1 = time.perf_counter()
+            assert ld.Compute(st, twk, os.path.join(tmp, "device_sorted"))
+            wall = time.perf_counter() - t1
+            best = wall if best is None else min(best, wall)
+        plain = os.path.join(tmp, "device_decode.two")
+        t1 = time.perf_counter()
+        n = tb.sort_two(plain, os.path.join(tmp, "host_sorted.two"), c_level=1, n_threads=a.threads)
+        t_host = time.perf_counter() - t1
+        same = np.array_equal(tf.read_two(os.path.join(tmp, "device_sorted.two")).view(np.uint8), tf.read_two(os.path.join(tmp, "host_sorted.two")).view(np.uint8))
+        row = {"arrangement": "sorted output", "records": int(n), "device_sort_file_to_file_s": best, "host_sorter_alone_s": t_host,
+               "identical_to_calc_then_sort": bool(same), "threads": a.threads}
+        if os.path.exists(lc.REF_SORT):
+            t1 = time.perf_counter()
+            r = subprocess.run([lc.REF_SORT, "sort", "-i", plain, "-o", os.path.join(tmp, "ref_sorted.two"), "-t", str(a.threads)], capture_output=True, text=True)
+            row["reference_sort_alone_s"] = time.perf_counter() - t1 if r.returncode == 0 else None
+        print(json.dumps(row), flush=True)
     if a.reference:
         from oracle import ldcore as lc
         sub = tf.synth_genotypes(a.samples, a.reference, seed=a.seed, rare_fraction=a.rare_fraction)
