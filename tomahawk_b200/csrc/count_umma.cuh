@@ -175,12 +175,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // TMA load executed by both CTAs of the pair; the transaction bytes are credited to the
 // LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared).
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+// `l2_policy`: an L2 eviction-priority descriptor (createpolicy encoding; L2_EVICT_* below).
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int32_t c0, int32_t c1,
+                                                uint64_t l2_policy) {
     const uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
     asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
             smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_addr), "r"(c0), "r"(c1)
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_addr), "r"(c0), "r"(c1), "l"(l2_policy)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
@@ -1091,7 +1094,8 @@ __device__ __forceinline__ void umma_planes_epilogue_loop(const CountArgs& args,
 template <bool FP4, bool SCREEN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UMMA3_THREADS, 1)
 count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, CountArgs args,
-                   DevParams prm, uint32_t num_kblocks, uint32_t n_tiles, uint32_t* pace, uint32_t pace_kb, uint32_t pace_depth) {
+                   DevParams prm, uint32_t num_kblocks, uint32_t n_tiles, uint32_t* pace, uint32_t pace_kb, uint32_t pace_depth,
+                   uint64_t l2_policy_a, uint64_t l2_policy_b) {
     using Cfg = Umma3Cfg<FP4>;
     constexpr uint32_t TILE_N = Cfg::TILE_N;
     constexpr int STAGES = Cfg::STAGES;
@@ -1175,7 +1179,8 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         const uint32_t seq = wave * pace_cpt + pace_chunk;
                         atomicAdd(&pace[seq], 1u);
                         if (seq >= pace_depth) {
-                            const uint32_t w_back = pace_chunk >= pace_depth ? wave : wave - 1u;  // pace_depth <= pace_cpt
+                            // wave of chunk seq - pace_depth (one chunk per tile: any depth; else pace_depth <= pace_cpt)
+                            const uint32_t w_back = pace_cpt == 1u ? seq - pace_depth : (pace_chunk >= pace_depth ? wave : wave - 1u);
                             const uint32_t expect = min(n_clusters, n_tiles - w_back * n_clusters);
                             const volatile uint32_t* c = pace + (seq - pace_depth);
                             while (*c < expect) __nanosleep(64);
@@ -1192,8 +1197,8 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 if (elect_one_sync()) {
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], skip_loads ? 0u : 2u * Cfg::STAGE_BYTES);
                     if (!skip_loads) {
-                        tma_load_2d_2sm(sA, &tmap_a, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)a_row);
-                        tma_load_2d_2sm(sB, &tmap_b, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)b_row);
+                        tma_load_2d_2sm(sA, &tmap_a, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)a_row, l2_policy_a);
+                        tma_load_2d_2sm(sB, &tmap_b, &full_bar[s], (int32_t)(kb * UMMA_BLOCK_K), (int32_t)b_row, l2_policy_b);
                     }
                 }
                 __syncwarp();
@@ -1459,6 +1464,7 @@ inline int umma_prepare_planes(UmmaOperand& op, int mode, const uint32_t* d_plan
     return 0;
 }
 
+constexpr uint64_t UMMA3_L2_POLICY_A = L2_EVICT_NORMAL, UMMA3_L2_POLICY_B = L2_EVICT_NORMAL;
 template <bool FP4, bool SCREEN, int MODE>
 inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const DevParams& prm, uint32_t n_tiles, cudaStream_t stream) {
     // function attributes and the SM count belong to a device: one process may drive several
@@ -1480,17 +1486,27 @@ inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const De
     const int n_sm = n_sm_of[dev & 63].load();
     const uint32_t n_clusters = std::min<uint32_t>(n_tiles, (uint32_t)std::max(1, n_sm / 2));
     const uint32_t num_kblocks = op.Kbytes / UMMA_BLOCK_K;
-    // K-sweep pacing (see the producer warp): rows of >= 16 KB, more than one CTA pair. Chunk = 16 K blocks (2 KB per
-    // row), look-ahead 2 chunks: wave rows (<= ~8,000) x ~3 chunks in flight = <= ~50 MB of L2.
-    uint32_t pace_kb = 16, pace_depth = 2;
+    // Pacing (see the producer warp), whenever there is more than one CTA pair.
+    //  * rows of >= 16 KB: chunks of 16 K blocks (2 KB per row), look-ahead 2 chunks: wave rows (<= ~8,000) x ~3 chunks in
+    //    flight = <= ~50 MB of L2;
+    //  * shorter rows: one chunk per tile, look-ahead 8 tiles. The tiles are dealt round-robin, so the tiles in flight are a
+    //    compact block of the super-tile order only while the pairs advance at the same rate; free running they drift apart
+    //    over the ~4,400 tiles each runs at C2 (a pair that meets more survivors, or sits farther from the L2 slices it
+    //    reads, never catches up) until the tiles in flight span several super-tiles and stop sharing operand rows in L2.
+    //    ncu, C2, per launch (profiles/round2_drift_probe_c2.log): DRAM 52-75 GB free running, 7.2 GB paced (compulsory
+    //    ~6.5 GB), L2 hit rate 76-80 % -> 96 %; back to back 25.2 -> 26.9 ms free running (the board reaches its power
+    //    cap), 24.47 ms paced. Look-ahead 1 / 2 / 4 / 8 / 16 / 32 tiles: 25.24 / 24.85 / 24.59 / 24.47 / 24.5-24.9 / 24.9-25.4 ms.
+    uint32_t pace_kb = 16, pace_depth = 2, pace_min_kblocks = 1;
+    if (num_kblocks < UMMA3_PACE_MIN_KBLOCKS) { pace_kb = num_kblocks; pace_depth = 8; }
     uint32_t* pace = nullptr;
 #ifdef TWKB_PROFILING
     if (const char* e = getenv("TWKB_PACE_KB")) pace_kb = (uint32_t)std::max(1, atoi(e));
     if (const char* e = getenv("TWKB_PACE_DEPTH")) pace_depth = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("TWKB_PACE_MIN_KB")) pace_min_kblocks = (uint32_t)std::max(1, atoi(e));
 #endif
-    if (num_kblocks >= UMMA3_PACE_MIN_KBLOCKS && n_clusters > 1 && pace_depth > 0) {
+    if (num_kblocks >= pace_min_kblocks && n_clusters > 1 && pace_depth > 0) {
         const uint32_t cpt = (num_kblocks + pace_kb - 1) / pace_kb;
-        pace_depth = std::min(pace_depth, cpt);
+        if (cpt > 1) pace_depth = std::min(pace_depth, cpt);
         const size_t need = (size_t)((n_tiles + n_clusters - 1) / n_clusters) * cpt;
         if (op.pace_capacity < need) {
             if (op.d_pace) cudaFree(op.d_pace);
@@ -1504,8 +1520,19 @@ inline cudaError_t umma3_launch(UmmaOperand& op, const CountArgs& args, const De
         if (e != cudaSuccess) return e;
         pace = op.d_pace;
     }
+    // L2 eviction priority of the operand loads (UMMA3_L2_POLICY_*: see the C2 sweep in profiles/round2_l2_sweep_c2.log)
+    uint64_t pol_a = UMMA3_L2_POLICY_A, pol_b = UMMA3_L2_POLICY_B;
+#ifdef TWKB_PROFILING
+    auto pol_of = [](const char* name, uint64_t dflt) {
+        const char* e = getenv(name);
+        if (!e) return dflt;
+        return e[0] == '1' ? L2_EVICT_FIRST : e[0] == '2' ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+    };
+    pol_a = pol_of("TWKB_L2_HINT_A", pol_a);
+    pol_b = pol_of("TWKB_L2_HINT_B", pol_b);
+#endif
     count_umma3_kernel<FP4, SCREEN, MODE><<<2 * n_clusters, UMMA3_THREADS, Umma3Cfg<FP4>::SMEM_BYTES, stream>>>(
-        op.tmap, op.tmap_b, args, prm, num_kblocks, n_tiles, pace, pace_kb, pace_depth);
+        op.tmap, op.tmap_b, args, prm, num_kblocks, n_tiles, pace, pace_kb, pace_depth, pol_a, pol_b);
     return cudaGetLastError();
 }
 

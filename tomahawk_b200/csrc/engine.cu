@@ -452,10 +452,21 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
     // balances any grid size.
     uint64_t group = 0;
     enum { COUNT_ONLY, EMIT_ALL, EMIT_ROUND_ROBIN };
+    // Order inside a super-tile: row-major. (Profiling build: row-major over INNER_I x INNER_J sub-blocks of tiles, so that
+    // the tiles in flight together are a compact rectangle -- measured at C2 with paced CTA pairs: DRAM 7.3 -> 6.8 GB per
+    // launch, time +0.4 %, not adopted; scripts/l2_sweep.py, profiles/round2_l2_sweep_c2.log.)
+    uint32_t INNER_I = SUPER, INNER_J = SUPER;
+#ifdef TWKB_PROFILING
+    if (const char* e = getenv("TWKB_INNER_I")) { if (atoi(e) > 0) INNER_I = std::min<uint32_t>((uint32_t)atoi(e), SUPER); }
+    if (const char* e = getenv("TWKB_INNER_J")) { if (atoi(e) > 0) INNER_J = std::min<uint32_t>((uint32_t)atoi(e), SUPER); }
+#endif
     auto walk_super = [&](uint32_t si, uint32_t sj, int what) -> uint64_t {
         uint64_t n = 0;
-        for (uint32_t ti = si; ti < std::min(si + SUPER, ti1); ++ti)
-            for (uint32_t tj = sj; tj < std::min(sj + SUPER, tj1); ++tj) {
+        const uint32_t se_i = std::min(si + SUPER, ti1), se_j = std::min(sj + SUPER, tj1);
+        for (uint32_t bi = si; bi < se_i; bi += INNER_I)
+        for (uint32_t bj = sj; bj < se_j; bj += INNER_J)
+        for (uint32_t ti = bi; ti < std::min(bi + INNER_I, se_i); ++ti)
+            for (uint32_t tj = bj; tj < std::min(bj + INNER_J, se_j); ++tj) {
                 const uint32_t i0 = ti * TI, j0 = tj * TJ;
                 if (pb.diag && j0 + TJ - 1 <= i0) continue;  // no i<j in this tile
                 if (window) {

@@ -229,7 +229,7 @@ __device__ __forceinline__ void st_f64_2(uint8_t* p, double d) {
     st_u16(p + 6, (uint32_t)(v >> 48));
 }
 // lib/core.cpp:470-490. Records are only 2-byte aligned (106 = 2*53).
-__device__ void write_record(uint8_t* dst, const PairStats& s, const DevVariant& a, const DevVariant& b) {
+__device__ __forceinline__ void write_record(uint8_t* dst, const PairStats& s, const DevVariant& a, const DevVariant& b) {
     st_u16(dst, s.flags);
     st_u32_2(dst + 2, a.rid);
     st_u32_2(dst + 6, b.rid);
@@ -484,6 +484,8 @@ __device__ bool unphased_stats(const uint32_t* t, const DevParams& prm, const Lg
 // is still evaluated by ONE thread with the reference's operation order: results are unchanged.
 constexpr int STATS_THREADS = 256;
 constexpr int STATS_PER_BLOCK = 1024;
+// Record staging area of a block, 32 x 106 B per warp.
+constexpr uint32_t STATS_STAGE_BYTES = (STATS_THREADS / 32) * 32 * 106;
 
 // Estimated walk length of kt_fisher_exact for a candidate, as a bin 0..63 (4 bins per octave).
 __device__ __forceinline__ uint32_t fisher_cost_bin(const Candidate& cd) {
@@ -510,14 +512,24 @@ __device__ __forceinline__ uint32_t fisher_cost_bin(const Candidate& cd) {
 
 // UNPHASED = false: every candidate carries a 2x2 table (mode 0) -- the instantiation of the phased passes,
 // without the cubic solver's registers.
+//
+// Records leave through shared memory: a warp builds the records of its passing lanes in a staging area in output
+// order and copies the contiguous run out in aligned 8-byte words (the run starts at slot0 * 106, which is only 2-byte
+// aligned: up to 3 leading and 3 trailing half-words go out singly). Written straight from the lanes a record is 53
+// two-byte stores at a 106-byte lane stride -- 32 sectors per store instruction; C1 (every pair a record): 29.5 -> 24.0 ms.
+// (Tried and dropped: a per-block copy of the log-factorial table in shared memory, 40 KB at 2,504 samples. With three
+// blocks per SM it leaves the unified L1 ~20 KB for the candidate / metadata gathers and the kernel slows to 26-28 ms;
+// the table's ~225 divergent lookups per candidate already hit L1. profiles/round2_stats_c1_staging.log)
 template <bool UNPHASED, int MIN_BLOCKS>
 __global__ void __launch_bounds__(STATS_THREADS, MIN_BLOCKS)
 stats_kernel(const Candidate* __restrict__ cands, uint32_t n_cands, const DevVariant* __restrict__ meta,
              DevParams prm, const double* __restrict__ lgamma_tab, uint8_t* __restrict__ records,
              unsigned long long rec_capacity, unsigned long long* __restrict__ rec_count) {
+    __shared__ __align__(16) uint8_t s_stage_all[STATS_STAGE_BYTES];
     __shared__ uint16_t s_perm[STATS_PER_BLOCK];
     __shared__ uint8_t s_bin[STATS_PER_BLOCK];
     __shared__ uint32_t s_off[64];
+    uint8_t* s_stage = s_stage_all + (threadIdx.x >> 5) * (32 * 106);  // this warp's 32 records
     const uint32_t base = blockIdx.x * (uint32_t)STATS_PER_BLOCK;
     const uint32_t cnt = min((uint32_t)STATS_PER_BLOCK, n_cands - base);
     const int lane = threadIdx.x & 31;
@@ -570,13 +582,36 @@ stats_kernel(const Candidate* __restrict__ cands, uint32_t n_cands, const DevVar
         const unsigned ballot = __ballot_sync(0xffffffffu, pass);
         if (ballot == 0) continue;
         const int leader = __ffs(ballot) - 1;
+        const uint32_t n_pass = (uint32_t)__popc(ballot);
         unsigned long long slot0 = 0;
-        if (lane == leader) slot0 = atomicAdd(rec_count, (unsigned long long)__popc(ballot));
+        if (lane == leader) slot0 = atomicAdd(rec_count, (unsigned long long)n_pass);
         slot0 = __shfl_sync(0xffffffffu, slot0, leader);
-        if (pass) {
-            const unsigned long long slot = slot0 + __popc(ballot & ((1u << lane) - 1));
-            if (slot < rec_capacity) write_record(records + slot * 106ull, s, a, b);
+        if (pass) write_record(s_stage + (uint32_t)__popc(ballot & ((1u << lane) - 1)) * 106u, s, a, b);
+        __syncwarp();
+        // the records that fit the buffer (the host re-runs the batch after an overflow), as one contiguous run
+        const unsigned long long room = slot0 < rec_capacity ? rec_capacity - slot0 : 0ull;
+        const uint32_t total_h = (uint32_t)(room < n_pass ? room : n_pass) * 53u;  // half-words to copy
+        uint8_t* g = records + slot0 * 106ull;
+        const uint16_t* st16 = reinterpret_cast<const uint16_t*>(s_stage);
+        uint32_t head_h = (uint32_t)((8u - (uint32_t)(reinterpret_cast<uintptr_t>(g) & 7u)) & 7u) >> 1;  // to the first 8-byte boundary
+        head_h = min(head_h, total_h);
+        if ((uint32_t)lane < head_h) reinterpret_cast<uint16_t*>(g)[lane] = st16[lane];
+        const uint32_t n_words = (total_h - head_h) >> 2;
+        unsigned long long* g8 = reinterpret_cast<unsigned long long*>(g + 2u * head_h);
+        if ((head_h & 1u) == 0u) {  // staging offset 4-byte aligned
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(st16 + head_h);
+            for (uint32_t w = lane; w < n_words; w += 32) g8[w] = (unsigned long long)s32[2 * w] | ((unsigned long long)s32[2 * w + 1] << 32);
+        } else {
+            const uint16_t* sh = st16 + head_h;
+            for (uint32_t w = lane; w < n_words; w += 32) {
+                const uint32_t lo = (uint32_t)sh[4 * w] | ((uint32_t)sh[4 * w + 1] << 16);
+                const uint32_t hi = (uint32_t)sh[4 * w + 2] | ((uint32_t)sh[4 * w + 3] << 16);
+                g8[w] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+            }
         }
+        const uint32_t done_h = head_h + 4u * n_words;
+        if ((uint32_t)lane < total_h - done_h) reinterpret_cast<uint16_t*>(g)[done_h + lane] = st16[done_h + lane];
+        __syncwarp();  // the staging area is rewritten by the next round
     }
 }
 
