@@ -1317,9 +1317,10 @@ static int load_begin_shapes(Context* ctx, uint32_t n_samples, uint32_t n_varian
 // rules, chunks and the rare-variant class) and (b) the 16-byte device records, staged in pinned memory. At 566,000
 // variants (8-GPU weak scaling) that is 18 MB read twice and 27 MB written -- 8 ms when done serially in front of the
 // upload, with 8 ranks competing for the host's memory bandwidth. The matrix loads therefore enqueue the row upload (and
-// the all-gather) FIRST, then run (a) and (b) on a small team of threads (host_meta_work), hidden behind the transfer.
+// the all-gather) FIRST, then run (a) on a helper thread and (b) on the calling thread, both hidden behind the transfer.
 static void copy_meta(Context* ctx, const twkb_variant* meta) { ctx->h_meta.assign(meta, meta + ctx->n_variants); }
-static int ensure_dm(Context* ctx) {
+static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing) {
+    const uint32_t n_variants = ctx->n_variants;
     if (ctx->h_dm_cap < ctx->Mpad) {
         if (ctx->h_dm) cudaFreeHost(ctx->h_dm);
         ctx->h_dm = nullptr;
@@ -1327,12 +1328,9 @@ static int ensure_dm(Context* ctx) {
         CUDA_TRY(cudaMallocHost((void**)&ctx->h_dm, (size_t)ctx->Mpad * sizeof(DevVariant)));
         ctx->h_dm_cap = ctx->Mpad;
     }
-    return TWKB_OK;
-}
-// device records of variants [v0, v1); returns whether any of them has missing genotypes
-static bool fill_dm_range(DevVariant* dm, const twkb_variant* meta, uint32_t v0, uint32_t v1) {
+    DevVariant* dm = ctx->h_dm;
     bool miss = false;
-    for (uint32_t v = v0; v < v1; ++v) {
+    for (uint32_t v = 0; v < n_variants; ++v) {
         dm[v].pos = meta[v].pos;
         dm[v].ac = meta[v].ac;
         dm[v].rid = meta[v].rid;
@@ -1340,43 +1338,8 @@ static bool fill_dm_range(DevVariant* dm, const twkb_variant* meta, uint32_t v0,
                       (meta[v].gt_missing ? VF_GT_MISSING : 0u);
         miss = miss || meta[v].gt_missing || meta[v].an;
     }
-    return miss;
-}
-static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing) {
-    const uint32_t n_variants = ctx->n_variants;
-    const int rc = ensure_dm(ctx);
-    if (rc) return rc;
-    const bool miss = fill_dm_range(ctx->h_dm, meta, 0, n_variants);
-    std::memset(ctx->h_dm + n_variants, 0, (size_t)(ctx->Mpad - n_variants) * sizeof(DevVariant));
+    std::memset(dm + n_variants, 0, (size_t)(ctx->Mpad - n_variants) * sizeof(DevVariant));
     if (any_missing) *any_missing = miss;
-    return TWKB_OK;
-}
-// (a) + (b) of the matrix loads behind the transfer: one pass over the caller's metadata per chunk of variants, on a small
-// team of threads (the calling thread is one of them). At 566,000 variants with 8 ranks loading at once a single pair of
-// threads was the longest item of the load (5.5 ms against ~2.6 ms of upload + all-gather + layout kernels).
-static int host_meta_work(Context* ctx, const twkb_variant* meta, bool* any_missing) {
-    const uint32_t M = ctx->n_variants;
-    const int rc = ensure_dm(ctx);
-    if (rc) return rc;
-    ctx->h_meta.resize(M);
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 4;
-    const unsigned share = std::max(1u, hw / (unsigned)std::max(1, ctx->comm_size));  // ranks of one node load together
-    const unsigned team = M < 65536u ? 1u : std::min({8u, share, (M + 65535u) / 65536u});
-    std::vector<uint8_t> miss(team, 0);
-    auto work = [&](unsigned k) {
-        const uint32_t v0 = (uint32_t)((uint64_t)M * k / team), v1 = (uint32_t)((uint64_t)M * (k + 1) / team);
-        std::memcpy(ctx->h_meta.data() + v0, meta + v0, (size_t)(v1 - v0) * sizeof(twkb_variant));
-        miss[k] = fill_dm_range(ctx->h_dm, meta, v0, v1) ? 1 : 0;
-    };
-    std::vector<std::thread> helpers;
-    for (unsigned k = 1; k < team; ++k) helpers.emplace_back(work, k);
-    work(0);
-    for (std::thread& t : helpers) t.join();
-    std::memset(ctx->h_dm + M, 0, (size_t)(ctx->Mpad - M) * sizeof(DevVariant));
-    bool any = false;
-    for (uint8_t m : miss) any = any || m;
-    if (any_missing) *any_missing = any;
     return TWKB_OK;
 }
 static void load_meta(Context* ctx, const twkb_variant* meta) {
@@ -1459,8 +1422,10 @@ static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, co
     CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_data.p, data, words * 8, kind, ctx->stream));
     ctx->stats.bytes_h2d = device_src ? 0 : words * 8;
     // host metadata work behind the transfer: copy on a helper thread, device records (+ the missing-data flag) here
+    std::thread helper(copy_meta, ctx, meta);
     bool miss = false;
-    rc = host_meta_work(ctx, meta, &miss);
+    rc = fill_dm(ctx, meta, &miss);
+    helper.join();
     if (rc) return rc;
     ctx->any_missing = miss;
     if (miss && !mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
@@ -1615,8 +1580,10 @@ static int load_matrix_sliced(Context* ctx, uint32_t n_samples, uint32_t n_varia
     // host metadata work behind the transfer + collective: copy on a helper thread, device records here. The
     // missing-data flag comes out of the same pass; it is identical on every rank (same metadata), so all ranks
     // agree on whether a mask exchange follows.
+    std::thread helper(copy_meta, ctx, meta);
     bool miss = false;
-    rc = host_meta_work(ctx, meta, &miss);
+    rc = fill_dm(ctx, meta, &miss);
+    helper.join();
     if (rc) return rc;
     ctx->any_missing = miss;
     if (miss && rows && !slice_mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
