@@ -541,6 +541,88 @@ def test_config1_full_size_tensor_records_equal_popc_records():
     assert np.array_equal(out[tb.KERNEL_AUTO], out[tb.KERNEL_POPC])
 
 
+def test_small_work_buffers_overflow_retry_and_record_rotation(monkeypatch):
+    """Candidate buffer of little more than one tile and a record buffer of the same size (TWKB_CAND_CAP / TWKB_REC_CAP are
+    read when a context allocates them): (a) R2 >= 0, every pair a record -- one tile per batch, the record buffers rotate
+    through the drain thread a dozen times; (b) a matrix with little LD, then one of the SAME shape in long LD blocks --
+    the survivor rate kept from the first run sizes a first batch that overflows the candidate buffer, which must be
+    retried with fewer tiles. Records identical to runs with the default 16 M-entry buffers."""
+    def records(eng, s, **kw):
+        data, mask = tf.pack_bits(s)
+        eng.load(s.n_samples, data, mask, lc.variant_meta(s))
+        return tf.canonical(eng.compute(), forward_only=False).view(np.uint8)
+
+    s0 = tf.synth_genotypes(600, 1500, seed=11)
+    sa = tf.synth_genotypes(600, 12_000, seed=12, p_copy=0.0)
+    sb = tf.synth_genotypes(600, 12_000, seed=13, p_copy=0.98, redraw=0.01)
+    ref = {}
+    eng = tb.Engine(force_phased=1, minR2=0.0)
+    ref["s0"] = records(eng, s0)
+    eng.close()
+    eng = tb.Engine(force_phased=1, minR2=0.1)
+    ref["sa"], ref["sb"] = records(eng, sa), records(eng, sb)
+    eng.close()
+    assert len(ref["s0"]) > 4 * 70_000 * 106 and len(ref["sb"]) > 70_000 * 106 > len(ref["sa"])
+
+    monkeypatch.setenv("TWKB_CAND_CAP", "70000")
+    monkeypatch.setenv("TWKB_REC_CAP", "70000")
+    eng = tb.Engine(force_phased=1, minR2=0.0)
+    got = records(eng, s0)
+    st = eng.stats()
+    assert st.count_launches >= 20                       # 27 tiles of 256 x 240, one per batch
+    assert np.array_equal(got, ref["s0"])
+    eng.close()
+    eng = tb.Engine(force_phased=1, minR2=0.1)
+    assert np.array_equal(records(eng, sa), ref["sa"])
+    n_sa = eng.stats().count_launches
+    assert np.array_equal(records(eng, sb), ref["sb"])   # first batch sized by sa's survivor rate: overflow, retry
+    assert eng.stats().count_launches > n_sa + 2
+    eng.close()
+
+
+@pytest.mark.timeout(300)
+def test_two_contexts_on_one_device_run_concurrently_without_hanging():
+    """Two contexts on ONE device, each launching full-grid (148-CTA) persistent count kernels from its own host thread
+    and stream at the same time. The CTA pairs of a launch pace each other through global counters; if the two grids
+    ever shared the SMs, pairs spinning for non-resident siblings would hold the SMs those need -- the wait is bounded
+    (count_umma.cuh, UMMA3_PACE_MAX_SPINS) so the worst case is an un-paced launch. Both runs must finish and give the
+    records of a run that had the device to itself."""
+    import threading
+
+    s = tf.synth_genotypes(2504, 40_000, seed=7)
+    data, mask = tf.pack_bits(s)
+    meta = lc.variant_meta(s)
+    del s
+    engines = [tb.Engine(force_phased=1, minR2=0.1) for _ in range(2)]
+    for e in engines:
+        e.load(2504, data, mask, meta)
+    alone = tf.canonical(engines[0].compute(), forward_only=False).view(np.uint8)
+    assert engines[0].stats().kernel_used == tb.KERNEL_UMMA_FP4
+    results, errors = [None, None], []
+    gate = threading.Barrier(2)
+
+    def worker(k):
+        try:
+            gate.wait()
+            for _ in range(6):
+                engines[k].compute_resident()          # ctypes releases the GIL: the two launch streams overlap
+            results[k] = tf.canonical(engines[k].compute(), forward_only=False).view(np.uint8)
+        except Exception as ex:                        # noqa: BLE001 -- reported by the main thread
+            errors.append(ex)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=240)
+    assert not any(t.is_alive() for t in threads), "a concurrent run did not finish"
+    assert not errors, errors
+    for k in range(2):
+        assert np.array_equal(results[k], alone)
+    for e in engines:
+        e.close()
+
+
 def _live_reference(s, cli, tmpdir, name, threads=None):
     twk = os.path.join(tmpdir, f"{name}.twk")
     tf.write_twk(twk, s)

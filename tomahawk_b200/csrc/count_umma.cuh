@@ -306,6 +306,7 @@ __device__ __forceinline__ void tmem_fill_32x32(uint32_t taddr, uint32_t v) {
 // while chunk c is screened, and the release of the accumulator is a CTA-scope arrive.
 constexpr int UMMA3_EPI_WARPS = 8;
 constexpr int UMMA3_THREADS = 128 + 32 * UMMA3_EPI_WARPS;
+constexpr uint32_t UMMA3_PACE_MAX_SPINS = 20000;  // polls of ~100 ns before a CTA pair stops waiting for the others (see the producer warp)
 constexpr uint32_t UMMA3_PACE_MIN_KBLOCKS = 128;  // operand rows of >= 16 KB sweep K in paced chunks (count_umma3_kernel)
 
 __device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
@@ -1164,8 +1165,13 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // starts in a global counter (one per wave and chunk) and does not start chunk c before ALL pairs of the
         // wave have started chunk c - pace_depth: the spread of the wave's K positions -- and with it the L2
         // working set, rows of the wave x (pace_depth + 1) chunks -- is bounded. Pure pacing: no data depends on
-        // it, the slowest pair never waits, all pairs are co-resident (grid <= SMs), so it cannot deadlock.
+        // it and the slowest pair never waits. The wait is BOUNDED: the grid is sized to be co-resident (<= one CTA per
+        // SM), but when other work holds SMs -- a second context's persistent kernel on the same device, MPS -- part of
+        // the grid may not be resident, and pairs spinning for it would never free the SMs it needs. A pair whose wait
+        // exceeds UMMA3_PACE_MAX_SPINS polls (~2 ms) stops waiting for the rest of the launch (it keeps announcing its
+        // own progress), so the worst case is an un-paced kernel, never a hang.
         const uint32_t pace_cpt = pace ? (num_kblocks + pace_kb - 1u) / pace_kb : 0u;  // chunks per tile
+        bool pace_wait = true;
         uint32_t wave = 0;
         for (uint32_t t = cluster_id; t < n_tiles; t += n_clusters, ++wave) {
             const uint2 tile = args.tiles[t];
@@ -1175,18 +1181,23 @@ count_umma3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             uint32_t pace_next = 0, pace_chunk = 0;
             for (uint32_t kb = 0; kb < num_kblocks; ++kb) {
                 if (pace != nullptr && leader && kb == pace_next) {
+                    bool gave_up = false;
                     if (elect_one_sync()) {
                         const uint32_t seq = wave * pace_cpt + pace_chunk;
                         atomicAdd(&pace[seq], 1u);
-                        if (seq >= pace_depth) {
+                        if (pace_wait && seq >= pace_depth) {
                             // wave of chunk seq - pace_depth (one chunk per tile: any depth; else pace_depth <= pace_cpt)
                             const uint32_t w_back = pace_cpt == 1u ? seq - pace_depth : (pace_chunk >= pace_depth ? wave : wave - 1u);
                             const uint32_t expect = min(n_clusters, n_tiles - w_back * n_clusters);
                             const volatile uint32_t* c = pace + (seq - pace_depth);
-                            while (*c < expect) __nanosleep(64);
+                            uint32_t spins = 0;
+                            while (*c < expect) {
+                                __nanosleep(64);
+                                if (++spins > UMMA3_PACE_MAX_SPINS) { gave_up = true; break; }
+                            }
                         }
                     }
-                    __syncwarp();
+                    if (__any_sync(0xffffffffu, gave_up)) pace_wait = false;
                     pace_next += pace_kb;
                     ++pace_chunk;
                 }

@@ -885,6 +885,7 @@ static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, 
         if (ncand > ctx->cand_cap) {  // overflow: redo this batch with fewer tiles
             if (nb == 1) { ctx->err = "candidate buffer smaller than one tile"; return TWKB_ENOMEM; }
             batch = std::max<uint64_t>(1, nb / 2);
+            if (!bp.no_screen) *bp.est_cand_per_tile = std::max(*bp.est_cand_per_tile, (double)ncand / nb);  // the counter runs past the capacity
             continue;
         }
         account(t, nb);
@@ -1303,7 +1304,10 @@ static int load_begin_shapes(Context* ctx, uint32_t n_samples, uint32_t n_varian
     ctx->mode = -1;
     ctx->umma.valid = false;
     ctx->matrix_epoch += 1;
-    ctx->est_cand_per_tile = -1.0;
+    // the survivor rate the previous run measured sizes the first batch of the next one; it is kept across a reload of a
+    // matrix of the same shape (a file processed chunk by chunk, the end-to-end bench): a guess that turns out too low
+    // costs one retry of the batch (run_batches), a reset costs an extra batch boundary on every run
+    if (n_samples != ctx->n_samples || n_variants != ctx->n_variants) ctx->est_cand_per_tile = -1.0;
     ctx->n_samples = n_samples;
     ctx->n_variants = n_variants;
     ctx->Mpad = (n_variants + 255) / 256 * 256;
