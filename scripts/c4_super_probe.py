@@ -9,7 +9,7 @@ d, _, meta = tools.synth_device(n, m, seed=20)
 for sup in (32, 16, 12, 9, 8, 6, 0):
     if sup: os.environ["TWKB_SUPER"] = str(sup)
     else: os.environ.pop("TWKB_SUPER", None)
-    eng = tb.Engine(force_phased=1, minR2=0.1, sparse_max_words=-1)
+    eng = tb.Engine(force_phased=1, minR2=0.1, sparse_max_words=-1, profiling=True)
     eng.load_device(n, m, d.data_ptr(), None, d.shape[1], meta)
     ms = []
     for _ in range(2):

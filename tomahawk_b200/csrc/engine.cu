@@ -62,6 +62,14 @@ struct DevBuf {
     }
 };
 
+// Tuning knobs of the development scripts (super-tile edge, batch size, kernel choice overrides ...) are read from the
+// environment by the profiling build only; the product library has no switch that changes what runs.
+#ifdef TWKB_PROFILING
+static inline const char* tuning_env(const char* name) { return getenv(name); }
+#else
+static inline const char* tuning_env(const char*) { return nullptr; }
+#endif
+
 struct Problem {  // one rectangular sub-problem of the pair grid
     uint32_t row_begin, row_end, col_begin, col_end;
     bool diag;
@@ -863,7 +871,7 @@ static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, 
                                   : std::max<uint64_t>(1, ctx->cand_cap / bp.tile_pairs * 64);
     if (!bp.no_screen && *bp.est_cand_per_tile >= 0.0)  // the previous run over this matrix measured the survivor rate
         batch = std::max<uint64_t>(batch, (uint64_t)(0.25 * ctx->cand_cap / std::max(1.0, *bp.est_cand_per_tile)));
-    if (const char* e = getenv("TWKB_BATCH_TILES")) batch = std::max<uint64_t>(1, (uint64_t)atoll(e));
+    if (const char* e = tuning_env("TWKB_BATCH_TILES")) batch = std::max<uint64_t>(1, (uint64_t)atoll(e));
     size_t t = 0;
     while (t < bp.n_tiles) {
         const uint32_t nb = (uint32_t)std::min<uint64_t>(batch, bp.n_tiles - t);
@@ -907,7 +915,7 @@ static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, 
             const unsigned grid = (unsigned)((ncand + STATS_PER_BLOCK - 1) / STATS_PER_BLOCK);
             uint8_t* recs = ctx->d_records[ctx->rec_cur].p;
             unsigned long long* rec_count = ctx->d_counters.p + 1 + ctx->rec_cur;
-            static const int occ3 = [] { const char* e = getenv("TWKB_STATS_OCC"); return e ? atoi(e) : 3; }();
+            static const int occ3 = [] { const char* e = tuning_env("TWKB_STATS_OCC"); return e ? atoi(e) : 3; }();
             if (prm.unphased)
                 stats_kernel<true, 2><<<grid, STATS_THREADS, 0, ctx->stream>>>(ctx->d_cands.p, (uint32_t)ncand, ctx->d_meta.p, prm,
                                                                               ctx->d_lgamma.p, recs, ctx->rec_cap, rec_count);
@@ -923,7 +931,7 @@ static int run_batches(Context* ctx, const BatchPlan& bp, const DevParams& prm, 
             ctx->stats.stats_launches += 1;
         }
         // adapt: aim for a half-full candidate buffer
-        if (!bp.no_screen && !getenv("TWKB_BATCH_TILES")) {
+        if (!bp.no_screen && !tuning_env("TWKB_BATCH_TILES")) {
             const double per_tile = std::max(1.0, (double)ncand / nb);
             batch = std::max<uint64_t>(1, (uint64_t)(0.5 * ctx->cand_cap / per_tile));
             *bp.est_cand_per_tile = std::max(*bp.est_cand_per_tile, per_tile);
@@ -961,7 +969,7 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
     // single mode (scalc): a handful of target rows against a neighbourhood -- the 128-row LOP3+POPC tiles, not 256 x 240 MMA tiles
     if (ctx->st.kernel != TWKB_KERNEL_POPC && !ctx->st.single && umma_supported()) {
         if (!planes_mode) use_umma = true;
-        else use_umma = ctx->st.kernel != TWKB_KERNEL_UMMA && umma_fp4_possible(ctx->n_samples) && !getenv("TWKB_PLANES_POPC");
+        else use_umma = ctx->st.kernel != TWKB_KERNEL_UMMA && umma_fp4_possible(ctx->n_samples) && !tuning_env("TWKB_PLANES_POPC");
     }
     if ((ctx->st.kernel == TWKB_KERNEL_UMMA || ctx->st.kernel == TWKB_KERNEL_UMMA_FP4) && !use_umma && !ctx->st.single) {
         ctx->err = planes_mode ? "the int8 tensor-core kernel only serves phased data without missing genotypes (use AUTO or UMMA_FP4)"
@@ -972,7 +980,7 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
         // operand encoding: e2m1 (kind::mxf4, 2x the MAC rate of int8) whenever its fp32
         // accumulation is exact (2N < 2^24), int8 otherwise or on request
         use_fp4 = ctx->st.kernel != TWKB_KERNEL_UMMA && umma_fp4_possible(ctx->n_samples);
-        if (const char* e = getenv("TWKB_UMMA_KIND")) {
+        if (const char* e = tuning_env("TWKB_UMMA_KIND")) {
             if (e[0] == 'i') use_fp4 = false;
         }
         if (ctx->st.kernel == TWKB_KERNEL_UMMA_FP4 && !use_fp4) {
@@ -1007,7 +1015,7 @@ static int run_pass(Context* ctx, const Problem& pb_in, int mode, uint32_t pair_
         const size_t row_bytes = ctx->umma.valid ? ctx->umma.Kbytes : (size_t)ctx->K32 * 4;
         if ((size_t)32 * (TI + TJ) * row_bytes > ((size_t)96 << 20)) super = 8u;  // B200, 1 M haplotypes: 32/16/12/9/8/6 -> 108.7 / 114.6 / 117.5 / 102.4 / 98.8 / 106.2 ms
     }
-    if (const char* e = getenv("TWKB_SUPER")) super = (uint32_t)std::max(1, atoi(e));
+    if (const char* e = tuning_env("TWKB_SUPER")) super = (uint32_t)std::max(1, atoi(e));
     char keybuf[256];
     std::snprintf(keybuf, sizeof(keybuf), "%llu|%u-%u,%u-%u,%d|%ux%u/%u|w%d:%d:%d|p%d/%d|s%d",
                   (unsigned long long)(ctx->st.window ? ctx->matrix_epoch : 0ull),
@@ -1238,7 +1246,7 @@ static int classify_sparse(Context* ctx) {
     if (st.sparse_max_words > 0) T = st.sparse_max_words;
     else if (st.sparse_max_words == 0 && st.kernel == TWKB_KERNEL_AUTO && n_bits >= 32768u) T = K32raw / 64;
     if (st.sparse_max_words >= 0) {
-        if (const char* e = getenv("TWKB_SPARSE_T")) T = atoll(e);
+        if (const char* e = tuning_env("TWKB_SPARSE_T")) T = atoll(e);
     }
     if (T <= 0 || ctx->any_missing || st.forced_unphased || st.n_chunks != 1 || M < 2 || st.single) return TWKB_OK;
     DevBuf<uint32_t> d_nnz;
@@ -1253,7 +1261,7 @@ static int classify_sparse(Context* ctx) {
     uint32_t nS = 0;
     for (uint32_t v = 0; v < M; ++v) nS += (nnz[v] <= (uint64_t)T) ? 1u : 0u;
     // an automatic threshold only pays when a real share of the variants is rare
-    if (nS == 0 || (st.sparse_max_words == 0 && !getenv("TWKB_SPARSE_T") && nS < std::max<uint32_t>(256u, M / 20))) return TWKB_OK;
+    if (nS == 0 || (st.sparse_max_words == 0 && !tuning_env("TWKB_SPARSE_T") && nS < std::max<uint32_t>(256u, M / 20))) return TWKB_OK;
     const uint32_t nD = M - nS;
     uint32_t d = 0, sidx = nD;
     ctx->h_sp_off.assign(nS + 1, 0);
@@ -1458,7 +1466,7 @@ static int load_runs(Context* ctx, uint32_t n_samples, uint32_t n_variants, cons
         }
     }
     const size_t words = (size_t)n_variants * stride;
-    const bool trace = getenv("TWKB_TRACE") != nullptr;
+    const bool trace = tuning_env("TWKB_TRACE") != nullptr;
     const auto tr0 = std::chrono::steady_clock::now();
     auto mark = [&](const char* what) {
         if (!trace) return;
@@ -1566,7 +1574,7 @@ static int load_matrix_sliced(Context* ctx, uint32_t n_samples, uint32_t n_varia
         if (rows < S) CUDA_TRY(cudaMemsetAsync(d_rows + (base + rows) * stride, 0, (S - rows) * stride * 8, ctx->copy_stream));
         return TWKB_OK;
     };
-    const bool trace = getenv("TWKB_TRACE") != nullptr;  // development aid: synchronous phase times on stderr
+    const bool trace = tuning_env("TWKB_TRACE") != nullptr;  // development aid: synchronous phase times on stderr
     const auto tr0 = std::chrono::steady_clock::now();
     auto mark = [&](const char* what) {
         if (!trace) return;
