@@ -104,6 +104,7 @@ struct Context {
     bool permuted = false;
     uint32_t nD = 0, nS = 0, sparse_T = 0;
     std::vector<uint32_t> h_orig;            // resident -> original index (identity when !permuted)
+    bool h_orig_identity = false;            // h_orig currently holds 0, 1, 2, ...
     std::vector<twkb_variant> h_meta_orig;   // metadata in file order -- filled only when the rows were re-ordered (meta_orig())
     DevVariant* h_dm = nullptr;              // pinned staging of the device metadata
     size_t h_dm_cap = 0;
@@ -1237,8 +1238,11 @@ static int classify_sparse(Context* ctx) {
     ctx->sp_entries = 0;
     ctx->sp_plan_key.clear();
     ctx->est_cand_per_sp_tile = -1.0;
-    ctx->h_orig.resize(M);
-    for (uint32_t x = 0; x < M; ++x) ctx->h_orig[x] = x;
+    if (ctx->h_orig.size() != M || !ctx->h_orig_identity) {  // (kept across loads of the same shape: 566,000 stores otherwise)
+        ctx->h_orig.resize(M);
+        for (uint32_t x = 0; x < M; ++x) ctx->h_orig[x] = x;
+        ctx->h_orig_identity = true;
+    }
     const twkb_settings& st = ctx->st;
     const uint32_t n_bits = 2 * ctx->n_samples;
     const uint32_t K32raw = (n_bits + 31) / 32;
@@ -1263,6 +1267,7 @@ static int classify_sparse(Context* ctx) {
     // an automatic threshold only pays when a real share of the variants is rare
     if (nS == 0 || (st.sparse_max_words == 0 && !tuning_env("TWKB_SPARSE_T") && nS < std::max<uint32_t>(256u, M / 20))) return TWKB_OK;
     const uint32_t nD = M - nS;
+    ctx->h_orig_identity = false;
     uint32_t d = 0, sidx = nD;
     ctx->h_sp_off.assign(nS + 1, 0);
     for (uint32_t v = 0; v < M; ++v) {
@@ -1329,10 +1334,9 @@ static int load_begin_shapes(Context* ctx, uint32_t n_samples, uint32_t n_varian
 // rules, chunks and the rare-variant class) and (b) the 16-byte device records, staged in pinned memory. At 566,000
 // variants (8-GPU weak scaling) that is 18 MB read twice and 27 MB written -- 8 ms when done serially in front of the
 // upload, with 8 ranks competing for the host's memory bandwidth. The matrix loads therefore enqueue the row upload (and
-// the all-gather) FIRST, then run (a) on a helper thread and (b) on the calling thread, both hidden behind the transfer.
+// the all-gather) FIRST, then run (a) and (b) behind the transfer (host_meta_work).
 static void copy_meta(Context* ctx, const twkb_variant* meta) { ctx->h_meta.assign(meta, meta + ctx->n_variants); }
-static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing) {
-    const uint32_t n_variants = ctx->n_variants;
+static int ensure_dm(Context* ctx) {
     if (ctx->h_dm_cap < ctx->Mpad) {
         if (ctx->h_dm) cudaFreeHost(ctx->h_dm);
         ctx->h_dm = nullptr;
@@ -1340,9 +1344,12 @@ static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing) {
         CUDA_TRY(cudaMallocHost((void**)&ctx->h_dm, (size_t)ctx->Mpad * sizeof(DevVariant)));
         ctx->h_dm_cap = ctx->Mpad;
     }
-    DevVariant* dm = ctx->h_dm;
+    return TWKB_OK;
+}
+// device records of variants [v0, v1); returns whether any of them has missing genotypes
+static bool fill_dm_range(DevVariant* dm, const twkb_variant* meta, uint32_t v0, uint32_t v1) {
     bool miss = false;
-    for (uint32_t v = 0; v < n_variants; ++v) {
+    for (uint32_t v = v0; v < v1; ++v) {
         dm[v].pos = meta[v].pos;
         dm[v].ac = meta[v].ac;
         dm[v].rid = meta[v].rid;
@@ -1350,8 +1357,51 @@ static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing) {
                       (meta[v].gt_missing ? VF_GT_MISSING : 0u);
         miss = miss || meta[v].gt_missing || meta[v].an;
     }
-    std::memset(dm + n_variants, 0, (size_t)(ctx->Mpad - n_variants) * sizeof(DevVariant));
+    return miss;
+}
+static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing) {
+    const uint32_t n_variants = ctx->n_variants;
+    const int rc = ensure_dm(ctx);
+    if (rc) return rc;
+    const bool miss = fill_dm_range(ctx->h_dm, meta, 0, n_variants);
+    std::memset(ctx->h_dm + n_variants, 0, (size_t)(ctx->Mpad - n_variants) * sizeof(DevVariant));
     if (any_missing) *any_missing = miss;
+    return TWKB_OK;
+}
+// (a) + (b) of the matrix loads, behind the transfer. Up to META_TEAM_MIN variants: (a) on a helper thread, (b) on the
+// calling thread -- the transfer (2.4 ms for the 131 MB of C2) outlasts both. Beyond it the passes are what the load waits
+// for: at 8 ranks the weak-scaled matrix has 566,000 variants but a rank uploads only 1/8 of the rows (46 MB, < 1 ms) and
+// the load still took 5.8 ms. There one pass per chunk of variants runs on a small team of threads (the calling thread is
+// one of them; the ranks of a node share the host's cores).
+constexpr uint32_t META_TEAM_MIN = 400000;
+static int host_meta_work(Context* ctx, const twkb_variant* meta, bool* any_missing) {
+    const uint32_t M = ctx->n_variants;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    const unsigned team = std::min(4u, std::max(1u, hw / (unsigned)std::max(1, ctx->comm_size)));
+    if (M < META_TEAM_MIN || team < 3) {
+        std::thread helper(copy_meta, ctx, meta);
+        const int rc = fill_dm(ctx, meta, any_missing);
+        helper.join();
+        return rc;
+    }
+    const int rc = ensure_dm(ctx);
+    if (rc) return rc;
+    ctx->h_meta.resize(M);
+    std::vector<uint8_t> miss(team, 0);
+    auto work = [&](unsigned k) {
+        const uint32_t v0 = (uint32_t)((uint64_t)M * k / team), v1 = (uint32_t)((uint64_t)M * (k + 1) / team);
+        std::memcpy(ctx->h_meta.data() + v0, meta + v0, (size_t)(v1 - v0) * sizeof(twkb_variant));
+        miss[k] = fill_dm_range(ctx->h_dm, meta, v0, v1) ? 1 : 0;
+    };
+    std::vector<std::thread> helpers;
+    for (unsigned k = 1; k < team; ++k) helpers.emplace_back(work, k);
+    work(0);
+    for (std::thread& t : helpers) t.join();
+    std::memset(ctx->h_dm + M, 0, (size_t)(ctx->Mpad - M) * sizeof(DevVariant));
+    bool any = false;
+    for (uint8_t m : miss) any = any || m;
+    if (any_missing) *any_missing = any;
     return TWKB_OK;
 }
 static void load_meta(Context* ctx, const twkb_variant* meta) {
@@ -1434,10 +1484,8 @@ static int load_common(Context* ctx, uint32_t n_samples, uint32_t n_variants, co
     CUDA_TRY(cudaMemcpyAsync(ctx->d_raw_data.p, data, words * 8, kind, ctx->stream));
     ctx->stats.bytes_h2d = device_src ? 0 : words * 8;
     // host metadata work behind the transfer: copy on a helper thread, device records (+ the missing-data flag) here
-    std::thread helper(copy_meta, ctx, meta);
     bool miss = false;
-    rc = fill_dm(ctx, meta, &miss);
-    helper.join();
+    rc = host_meta_work(ctx, meta, &miss);
     if (rc) return rc;
     ctx->any_missing = miss;
     if (miss && !mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
@@ -1592,10 +1640,8 @@ static int load_matrix_sliced(Context* ctx, uint32_t n_samples, uint32_t n_varia
     // host metadata work behind the transfer + collective: copy on a helper thread, device records here. The
     // missing-data flag comes out of the same pass; it is identical on every rank (same metadata), so all ranks
     // agree on whether a mask exchange follows.
-    std::thread helper(copy_meta, ctx, meta);
     bool miss = false;
-    rc = fill_dm(ctx, meta, &miss);
-    helper.join();
+    rc = host_meta_work(ctx, meta, &miss);
     if (rc) return rc;
     ctx->any_missing = miss;
     if (miss && rows && !slice_mask) { ctx->err = "variants flagged missing but mask_bits is NULL"; return TWKB_EINVAL; }
