@@ -70,6 +70,11 @@ static inline const char* tuning_env(const char* name) { return getenv(name); }
 static inline const char* tuning_env(const char*) { return nullptr; }
 #endif
 
+// The host keeps 8 of the 32 bytes of a caller's twkb_variant: contig and position are all the scheduler consults (window
+// rules, .twk blocks, -c chunks). Every load rewrites this copy for every variant, on every rank: at 566,000 variants x 8
+// ranks the full 32-byte copy was a third of the host-memory traffic of a load that is bound by exactly that.
+struct HostVar { uint32_t rid, pos; };
+
 struct Problem {  // one rectangular sub-problem of the pair grid
     uint32_t row_begin, row_end, col_begin, col_end;
     bool diag;
@@ -95,7 +100,7 @@ struct Context {
     DevBuf<DevVariant> d_meta;
     DevBuf<double> d_lgamma;
     uint32_t lgamma_len = 0;
-    std::vector<twkb_variant> h_meta;
+    std::vector<HostVar> h_meta;             // what the scheduler reads of a variant, resident order
     UmmaOperand umma;  // int8-expanded operand of the tensor-core kernel
 
     // Rare-variant (list) class. When active the resident matrix is ordered
@@ -105,7 +110,7 @@ struct Context {
     uint32_t nD = 0, nS = 0, sparse_T = 0;
     std::vector<uint32_t> h_orig;            // resident -> original index (identity when !permuted)
     bool h_orig_identity = false;            // h_orig currently holds 0, 1, 2, ...
-    std::vector<twkb_variant> h_meta_orig;   // metadata in file order -- filled only when the rows were re-ordered (meta_orig())
+    std::vector<HostVar> h_meta_orig;   // metadata in file order -- filled only when the rows were re-ordered (meta_orig())
     DevVariant* h_dm = nullptr;              // pinned staging of the device metadata
     size_t h_dm_cap = 0;
     uint32_t lgamma_ready = 0;               // length of the log-factorial table resident in d_lgamma
@@ -175,7 +180,7 @@ struct Context {
 };
 
 // Metadata in FILE order (block structure, visited pairs): h_meta itself unless the rare-variant class re-ordered the rows.
-static const std::vector<twkb_variant>& meta_orig(const Context* ctx) { return ctx->permuted ? ctx->h_meta_orig : ctx->h_meta; }
+static const std::vector<HostVar>& meta_orig(const Context* ctx) { return ctx->permuted ? ctx->h_meta_orig : ctx->h_meta; }
 
 static void settings_defaults(twkb_settings* s) {
     // reference lib/core.cpp:297-306
@@ -289,7 +294,7 @@ static int ensure_planes(Context* ctx, int mode) {
 // ld_balancing.h:189-196.
 // First variant of every .twk block in file order (+ M at the end): from the file's index when the caller supplied it
 // (twkb_set_blocks), else blocks of twk_block_size variants that never span two contigs (lib/importer.cpp:196-236).
-static std::vector<uint32_t> block_starts(const Context* ctx, const std::vector<twkb_variant>& mo) {
+static std::vector<uint32_t> block_starts(const Context* ctx, const std::vector<HostVar>& mo) {
     const uint32_t M = ctx->n_variants;
     std::vector<uint32_t> first;
     if (!ctx->file_blocks.empty() && ctx->file_blocks.back() < M) {
@@ -310,7 +315,7 @@ static std::vector<uint32_t> block_starts(const Context* ctx, const std::vector<
 
 static void build_blocks_host(Context* ctx, std::vector<uint32_t>& blk_of_orig) {
     const uint32_t M = ctx->n_variants;
-    const std::vector<twkb_variant>& mo = meta_orig(ctx);  // blocks are defined on the file order
+    const std::vector<HostVar>& mo = meta_orig(ctx);  // blocks are defined on the file order
     blk_of_orig.assign(M, 0);
     ctx->h_blk_first.clear();
     ctx->h_blk_last.clear();
@@ -371,10 +376,10 @@ static uint64_t visited_pairs(const Context* ctx, const Problem& pb) {
     const uint32_t own = ctx->st.shard_blocks > 0 ? std::min(nb, (uint32_t)ctx->st.shard_blocks) : nb;  // a position shard counts its own block rows
     for (uint32_t bi = 0; bi < own; ++bi) {
         const uint64_t ni = ctx->h_blk_last[bi] - ctx->h_blk_first[bi] + 1;
-        const twkb_variant& vf = meta_orig(ctx)[ctx->h_blk_first[bi]];
+        const HostVar& vf = meta_orig(ctx)[ctx->h_blk_first[bi]];
         for (uint32_t bj = bi; bj < ctx->h_blk_prune[bi] || bj == bi; ++bj) {
             if (bj >= nb) break;
-            const twkb_variant& vl = meta_orig(ctx)[ctx->h_blk_last[bj]];
+            const HostVar& vl = meta_orig(ctx)[ctx->h_blk_last[bj]];
             const bool aborted = kind == 1u && vf.rid == vl.rid && (uint32_t)(vl.pos - vf.pos) > w;
             if (!aborted) {
                 const uint64_t nj = ctx->h_blk_last[bj] - ctx->h_blk_first[bj] + 1;
@@ -483,8 +488,8 @@ static void build_tiles(const Context* ctx, const Problem& pb, uint32_t TI, uint
                     const uint32_t il = std::min(i0 + TI, std::min(M, pb.row_end)) - 1;
                     const uint32_t jf = std::max(j0, pb.col_begin), jl = std::min(j0 + TJ, std::min(M, pb.col_end)) - 1;
                     if (jf > il) {
-                        const twkb_variant &a0 = ctx->h_meta[std::max(i0, pb.row_begin)], &a1 = ctx->h_meta[il];
-                        const twkb_variant &b0 = ctx->h_meta[jf], &b1 = ctx->h_meta[jl];
+                        const HostVar &a0 = ctx->h_meta[std::max(i0, pb.row_begin)], &a1 = ctx->h_meta[il];
+                        const HostVar &b0 = ctx->h_meta[jf], &b1 = ctx->h_meta[jl];
                         if (a0.rid == a1.rid && a1.rid == b0.rid && b0.rid == b1.rid && b0.pos >= a1.pos &&
                             (uint32_t)(b0.pos - a1.pos) > w)
                             continue;
@@ -569,7 +574,7 @@ static void build_sparse_tiles(const Context* ctx, std::vector<uint2>& tiles, ui
     uint64_t group = 0, pairs = 0;
     for (uint32_t r0 = nD; r0 < M; r0 += SP_ROWS) {
         const uint32_t r1 = std::min<uint32_t>(r0 + SP_ROWS, M);
-        const twkb_variant &a0 = ctx->h_meta[r0], &a1 = ctx->h_meta[r1 - 1];
+        const HostVar &a0 = ctx->h_meta[r0], &a1 = ctx->h_meta[r1 - 1];
         for (uint32_t j0 = 0; j0 < M; j0 += SP_TJ) {
             const uint32_t j1 = std::min<uint32_t>(j0 + SP_TJ, M);
             const uint32_t da = j0, db = std::min(j1, nD);        // dense columns of the tile
@@ -581,7 +586,7 @@ static void build_sparse_tiles(const Context* ctx, std::vector<uint2>& tiles, ui
                 continue;  // position shard: halo rows x halo columns
             if (window) {
                 auto far = [&](uint32_t ca, uint32_t cb) {
-                    const twkb_variant &b0 = ctx->h_meta[ca], &b1 = ctx->h_meta[cb - 1];
+                    const HostVar &b0 = ctx->h_meta[ca], &b1 = ctx->h_meta[cb - 1];
                     if (!(a0.rid == a1.rid && b0.rid == b1.rid && a0.rid == b0.rid)) return false;
                     if (b0.pos >= a1.pos && (uint32_t)(b0.pos - a1.pos) > w) return true;
                     if (a0.pos >= b1.pos && (uint32_t)(a0.pos - b1.pos) > w) return true;
@@ -1335,7 +1340,13 @@ static int load_begin_shapes(Context* ctx, uint32_t n_samples, uint32_t n_varian
 // variants (8-GPU weak scaling) that is 18 MB read twice and 27 MB written -- 8 ms when done serially in front of the
 // upload, with 8 ranks competing for the host's memory bandwidth. The matrix loads therefore enqueue the row upload (and
 // the all-gather) FIRST, then run (a) and (b) behind the transfer (host_meta_work).
-static void copy_meta(Context* ctx, const twkb_variant* meta) { ctx->h_meta.assign(meta, meta + ctx->n_variants); }
+static void copy_meta_range(HostVar* dst, const twkb_variant* meta, uint32_t v0, uint32_t v1) {
+    for (uint32_t v = v0; v < v1; ++v) dst[v] = HostVar{meta[v].rid, meta[v].pos};
+}
+static void copy_meta(Context* ctx, const twkb_variant* meta) {
+    ctx->h_meta.resize(ctx->n_variants);
+    copy_meta_range(ctx->h_meta.data(), meta, 0, ctx->n_variants);
+}
 static int ensure_dm(Context* ctx) {
     if (ctx->h_dm_cap < ctx->Mpad) {
         if (ctx->h_dm) cudaFreeHost(ctx->h_dm);
@@ -1346,24 +1357,25 @@ static int ensure_dm(Context* ctx) {
     }
     return TWKB_OK;
 }
-// device records of variants [v0, v1); returns whether any of them has missing genotypes
-static bool fill_dm_range(DevVariant* dm, const twkb_variant* meta, uint32_t v0, uint32_t v1) {
+// device records of resident variants [v0, v1) from the caller's (file-order) metadata; perm (nullable) = file index of a
+// resident variant. Returns whether any of them has missing genotypes.
+static bool fill_dm_range(DevVariant* dm, const twkb_variant* meta, uint32_t v0, uint32_t v1, const uint32_t* perm = nullptr) {
     bool miss = false;
     for (uint32_t v = v0; v < v1; ++v) {
-        dm[v].pos = meta[v].pos;
-        dm[v].ac = meta[v].ac;
-        dm[v].rid = meta[v].rid;
-        dm[v].flags = (meta[v].an ? VF_HAS_MISSING : 0u) | (meta[v].hwe < 1e-4 ? VF_BAD_HWE : 0u) |
-                      (meta[v].gt_missing ? VF_GT_MISSING : 0u);
-        miss = miss || meta[v].gt_missing || meta[v].an;
+        const twkb_variant& m = meta[perm ? perm[v] : v];
+        dm[v].pos = m.pos;
+        dm[v].ac = m.ac;
+        dm[v].rid = m.rid;
+        dm[v].flags = (m.an ? VF_HAS_MISSING : 0u) | (m.hwe < 1e-4 ? VF_BAD_HWE : 0u) | (m.gt_missing ? VF_GT_MISSING : 0u);
+        miss = miss || m.gt_missing || m.an;
     }
     return miss;
 }
-static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing) {
+static int fill_dm(Context* ctx, const twkb_variant* meta, bool* any_missing, const uint32_t* perm = nullptr) {
     const uint32_t n_variants = ctx->n_variants;
     const int rc = ensure_dm(ctx);
     if (rc) return rc;
-    const bool miss = fill_dm_range(ctx->h_dm, meta, 0, n_variants);
+    const bool miss = fill_dm_range(ctx->h_dm, meta, 0, n_variants, perm);
     std::memset(ctx->h_dm + n_variants, 0, (size_t)(ctx->Mpad - n_variants) * sizeof(DevVariant));
     if (any_missing) *any_missing = miss;
     return TWKB_OK;
@@ -1391,7 +1403,7 @@ static int host_meta_work(Context* ctx, const twkb_variant* meta, bool* any_miss
     std::vector<uint8_t> miss(team, 0);
     auto work = [&](unsigned k) {
         const uint32_t v0 = (uint32_t)((uint64_t)M * k / team), v1 = (uint32_t)((uint64_t)M * (k + 1) / team);
-        std::memcpy(ctx->h_meta.data() + v0, meta + v0, (size_t)(v1 - v0) * sizeof(twkb_variant));
+        copy_meta_range(ctx->h_meta.data(), meta, v0, v1);
         miss[k] = fill_dm_range(ctx->h_dm, meta, v0, v1) ? 1 : 0;
     };
     std::vector<std::thread> helpers;
@@ -1431,11 +1443,11 @@ static int load_finish(Context* ctx, const twkb_variant* meta, bool dm_ready = f
         ctx->h_meta_orig = ctx->h_meta;
         for (uint32_t x = 0; x < n_variants; ++x) ctx->h_meta[x] = ctx->h_meta_orig[ctx->h_orig[x]];
     }
-    meta = ctx->h_meta.data();  // resident order from here on
     // device metadata, staged in pinned memory so that the copy is asynchronous (already filled by the matrix loads
-    // while the rows were in flight, unless the rare-variant class re-ordered the variants)
+    // while the rows were in flight, unless the rare-variant class re-ordered the variants: then in resident order,
+    // from the caller's file-order metadata through h_orig)
     if (!dm_ready || ctx->permuted) {
-        const int rc_dm = fill_dm(ctx, meta, nullptr);
+        const int rc_dm = fill_dm(ctx, meta, nullptr, ctx->permuted ? ctx->h_orig.data() : nullptr);
         if (rc_dm) return rc_dm;
     }
     DevVariant* dm = ctx->h_dm;
@@ -2522,7 +2534,7 @@ static int twkb_plan_tiles_impl(const twkb_settings* s, uint32_t n_variants, con
     ctx.st = *s;
     if (ctx.st.part_count <= 0) { ctx.st.part_count = 1; ctx.st.part_index = 0; }
     ctx.n_variants = n_variants;
-    ctx.h_meta.assign(meta, meta + n_variants);
+    copy_meta(&ctx, meta);
     Problem pb;
     rc = select_problem(&ctx, pb);
     if (rc) return rc;
