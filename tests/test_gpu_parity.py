@@ -580,6 +580,32 @@ def test_small_work_buffers_overflow_retry_and_record_rotation(monkeypatch):
     eng.close()
 
 
+def test_400k_variant_load_equals_union_of_two_overlapping_loads():
+    """Loads of >= 400,000 variants run the host-side metadata passes (the scheduler's copy of contig / position, the
+    device records) chunk-wise on a thread team (engine.cu: host_meta_work); smaller loads use the two-thread arrangement.
+    A -w run over 400,000 variants (window 60 kb = 600 variants, above the 50 kb span of a .twk block) must give exactly the
+    union of the same run over two overlapping, block-aligned halves of the matrix."""
+    s = tf.synth_genotypes(300, 400_000, seed=41, p_copy=0.9)
+    data, mask = tf.pack_bits(s)
+    meta = lc.variant_meta(s)
+    prm = dict(force_phased=1, minR2=0.3, window=1, l_window=60_000)
+
+    def run(lo, hi):
+        eng = tb.Engine(**prm)
+        eng.load(300, np.ascontiguousarray(data[lo:hi]), None if mask is None else np.ascontiguousarray(mask[lo:hi]),
+                 np.ascontiguousarray(meta[lo:hi]))
+        recs = eng.compute()
+        eng.close()
+        return tf.canonical(recs, forward_only=False)
+
+    whole = run(0, 400_000)
+    parts = np.concatenate([run(0, 250_000), run(150_000, 400_000)])
+    parts = np.unique(parts.view(np.dtype((np.void, 106)))).view(np.uint8).reshape(-1, 106)
+    whole_u = np.unique(whole.view(np.dtype((np.void, 106)))).view(np.uint8).reshape(-1, 106)
+    assert len(whole_u) == len(whole) > 100_000           # keys are unique; plenty of records
+    assert np.array_equal(whole_u, parts)
+
+
 @pytest.mark.timeout(300)
 def test_two_contexts_on_one_device_run_concurrently_without_hanging():
     """Two contexts on ONE device, each launching full-grid (148-CTA) persistent count kernels from its own host thread
