@@ -12,7 +12,10 @@ CASES = [("phased", dict(n_samples=300, n_variants=700, seed=1), dict(force_phas
          ("unphased_missing", dict(n_samples=300, n_variants=500, seed=5, missing_rate=0.05), dict(forced_unphased=1, minR2=0.1)),
          ("sparse", dict(n_samples=1000, n_variants=600, seed=6, rare_fraction=0.8), dict(force_phased=1, minR2=0.2, sparse_max_words=6))]
 kernels = [tb.KERNEL_AUTO, tb.KERNEL_POPC] if "--popc" in sys.argv else [tb.KERNEL_AUTO]
+only = [a for a in sys.argv[1:] if not a.startswith("--")]   # optional: names of the cases to run
 for name, skw, prm in CASES:
+    if only and name not in only:
+        continue
     s = synth.synth_genotypes(**skw)
     data, mask = synth.pack_bits(s); meta = synth.variant_meta(s)
     for k in kernels:
