@@ -330,6 +330,24 @@ int read_twk(const std::string& path, int n_threads, TwkFile& out, std::string& 
         blocks.swap(kept);
     }
     n_ent = blocks.size();
+    // Plausibility of the (attacker-controlled) index BEFORE anything is sized by it: a block's variant count has to fit the
+    // block's own uncompressed size -- 38 bytes of fixed twk1_t fields and at least one run word per variant behind the 12-byte
+    // block header -- and that size has to be one a zstd frame of the block's compressed size can expand to. Without it a
+    // corrupt count (up to 2^32 - 1 variants) became a 137 GB metadata allocation that the kernel's OOM killer answered.
+    {
+        uint64_t checked = 0;
+        for (uint64_t b = 0; b < n_ent; ++b) {
+            const BlockRef& br = blocks[b];
+            if (br.foff > file.size() || file.size() - br.foff < 9) { err = "block offset beyond file"; return TWKB_EIO; }
+            Cursor bc{file.data() + br.foff, file.data() + file.size()};
+            if (bc.get<uint8_t>() != 1) { err = "bad block marker"; return TWKB_EIO; }
+            const uint64_t unc = bc.get<uint32_t>(), cmp = bc.get<uint32_t>();
+            if (cmp > (uint64_t)(bc.end - bc.p) || unc > (1ull << 20) + 32768ull * cmp) { err = "Failed to load block " + std::to_string(b); return TWKB_EIO; }
+            if ((uint64_t)br.n * 39ull + 12ull > unc) { err = "index/block variant count mismatch"; return TWKB_EIO; }
+            checked += br.n;
+        }
+        if (checked != total) { err = "corrupt index (variant count)"; return TWKB_EIO; }
+    }
     out.n_blocks = (uint32_t)blocks.size();
     out.block_first.clear();
     for (const BlockRef& b : blocks) out.block_first.push_back(b.first_variant);
